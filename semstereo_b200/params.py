@@ -1,0 +1,134 @@
+"""Parameter inventory and seeded synthetic data for the disparity hot path.
+
+The key names and shapes are the reference's `state_dict` entries for the modules on the
+path (`models/SemStereo.py:204-239`), so a reference checkpoint's
+tensors can be handed to `semstereo_b200.hotpath.DisparityHotPath.load_state_dict` unchanged.
+ConvTranspose3d weights keep PyTorch's (Cin, Cout, kD, kH, kW) layout.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import torch
+
+
+def _bn(d, prefix, c):
+    d[prefix + ".weight"] = (c,)
+    d[prefix + ".bias"] = (c,)
+    d[prefix + ".running_mean"] = (c,)
+    d[prefix + ".running_var"] = (c,)
+
+
+def _hourglass(d, hg, c=32):
+    """hourglass / hourglass2 (`models/SemStereo.py:106-182`)."""
+    for name, ci, co in (("conv1", c, 2 * c), ("conv2", 2 * c, 2 * c), ("conv3", 2 * c, 4 * c), ("conv4", 4 * c, 4 * c)):
+        d[f"{hg}.{name}.0.0.weight"] = (co, ci, 3, 3, 3)
+        _bn(d, f"{hg}.{name}.0.1", co)
+    d[f"{hg}.attention_block.qkv_3d.weight"] = (12 * c, 4 * c)
+    d[f"{hg}.attention_block.qkv_3d.bias"] = (12 * c,)
+    d[f"{hg}.attention_block.final1x1.weight"] = (4 * c, 4 * c, 1, 1, 1)
+    d[f"{hg}.attention_block.final1x1.bias"] = (4 * c,)
+    d[f"{hg}.conv5.0.weight"] = (4 * c, 2 * c, 3, 3, 3)
+    _bn(d, f"{hg}.conv5.1", 2 * c)
+    d[f"{hg}.conv6.0.weight"] = (2 * c, c, 3, 3, 3)
+    _bn(d, f"{hg}.conv6.1", c)
+    d[f"{hg}.redir1.0.weight"] = (c, c, 1, 1, 1)
+    _bn(d, f"{hg}.redir1.1", c)
+    d[f"{hg}.redir2.0.weight"] = (2 * c, 2 * c, 1, 1, 1)
+    _bn(d, f"{hg}.redir2.1", 2 * c)
+
+
+def hotpath_param_shapes(num_classes: int = 6) -> "OrderedDict[str, tuple]":
+    d: "OrderedDict[str, tuple]" = OrderedDict()
+    d["gamma"] = (1,)
+    d["beta"] = (1,)
+    d["patch.weight"] = (32, 1, 1, 3, 3)
+    for pre, cin in (("corr_feature_att_8", 256), ("concat_feature_att_4", 128)):
+        d[pre + ".im_att.0.conv.weight"] = (cin // 2, cin, 1, 1)
+        _bn(d, pre + ".im_att.0.bn", cin // 2)
+        d[pre + ".im_att.1.weight"] = (32, cin // 2, 1, 1)
+        d[pre + ".im_att.1.bias"] = (32,)
+    _hourglass(d, "hourglass_att")
+    _hourglass(d, "hourglass")
+    for cl in ("classif_att_", "classif"):
+        d[cl + ".0.0.weight"] = (32, 32, 3, 3, 3)
+        _bn(d, cl + ".0.1", 32)
+        d[cl + ".2.weight"] = (1, 32, 3, 3, 3)
+    d["concat_stem.conv.weight"] = (32, 64, 3, 3, 3)
+    _bn(d, "concat_stem.bn", 32)
+    nc = num_classes
+    _bn(d, "ssr_upsample.conv.0", 1)
+    d["ssr_upsample.conv.1.weight"] = (nc, 1, 3, 3)
+    d["ssr_upsample.conv.1.bias"] = (nc,)
+    _bn(d, "ssr_upsample.conv.2", nc)
+    for k in ("conv1", "conv2"):
+        d[f"ssr_upsample.{k}.0.weight"] = (nc, nc, 1, 1)
+        d[f"ssr_upsample.{k}.0.bias"] = (nc,)
+        _bn(d, f"ssr_upsample.{k}.1", nc)
+    d["ssr_upsample.conv3.weight"] = (1, nc, 1, 1)
+    d["ssr_upsample.conv3.bias"] = (1,)
+    return d
+
+
+def make_params(seed: int = 1, peaked: float = 1.0, gamma: float = 0.05) -> "OrderedDict[str, torch.Tensor]":
+    """Seeded random parameters (CPU fp32).  Conv/linear weights ~ U(-b, b), b = sqrt(3/fan_in)
+    (unit-gain, keeps activations O(1) through the stack); BN statistics are deliberately
+    non-trivial so that BN folding is exercised.  `peaked` scales the two 32->1 classifier heads:
+    with peaked >> 1 the disparity softmaxes are sharp and top-k selection is well conditioned
+    (SURVEY.md section 0.7)."""
+    g = torch.Generator().manual_seed(seed)
+    p: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for name, shape in hotpath_param_shapes().items():
+        if name == "gamma":
+            t = torch.full(shape, float(gamma))
+        elif name == "beta":
+            t = torch.full(shape, 2.0)
+        elif name.endswith("running_var"):
+            t = torch.rand(shape, generator=g) + 0.5
+        elif name.endswith("running_mean"):
+            t = 0.1 * torch.randn(shape, generator=g)
+        elif len(shape) == 1 and name.endswith(".weight"):       # BN gamma
+            t = torch.rand(shape, generator=g) + 0.5
+        elif len(shape) == 1:                                     # biases
+            t = 0.1 * torch.randn(shape, generator=g)
+        else:
+            if ".conv5.0." in name or ".conv6.0." in name:       # ConvTranspose3d (Cin,Cout,k,k,k)
+                fan_in = shape[0] * 27 / 8.0                      # ~27/8 taps hit each output voxel
+            else:
+                fan_in = 1
+                for s in shape[1:]:
+                    fan_in *= s
+            b = (3.0 / fan_in) ** 0.5
+            t = (torch.rand(shape, generator=g) * 2 - 1) * b
+        if name in ("classif_att_.2.weight", "classif.2.weight"):
+            t = t * peaked
+        p[name] = t.contiguous()
+    return p
+
+
+def make_inputs(seed: int, B: int, H: int, W: int, num_classes: int = 6, max_shift: int = 3):
+    """Seeded synthetic inputs of the hot path for a (B,3,H,W) stereo pair (CPU fp32).
+    Right features are the left ones displaced along x by a row-block-dependent shift plus noise,
+    so the cost volumes have real structure.  H, W must be multiples of 128 (the two
+    window-attention stages need H/32 % 4 == 0 and W/32 % 4 == 0)."""
+    assert H % 128 == 0 and W % 128 == 0, "H and W must be multiples of 128"
+    g = torch.Generator().manual_seed(seed)
+
+    def pair(c, h, w, scale):
+        l = torch.randn(B, c, h, w, generator=g)
+        r = torch.empty_like(l)
+        nblk = 4
+        for i in range(nblk):
+            s = (i % (2 * max_shift + 1)) - max_shift
+            ys = slice(i * h // nblk, (i + 1) * h // nblk)
+            r[:, :, ys] = torch.roll(l[:, :, ys], shifts=-s * scale, dims=-1)
+        r = r + 0.25 * torch.randn(B, c, h, w, generator=g)
+        return l.contiguous(), r.contiguous()
+
+    f8_l, f8_r = pair(256, H // 8, W // 8, 1)
+    f4_l, f4_r = pair(128, H // 4, W // 4, 2)
+    cf_l, cf_r = pair(32, H // 4, W // 4, 2)
+    spx = torch.randn(B, num_classes, H, W, generator=g)
+    lab = 2.0 * torch.randn(B, num_classes, H, W, generator=g)
+    return dict(f8_l=f8_l, f8_r=f8_r, f4_l=f4_l, f4_r=f4_r, cf_l=cf_l, cf_r=cf_r,
+                spx_pred=spx.contiguous(), pred_label=lab.contiguous())
