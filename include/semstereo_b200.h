@@ -1,0 +1,117 @@
+/* semstereo_b200.h — C-ABI of the B200-native disparity hot path of SemStereo.
+ *
+ * Every entry point replaces one function / module of the reference's Python operator surface
+ * (cited per function as file:line under /root/reference).  Conventions:
+ *   - all pointers are DEVICE pointers to contiguous fp32 NCHW / NCDHW tensors unless stated otherwise;
+ *   - the library never allocates, frees or retains caller memory; outputs are fully overwritten;
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream),
+ *     never synchronises, and is CUDA-graph capturable; entry points are re-entrant (one Python thread per GPU
+ *     as nn.DataParallel does is fine);
+ *   - return value: 0 on success, <0 on error (SS_ERR_*), with a thread-local message from ss_last_error();
+ *     no exceptions cross the ABI.  Unsupported shapes return SS_ERR_UNSUPPORTED: there is no CPU / cuDNN fallback;
+ *   - `flags` bit 0 (SS_SIGNED): disparity range -maxdisp..maxdisp-1, depth 2*maxdisp  (models/submodule.py)
+ *                     else       0..maxdisp-1, depth maxdisp                       (models/submodule_.py).
+ */
+#ifndef SEMSTEREO_B200_H
+#define SEMSTEREO_B200_H
+
+#ifdef __cplusplus
+#define SS_API extern "C" __attribute__((visibility("default")))
+#else
+#define SS_API __attribute__((visibility("default")))
+#endif
+
+#define SS_SIGNED 1
+#define SS_NORM 2
+
+#define SS_ERR_BAD_ARG (-1)
+#define SS_ERR_UNSUPPORTED (-2)
+#define SS_ERR_CUDA (-3)
+
+/* ---- library ---------------------------------------------------------------------------------------- */
+SS_API int ss_version(void);                /* major*10000 + minor*100 + patch */
+SS_API const char* ss_last_error(void);     /* thread-local, valid until the next failing call of this thread */
+SS_API int ss_sm_count(void);               /* SM count of the current device */
+
+/* ---- K1/K2: cost-volume builders -------------------------------------------------------------------- */
+/* build_gwc_volume (submodule.py:198-211, submodule_.py:188-198), build_gwc_volume_norm (submodule.py:224-238,
+ * submodule_.py:211-221; flags |= SS_NORM) and build_norm_correlation_volume (submodule.py:244-255; num_groups = 1, SS_NORM).
+ * left/right (B,C,H,W) -> volume (B,num_groups,D,H,W), D = 2*maxdisp (signed) or maxdisp. */
+SS_API int ss_gwc_volume(const float* left, const float* right, float* volume, int B, int C, int H, int W, int maxdisp,
+                         int num_groups, int flags, void* stream);
+/* build_concat_volume (submodule.py:173-187; unsigned submodule_.py:166-178 leaves the left half unmasked).
+ * -> volume (B,2C,D,H,W). */
+SS_API int ss_concat_volume(const float* left, const float* right, float* volume, int B, int C, int H, int W, int maxdisp,
+                            int flags, void* stream);
+
+/* ---- K3: patch depthwise conv + channel gate -------------------------------------------------------- */
+/* `patch` = Conv3d(G,G,(1,3,3),groups=G,bias=False) (SemStereo.py:219,274), weight (G,1,1,3,3) as (G,9), fused with the
+ * channelAtt product sigmoid(gate_logits (B,G,H,W))[:, :, None] * cv (SemStereo.py:98-103).  Either may be NULL. */
+SS_API int ss_patch_gate(const float* volume, const float* patch_w_or_null, const float* gate_logits_or_null, float* out, int B,
+                         int G, int D, int H, int W, void* stream);
+/* 1x1 Conv2d of channelAtt.im_att (SemStereo.py:93-95): out = act(scale*W.x + shift); weight (Cout,Cin); P = H*W. */
+SS_API int ss_pointwise_conv2d(const float* in, const float* weight, const float* scale_or_null, const float* shift_or_null,
+                               float* out, int B, int Cin, int Cout, int P, int relu, void* stream);
+
+/* ---- K4: 3-D convolutions, fp32-accurate mode ------------------------------------------------------- */
+/* convbn_3d (submodule_other.py:845-848), BasicConv(is_3d) (submodule.py:89-116), nn.ConvTranspose3d(k3,s2,p1,op1)
+ * (SemStereo.py:124-130), with eval BatchNorm folded into scale/shift and the hourglass residual/ReLU (SemStereo.py:141-142)
+ * and the channelAtt gate (SemStereo.py:320) as epilogue.  weight_packed is [K^3][Cin][Cout] (tap = (kd*K+kh)*K+kw; for
+ * mode 1 the tap indexes the ConvTranspose3d weight (Cin,Cout,kd,kh,kw) directly).  mode 0: Conv3d(K,stride,pad=K/2);
+ * mode 1: ConvTranspose3d(3,2,1,1), out dims = 2x in dims.  residual: same shape as out.  gate: (B,Cout,Ho,Wo) logits. */
+SS_API int ss_conv3d_f32(const float* in, const float* weight_packed, const float* scale_or_null, const float* shift_or_null,
+                         const float* residual_or_null, const float* gate_logits_or_null, float* out, int B, int Cin, int Cout,
+                         int Di, int Hi, int Wi, int K, int stride, int mode, int relu, void* stream);
+/* nn.Conv3d(Cin,1,3,padding=1,bias=False) classifier head (SemStereo.py:230,234); weight in PyTorch layout (1,Cin,3,3,3). */
+SS_API int ss_conv3d_cout1_f32(const float* in, const float* weight, float* out, int B, int Cin, int D, int H, int W, void* stream);
+
+/* ---- K5: windowed 3-D attention --------------------------------------------------------------------- */
+/* attention_block.forward (submodule_other.py:805-837) for window-divisible D,H,W.  wqkv_t = qkv_3d.weight^T [C][3C],
+ * wo_t = final1x1.weight^T [C][C] (wo_t[c][co]).  Only C=128, 16 heads, windows of 64 or 96 tokens. */
+SS_API int ss_window_attention3d(const float* x, const float* wqkv_t, const float* bqkv, const float* wo_t, const float* bo,
+                                 float* out, int B, int C, int D, int H, int W, int bd, int bh, int bw, int num_heads,
+                                 void* stream);
+
+/* ---- K6/K7/K8: attention statistics, sample strength, top-k selection -------------------------------- */
+/* F.interpolate(trilinear, x2) -> softmax(dim=1) -> disparity_regression -> disparity_variance -> sigmoid(beta+gamma*var)
+ * (SemStereo.py:279-287).  cost_att (B,1,D8,H8,W8) -> att_up (B,2*D8,2*H8,2*W8) logits, mu (B,2H8,2W8), gate (B,1,2H8,2W8).
+ * beta/gamma: device pointers to the 1-element parameters.  dmin = disparity value of bin 0. */
+SS_API int ss_att_stats(const float* cost_att, const float* beta, const float* gamma, float* att_up, float* mu, float* gate, int B,
+                        int D8, int H8, int W8, float dmin, void* stream);
+/* Propagation x2 + SpatialTransformer_grid + (L*Rwarp).mean(C) + softmax(strength*var) (SemStereo.py:288-293)
+ * -> strength (B,5,H,W). */
+SS_API int ss_sample_strength(const float* feat_l, const float* feat_r, const float* mu, const float* gate, float* strength, int B,
+                              int C, int H, int W, void* stream);
+/* Propagation_prob, mix, softmax, top-K (ascending bin order; ties toward the lower bin), gathers, renormalised expectation
+ * (SemStereo.py:295-310).  ind_k (B,1,K,H,W) int64 (may be NULL), att_topk/disp_topk (B,K,H,W), pred_att (B,H,W),
+ * prob_or_null (B,nbins,H,W) = the full softmax.  disp_topk = bin - disp_offset. */
+SS_API int ss_topk_select(const float* att_up, const float* strength, long long* ind_k_or_null, float* att_topk, float* disp_topk,
+                          float* pred_att, float* prob_or_null, int B, int nbins, int K, int H, int W, float disp_offset,
+                          void* stream);
+
+/* ---- K9/K10/K11/K12 ----------------------------------------------------------------------------------- */
+/* concat_volume_generator (SemStereo.py:241-244) * att_topk (:318) -> volume (B,2C,K,H,W). att_topk may be NULL (= 1). */
+SS_API int ss_sparse_concat_volume(const float* cf_l, const float* cf_r, const float* disp_topk, const float* att_topk_or_null,
+                                   float* volume, int B, int C, int K, int H, int W, void* stream);
+/* regression_topk (submodule.py:434-442): cost, disp_samples (B,D,H,W) -> pred (B,1,H,W); ties toward the lower index. */
+SS_API int ss_regression_topk(const float* cost, const float* disp_samples, float* pred, int B, int D, int K, int H, int W,
+                              void* stream);
+/* SSR_upsample.forward (submodule.py:421-431), eval BatchNorm.  packed_host: HOST array of ss_ssr_param_count(nc) floats:
+ * a0,b0 | wc[nc][9], bc[nc] | s2[nc], t2[nc] | w1[nc][nc], b1[nc], s1[nc], t1[nc] | w2[nc][nc], b2[nc], s2b[nc], t2b[nc] |
+ * w3[nc], b3   (BN layers as scale/shift).  depth_low (B,1,h,w); spx, label (B,nc,4h,4w) -> out (B,4h,4w). */
+SS_API int ss_ssr_param_count(int num_classes);
+SS_API int ss_ssr_upsample(const float* depth_low, const float* spx, const float* label, float* out, const float* packed_host, int B,
+                           int h, int w, int num_classes, void* stream);
+/* context_upsample (submodule_.py:311-323): depth_low (B,1,h,w), up_weights (B,9,4h,4w) -> out (B,4h,4w). */
+SS_API int ss_context_upsample(const float* depth_low, const float* up_weights, float* out, int B, int h, int w, void* stream);
+/* disparity_regression (submodule.py:164-170) / disparity_variance (:257-263): prob (B,D,H,W); dmin = value of bin 0. */
+SS_API int ss_disparity_regression(const float* prob, float* out, int B, int D, int H, int W, float dmin, void* stream);
+SS_API int ss_disparity_variance(const float* prob, const float* disparity, float* out, int B, int D, int H, int W, float dmin,
+                                 void* stream);
+/* Propagation (submodule.py:290-307; D=1) and Propagation_prob (:361-377): in (B,1,D,H,W) -> out (B,5,D,H,W). */
+SS_API int ss_propagation(const float* in, float* out, int B, int D, int H, int W, void* stream);
+/* SpatialTransformer_grid (submodule.py:265-288): x,y (B,C,H,W), disp_samples (B,K,H,W) -> y_warped, x_rep (B,C,K,H,W). */
+SS_API int ss_spatial_transformer_grid(const float* x, const float* y, const float* disp_samples, float* y_warped,
+                                       float* x_rep_or_null, int B, int C, int K, int H, int W, void* stream);
+
+#endif /* SEMSTEREO_B200_H */

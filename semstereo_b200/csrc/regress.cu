@@ -1,0 +1,385 @@
+// K6, K7, K8, K10, K12 and the standalone warps/propagations: single-pass, HBM-bound kernels that keep
+// the whole disparity column of a pixel in registers.
+//   att_stats            : trilinear x2 -> softmax -> mean -> variance -> sigmoid gate   (SemStereo.py:279-287)
+//   sample_strength      : Propagation x2 -> SpatialTransformer_grid -> corr -> softmax   (SemStereo.py:288-293)
+//   topk_select          : Propagation_prob -> mix -> softmax -> top-k -> gathers          (SemStereo.py:295-310)
+//   regression_topk      : models/submodule.py:434-442
+//   disparity_regression / disparity_variance : models/submodule.py:164-170, 257-263
+//   propagation / propagation_prob / spatial_transformer_grid : models/submodule.py:265-307, 361-377
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// linear-resize source index, PyTorch align_corners=False: src = max(0,(dst+.5)*scale-.5)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lin_src(int dst, float scale, int n_in, int& i0, int& i1, float& l0, float& l1) {
+  float src = fmaxf(((float)dst + 0.5f) * scale - 0.5f, 0.0f);
+  i0 = min((int)src, n_in - 1);
+  i1 = min(i0 + 1, n_in - 1);
+  l1 = src - (float)i0;
+  l0 = 1.0f - l1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6
+// ---------------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(128) att_stats_kernel(const float* __restrict__ cost, const float* __restrict__ beta,
+                                                        const float* __restrict__ gamma, float* __restrict__ att_up,
+                                                        float* __restrict__ mu_out, float* __restrict__ gate_out,
+                                                        int B, int D8, int H8, int W8, float dmin) {
+  const int H4 = 2 * H8, W4 = 2 * W8, nb = 2 * D8;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, b = blockIdx.z;
+  if (x >= W4) return;
+  int y0, y1, x0, x1;
+  float hy0, hy1, wx0, wx1;
+  lin_src(y, 0.5f, H8, y0, y1, hy0, hy1);
+  lin_src(x, 0.5f, W8, x0, x1, wx0, wx1);
+  const float* cb = cost + (size_t)b * D8 * H8 * W8;
+  float v[NB / 2];
+#pragma unroll
+  for (int d = 0; d < NB / 2; ++d) {
+    if (d < D8) {
+      const float* s = cb + (size_t)d * H8 * W8;
+      float a = __ldg(s + y0 * W8 + x0), bb = __ldg(s + y0 * W8 + x1);
+      float c = __ldg(s + y1 * W8 + x0), dd = __ldg(s + y1 * W8 + x1);
+      v[d] = hy0 * (wx0 * a + wx1 * bb) + hy1 * (wx0 * c + wx1 * dd);
+    } else v[d] = 0.0f;
+  }
+  float u[NB];
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    if (k < nb) {
+      int i0, i1;
+      float l0, l1;
+      lin_src(k, 0.5f, D8, i0, i1, l0, l1);
+      // i0/i1 are compile-time foldable per k only when D8 is known; select from registers
+      float a = 0.f, c = 0.f;
+#pragma unroll
+      for (int d = 0; d < NB / 2; ++d) { a = (d == i0) ? v[d] : a; c = (d == i1) ? v[d] : c; }
+      u[k] = l0 * a + l1 * c;
+      m = fmaxf(m, u[k]);
+    } else u[k] = -INFINITY;
+  }
+  const size_t pix = (size_t)y * W4 + x;
+  float* ao = att_up + (size_t)b * nb * H4 * W4 + pix;
+  float s = 0.0f;
+  float e[NB];
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    if (k < nb) {
+      ao[(size_t)k * H4 * W4] = u[k];
+      e[k] = expf(u[k] - m);
+      s += e[k];
+    } else e[k] = 0.0f;
+  }
+  float mu = 0.0f;
+#pragma unroll
+  for (int k = 0; k < NB; ++k)
+    if (k < nb) { e[k] = e[k] / s; mu += e[k] * (dmin + (float)k); }
+  float var = 0.0f;
+#pragma unroll
+  for (int k = 0; k < NB; ++k)
+    if (k < nb) { float t = (dmin + (float)k) - mu; var += e[k] * (t * t); }
+  mu_out[(size_t)b * H4 * W4 + pix] = mu;
+  gate_out[(size_t)b * H4 * W4 + pix] = sigmoidf_(__ldg(beta) + __ldg(gamma) * var);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7: block = (64 pixels) x (5 hypotheses)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(320) sample_strength_kernel(const float* __restrict__ fl, const float* __restrict__ fr,
+                                                              const float* __restrict__ mu, const float* __restrict__ gate,
+                                                              float* __restrict__ strength, int B, int C, int H, int W) {
+  __shared__ float logit[5][64];
+  const int tx = threadIdx.x, s = threadIdx.y;
+  const int x = blockIdx.x * 64 + tx, y = blockIdx.y, b = blockIdx.z;
+  const size_t HW = (size_t)H * W;
+  if (x < W) {
+    const int ty = min(max(y + kPropDy[s], 0), H - 1), txx = min(max(x + kPropDx[s], 0), W - 1);
+    const float d = __ldg(mu + (size_t)b * HW + (size_t)ty * W + txx);
+    const float g = __ldg(gate + (size_t)b * HW + (size_t)ty * W + txx);
+    const float ix = warp_coord((float)x - d, (float)(W - 1));
+    const float iy = warp_coord((float)y, (float)(H - 1));
+    const Bilin q = make_bilin(ix, iy, H, W);
+    const float* lp = fl + (size_t)b * C * HW + (size_t)y * W + x;
+    const float* rp = fr + (size_t)b * C * HW;
+    float acc = 0.0f;
+#pragma unroll 4
+    for (int c = 0; c < C; ++c) acc += __ldg(lp + (size_t)c * HW) * bilin_fetch(rp + (size_t)c * HW, q);
+    logit[s][tx] = (acc / (float)C) * g;
+  }
+  __syncthreads();
+  if (x < W) {
+    float m = logit[0][tx];
+#pragma unroll
+    for (int i = 1; i < 5; ++i) m = fmaxf(m, logit[i][tx]);
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) sum += expf(logit[i][tx] - m);
+    strength[((size_t)b * 5 + s) * HW + (size_t)y * W + x] = expf(logit[s][tx] - m) / sum;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8
+// ---------------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(128) topk_select_kernel(const float* __restrict__ att, const float* __restrict__ strength,
+                                                          long long* __restrict__ ind_k, float* __restrict__ att_topk,
+                                                          float* __restrict__ disp_topk, float* __restrict__ pred_att,
+                                                          float* __restrict__ prob_out, int B, int nb, int K, int H, int W,
+                                                          float disp_offset) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, b = blockIdx.z;
+  if (x >= W) return;
+  const size_t HW = (size_t)H * W, pix = (size_t)y * W + x;
+  size_t tap[5];
+  float st[5];
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const int ty = min(max(y + kPropDy[s], 0), H - 1), tx = min(max(x + kPropDx[s], 0), W - 1);
+    tap[s] = (size_t)ty * W + tx;
+    st[s] = __ldg(strength + ((size_t)b * 5 + s) * HW + pix);
+  }
+  const float* ab = att + (size_t)b * nb * HW;
+  float mix[NB], p[NB];
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    if (k < nb) {
+      const float* a = ab + (size_t)k * HW;
+      float acc = __fmul_rn(__ldg(a + tap[0]), st[0]);       // products then a sequential sum, as torch.sum(dim=1)
+#pragma unroll
+      for (int s = 1; s < 5; ++s) acc = __fadd_rn(acc, __fmul_rn(__ldg(a + tap[s]), st[s]));
+      mix[k] = acc;
+      m = fmaxf(m, acc);
+    } else mix[k] = -INFINITY;
+  }
+  float sum = 0.0f;
+#pragma unroll
+  for (int k = 0; k < NB; ++k) { p[k] = (k < nb) ? expf(mix[k] - m) : 0.0f; sum += p[k]; }
+#pragma unroll
+  for (int k = 0; k < NB; ++k) p[k] = (k < nb) ? p[k] / sum : -1.0f;
+  if (prob_out) {
+#pragma unroll
+    for (int k = 0; k < NB; ++k)
+      if (k < nb) prob_out[((size_t)b * nb + k) * HW + pix] = p[k];
+  }
+  // rank of bin k among the probabilities, ties broken toward the lower index; keep rank < K
+  unsigned long long keep = 0ull;
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) rank += (p[j] > p[k] || (p[j] == p[k] && j < k)) ? 1 : 0;
+    if (k < nb && rank < K) keep |= 1ull << k;
+  }
+  float m2 = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < NB; ++k)
+    if ((keep >> k) & 1ull) m2 = fmaxf(m2, mix[k]);
+  float s2 = 0.0f;
+#pragma unroll
+  for (int k = 0; k < NB; ++k)
+    if ((keep >> k) & 1ull) s2 += expf(mix[k] - m2);
+  float pred = 0.0f;
+  int j = 0;
+  const size_t obase = (size_t)b * K * HW + pix;
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    if ((keep >> k) & 1ull) {
+      const float d = (float)k - disp_offset;
+      if (ind_k) ind_k[obase + (size_t)j * HW] = k;
+      att_topk[obase + (size_t)j * HW] = p[k];
+      disp_topk[obase + (size_t)j * HW] = d;
+      pred += (expf(mix[k] - m2) / s2) * d;
+      ++j;
+    }
+  }
+  pred_att[(size_t)b * HW + pix] = pred;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K10
+// ---------------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(128) regression_topk_kernel(const float* __restrict__ cost, const float* __restrict__ samples,
+                                                              float* __restrict__ out, int B, int D, int K, size_t HW) {
+  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (pix >= HW) return;
+  float c[NB];
+#pragma unroll
+  for (int k = 0; k < NB; ++k) c[k] = (k < D) ? __ldg(cost + ((size_t)b * D + k) * HW + pix) : -INFINITY;
+  unsigned long long taken = 0ull;
+  float top = 0.0f, sum = 0.0f, acc = 0.0f;
+  for (int r = 0; r < K; ++r) {
+    float best = -INFINITY;
+    int bi = 0;
+    bool found = false;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      bool free_ = k < D && !((taken >> k) & 1ull);
+      if (free_ && (!found || c[k] > best)) { best = c[k]; bi = k; found = true; }   // strict > keeps the lower index on ties
+    }
+    taken |= 1ull << bi;
+    if (r == 0) top = best;
+    const float e = expf(best - top);
+    sum += e;
+    acc += e * __ldg(samples + ((size_t)b * D + bi) * HW + pix);
+  }
+  out[(size_t)b * HW + pix] = acc / sum;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K12 + standalone propagation / warp
+// ---------------------------------------------------------------------------------------------
+__global__ void regress_var_kernel(const float* __restrict__ p, const float* __restrict__ mu_in, float* __restrict__ out,
+                                   int D, size_t HW, float dmin, int variance) {
+  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (pix >= HW) return;
+  const float mu = variance ? __ldg(mu_in + (size_t)b * HW + pix) : 0.0f;
+  float acc = 0.0f;
+  for (int k = 0; k < D; ++k) {
+    const float v = __ldg(p + ((size_t)b * D + k) * HW + pix);
+    const float d = dmin + (float)k;
+    acc += variance ? v * ((d - mu) * (d - mu)) : v * d;
+  }
+  out[(size_t)b * HW + pix] = acc;
+}
+
+// in (B,D,H,W) -> out (B,5,D,H,W); D = 1 for Propagation
+__global__ void propagation_kernel(const float* __restrict__ in, float* __restrict__ out, int D, int H, int W) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= W) return;
+  const int y = blockIdx.y % H, d = blockIdx.y / H, b = blockIdx.z;
+  const size_t HW = (size_t)H * W;
+  const float* ib = in + ((size_t)b * D + d) * HW;
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const int ty = min(max(y + kPropDy[s], 0), H - 1), tx = min(max(x + kPropDx[s], 0), W - 1);
+    out[(((size_t)b * 5 + s) * D + d) * HW + (size_t)y * W + x] = __ldg(ib + (size_t)ty * W + tx);
+  }
+}
+
+// y_warped[b,c,k,y,x] = bilinear(src[b,c], x - disp[b,k,y,x], y);  x_rep[b,c,k,y,x] = xin[b,c,y,x]
+__global__ void __launch_bounds__(128) stn_kernel(const float* __restrict__ xin, const float* __restrict__ src,
+                                                  const float* __restrict__ disp, float* __restrict__ y_warped,
+                                                  float* __restrict__ x_rep, int C, int K, int H, int W) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= W) return;
+  const int y = blockIdx.y % H, k = blockIdx.y / H, b = blockIdx.z;
+  const size_t HW = (size_t)H * W;
+  const float d = __ldg(disp + ((size_t)b * K + k) * HW + (size_t)y * W + x);
+  const Bilin q = make_bilin(warp_coord((float)x - d, (float)(W - 1)), warp_coord((float)y, (float)(H - 1)), H, W);
+  for (int c = 0; c < C; ++c) {
+    const size_t o = (((size_t)b * C + c) * K + k) * HW + (size_t)y * W + x;
+    y_warped[o] = bilin_fetch(src + ((size_t)b * C + c) * HW, q);
+    if (x_rep) x_rep[o] = __ldg(xin + ((size_t)b * C + c) * HW + (size_t)y * W + x);
+  }
+}
+
+}  // namespace
+
+#define SS_GRID_LIMIT(cond, name) SS_UNSUPPORTED(!(cond), "%s: grid dimension exceeds 65535", name)
+
+extern "C" int ss_att_stats(const float* cost_att, const float* beta, const float* gamma, float* att_up, float* mu, float* gate,
+                            int B, int D8, int H8, int W8, float dmin, void* stream) {
+  SS_REQUIRE(cost_att && beta && gamma && att_up && mu && gate, "ss_att_stats: null pointer");
+  SS_REQUIRE(B > 0 && D8 > 0 && H8 > 0 && W8 > 0, "ss_att_stats: non-positive dimension");
+  SS_UNSUPPORTED(2 * D8 > 64, "ss_att_stats: more than 64 disparity bins (%d) unsupported", 2 * D8);
+  SS_GRID_LIMIT(2 * H8 <= 65535 && B <= 65535, "ss_att_stats");
+  dim3 grid(ceil_div(2 * W8, 128), 2 * H8, B);
+  if (2 * D8 <= 32)
+    att_stats_kernel<32><<<grid, 128, 0, (cudaStream_t)stream>>>(cost_att, beta, gamma, att_up, mu, gate, B, D8, H8, W8, dmin);
+  else
+    att_stats_kernel<64><<<grid, 128, 0, (cudaStream_t)stream>>>(cost_att, beta, gamma, att_up, mu, gate, B, D8, H8, W8, dmin);
+  SS_CHECK_LAUNCH("ss_att_stats");
+  return SS_OK;
+}
+
+extern "C" int ss_sample_strength(const float* feat_l, const float* feat_r, const float* mu, const float* gate, float* strength,
+                                  int B, int C, int H, int W, void* stream) {
+  SS_REQUIRE(feat_l && feat_r && mu && gate && strength, "ss_sample_strength: null pointer");
+  SS_REQUIRE(B > 0 && C > 0 && H > 1 && W > 1, "ss_sample_strength: bad dimension");
+  SS_GRID_LIMIT(H <= 65535 && B <= 65535, "ss_sample_strength");
+  dim3 grid(ceil_div(W, 64), H, B), block(64, 5);
+  sample_strength_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(feat_l, feat_r, mu, gate, strength, B, C, H, W);
+  SS_CHECK_LAUNCH("ss_sample_strength");
+  return SS_OK;
+}
+
+extern "C" int ss_topk_select(const float* att_up, const float* strength, long long* ind_k, float* att_topk, float* disp_topk,
+                              float* pred_att, float* prob_or_null, int B, int nbins, int K, int H, int W, float disp_offset,
+                              void* stream) {
+  SS_REQUIRE(att_up && strength && att_topk && disp_topk && pred_att, "ss_topk_select: null pointer");
+  SS_REQUIRE(B > 0 && nbins > 0 && K > 0 && K <= nbins && H > 0 && W > 0, "ss_topk_select: need 0 < K <= nbins");
+  SS_UNSUPPORTED(nbins > 64, "ss_topk_select: more than 64 disparity bins (%d) unsupported", nbins);
+  SS_GRID_LIMIT(H <= 65535 && B <= 65535, "ss_topk_select");
+  dim3 grid(ceil_div(W, 128), H, B);
+  if (nbins <= 32)
+    topk_select_kernel<32><<<grid, 128, 0, (cudaStream_t)stream>>>(att_up, strength, ind_k, att_topk, disp_topk, pred_att,
+                                                                    prob_or_null, B, nbins, K, H, W, disp_offset);
+  else
+    topk_select_kernel<64><<<grid, 128, 0, (cudaStream_t)stream>>>(att_up, strength, ind_k, att_topk, disp_topk, pred_att,
+                                                                    prob_or_null, B, nbins, K, H, W, disp_offset);
+  SS_CHECK_LAUNCH("ss_topk_select");
+  return SS_OK;
+}
+
+extern "C" int ss_regression_topk(const float* cost, const float* disp_samples, float* pred, int B, int D, int K, int H, int W,
+                                  void* stream) {
+  SS_REQUIRE(cost && disp_samples && pred, "ss_regression_topk: null pointer");
+  SS_REQUIRE(B > 0 && D > 0 && K > 0 && K <= D && H > 0 && W > 0, "ss_regression_topk: need 0 < k <= D");
+  SS_UNSUPPORTED(D > 64, "ss_regression_topk: more than 64 samples (%d) unsupported", D);
+  SS_GRID_LIMIT(B <= 65535, "ss_regression_topk");
+  const size_t HW = (size_t)H * W;
+  dim3 grid((unsigned)ceil_div64(HW, 128), B);
+  if (D <= 32) regression_topk_kernel<32><<<grid, 128, 0, (cudaStream_t)stream>>>(cost, disp_samples, pred, B, D, K, HW);
+  else         regression_topk_kernel<64><<<grid, 128, 0, (cudaStream_t)stream>>>(cost, disp_samples, pred, B, D, K, HW);
+  SS_CHECK_LAUNCH("ss_regression_topk");
+  return SS_OK;
+}
+
+extern "C" int ss_disparity_regression(const float* prob, float* out, int B, int D, int H, int W, float dmin, void* stream) {
+  SS_REQUIRE(prob && out && B > 0 && D > 0 && H > 0 && W > 0, "ss_disparity_regression: bad argument");
+  SS_GRID_LIMIT(B <= 65535, "ss_disparity_regression");
+  const size_t HW = (size_t)H * W;
+  regress_var_kernel<<<dim3((unsigned)ceil_div64(HW, 256), B), 256, 0, (cudaStream_t)stream>>>(prob, nullptr, out, D, HW, dmin, 0);
+  SS_CHECK_LAUNCH("ss_disparity_regression");
+  return SS_OK;
+}
+
+extern "C" int ss_disparity_variance(const float* prob, const float* disparity, float* out, int B, int D, int H, int W, float dmin,
+                                     void* stream) {
+  SS_REQUIRE(prob && disparity && out && B > 0 && D > 0 && H > 0 && W > 0, "ss_disparity_variance: bad argument");
+  SS_GRID_LIMIT(B <= 65535, "ss_disparity_variance");
+  const size_t HW = (size_t)H * W;
+  regress_var_kernel<<<dim3((unsigned)ceil_div64(HW, 256), B), 256, 0, (cudaStream_t)stream>>>(prob, disparity, out, D, HW, dmin, 1);
+  SS_CHECK_LAUNCH("ss_disparity_variance");
+  return SS_OK;
+}
+
+extern "C" int ss_propagation(const float* in, float* out, int B, int D, int H, int W, void* stream) {
+  SS_REQUIRE(in && out && B > 0 && D > 0 && H > 0 && W > 0, "ss_propagation: bad argument");
+  SS_GRID_LIMIT((int64_t)D * H <= 65535 && B <= 65535, "ss_propagation");
+  propagation_kernel<<<dim3(ceil_div(W, 128), D * H, B), 128, 0, (cudaStream_t)stream>>>(in, out, D, H, W);
+  SS_CHECK_LAUNCH("ss_propagation");
+  return SS_OK;
+}
+
+extern "C" int ss_spatial_transformer_grid(const float* x, const float* y, const float* disp_samples, float* y_warped,
+                                           float* x_rep_or_null, int B, int C, int K, int H, int W, void* stream) {
+  SS_REQUIRE(y && disp_samples && y_warped && (x || !x_rep_or_null), "ss_spatial_transformer_grid: null pointer");
+  SS_REQUIRE(B > 0 && C > 0 && K > 0 && H > 1 && W > 1, "ss_spatial_transformer_grid: bad dimension");
+  SS_GRID_LIMIT((int64_t)K * H <= 65535 && B <= 65535, "ss_spatial_transformer_grid");
+  stn_kernel<<<dim3(ceil_div(W, 128), K * H, B), 128, 0, (cudaStream_t)stream>>>(x, y, disp_samples, y_warped, x_rep_or_null,
+                                                                                C, K, H, W);
+  SS_CHECK_LAUNCH("ss_spatial_transformer_grid");
+  return SS_OK;
+}

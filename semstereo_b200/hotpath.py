@@ -1,0 +1,264 @@
+"""DisparityHotPath — the reference's disparity path (models/SemStereo.py:273-324 and
+models/SemStereo_WHU.py:273-324) executed by the sm_100a kernels behind the C-ABI.
+
+The module owns ordinary torch parameter containers (nn.Conv3d, nn.BatchNorm3d, nn.Linear ...) laid out
+exactly like the reference's sub-modules, so `state_dict()` keys/shapes equal the reference's
+ and a reference checkpoint loads with `load_state_dict(..., strict=False)`.
+Those containers are storage only: their `forward` is never called.  `forward` here issues the fused
+CUDA kernels; folded/packed weights are cached and rebuilt after `load_state_dict` / parameter edits
+(`refresh()`).
+
+Inputs (what the out-of-scope 2-D part of the model produces):
+  f8_l,f8_r (B,256,H/8,W/8); f4_l,f4_r (B,128,H/4,W/4); cf_l,cf_r (B,32,H/4,W/4) = concat_feature(f4_*);
+  spx_pred (B,6,H,W); pred_label (B,6,H,W).
+Outputs are in 1/4-res disparity units exactly as `ssr_upsample` returns them; `SemStereo.forward`
+multiplies by 4 (SemStereo.py:329-346) — `as_model_outputs` does the same.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+TOPK = 24  # SemStereo.py:301
+
+
+def _convbn3d(cin, cout, k, stride, pad):
+    """Parameter container with the key layout of convbn_3d (submodule_other.py:845-848): '0' conv, '1' bn."""
+    return nn.Sequential(nn.Conv3d(cin, cout, k, stride, pad, bias=False), nn.BatchNorm3d(cout))
+
+
+class _AttentionParams(nn.Module):
+    """Keys of attention_block (submodule_other.py:790-803)."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.qkv_3d = nn.Linear(c, 3 * c, bias=True)
+        self.final1x1 = nn.Conv3d(c, c, 1)
+
+
+class _HourglassParams(nn.Module):
+    """Keys of hourglass / hourglass2 (SemStereo.py:106-132, 145-171)."""
+
+    def __init__(self, c, block):
+        super().__init__()
+        self.block = tuple(block)
+        self.conv1 = nn.Sequential(_convbn3d(c, 2 * c, 3, 2, 1), nn.ReLU())
+        self.conv2 = nn.Sequential(_convbn3d(2 * c, 2 * c, 3, 1, 1), nn.ReLU())
+        self.conv3 = nn.Sequential(_convbn3d(2 * c, 4 * c, 3, 2, 1), nn.ReLU())
+        self.conv4 = nn.Sequential(_convbn3d(4 * c, 4 * c, 3, 1, 1), nn.ReLU())
+        self.attention_block = _AttentionParams(4 * c)
+        self.conv5 = nn.Sequential(nn.ConvTranspose3d(4 * c, 2 * c, 3, 2, 1, 1, bias=False), nn.BatchNorm3d(2 * c))
+        self.conv6 = nn.Sequential(nn.ConvTranspose3d(2 * c, c, 3, 2, 1, 1, bias=False), nn.BatchNorm3d(c))
+        self.redir1 = _convbn3d(c, c, 1, 1, 0)
+        self.redir2 = _convbn3d(2 * c, 2 * c, 1, 1, 0)
+
+
+class _ConvBN(nn.Module):
+    """Keys of BasicConv (submodule.py:89-107): 'conv', 'bn'."""
+
+    def __init__(self, conv, bn):
+        super().__init__()
+        self.conv, self.bn = conv, bn
+
+
+class _ChannelAttParams(nn.Module):
+    """Keys of channelAtt (SemStereo.py:89-96)."""
+
+    def __init__(self, cv_chan, im_chan):
+        super().__init__()
+        self.im_att = nn.Sequential(_ConvBN(nn.Conv2d(im_chan, im_chan // 2, 1, bias=False), nn.BatchNorm2d(im_chan // 2)),
+                                    nn.Conv2d(im_chan // 2, cv_chan, 1))
+
+
+class _SSRParams(nn.Module):
+    """Keys of SSR_upsample (submodule.py:413-419)."""
+
+    def __init__(self, nc):
+        super().__init__()
+        self.conv = nn.Sequential(nn.BatchNorm2d(1), nn.Conv2d(1, nc, 3, padding=1), nn.BatchNorm2d(nc))
+        self.conv1 = nn.Sequential(nn.Conv2d(nc, nc, 1), nn.BatchNorm2d(nc))
+        self.conv2 = nn.Sequential(nn.Conv2d(nc, nc, 1), nn.BatchNorm2d(nc))
+        self.conv3 = nn.Conv2d(nc, 1, 1)
+
+
+def bn_affine(bn):
+    """Eval-mode BatchNorm as per-channel (scale, shift) from the running statistics."""
+    scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+    shift = bn.bias.detach() - bn.running_mean * scale
+    return scale.float().contiguous(), shift.float().contiguous()
+
+
+def pack_ssr(ssr: nn.Module) -> torch.Tensor:
+    """Folded SSR_upsample parameters in the order ss_ssr_upsample expects (include/semstereo_b200.h)."""
+    a0, b0 = bn_affine(ssr.conv[0])
+    s2, t2 = bn_affine(ssr.conv[2])
+    s1, t1 = bn_affine(ssr.conv1[1])
+    sb, tb = bn_affine(ssr.conv2[1])
+    parts = [a0, b0, ssr.conv[1].weight.detach().reshape(-1), ssr.conv[1].bias.detach(), s2, t2,
+             ssr.conv1[0].weight.detach().reshape(-1), ssr.conv1[0].bias.detach(), s1, t1,
+             ssr.conv2[0].weight.detach().reshape(-1), ssr.conv2[0].bias.detach(), sb, tb,
+             ssr.conv3.weight.detach().reshape(-1), ssr.conv3.bias.detach()]
+    return torch.cat([p.float().reshape(-1).cpu() for p in parts]).contiguous()
+
+
+class DisparityHotPath(nn.Module):
+    def __init__(self, maxdisp: int, att_weights_only: bool = False, signed: bool = True, num_classes: int = 6):
+        super().__init__()
+        if maxdisp % 8:
+            raise ValueError("maxdisp must be a multiple of 8 (the 1/8-res volume is upsampled exactly x2)")
+        nb = (2 if signed else 1) * (maxdisp // 4)
+        if nb < TOPK or nb > 64:
+            raise NotImplementedError(f"{nb} attention bins unsupported (need {TOPK} <= bins <= 64)")
+        self.maxdisp, self.att_weights_only, self.signed, self.num_classes = maxdisp, att_weights_only, signed, num_classes
+        self.gamma = nn.Parameter(torch.zeros(1))
+        self.beta = nn.Parameter(2 * torch.ones(1))
+        self.patch = nn.Conv3d(32, 32, (1, 3, 3), 1, (0, 1, 1), groups=32, bias=False)
+        self.corr_feature_att_8 = _ChannelAttParams(32, 256)
+        self.concat_feature_att_4 = _ChannelAttParams(32, 128)
+        self.hourglass_att = _HourglassParams(32, (4, 4, 4))
+        self.classif_att_ = nn.Sequential(_convbn3d(32, 32, 3, 1, 1), nn.ReLU(), nn.Conv3d(32, 1, 3, 1, 1, bias=False))
+        self.hourglass = _HourglassParams(32, (6, 4, 4))
+        self.classif = nn.Sequential(_convbn3d(32, 32, 3, 1, 1), nn.ReLU(), nn.Conv3d(32, 1, 3, 1, 1, bias=False))
+        self.concat_stem = _ConvBN(nn.Conv3d(64, 32, 3, 1, 1, bias=False), nn.BatchNorm3d(32))
+        self.ssr_upsample = _SSRParams(num_classes)
+        self._cache = None
+        self.eval()
+        for p in self.parameters():
+            p.requires_grad_(False)
+
+    # ------------------------------------------------------------------------------------------
+    def load_state_dict(self, state_dict, strict=False, **kw):
+        """Accepts a full reference checkpoint: keys outside the path are ignored, a leading 'module.' (DataParallel,
+        main_us3d.py:100) is stripped."""
+        own = self.state_dict()
+        sd = {}
+        for k, v in state_dict.items():
+            k = k[7:] if k.startswith("module.") else k
+            if k in own:
+                sd[k] = v
+        missing = [k for k in own if k not in sd and not k.endswith("num_batches_tracked")]
+        if strict and missing:
+            raise KeyError(f"missing hot-path keys: {missing[:5]} ...")
+        out = super().load_state_dict(sd, strict=False, **kw)
+        self._cache = None
+        return out
+
+    def refresh(self):
+        self._cache = None
+
+    def _apply(self, fn, *a, **k):
+        self._cache = None
+        return super()._apply(fn, *a, **k)
+
+    # ------------------------------------------------------------------------------------------
+    def _packed(self):
+        if self._cache is not None:
+            return self._cache
+        if self.training:
+            raise NotImplementedError("DisparityHotPath is inference-only (eval-mode BatchNorm is folded)")
+        c = {}
+
+        def conv(name, convmod, bn, transposed=False):
+            c[name + ".w"] = ops.pack_conv3d_weight(convmod.weight.detach().float(), transposed)
+            if bn is not None:
+                c[name + ".scale"], c[name + ".shift"] = bn_affine(bn)
+
+        for hg in ("hourglass_att", "hourglass"):
+            m = getattr(self, hg)
+            for n in ("conv1", "conv2", "conv3", "conv4"):
+                conv(f"{hg}.{n}", getattr(m, n)[0][0], getattr(m, n)[0][1])
+            conv(f"{hg}.conv5", m.conv5[0], m.conv5[1], True)
+            conv(f"{hg}.conv6", m.conv6[0], m.conv6[1], True)
+            conv(f"{hg}.redir1", m.redir1[0], m.redir1[1])
+            conv(f"{hg}.redir2", m.redir2[0], m.redir2[1])
+            a = m.attention_block
+            c[hg + ".wqkv_t"] = a.qkv_3d.weight.detach().float().t().contiguous()
+            c[hg + ".bqkv"] = a.qkv_3d.bias.detach().float().contiguous()
+            c[hg + ".wo_t"] = a.final1x1.weight.detach().float().reshape(a.final1x1.out_channels, -1).t().contiguous()
+            c[hg + ".bo"] = a.final1x1.bias.detach().float().contiguous()
+        for cl in ("classif_att_", "classif"):
+            m = getattr(self, cl)
+            conv(cl + ".0", m[0][0], m[0][1])
+            c[cl + ".2.w"] = m[2].weight.detach().float().contiguous()
+        conv("concat_stem", self.concat_stem.conv, self.concat_stem.bn)
+        for ca in ("corr_feature_att_8", "concat_feature_att_4"):
+            m = getattr(self, ca).im_att
+            c[ca + ".w0"] = m[0].conv.weight.detach().float().reshape(m[0].conv.out_channels, -1).contiguous()
+            c[ca + ".s0"], c[ca + ".t0"] = bn_affine(m[0].bn)
+            c[ca + ".w1"] = m[1].weight.detach().float().reshape(m[1].out_channels, -1).contiguous()
+            c[ca + ".b1"] = m[1].bias.detach().float().contiguous()
+        c["patch.w"] = self.patch.weight.detach().float().reshape(32, 9).contiguous()
+        c["ssr"] = pack_ssr(self.ssr_upsample)
+        self._cache = c
+        return c
+
+    # ------------------------------------------------------------------------------------------
+    def _gate_logits(self, c, name, im):
+        y = ops.pointwise_conv2d(im, c[name + ".w0"], c[name + ".s0"], c[name + ".t0"], relu=True)
+        return ops.pointwise_conv2d(y, c[name + ".w1"], None, c[name + ".b1"], relu=False)
+
+    def _conv(self, c, name, x, k=3, stride=1, relu=True, transposed=False, residual=None, gate=None):
+        with ops.label(name):
+            return self._conv_impl(c, name, x, k, stride, relu, transposed, residual, gate)
+
+    def _conv_impl(self, c, name, x, k, stride, relu, transposed, residual, gate):
+        return ops.conv3d_f32(x, c[name + ".w"], c.get(name + ".scale"), c.get(name + ".shift"), residual, gate,
+                              k=k, stride=stride, transposed=transposed, relu=relu)
+
+    def _hourglass(self, c, hg, x):
+        """hourglass.forward (SemStereo.py:134-143): residual adds and ReLUs ride in the deconv epilogues."""
+        block = getattr(self, hg).block
+        c1 = self._conv(c, hg + ".conv1", x, stride=2)
+        c2 = self._conv(c, hg + ".conv2", c1)
+        c3 = self._conv(c, hg + ".conv3", c2, stride=2)
+        c4 = self._conv(c, hg + ".conv4", c3)
+        c4 = ops.window_attention3d(c4, c[hg + ".wqkv_t"], c[hg + ".bqkv"], c[hg + ".wo_t"], c[hg + ".bo"], block, 16)
+        r2 = self._conv(c, hg + ".redir2", c2, k=1, relu=False)
+        c5 = self._conv(c, hg + ".conv5", c4, stride=2, transposed=True, residual=r2, relu=True)
+        r1 = self._conv(c, hg + ".redir1", x, k=1, relu=False)
+        return self._conv(c, hg + ".conv6", c5, stride=2, transposed=True, residual=r1, relu=True)
+
+    def _classifier(self, c, cl, x):
+        y = self._conv(c, cl + ".0", x)
+        with ops.label(cl + ".2"):
+            return ops.conv3d_cout1_f32(y, c[cl + ".2.w"])
+
+    @torch.no_grad()
+    def forward(self, f8_l, f8_r, f4_l, f4_r, cf_l, cf_r, spx_pred, pred_label, keep: bool = False):
+        c = self._packed()
+        m8, m4 = self.maxdisp // 8, self.maxdisp // 4
+        out = {}
+        # --- attention branch @1/8 (SemStereo.py:273-278) ---
+        corr = ops.gwc_volume(f8_l, f8_r, m8, 32, signed=self.signed, norm=True)
+        vol = ops.patch_gate(corr, c["patch.w"], self._gate_logits(c, "corr_feature_att_8", f8_l))
+        vol = self._hourglass(c, "hourglass_att", vol)
+        cost_att = self._classifier(c, "classif_att_", vol)
+        # --- statistics, propagation, top-k @1/4 (SemStereo.py:279-310) ---
+        dmin = float(-m4) if self.signed else 0.0
+        att_up, mu, gate = ops.att_stats(cost_att, self.beta.data, self.gamma.data, dmin)
+        strength = ops.sample_strength(f4_l, f4_r, mu, gate)
+        ind_k, att_topk, disp_topk, pred_att, prob = ops.topk_select(att_up, strength, TOPK, -dmin, want_indices=keep, want_prob=keep)
+        out.update(cost_att=cost_att, pred_att=pred_att, disp_topk=disp_topk, att_topk=att_topk)
+        if keep:
+            out.update(corr_volume=corr, att_weights=att_up, pred_att0=mu, var_gate=gate, strength=strength, ind_k=ind_k, prob=prob)
+        out["pred_att_up"] = ops.ssr_upsample(pred_att.unsqueeze(1), spx_pred, pred_label, c["ssr"])
+        if self.att_weights_only:
+            return out
+        # --- sparse concat volume + aggregation (SemStereo.py:314-324) ---
+        volume = ops.sparse_concat_volume(cf_l, cf_r, disp_topk, att_topk)
+        v = self._conv(c, "concat_stem", volume, gate=self._gate_logits(c, "concat_feature_att_4", f4_l))
+        v = self._hourglass(c, "hourglass", v)
+        cost = self._classifier(c, "classif", v)
+        pred = ops.regression_topk(cost.squeeze(1), disp_topk, 2)
+        out.update(cost=cost, pred=pred)
+        if keep:
+            out["volume"] = volume
+        out["pred_up"] = ops.ssr_upsample(pred, spx_pred, pred_label, c["ssr"])
+        return out
+
+    def as_model_outputs(self, out, pred_label):
+        """What SemStereo.forward returns in eval mode with seg_if (SemStereo.py:338-346)."""
+        key = "pred_att_up" if self.att_weights_only else "pred_up"
+        return [out[key] * 4], pred_label
