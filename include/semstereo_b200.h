@@ -65,6 +65,18 @@ SS_API int ss_conv3d_f32(const float* in, const float* weight_packed, const floa
 /* nn.Conv3d(Cin,1,3,padding=1,bias=False) classifier head (SemStereo.py:230,234); weight in PyTorch layout (1,Cin,3,3,3). */
 SS_API int ss_conv3d_cout1_f32(const float* in, const float* weight, float* out, int B, int Cin, int D, int H, int W, void* stream);
 
+/* ---- K4: 3-D convolutions, tensor-core mode (tcgen05 / TMEM / TMA, bf16 operands, fp32 accumulation) ------ */
+/* Activations in the "blocked channels" layout: bf16 [B][C/8][D][H][W][8].  Converters from / to fp32 NCDHW: */
+SS_API int ss_to_blocked_bf16(const float* in_ncdhw, void* out_blocked, int B, int C, int D, int H, int W, void* stream);
+SS_API int ss_from_blocked_bf16(const void* in_blocked, float* out_ncdhw, int B, int C, int D, int H, int W, void* stream);
+/* Conv3d k3 s1 p1 + folded eval-BN + ReLU + channelAtt gate (same layers as ss_conv3d_f32 mode 0, K=3, stride 1).
+ * weight_packed: bf16 [Cout/N][27][Cin/8][N][8] with N = ss_conv3d_tc_ntile(Cin,Cout) (0 = configuration unsupported).
+ * out: bf16 blocked (out_is_f32 = 0) or fp32 NCDHW (out_is_f32 = 1). */
+SS_API int ss_conv3d_tc_ntile(int Cin, int Cout);
+SS_API int ss_conv3d_tc(const void* in_blocked, const void* weight_packed, const float* scale_or_null, const float* shift_or_null,
+                        const float* gate_logits_or_null, void* out, int out_is_f32, int B, int Cin, int Cout, int D, int H, int W,
+                        int relu, void* stream);
+
 /* ---- K5: windowed 3-D attention --------------------------------------------------------------------- */
 /* attention_block.forward (submodule_other.py:805-837) for window-divisible D,H,W.  wqkv_t = qkv_3d.weight^T [C][3C],
  * wo_t = final1x1.weight^T [C][C] (wo_t[c][co]).  Only C=128, 16 heads, windows of 64 or 96 tokens. */
