@@ -47,9 +47,14 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_const
   uint8_t* Wbase = smem + NS * SLICE;
   __shared__ __align__(8) uint64_t a_full[NS], a_empty[NS], w_full[NWS], w_empty[NWS], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float s_scale[N], s_shift[N];     // folded BatchNorm of this CTA's Cout tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = blockIdx.x % p.n_tiles;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    s_scale[i] = p.scale ? __ldg(p.scale + nt * N + i) : 1.0f;
+    s_shift[i] = p.shift ? __ldg(p.shift + nt * N + i) : 0.0f;
+  }
   const int cta_s = blockIdx.x / p.n_tiles, cta_stride = gridDim.x / p.n_tiles;
 
   if (threadIdx.x == 0) {
@@ -115,9 +120,12 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_const
           }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===== MMA issuer =====
-    const uint32_t a_s = tc::smem_u32(Abase), w_s = tc::smem_u32(Wbase);
+  } else if (warp == 1) {
+    // ===== MMA issuer: the whole warp runs the (uniform) control flow so that descriptors live in uniform registers;
+    //       one elected lane issues the tcgen05 instructions =====
+    const bool leader = tc::elect_one();
+    const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(Abase), LBO_A), a_hi = tc::desc_hi(SBO_A);
+    const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(Wbase), LBO_B), b_hi = tc::desc_hi(SBO_B);
     if (kResident && cta_s < p.items) tc::mbar_wait(&w_full[0], 0);
     uint32_t g_base = 0, acc_it = 0, wc = 0;
     for (int s = cta_s; s < p.items; s += cta_stride) {
@@ -130,40 +138,49 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_const
         tc::fence_after_sync();
         const uint32_t tmem_d = tmem_base + as * N;
         uint32_t accumulate = 0;
+#pragma unroll 1
         for (int kd = 0; kd < 3; ++kd) {
           const int d_in = d_out + kd - 1;
           if (d_in < 0 || d_in >= p.D) continue;
           const uint32_t gs = g_base + (uint32_t)(d_in - din0), slot = gs % NS;
           tc::mbar_wait(&a_full[slot], (gs / NS) & 1);
           tc::fence_after_sync();
+          const uint32_t a_lo = a_lo0 + slot * (SLICE >> 4);
+#pragma unroll
           for (int t9 = 0; t9 < 9; ++t9) {
             const int kh = t9 / 3, kw = t9 - 3 * kh;
-            uint32_t wslot;
-            if (kResident) wslot = kd * 9 + t9;
+            uint32_t b_lo;
+            uint32_t wslot = 0;
+            if (kResident) b_lo = b_lo0 + (uint32_t)(kd * 9 + t9) * (TAPB >> 4);
             else {
               wslot = wc % NWS;
               tc::mbar_wait(&w_full[wslot], (wc / NWS) & 1);
               tc::fence_after_sync();
+              b_lo = b_lo0 + wslot * (TAPB >> 4);
             }
-            const uint32_t a_tap = a_s + slot * SLICE + (uint32_t)(kh * WW + kw) * 16;
-            const uint32_t b_tap = w_s + wslot * TAPB;
+            if (leader) {
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-              const uint64_t ad = tc::make_smem_desc(a_tap + ks * 2 * LBO_A, LBO_A, SBO_A);
-              const uint64_t bd = tc::make_smem_desc(b_tap + ks * 2 * LBO_B, LBO_B, SBO_B);
-              tc::mma_bf16(tmem_d, ad, bd, IDESC, accumulate);
-              accumulate = 1;
+              for (int ks = 0; ks < KS; ++ks) {
+                tc::mma_bf16_lohi(tmem_d, a_lo + (uint32_t)((kh * WW + kw) * 16 + ks * 2 * LBO_A) / 16, a_hi,
+                                  b_lo + (uint32_t)(ks * 2 * LBO_B) / 16, b_hi, IDESC, accumulate);
+                accumulate = 1;
+              }
+              if (!kResident) tc::mma_commit(&w_empty[wslot]);
             }
-            if (!kResident) { tc::mma_commit(&w_empty[wslot]); ++wc; }
+            accumulate = 1;
+            if (!kResident) ++wc;
           }
         }
-        tc::mma_commit(&acc_full[as]);
-        // input slices no output slice of this item needs any more
-        if (d_out - 1 >= din0) tc::mma_commit(&a_empty[(g_base + (uint32_t)(d_out - 1 - din0)) % NS]);
-        if (d_out == dhi - 1) {
-          tc::mma_commit(&a_empty[(g_base + (uint32_t)(d_out - din0)) % NS]);
-          if (d_out + 1 <= din1) tc::mma_commit(&a_empty[(g_base + (uint32_t)(d_out + 1 - din0)) % NS]);
+        if (leader) {
+          tc::mma_commit(&acc_full[as]);
+          // input slices no output slice of this item needs any more
+          if (d_out - 1 >= din0) tc::mma_commit(&a_empty[(g_base + (uint32_t)(d_out - 1 - din0)) % NS]);
+          if (d_out == dhi - 1) {
+            tc::mma_commit(&a_empty[(g_base + (uint32_t)(d_out - din0)) % NS]);
+            if (d_out + 1 <= din1) tc::mma_commit(&a_empty[(g_base + (uint32_t)(d_out + 1 - din0)) % NS]);
+          }
         }
+        __syncwarp();
       }
       g_base += (uint32_t)(din1 - din0 + 1);
     }
@@ -191,15 +208,16 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_const
           }
           if (!valid) continue;
           const int co0 = nt * N + j * 32;
+          const float lo = p.relu ? 0.0f : -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int co = co0 + i;
-            float x = v[i];
-            if (p.scale) x *= __ldg(p.scale + co);
-            if (p.shift) x += __ldg(p.shift + co);
-            if (p.relu) x = fmaxf(x, 0.0f);
-            if (p.gate) x *= sigmoidf_(__ldg(p.gate + ((size_t)b * p.Cout + co) * HWs + (size_t)h * p.W + w));
-            v[i] = x;
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(fmaf(v[i], s_scale[j * 32 + i], s_shift[j * 32 + i]), lo);
+          if (p.gate) {                     // branch hoisted out of the channel loop: 32 independent loads in flight
+            const float* gp = p.gate + ((size_t)b * p.Cout + co0) * HWs + (size_t)h * p.W + w;
+            float gl[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) gl[i] = __ldg(gp + (size_t)i * HWs);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= sigmoidf_(gl[i]);
           }
           if (p.out_f32) {
             float* o = reinterpret_cast<float*>(p.out) + (((size_t)b * p.Cout + co0) * p.D + d_out) * HWs + (size_t)h * p.W + w;

@@ -83,6 +83,27 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with the descriptors given as (lo, hi) 32-bit halves: only `lo` (start address field) changes between MMAs.
+__device__ __forceinline__ void mma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // arrives on `bar` once every previously issued tcgen05.mma of this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -116,6 +137,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)1 << 46;                            // [46,48) descriptor version = 1 (sm_100)
   return d;                                          // base_offset = 0, lbo_mode = 0, layout_type [61,64) = 0 (no swizzle)
 }
+// The two 32-bit halves of the same descriptor: lo = start address | LBO, hi = SBO | version.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFF) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14); }
 // Instruction descriptor for kind::f16: A,B = bf16 (K-major), D = fp32, dense.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4)                      // [4,6)   D format  = F32

@@ -104,8 +104,14 @@ def pack_ssr(ssr: nn.Module) -> torch.Tensor:
 
 
 class DisparityHotPath(nn.Module):
-    def __init__(self, maxdisp: int, att_weights_only: bool = False, signed: bool = True, num_classes: int = 6):
+    def __init__(self, maxdisp: int, att_weights_only: bool = False, signed: bool = True, num_classes: int = 6,
+                 precision: str = "fp32"):
+        """precision: "fp32" = every 3-D conv on the fp32 pipe (index-exact parity mode); "bf16" = the k3 s1 convolutions
+        (78 % of the FLOPs) run on the tcgen05 tensor cores with bf16 operands and fp32 accumulation."""
         super().__init__()
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
         if maxdisp % 8:
             raise ValueError("maxdisp must be a multiple of 8 (the 1/8-res volume is upsampled exactly x2)")
         nb = (2 if signed else 1) * (maxdisp // 4)
@@ -161,7 +167,11 @@ class DisparityHotPath(nn.Module):
         c = {}
 
         def conv(name, convmod, bn, transposed=False):
-            c[name + ".w"] = ops.pack_conv3d_weight(convmod.weight.detach().float(), transposed)
+            w = convmod.weight.detach().float()
+            c[name + ".w"] = ops.pack_conv3d_weight(w, transposed)
+            if (self.precision == "bf16" and not transposed and tuple(w.shape[2:]) == (3, 3, 3) and convmod.stride == (1, 1, 1)
+                    and ops.conv3d_tc_ntile(w.shape[1], w.shape[0]) > 0):
+                c[name + ".wtc"] = ops.pack_conv3d_weight_tc(w)
             if bn is not None:
                 c[name + ".scale"], c[name + ".shift"] = bn_affine(bn)
 
@@ -204,6 +214,9 @@ class DisparityHotPath(nn.Module):
             return self._conv_impl(c, name, x, k, stride, relu, transposed, residual, gate)
 
     def _conv_impl(self, c, name, x, k, stride, relu, transposed, residual, gate):
+        if name + ".wtc" in c and residual is None:
+            return ops.conv3d_tc(ops.to_blocked_bf16(x), c[name + ".wtc"], c.get(name + ".scale"), c.get(name + ".shift"), gate,
+                                 relu=relu, out_f32=True)
         return ops.conv3d_f32(x, c[name + ".w"], c.get(name + ".scale"), c.get(name + ".shift"), residual, gate,
                               k=k, stride=stride, transposed=transposed, relu=relu)
 
