@@ -66,16 +66,22 @@ SS_API int ss_conv3d_f32(const float* in, const float* weight_packed, const floa
 SS_API int ss_conv3d_cout1_f32(const float* in, const float* weight, float* out, int B, int Cin, int D, int H, int W, void* stream);
 
 /* ---- K4: 3-D convolutions, tensor-core mode (tcgen05 / TMEM / TMA, bf16 operands, fp32 accumulation) ------ */
-/* Activations in the "blocked channels" layout: bf16 [B][C/8][D][H][W][8].  Converters from / to fp32 NCDHW: */
-SS_API int ss_to_blocked_bf16(const float* in_ncdhw, void* out_blocked, int B, int C, int D, int H, int W, void* stream);
+/* Activations in the "blocked channels" layout: bf16 [B][C/8][D][H][W][8], or its phase-split ("s2d") form
+ * [B][8 = (d&1,h&1,w&1)][C/8][D/2][H/2][W/2][8] that the stride-2 layer reads and the transposed layer's residual uses.
+ * Converters: fp32 NCDHW -> blocked (s2d = 1: phase-split), blocked -> fp32 NCDHW, blocked -> phase-split. */
+SS_API int ss_to_blocked_bf16(const float* in_ncdhw, void* out_blocked, int B, int C, int D, int H, int W, int s2d, void* stream);
 SS_API int ss_from_blocked_bf16(const void* in_blocked, float* out_ncdhw, int B, int C, int D, int H, int W, void* stream);
-/* Conv3d k3 s1 p1 + folded eval-BN + ReLU + channelAtt gate (same layers as ss_conv3d_f32 mode 0, K=3, stride 1).
- * weight_packed: bf16 [Cout/N][27][Cin/8][N][8] with N = ss_conv3d_tc_ntile(Cin,Cout) (0 = configuration unsupported).
- * out: bf16 blocked (out_is_f32 = 0) or fp32 NCDHW (out_is_f32 = 1). */
-SS_API int ss_conv3d_tc_ntile(int Cin, int Cout);
-SS_API int ss_conv3d_tc(const void* in_blocked, const void* weight_packed, const float* scale_or_null, const float* shift_or_null,
-                        const float* gate_logits_or_null, void* out, int out_is_f32, int B, int Cin, int Cout, int D, int H, int W,
-                        int relu, void* stream);
+SS_API int ss_blocked_to_s2d(const void* in_blocked, void* out_s2d, int B, int C, int D, int H, int W, void* stream);
+/* The 3-D layers of the hourglass stack (same layers as ss_conv3d_f32) + folded eval-BN + residual + ReLU + channelAtt gate.
+ * kind 0: Conv3d k3 s1 p1;  1: Conv3d k1;  2: Conv3d k3 s2 p1 (input tensor phase-split);  3: ConvTranspose3d k3 s2 p1 op1
+ * (residual_s2d: the skip tensor in phase-split layout at OUTPUT resolution, added before the ReLU; SemStereo.py:141-142).
+ * D,H,W: input dims of the layer (kind 2: of the un-split input).  weight_packed: bf16 [ceil(Cout/N)][taps][Cin/8][N][8],
+ * N = ss_conv3d_tc_ntile(kind,Cin,Cout) (0 = unsupported), Cout zero-padded to a multiple of N, tap = (kd*3+kh)*3+kw (kind 3:
+ * of the ConvTranspose3d weight (Cin,Cout,kd,kh,kw)).  out: bf16 blocked (Cout % 8 == 0) or fp32 NCDHW with Cout channels. */
+SS_API int ss_conv3d_tc_ntile(int kind, int Cin, int Cout);
+SS_API int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight_packed, const float* scale_or_null,
+                        const float* shift_or_null, const float* gate_logits_or_null, const void* residual_s2d_or_null, void* out,
+                        int out_is_f32, int B, int Cin, int Cout, int D, int H, int W, int relu, void* stream);
 
 /* ---- K5: windowed 3-D attention --------------------------------------------------------------------- */
 /* attention_block.forward (submodule_other.py:805-837) for window-divisible D,H,W.  wqkv_t = qkv_3d.weight^T [C][3C],

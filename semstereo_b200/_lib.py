@@ -27,10 +27,11 @@ SIGNATURES = {
     "ss_pointwise_conv2d": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "ss_conv3d_f32": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "ss_conv3d_cout1_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "ss_to_blocked_bf16": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "ss_to_blocked_bf16": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ss_from_blocked_bf16": [_P, _P, _I, _I, _I, _I, _I, _P],
-    "ss_conv3d_tc_ntile": [_I, _I],
-    "ss_conv3d_tc": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "ss_blocked_to_s2d": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "ss_conv3d_tc_ntile": [_I, _I, _I],
+    "ss_conv3d_tc": [_I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "ss_window_attention3d": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "ss_att_stats": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "ss_sample_strength": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],

@@ -1,92 +1,167 @@
-// K4, tensor-core mode: Conv3d k3 s1 p1 (+ folded eval-BatchNorm, ReLU, channelAtt gate) as an implicit GEMM on the
-// 5th-generation tensor cores: TMA -> shared memory -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld epilogue.
-// Reference layers: convbn_3d / BasicConv(is_3d) k3 s1 (models/submodule_other.py:845-848, models/submodule.py:89-116)
-// as instantiated at models/SemStereo.py:109-119, 228-236 (concat_stem, classif*.0, hourglass*.conv2/conv4).
+// K4, tensor-core mode: every 3-D convolution of the hourglass stack as an implicit GEMM on the 5th-generation tensor
+// cores: TMA -> shared memory -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld epilogue.
+// Reference layers: convbn_3d / BasicConv(is_3d) (models/submodule_other.py:845-848, models/submodule.py:89-116) and
+// nn.ConvTranspose3d(k3,s2,p1,op1) as instantiated at models/SemStereo.py:106-182, 228-236.
 //
 // Data layout ("blocked channels", bf16): activations are [B][C/8][D][H][W][8]: the 8 channels of a chunk are the 16 bytes
 // one UMMA core-matrix row needs, and voxels that are neighbours along W are neighbours in memory.  A (TH+2)x(TW+2) halo
 // tile of one depth slice therefore lands in shared memory (one TMA box, zero-filled outside the volume = the conv padding)
-// as [C/8][TH+2][TW+2][16 B], which IS the canonical K-major no-swizzle UMMA layout for every one of the 9 in-plane taps:
-// a tap (kh,kw) is just a different start address (SBO = (TW+2)*16 B between 8-voxel row groups, LBO = chunk pitch).
-// So an input slice is fetched ONCE per output tile column and reused by 9 taps x 3 output slices (depth sliding ring),
-// instead of 27 shifted re-loads.  GEMM tile: M = 128 voxels (16 h x 8 w of one depth slice), N = Cout tile, K = 27*Cin.
+// as [C/8][TH+2][TW+2][16 B], which IS the canonical K-major no-swizzle UMMA layout for every in-plane tap: a tap (kh,kw)
+// is just a different start address (SBO = (TW+2)*16 B between 8-voxel row groups, LBO = chunk pitch).  An input slice is
+// fetched ONCE per output tile column and reused by all its taps and by up to 3 output slices (depth-sliding ring).
+// GEMM tile: M = 128 voxels (16 h x 8 w of one depth slice), N = Cout tile, K = taps * Cin.
 //
-// Warp roles (256 threads, 1 CTA/SM, persistent over work items): warp 0 = TMA producer of input slices, warp 3 = weight
-// producer (resident: all 27 taps once; streamed: per-tap ring), warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
-// warps 4-7 = epilogue (TMEM -> registers -> scale/shift/ReLU/gate -> bf16 blocked or fp32 NCDHW stores).
-// Accumulators are double-buffered in TMEM so the epilogue of slice d overlaps the MMAs of slice d+1.
+// Three kernels share the skeleton (persistent CTAs, 256 threads, 1 CTA/SM; warp 0 = TMA slice producer, warp 3 = weight
+// producer (resident: all taps once; streamed: per-tap ring), warp 1 = MMA issuer (warp-uniform control flow, one elected
+// lane issues), warp 2 = TMEM allocator, warps 4-7 = epilogue; accumulators double-buffered in TMEM):
+//   s1 : Conv3d k3 s1 p1 (TAPS=27) and Conv3d k1 (TAPS=1).
+//   s2 : Conv3d k3 s2 p1 on a phase-split ("s2d") input [B][8 phases (d,h,w parity)][C/8][D/2][H/2][W/2][8]: input index
+//        2o-1+k is (phase 1, o-1), (phase 0, o), (phase 1, o) for k = 0,1,2, so every tap is a dense half-resolution tile.
+//   t2 : ConvTranspose3d k3 s2 p1 op1 as 8 sub-pixel output phases (1/2/4/8 taps each, no zero insertion); the hourglass
+//        skip connection (redir conv output, stored phase-split) is added in the epilogue before the ReLU.
+// Epilogue: y = acc*scale[co] + shift[co] (+ residual) -> ReLU -> * sigmoid(gate[b,co,h,w]) -> bf16 blocked or fp32 NCDHW.
 #include "tc_common.cuh"
 
 namespace {
 
 constexpr int TH = 16, TW = 8, HH = TH + 2, WW = TW + 2;
+constexpr uint32_t TILE_B = HH * WW * 16;       // bytes of one channel chunk of a halo tile (2880)
 
 struct TcP {
-  const __nv_bfloat16* w;   // [n_tiles][27][CIN/8][N][8]
-  const float* scale;       // [Cout] or null
-  const float* shift;       // [Cout] or null
-  const float* gate;        // (B,Cout,H,W) logits or null
+  const __nv_bfloat16* w;         // [n_tiles][TAPS][CIN/8][N][8]
+  const float* scale;             // [Cout] or null
+  const float* shift;             // [Cout] or null
+  const float* gate;              // (B,Cout,OH,OW) logits or null
+  const __nv_bfloat16* residual;  // t2 only: phase-split blocked [B][8][Cout/8][D][H][W][8], or null
   void* out;
-  int out_f32;              // 0: bf16 blocked, 1: fp32 NCDHW
-  int B, D, H, W, Cout, relu;
+  int out_f32;                    // 0: bf16 blocked, 1: fp32 NCDHW
+  int cout_valid;                 // channels actually stored (Cout = n_tiles*N may be zero-padded), also the channel count of out
+  int B, D, H, W;                 // tile space: output dims (s1, s2) / input dims (t2)
+  int relu;
   int n_tiles, HT, WT, DC, n_dc, items;   // items = B*HT*WT*n_dc per n-tile
 };
 
-template <int CIN, int N, int NS, int NWS>
-__global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_constant__ CUtensorMap tmA, const TcP p) {
-  constexpr bool kResident = (NWS == 27);
-  constexpr uint32_t SLICE = (CIN / 8) * HH * WW * 16;     // bytes of one staged input slice
-  constexpr uint32_t TAPB = CIN * N * 2;                   // bytes of one weight tap
-  constexpr int KS = CIN / 16;                             // UMMA_K = 16 steps per tap
-  constexpr uint32_t LBO_A = HH * WW * 16, SBO_A = WW * 16, LBO_B = N * 16, SBO_B = 128;
-  constexpr uint32_t TMEM_COLS = (2 * N <= 32) ? 32 : (2 * N <= 64) ? 64 : (2 * N <= 128) ? 128 : (2 * N <= 256) ? 256 : 512;
-  constexpr uint32_t IDESC = tc::make_idesc_bf16(128, N);
+__device__ __forceinline__ void decode_item(const TcP& p, int s, int& b, int& h0, int& w0, int& dlo, int& dhi) {
+  const int dc = s % p.n_dc;  s /= p.n_dc;
+  const int wt = s % p.WT;    s /= p.WT;
+  const int ht = s % p.HT;
+  b = s / p.HT;
+  h0 = ht * TH; w0 = wt * TW;
+  dlo = dc * p.DC; dhi = min(p.D, dlo + p.DC);
+}
 
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* Abase = smem;
-  uint8_t* Wbase = smem + NS * SLICE;
-  __shared__ __align__(8) uint64_t a_full[NS], a_empty[NS], w_full[NWS], w_empty[NWS], acc_full[2], acc_empty[2];
-  __shared__ uint32_t tmem_base_s;
-  __shared__ float s_scale[N], s_shift[N];     // folded BatchNorm of this CTA's Cout tile
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nt = blockIdx.x % p.n_tiles;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    s_scale[i] = p.scale ? __ldg(p.scale + nt * N + i) : 1.0f;
-    s_shift[i] = p.shift ? __ldg(p.shift + nt * N + i) : 0.0f;
+// Applies the fused epilogue to 32 consecutive output channels (co0 ...) of one voxel and stores them.
+// (od,oh,ow) / (OD,OH,OW): output voxel and output dims.  res: this voxel's residual chunk co0/8 (chunk stride res_cs uint4).
+__device__ __forceinline__ void epilogue_store32(const TcP& p, float (&v)[32], const float* sc, const float* sh, int co0, int b, int od,
+                                                 int oh, int ow, int OD, int OH, int OW, const uint4* res, size_t res_cs) {
+  const float lo = p.relu ? 0.0f : -INFINITY;
+  if (res) {
+    uint4 r[4];
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) r[c8] = __ldg(res + (size_t)c8 * res_cs);
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) {
+      const uint32_t u[4] = {r[c8].x, r[c8].y, r[c8].z, r[c8].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[8 * c8 + 2 * i] = fmaf(v[8 * c8 + 2 * i], sc[8 * c8 + 2 * i], sh[8 * c8 + 2 * i]) + __uint_as_float(u[i] << 16);
+        v[8 * c8 + 2 * i + 1] = fmaf(v[8 * c8 + 2 * i + 1], sc[8 * c8 + 2 * i + 1], sh[8 * c8 + 2 * i + 1]) + __uint_as_float(u[i] & 0xffff0000u);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], lo);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(fmaf(v[i], sc[i], sh[i]), lo);
   }
-  const int cta_s = blockIdx.x / p.n_tiles, cta_stride = gridDim.x / p.n_tiles;
-
-  if (threadIdx.x == 0) {
-    tc::prefetch_tmap(&tmA);
-    for (int i = 0; i < NS; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < (kResident ? 1 : NWS); ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
-    tc::fence_barrier_init();
+  const size_t OHW = (size_t)OH * OW;
+  if (p.gate) {                       // branch hoisted out of the channel loop: 32 independent loads in flight
+    const float* gp = p.gate + ((size_t)b * p.cout_valid + co0) * OHW + (size_t)oh * OW + ow;
+    float gl[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) gl[i] = (co0 + i < p.cout_valid) ? __ldg(gp + (size_t)i * OHW) : 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= sigmoidf_(gl[i]);
   }
-  if (warp == 2) tc::tmem_alloc(&tmem_base_s, TMEM_COLS);
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
+  const size_t sp = ((size_t)od * OH + oh) * OW + ow, OS = (size_t)OD * OHW;
+  if (p.out_f32) {
+    float* o = reinterpret_cast<float*>(p.out) + ((size_t)b * p.cout_valid + co0) * OS + sp;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (co0 + i < p.cout_valid) o[(size_t)i * OS] = v[i];
+  } else {
+    uint4* o = reinterpret_cast<uint4*>(p.out) + ((size_t)b * (p.cout_valid / 8) + co0 / 8) * OS + sp;
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) {
+      if (co0 + 8 * c8 >= p.cout_valid) break;
+      uint4 q;
+      q.x = tc::pack_bf16x2(v[8 * c8 + 0], v[8 * c8 + 1]);
+      q.y = tc::pack_bf16x2(v[8 * c8 + 2], v[8 * c8 + 3]);
+      q.z = tc::pack_bf16x2(v[8 * c8 + 4], v[8 * c8 + 5]);
+      q.w = tc::pack_bf16x2(v[8 * c8 + 6], v[8 * c8 + 7]);
+      o[(size_t)c8 * OS] = q;
+    }
+  }
+}
+
+// Common prologue: barriers, TMEM, folded-BN staging.
+#define TC_KERNEL_PROLOGUE(NSLOTS, NWSLOTS, RESIDENT)                                                                      \
+  extern __shared__ __align__(1024) uint8_t smem[];                                                                        \
+  __shared__ __align__(8) uint64_t a_full[NSLOTS], a_empty[NSLOTS], w_full[NWSLOTS], w_empty[NWSLOTS], acc_full[2], acc_empty[2]; \
+  __shared__ uint32_t tmem_base_s;                                                                                         \
+  __shared__ float s_scale[N], s_shift[N];                                                                                 \
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;                                                              \
+  const int nt = blockIdx.x % p.n_tiles;                                                                                   \
+  const int cta_s = blockIdx.x / p.n_tiles, cta_stride = gridDim.x / p.n_tiles;                                            \
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {                                                                      \
+    s_scale[i] = (p.scale && nt * N + i < p.cout_valid) ? __ldg(p.scale + nt * N + i) : 1.0f;                              \
+    s_shift[i] = (p.shift && nt * N + i < p.cout_valid) ? __ldg(p.shift + nt * N + i) : 0.0f;                              \
+  }                                                                                                                        \
+  if (threadIdx.x == 0) {                                                                                                  \
+    tc::prefetch_tmap(&tmA);                                                                                               \
+    for (int i = 0; i < NSLOTS; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1); }                      \
+    for (int i = 0; i < ((RESIDENT) ? 1 : NWSLOTS); ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }  \
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }                     \
+    tc::fence_barrier_init();                                                                                              \
+  }                                                                                                                        \
+  if (warp == 2) tc::tmem_alloc(&tmem_base_s, TMEM_COLS);                                                                  \
+  tc::fence_before_sync();                                                                                                 \
+  __syncthreads();                                                                                                         \
+  tc::fence_after_sync();                                                                                                  \
   const uint32_t tmem_base = tmem_base_s;
 
-  // work item s -> (b, h-tile, w-tile, depth chunk)
-  auto decode = [&](int s, int& b, int& h0, int& w0, int& dlo, int& dhi) {
-    const int dc = s % p.n_dc;  s /= p.n_dc;
-    const int wt = s % p.WT;    s /= p.WT;
-    const int ht = s % p.HT;
-    b = s / p.HT;
-    h0 = ht * TH; w0 = wt * TW;
-    dlo = dc * p.DC; dhi = min(p.D, dlo + p.DC);
-  };
+#define TC_KERNEL_EPILOGUE()                                   \
+  tc::fence_before_sync();                                     \
+  __syncthreads();                                             \
+  if (warp == 2) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+
+constexpr uint32_t tmem_cols_for(int n2) { return n2 <= 32 ? 32 : n2 <= 64 ? 64 : n2 <= 128 ? 128 : n2 <= 256 ? 256 : 512; }
+
+// =====================================================================================================================
+// s1: Conv3d k3 s1 p1 (TAPS = 27) / Conv3d k1 (TAPS = 1).  NWS == TAPS -> weights resident, else streamed tap ring.
+// =====================================================================================================================
+template <int CIN, int N, int NS, int NWS, int TAPS>
+__global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_constant__ CUtensorMap tmA, const TcP p) {
+  constexpr bool kResident = (NWS == TAPS);
+  constexpr bool k3 = (TAPS == 27);
+  constexpr uint32_t SLICE = (CIN / 8) * TILE_B;
+  constexpr uint32_t TAPB = CIN * N * 2;
+  constexpr int KS = CIN / 16;
+  constexpr uint32_t LBO_A = TILE_B, SBO_A = WW * 16, LBO_B = N * 16, SBO_B = 128;
+  constexpr uint32_t TMEM_COLS = tmem_cols_for(2 * N);
+  constexpr uint32_t IDESC = tc::make_idesc_bf16(128, N);
+  TC_KERNEL_PROLOGUE(NS, NWS, kResident)
+  uint8_t* Abase = smem;
+  uint8_t* Wbase = smem + NS * SLICE;
+  const int halo = k3 ? 1 : 0;
 
   if (warp == 0 && lane == 0) {
     // ===== input-slice producer =====
     uint32_t g = 0;
     for (int s = cta_s; s < p.items; s += cta_stride) {
       int b, h0, w0, dlo, dhi;
-      decode(s, b, h0, w0, dlo, dhi);
-      const int din0 = max(dlo - 1, 0), din1 = min(dhi, p.D - 1);
+      decode_item(p, s, b, h0, w0, dlo, dhi);
+      const int din0 = max(dlo - halo, 0), din1 = min(dhi - 1 + halo, p.D - 1);
       for (int d_in = din0; d_in <= din1; ++d_in, ++g) {
         const uint32_t slot = g % NS;
         tc::mbar_wait(&a_empty[slot], ((g / NS) & 1) ^ 1);
@@ -96,17 +171,17 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_const
     }
   } else if (warp == 3 && lane == 0) {
     // ===== weight producer =====
-    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)nt * 27 * TAPB;
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)nt * TAPS * TAPB;
     if (kResident) {
       if (cta_s < p.items) {
-        tc::mbar_expect_tx(&w_full[0], 27 * TAPB);
-        for (int tap = 0; tap < 27; ++tap) tc::bulk_load(Wbase + tap * TAPB, wsrc + (size_t)tap * TAPB, TAPB, &w_full[0]);
+        tc::mbar_expect_tx(&w_full[0], TAPS * TAPB);
+        for (int tap = 0; tap < TAPS; ++tap) tc::bulk_load(Wbase + tap * TAPB, wsrc + (size_t)tap * TAPB, TAPB, &w_full[0]);
       }
     } else {
       uint32_t wc = 0;
       for (int s = cta_s; s < p.items; s += cta_stride) {
         int b, h0, w0, dlo, dhi;
-        decode(s, b, h0, w0, dlo, dhi);
+        decode_item(p, s, b, h0, w0, dlo, dhi);
         for (int d_out = dlo; d_out < dhi; ++d_out)
           for (int kd = 0; kd < 3; ++kd) {
             const int d_in = d_out + kd - 1;
@@ -121,8 +196,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: the whole warp runs the (uniform) control flow so that descriptors live in uniform registers;
-    //       one elected lane issues the tcgen05 instructions =====
+    // ===== MMA issuer =====
     const bool leader = tc::elect_one();
     const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(Abase), LBO_A), a_hi = tc::desc_hi(SBO_A);
     const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(Wbase), LBO_B), b_hi = tc::desc_hi(SBO_B);
@@ -130,8 +204,8 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_const
     uint32_t g_base = 0, acc_it = 0, wc = 0;
     for (int s = cta_s; s < p.items; s += cta_stride) {
       int b, h0, w0, dlo, dhi;
-      decode(s, b, h0, w0, dlo, dhi);
-      const int din0 = max(dlo - 1, 0), din1 = min(dhi, p.D - 1);
+      decode_item(p, s, b, h0, w0, dlo, dhi);
+      const int din0 = max(dlo - halo, 0), din1 = min(dhi - 1 + halo, p.D - 1);
       for (int d_out = dlo; d_out < dhi; ++d_out, ++acc_it) {
         const uint32_t as = acc_it & 1;
         tc::mbar_wait(&acc_empty[as], ((acc_it >> 1) & 1) ^ 1);
@@ -139,7 +213,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_const
         const uint32_t tmem_d = tmem_base + as * N;
         uint32_t accumulate = 0;
 #pragma unroll 1
-        for (int kd = 0; kd < 3; ++kd) {
+        for (int kd = (k3 ? 0 : 1); kd < (k3 ? 3 : 2); ++kd) {
           const int d_in = d_out + kd - 1;
           if (d_in < 0 || d_in >= p.D) continue;
           const uint32_t gs = g_base + (uint32_t)(d_in - din0), slot = gs % NS;
@@ -147,11 +221,10 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_const
           tc::fence_after_sync();
           const uint32_t a_lo = a_lo0 + slot * (SLICE >> 4);
 #pragma unroll
-          for (int t9 = 0; t9 < 9; ++t9) {
+          for (int t9 = (k3 ? 0 : 4); t9 < (k3 ? 9 : 5); ++t9) {
             const int kh = t9 / 3, kw = t9 - 3 * kh;
-            uint32_t b_lo;
-            uint32_t wslot = 0;
-            if (kResident) b_lo = b_lo0 + (uint32_t)(kd * 9 + t9) * (TAPB >> 4);
+            uint32_t b_lo, wslot = 0;
+            if (kResident) b_lo = b_lo0 + (uint32_t)(k3 ? kd * 9 + t9 : 0) * (TAPB >> 4);
             else {
               wslot = wc % NWS;
               tc::mbar_wait(&w_full[wslot], (wc / NWS) & 1);
@@ -173,11 +246,14 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_const
         }
         if (leader) {
           tc::mma_commit(&acc_full[as]);
-          // input slices no output slice of this item needs any more
-          if (d_out - 1 >= din0) tc::mma_commit(&a_empty[(g_base + (uint32_t)(d_out - 1 - din0)) % NS]);
-          if (d_out == dhi - 1) {
+          if (k3) {   // input slices no later output slice of this item needs
+            if (d_out - 1 >= din0) tc::mma_commit(&a_empty[(g_base + (uint32_t)(d_out - 1 - din0)) % NS]);
+            if (d_out == dhi - 1) {
+              tc::mma_commit(&a_empty[(g_base + (uint32_t)(d_out - din0)) % NS]);
+              if (d_out + 1 <= din1) tc::mma_commit(&a_empty[(g_base + (uint32_t)(d_out + 1 - din0)) % NS]);
+            }
+          } else {
             tc::mma_commit(&a_empty[(g_base + (uint32_t)(d_out - din0)) % NS]);
-            if (d_out + 1 <= din1) tc::mma_commit(&a_empty[(g_base + (uint32_t)(d_out + 1 - din0)) % NS]);
           }
         }
         __syncwarp();
@@ -188,10 +264,9 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_const
     // ===== epilogue =====
     const int e = warp - 4, m = e * 32 + lane, hh = m >> 3, ww = m & 7;
     uint32_t acc_it = 0;
-    const size_t HWs = (size_t)p.H * p.W;
     for (int s = cta_s; s < p.items; s += cta_stride) {
       int b, h0, w0, dlo, dhi;
-      decode(s, b, h0, w0, dlo, dhi);
+      decode_item(p, s, b, h0, w0, dlo, dhi);
       const int h = h0 + hh, w = w0 + ww;
       const bool valid = h < p.H && w < p.W;
       for (int d_out = dlo; d_out < dhi; ++d_out, ++acc_it) {
@@ -206,46 +281,327 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_const
             tc::fence_before_sync();
             tc::mbar_arrive(&acc_empty[as]);
           }
-          if (!valid) continue;
-          const int co0 = nt * N + j * 32;
-          const float lo = p.relu ? 0.0f : -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(fmaf(v[i], s_scale[j * 32 + i], s_shift[j * 32 + i]), lo);
-          if (p.gate) {                     // branch hoisted out of the channel loop: 32 independent loads in flight
-            const float* gp = p.gate + ((size_t)b * p.Cout + co0) * HWs + (size_t)h * p.W + w;
-            float gl[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) gl[i] = __ldg(gp + (size_t)i * HWs);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= sigmoidf_(gl[i]);
-          }
-          if (p.out_f32) {
-            float* o = reinterpret_cast<float*>(p.out) + (((size_t)b * p.Cout + co0) * p.D + d_out) * HWs + (size_t)h * p.W + w;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[(size_t)i * p.D * HWs] = v[i];
-          } else {
-            uint4* o = reinterpret_cast<uint4*>(p.out) + (((size_t)b * (p.Cout / 8) + co0 / 8) * p.D + d_out) * HWs + (size_t)h * p.W + w;
-#pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
-              uint4 q;
-              q.x = tc::pack_bf16x2(v[8 * c8 + 0], v[8 * c8 + 1]);
-              q.y = tc::pack_bf16x2(v[8 * c8 + 2], v[8 * c8 + 3]);
-              q.z = tc::pack_bf16x2(v[8 * c8 + 4], v[8 * c8 + 5]);
-              q.w = tc::pack_bf16x2(v[8 * c8 + 6], v[8 * c8 + 7]);
-              o[(size_t)c8 * p.D * HWs] = q;
-            }
-          }
+          if (!valid || nt * N + j * 32 >= p.cout_valid) continue;
+          epilogue_store32(p, v, s_scale + j * 32, s_shift + j * 32, nt * N + j * 32, b, d_out, h, w, p.D, p.H, p.W, nullptr, 0);
         }
       }
     }
   }
-  tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 2) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+  TC_KERNEL_EPILOGUE()
 }
 
-// ---- layout converters: fp32 NCDHW <-> bf16 blocked [B][C/8][D][H][W][8] -------------------------------------------
-__global__ void __launch_bounds__(256) to_blocked_kernel(const float* __restrict__ in, uint4* __restrict__ out, int C, size_t S) {
+// =====================================================================================================================
+// s2: Conv3d k3 s2 p1 on the phase-split input.  A staged slice = (d-phase pd, half-res depth d') = 4 (h,w)-phase halo tiles.
+// Per output depth d the slice uses are, in order: (1,d-1) [kd=0], (0,d) [kd=1], (1,d) [kd=2, kept for d+1's kd=0].
+// =====================================================================================================================
+template <int CIN, int N, int NS, int NWS>
+__global__ void __launch_bounds__(256, 1) conv3d_tc_s2_kernel(const __grid_constant__ CUtensorMap tmA, const TcP p) {
+  constexpr bool kResident = (NWS == 27);
+  constexpr int C8 = CIN / 8;
+  constexpr uint32_t SLICE = 4 * C8 * TILE_B;
+  constexpr uint32_t TAPB = CIN * N * 2;
+  constexpr int KS = CIN / 16;
+  constexpr uint32_t LBO_A = TILE_B, SBO_A = WW * 16, LBO_B = N * 16, SBO_B = 128;
+  constexpr uint32_t TMEM_COLS = tmem_cols_for(2 * N);
+  constexpr uint32_t IDESC = tc::make_idesc_bf16(128, N);
+  TC_KERNEL_PROLOGUE(NS, NWS, kResident)
+  uint8_t* Abase = smem;
+  uint8_t* Wbase = smem + NS * SLICE;
+
+  if (warp == 0 && lane == 0) {
+    uint32_t g = 0;
+    auto load = [&](int b, int h0, int w0, int pd, int d) {
+      const uint32_t slot = g % NS;
+      tc::mbar_wait(&a_empty[slot], ((g / NS) & 1) ^ 1);
+      tc::mbar_expect_tx(&a_full[slot], SLICE);
+      tc::tma_load_4d(Abase + slot * SLICE, &tmA, &a_full[slot], (w0 - 1) * 8, h0 - 1, d, (b * 8 + pd * 4) * C8);
+      ++g;
+    };
+    for (int s = cta_s; s < p.items; s += cta_stride) {
+      int b, h0, w0, dlo, dhi;
+      decode_item(p, s, b, h0, w0, dlo, dhi);
+      if (dlo > 0) load(b, h0, w0, 1, dlo - 1);
+      for (int d = dlo; d < dhi; ++d) { load(b, h0, w0, 0, d); load(b, h0, w0, 1, d); }
+    }
+  } else if (warp == 3 && lane == 0) {
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)nt * 27 * TAPB;
+    if (kResident) {
+      if (cta_s < p.items) {
+        tc::mbar_expect_tx(&w_full[0], 27 * TAPB);
+        for (int tap = 0; tap < 27; ++tap) tc::bulk_load(Wbase + tap * TAPB, wsrc + (size_t)tap * TAPB, TAPB, &w_full[0]);
+      }
+    } else {
+      uint32_t wc = 0;
+      for (int s = cta_s; s < p.items; s += cta_stride) {
+        int b, h0, w0, dlo, dhi;
+        decode_item(p, s, b, h0, w0, dlo, dhi);
+        for (int d_out = dlo; d_out < dhi; ++d_out)
+          for (int kd = (d_out == 0 ? 1 : 0); kd < 3; ++kd)
+            for (int t9 = 0; t9 < 9; ++t9, ++wc) {
+              const uint32_t slot = wc % NWS;
+              tc::mbar_wait(&w_empty[slot], ((wc / NWS) & 1) ^ 1);
+              tc::mbar_expect_tx(&w_full[slot], TAPB);
+              tc::bulk_load(Wbase + slot * TAPB, wsrc + (size_t)(kd * 9 + t9) * TAPB, TAPB, &w_full[slot]);
+            }
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = tc::elect_one();
+    const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(Abase), LBO_A), a_hi = tc::desc_hi(SBO_A);
+    const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(Wbase), LBO_B), b_hi = tc::desc_hi(SBO_B);
+    if (kResident && cta_s < p.items) tc::mbar_wait(&w_full[0], 0);
+    uint32_t g_base = 0, acc_it = 0, wc = 0;
+    for (int s = cta_s; s < p.items; s += cta_stride) {
+      int b, h0, w0, dlo, dhi;
+      decode_item(p, s, b, h0, w0, dlo, dhi);
+      const uint32_t hp = dlo > 0 ? 1u : 0u;
+      for (int d_out = dlo; d_out < dhi; ++d_out, ++acc_it) {
+        const uint32_t j = (uint32_t)(d_out - dlo);
+        const uint32_t as = acc_it & 1;
+        tc::mbar_wait(&acc_empty[as], ((acc_it >> 1) & 1) ^ 1);
+        tc::fence_after_sync();
+        const uint32_t tmem_d = tmem_base + as * N;
+        uint32_t accumulate = 0;
+#pragma unroll 1
+        for (int kd = 0; kd < 3; ++kd) {
+          if (kd == 0 && d_out == 0) continue;
+          const uint32_t pos = kd == 0 ? (j == 0 ? 0u : hp + 2 * (j - 1) + 1) : hp + 2 * j + (uint32_t)(kd - 1);
+          const uint32_t gs = g_base + pos, slot = gs % NS;
+          tc::mbar_wait(&a_full[slot], (gs / NS) & 1);
+          tc::fence_after_sync();
+          const uint32_t a_lo = a_lo0 + slot * (SLICE >> 4);
+#pragma unroll
+          for (int t9 = 0; t9 < 9; ++t9) {
+            const int kh = t9 / 3, kw = t9 - 3 * kh;
+            const int ph = (kh == 1) ? 0 : 1, oh = (kh == 0) ? 0 : 1;     // input row 2h-1+kh = (phase, halo row offset)
+            const int pw = (kw == 1) ? 0 : 1, ow = (kw == 0) ? 0 : 1;
+            uint32_t b_lo, wslot = 0;
+            if (kResident) b_lo = b_lo0 + (uint32_t)(kd * 9 + t9) * (TAPB >> 4);
+            else {
+              wslot = wc % NWS;
+              tc::mbar_wait(&w_full[wslot], (wc / NWS) & 1);
+              tc::fence_after_sync();
+              b_lo = b_lo0 + wslot * (TAPB >> 4);
+            }
+            if (leader) {
+#pragma unroll
+              for (int ks = 0; ks < KS; ++ks) {
+                tc::mma_bf16_lohi(tmem_d, a_lo + (uint32_t)(((ph * 2 + pw) * C8 + 2 * ks) * LBO_A + (oh * WW + ow) * 16) / 16, a_hi,
+                                  b_lo + (uint32_t)(ks * 2 * LBO_B) / 16, b_hi, IDESC, accumulate);
+                accumulate = 1;
+              }
+              if (!kResident) tc::mma_commit(&w_empty[wslot]);
+            }
+            accumulate = 1;
+            if (!kResident) ++wc;
+          }
+          // last use of this slice?  (1,d-1) and (0,d) always; (1,d) only at the end of the item
+          if (leader && (kd < 2 || d_out == dhi - 1)) tc::mma_commit(&a_empty[slot]);
+        }
+        if (leader) tc::mma_commit(&acc_full[as]);
+        __syncwarp();
+      }
+      g_base += hp + 2 * (uint32_t)(dhi - dlo);
+    }
+  } else if (warp >= 4) {
+    const int e = warp - 4, m = e * 32 + lane, hh = m >> 3, ww = m & 7;
+    uint32_t acc_it = 0;
+    for (int s = cta_s; s < p.items; s += cta_stride) {
+      int b, h0, w0, dlo, dhi;
+      decode_item(p, s, b, h0, w0, dlo, dhi);
+      const int h = h0 + hh, w = w0 + ww;
+      const bool valid = h < p.H && w < p.W;
+      for (int d_out = dlo; d_out < dhi; ++d_out, ++acc_it) {
+        const uint32_t as = acc_it & 1;
+        tc::mbar_wait(&acc_full[as], (acc_it >> 1) & 1);
+        tc::fence_after_sync();
+#pragma unroll 1
+        for (int j = 0; j < N / 32; ++j) {
+          float v[32];
+          tc::tmem_ld32(tmem_base + ((uint32_t)(e * 32) << 16) + as * N + j * 32, v);
+          if (j == N / 32 - 1) {
+            tc::fence_before_sync();
+            tc::mbar_arrive(&acc_empty[as]);
+          }
+          if (!valid || nt * N + j * 32 >= p.cout_valid) continue;
+          epilogue_store32(p, v, s_scale + j * 32, s_shift + j * 32, nt * N + j * 32, b, d_out, h, w, p.D, p.H, p.W, nullptr, 0);
+        }
+      }
+    }
+  }
+  TC_KERNEL_EPILOGUE()
+}
+
+// =====================================================================================================================
+// t2: ConvTranspose3d k3 s2 p1 op1.  Tile space = INPUT voxels; output voxel 2i+p per dim:  p=0: tap k=1 from input i;
+// p=1: tap k=0 from input i+1 and tap k=2 from input i.  Per input depth i the 8 output phases are 8 accumulators in a row.
+// =====================================================================================================================
+template <int CIN, int N, int NS, int NWS>
+__global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_constant__ CUtensorMap tmA, const TcP p) {
+  constexpr bool kResident = (NWS == 27);
+  constexpr uint32_t SLICE = (CIN / 8) * TILE_B;
+  constexpr uint32_t TAPB = CIN * N * 2;
+  constexpr int KS = CIN / 16;
+  constexpr uint32_t LBO_A = TILE_B, SBO_A = WW * 16, LBO_B = N * 16, SBO_B = 128;
+  constexpr uint32_t TMEM_COLS = tmem_cols_for(2 * N);
+  constexpr uint32_t IDESC = tc::make_idesc_bf16(128, N);
+  TC_KERNEL_PROLOGUE(NS, NWS, kResident)
+  uint8_t* Abase = smem;
+  uint8_t* Wbase = smem + NS * SLICE;
+
+  // tap (shift, k) lists of one dimension for output parity q: q=0 -> {(0,1)}, q=1 -> {(1,0),(0,2)}
+  auto ntaps = [](int q) { return q ? 2 : 1; };
+  auto tap_shift = [](int q, int t) { return q ? (t == 0 ? 1 : 0) : 0; };
+  auto tap_k = [](int q, int t) { return q ? (t == 0 ? 0 : 2) : 1; };
+
+  if (warp == 0 && lane == 0) {
+    uint32_t g = 0;
+    for (int s = cta_s; s < p.items; s += cta_stride) {
+      int b, h0, w0, dlo, dhi;
+      decode_item(p, s, b, h0, w0, dlo, dhi);
+      const int din1 = min(dhi, p.D - 1);
+      for (int d_in = dlo; d_in <= din1; ++d_in, ++g) {
+        const uint32_t slot = g % NS;
+        tc::mbar_wait(&a_empty[slot], ((g / NS) & 1) ^ 1);
+        tc::mbar_expect_tx(&a_full[slot], SLICE);
+        tc::tma_load_4d(Abase + slot * SLICE, &tmA, &a_full[slot], w0 * 8, h0, d_in, b * (CIN / 8));
+      }
+    }
+  } else if (warp == 3 && lane == 0) {
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)nt * 27 * TAPB;
+    if (kResident) {
+      if (cta_s < p.items) {
+        tc::mbar_expect_tx(&w_full[0], 27 * TAPB);
+        for (int tap = 0; tap < 27; ++tap) tc::bulk_load(Wbase + tap * TAPB, wsrc + (size_t)tap * TAPB, TAPB, &w_full[0]);
+      }
+    } else {
+      uint32_t wc = 0;
+      for (int s = cta_s; s < p.items; s += cta_stride) {
+        int b, h0, w0, dlo, dhi;
+        decode_item(p, s, b, h0, w0, dlo, dhi);
+        for (int i = dlo; i < dhi; ++i)
+          for (int ph8 = 0; ph8 < 8; ++ph8) {
+            const int pd = ph8 >> 2, ph = (ph8 >> 1) & 1, pw = ph8 & 1;
+            for (int td = 0; td < ntaps(pd); ++td) {
+              if (i + tap_shift(pd, td) >= p.D) continue;
+              for (int th = 0; th < ntaps(ph); ++th)
+                for (int tw = 0; tw < ntaps(pw); ++tw, ++wc) {
+                  const int tap = tap_k(pd, td) * 9 + tap_k(ph, th) * 3 + tap_k(pw, tw);
+                  const uint32_t slot = wc % NWS;
+                  tc::mbar_wait(&w_empty[slot], ((wc / NWS) & 1) ^ 1);
+                  tc::mbar_expect_tx(&w_full[slot], TAPB);
+                  tc::bulk_load(Wbase + slot * TAPB, wsrc + (size_t)tap * TAPB, TAPB, &w_full[slot]);
+                }
+            }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = tc::elect_one();
+    const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(Abase), LBO_A), a_hi = tc::desc_hi(SBO_A);
+    const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(Wbase), LBO_B), b_hi = tc::desc_hi(SBO_B);
+    if (kResident && cta_s < p.items) tc::mbar_wait(&w_full[0], 0);
+    uint32_t g_base = 0, acc_it = 0, wc = 0;
+    for (int s = cta_s; s < p.items; s += cta_stride) {
+      int b, h0, w0, dlo, dhi;
+      decode_item(p, s, b, h0, w0, dlo, dhi);
+      const int din1 = min(dhi, p.D - 1);
+      for (int i = dlo; i < dhi; ++i) {
+        const uint32_t gs0 = g_base + (uint32_t)(i - dlo), slot0 = gs0 % NS, slot1 = (gs0 + 1) % NS;
+        tc::mbar_wait(&a_full[slot0], (gs0 / NS) & 1);
+        if (i + 1 <= din1) tc::mbar_wait(&a_full[slot1], ((gs0 + 1) / NS) & 1);
+        tc::fence_after_sync();
+#pragma unroll 1
+        for (int ph8 = 0; ph8 < 8; ++ph8, ++acc_it) {
+          const int pd = ph8 >> 2, ph = (ph8 >> 1) & 1, pw = ph8 & 1;
+          const uint32_t as = acc_it & 1;
+          tc::mbar_wait(&acc_empty[as], ((acc_it >> 1) & 1) ^ 1);
+          tc::fence_after_sync();
+          const uint32_t tmem_d = tmem_base + as * N;
+          uint32_t accumulate = 0;
+          for (int td = 0; td < ntaps(pd); ++td) {
+            const int sd = tap_shift(pd, td);
+            if (i + sd >= p.D) continue;
+            const uint32_t a_lo = a_lo0 + (sd ? slot1 : slot0) * (SLICE >> 4);
+            for (int th = 0; th < ntaps(ph); ++th)
+              for (int tw = 0; tw < ntaps(pw); ++tw) {
+                const int tap = tap_k(pd, td) * 9 + tap_k(ph, th) * 3 + tap_k(pw, tw);
+                const uint32_t a_off = (uint32_t)(tap_shift(ph, th) * WW + tap_shift(pw, tw));     // 16-byte units
+                uint32_t b_lo, wslot = 0;
+                if (kResident) b_lo = b_lo0 + (uint32_t)tap * (TAPB >> 4);
+                else {
+                  wslot = wc % NWS;
+                  tc::mbar_wait(&w_full[wslot], (wc / NWS) & 1);
+                  tc::fence_after_sync();
+                  b_lo = b_lo0 + wslot * (TAPB >> 4);
+                }
+                if (leader) {
+#pragma unroll
+                  for (int ks = 0; ks < KS; ++ks) {
+                    tc::mma_bf16_lohi(tmem_d, a_lo + a_off + (uint32_t)(ks * 2 * LBO_A) / 16, a_hi, b_lo + (uint32_t)(ks * 2 * LBO_B) / 16,
+                                      b_hi, IDESC, accumulate);
+                    accumulate = 1;
+                  }
+                  if (!kResident) tc::mma_commit(&w_empty[wslot]);
+                }
+                accumulate = 1;
+                if (!kResident) ++wc;
+              }
+          }
+          if (leader) tc::mma_commit(&acc_full[as]);
+          __syncwarp();
+        }
+        if (leader) {
+          tc::mma_commit(&a_empty[slot0]);                                   // depth i is done with slice i
+          if (i == dhi - 1 && i + 1 <= din1) tc::mma_commit(&a_empty[slot1]); // item ends: slice i+1 was loaded only for us
+        }
+        __syncwarp();
+      }
+      g_base += (uint32_t)(din1 - dlo + 1);
+    }
+  } else if (warp >= 4) {
+    const int e = warp - 4, m = e * 32 + lane, hh = m >> 3, ww = m & 7;
+    uint32_t acc_it = 0;
+    const size_t S_in = (size_t)p.D * p.H * p.W;
+    for (int s = cta_s; s < p.items; s += cta_stride) {
+      int b, h0, w0, dlo, dhi;
+      decode_item(p, s, b, h0, w0, dlo, dhi);
+      const int h = h0 + hh, w = w0 + ww;
+      const bool valid = h < p.H && w < p.W;
+      for (int i = dlo; i < dhi; ++i)
+        for (int ph8 = 0; ph8 < 8; ++ph8, ++acc_it) {
+          const int pd = ph8 >> 2, ph = (ph8 >> 1) & 1, pw = ph8 & 1;
+          const uint32_t as = acc_it & 1;
+          tc::mbar_wait(&acc_full[as], (acc_it >> 1) & 1);
+          tc::fence_after_sync();
+#pragma unroll 1
+          for (int j = 0; j < N / 32; ++j) {
+            float v[32];
+            tc::tmem_ld32(tmem_base + ((uint32_t)(e * 32) << 16) + as * N + j * 32, v);
+            if (j == N / 32 - 1) {
+              tc::fence_before_sync();
+              tc::mbar_arrive(&acc_empty[as]);
+            }
+            const int co0 = nt * N + j * 32;
+            if (!valid || co0 >= p.cout_valid) continue;
+            const uint4* res = nullptr;
+            if (p.residual)
+              res = reinterpret_cast<const uint4*>(p.residual) + (((size_t)b * 8 + ph8) * (p.cout_valid / 8) + co0 / 8) * S_in +
+                    ((size_t)i * p.H + h) * p.W + w;
+            epilogue_store32(p, v, s_scale + j * 32, s_shift + j * 32, co0, b, 2 * i + pd, 2 * h + ph, 2 * w + pw, 2 * p.D, 2 * p.H,
+                             2 * p.W, res, S_in);
+          }
+        }
+    }
+  }
+  TC_KERNEL_EPILOGUE()
+}
+
+// ---- layout converters ----------------------------------------------------------------------------------------------
+// fp32 NCDHW -> bf16 blocked [B][C/8][D][H][W][8], or (s2d) phase-split [B][8][C/8][D/2][H/2][W/2][8]
+__global__ void __launch_bounds__(256) to_blocked_kernel(const float* __restrict__ in, uint4* __restrict__ out, int C, int D, int H,
+                                                         int W, int s2d) {
+  const size_t S = (size_t)D * H * W;
   const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // voxel within (D,H,W)
   if (v >= S) return;
   const int chunk = blockIdx.y, b = blockIdx.z;
@@ -256,7 +612,14 @@ __global__ void __launch_bounds__(256) to_blocked_kernel(const float* __restrict
   uint4 q;
   q.x = tc::pack_bf16x2(f[0], f[1]); q.y = tc::pack_bf16x2(f[2], f[3]);
   q.z = tc::pack_bf16x2(f[4], f[5]); q.w = tc::pack_bf16x2(f[6], f[7]);
-  out[((size_t)b * (C / 8) + chunk) * S + v] = q;
+  size_t o;
+  if (!s2d) o = ((size_t)b * (C / 8) + chunk) * S + v;
+  else {
+    const int x = (int)(v % W), y = (int)((v / W) % H), d = (int)(v / ((size_t)W * H));
+    const int phase = ((d & 1) << 2) | ((y & 1) << 1) | (x & 1);
+    o = (((size_t)b * 8 + phase) * (C / 8) + chunk) * (S / 8) + ((size_t)(d >> 1) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
+  }
+  out[o] = q;
 }
 
 __global__ void __launch_bounds__(256) from_blocked_kernel(const uint4* __restrict__ in, float* __restrict__ out, int C, size_t S) {
@@ -273,50 +636,80 @@ __global__ void __launch_bounds__(256) from_blocked_kernel(const uint4* __restri
   }
 }
 
-int make_act_tmap(CUtensorMap* tm, const void* base, int B, int C, int D, int H, int W) {
+// bf16 blocked -> bf16 phase-split blocked (pure permutation of 16-byte voxel chunks)
+__global__ void __launch_bounds__(256) blocked_to_s2d_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int C8, int D, int H,
+                                                             int W) {
+  const size_t S = (size_t)D * H * W;
+  const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= S) return;
+  const int chunk = blockIdx.y, b = blockIdx.z;
+  const int x = (int)(v % W), y = (int)((v / W) % H), d = (int)(v / ((size_t)W * H));
+  const int phase = ((d & 1) << 2) | ((y & 1) << 1) | (x & 1);
+  out[(((size_t)b * 8 + phase) * C8 + chunk) * (S / 8) + ((size_t)(d >> 1) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)] =
+      in[((size_t)b * C8 + chunk) * S + v];
+}
+
+// dims: (W*8, H, D, outer) ; box (80, 18, 1, box_outer)
+int make_act_tmap(CUtensorMap* tm, const void* base, int W, int H, int D, long long outer, int box_outer) {
   ss_encode_tiled_fn enc = ss_get_encode_tiled();
   if (!enc) return SS_ERR_CUDA;
-  cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B * (C / 8)};
+  cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)outer};
   cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
-  cuuint32_t box[4] = {(cuuint32_t)WW * 8, (cuuint32_t)HH, 1u, (cuuint32_t)(C / 8)};
+  cuuint32_t box[4] = {(cuuint32_t)WW * 8, (cuuint32_t)HH, 1u, (cuuint32_t)box_outer};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    ss_set_error("cuTensorMapEncodeTiled failed with CUresult %d (B=%d C=%d D=%d H=%d W=%d)", (int)r, B, C, D, H, W);
+    ss_set_error("cuTensorMapEncodeTiled failed with CUresult %d (W=%d H=%d D=%d outer=%lld box_outer=%d)", (int)r, W, H, D, outer, box_outer);
     return SS_ERR_CUDA;
   }
   return SS_OK;
 }
 
-template <int CIN, int N, int NS, int NWS>
-int launch_s1(const CUtensorMap& tm, TcP p, cudaStream_t st) {
-  constexpr size_t smem = (size_t)NS * (CIN / 8) * HH * WW * 16 + (size_t)NWS * CIN * N * 2;
-  static_assert(smem <= 227 * 1024 - 2048, "shared memory budget");
-  auto k = conv3d_tc_s1_kernel<CIN, N, NS, NWS>;
-  SS_CUDA(ss_allow_smem(k, smem));
+// Picks the depth chunk (balances waves against the halo slices every chunk re-reads), sizes the grid, launches.
+template <typename K>
+int launch_tc(K kernel, size_t smem, const CUtensorMap& tm, TcP p, double halo_cost, cudaStream_t st, const char* name) {
+  SS_CUDA(ss_allow_smem(kernel, smem));
   int grid = ss_num_sms();
   grid -= grid % p.n_tiles;
-  // depth chunking: balance waves against the 2 extra halo slices every chunk re-reads
+  if (grid < p.n_tiles) grid = p.n_tiles;
   const int spatial = p.B * p.HT * p.WT;
   int best = p.D;
   double best_cost = 1e30;
-  for (int dc = 2; dc <= p.D; ++dc) {
-    if (p.D % dc && dc != p.D) continue;
-    const long long items = (long long)spatial * ceil_div(p.D, dc) * p.n_tiles;
-    const double cost = (double)ceil_div64(items, grid) * (dc + 0.35);
+  for (int dc = 1; dc <= p.D; ++dc) {
+    if (p.D % dc) continue;
+    const long long items = (long long)spatial * (p.D / dc) * p.n_tiles;
+    const double cost = (double)ceil_div64(items, grid) * (dc + halo_cost);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = dc; }
   }
-  if (p.D < 2) best = p.D;
   p.DC = best;
-  p.n_dc = ceil_div(p.D, best);
+  p.n_dc = p.D / best;
   p.items = spatial * p.n_dc;
   const long long total = (long long)p.items * p.n_tiles;
-  if (total < grid) { grid = (int)total; grid -= grid % p.n_tiles; if (grid < p.n_tiles) grid = p.n_tiles; }
-  k<<<grid, 256, smem, st>>>(tm, p);
-  SS_CHECK_LAUNCH("ss_conv3d_tc");
+  if (total < grid) grid = (int)total;
+  kernel<<<grid, 256, smem, st>>>(tm, p);
+  SS_CHECK_LAUNCH(name);
   return SS_OK;
+}
+
+template <int CIN, int N, int NS, int NWS, int TAPS>
+int launch_s1(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
+  constexpr size_t smem = (size_t)NS * (CIN / 8) * TILE_B + (size_t)NWS * CIN * N * 2;
+  static_assert(smem <= 227 * 1024 - 2048, "shared memory budget");
+  return launch_tc(conv3d_tc_s1_kernel<CIN, N, NS, NWS, TAPS>, smem, tm, p, TAPS == 27 ? 0.35 : 0.0, st, "ss_conv3d_tc(s1)");
+}
+template <int CIN, int N, int NS, int NWS>
+int launch_s2(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
+  constexpr size_t smem = (size_t)NS * 4 * (CIN / 8) * TILE_B + (size_t)NWS * CIN * N * 2;
+  static_assert(smem <= 227 * 1024 - 2048, "shared memory budget");
+  return launch_tc(conv3d_tc_s2_kernel<CIN, N, NS, NWS>, smem, tm, p, 0.4, st, "ss_conv3d_tc(s2)");
+}
+template <int CIN, int N, int NS, int NWS>
+int launch_t2(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
+  constexpr size_t smem = (size_t)NS * (CIN / 8) * TILE_B + (size_t)NWS * CIN * N * 2;
+  static_assert(smem <= 227 * 1024 - 2048, "shared memory budget");
+  return launch_tc(conv3d_tc_t2_kernel<CIN, N, NS, NWS>, smem, tm, p, 0.3, st, "ss_conv3d_tc(t2)");
 }
 
 }  // namespace
@@ -335,46 +728,88 @@ ss_encode_tiled_fn ss_get_encode_tiled() {
   return fn;
 }
 
-// Cout tile the kernel uses for (Cin, Cout): the weight must be packed as [Cout/N][27][Cin/8][N][8] bf16. 0 = unsupported.
-extern "C" int ss_conv3d_tc_ntile(int Cin, int Cout) {
-  if ((Cin == 32 || Cin == 64) && (Cout == 32 || Cout == 64)) return 32;
-  if (Cin == 128 && Cout == 128) return 128;
+// kind: 0 = Conv3d k3 s1, 1 = Conv3d k1, 2 = Conv3d k3 s2 (phase-split input), 3 = ConvTranspose3d k3 s2 p1 op1.
+// Returns the Cout tile N the kernel uses (weights are packed [ceil(Cout/N)][taps][Cin/8][N][8]); 0 = unsupported.
+extern "C" int ss_conv3d_tc_ntile(int kind, int Cin, int Cout) {
+  switch (kind) {
+    case 0:
+      if ((Cin == 32 || Cin == 64) && Cout <= 64 && (Cout <= 32 || Cout == 64)) return 32;
+      if (Cin == 128 && Cout == 128) return 128;
+      return 0;
+    case 1:
+      if ((Cin == 32 && Cout == 32) || (Cin == 64 && Cout == 64)) return Cout;
+      return 0;
+    case 2:
+      if (Cin == 32 && Cout == 64) return 64;
+      if (Cin == 64 && Cout == 128) return 128;
+      return 0;
+    case 3:
+      if (Cin == 128 && Cout == 64) return 64;
+      if (Cin == 64 && Cout == 32) return 32;
+      return 0;
+  }
   return 0;
 }
 
-extern "C" int ss_conv3d_tc(const void* in_blocked, const void* weight_packed, const float* scale_or_null, const float* shift_or_null,
-                            const float* gate_logits_or_null, void* out, int out_is_f32, int B, int Cin, int Cout, int D, int H,
-                            int W, int relu, void* stream) {
+// D,H,W are the INPUT dims of the layer (kind 2: of the full-resolution input, all even; the tensor itself is phase-split).
+extern "C" int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight_packed, const float* scale_or_null,
+                            const float* shift_or_null, const float* gate_logits_or_null, const void* residual_s2d_or_null, void* out,
+                            int out_is_f32, int B, int Cin, int Cout, int D, int H, int W, int relu, void* stream) {
   SS_REQUIRE(in_blocked && weight_packed && out, "ss_conv3d_tc: null pointer");
-  SS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "ss_conv3d_tc: non-positive dimension");
-  const int N = ss_conv3d_tc_ntile(Cin, Cout);
-  SS_UNSUPPORTED(N == 0, "ss_conv3d_tc: (Cin=%d, Cout=%d) has no tensor-core configuration", Cin, Cout);
+  SS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && Cout > 0, "ss_conv3d_tc: non-positive dimension");
+  const int N = ss_conv3d_tc_ntile(kind, Cin, Cout);
+  SS_UNSUPPORTED(N == 0, "ss_conv3d_tc: kind %d with (Cin=%d, Cout=%d) has no tensor-core configuration", kind, Cin, Cout);
   SS_REQUIRE((reinterpret_cast<uintptr_t>(in_blocked) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
-                 (reinterpret_cast<uintptr_t>(weight_packed) & 15) == 0, "ss_conv3d_tc: pointers must be 16-byte aligned");
-  SS_UNSUPPORTED((long long)B * (Cin / 8) > 0x7fffffffLL, "ss_conv3d_tc: too many channel chunks");
-  CUtensorMap tm;
-  int rc = make_act_tmap(&tm, in_blocked, B, Cin, D, H, W);
-  if (rc != SS_OK) return rc;
+                 (reinterpret_cast<uintptr_t>(weight_packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual_s2d_or_null) & 15) == 0,
+             "ss_conv3d_tc: pointers must be 16-byte aligned");
+  SS_REQUIRE(out_is_f32 || Cout % 8 == 0, "ss_conv3d_tc: a bf16 blocked output needs Cout %% 8 == 0");
+  SS_REQUIRE(kind == 3 || !residual_s2d_or_null, "ss_conv3d_tc: the residual input exists only for the transposed layer");
+  SS_REQUIRE(kind != 2 || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "ss_conv3d_tc: stride-2 layer needs even input dims");
   TcP p;
   p.w = reinterpret_cast<const __nv_bfloat16*>(weight_packed);
   p.scale = scale_or_null; p.shift = shift_or_null; p.gate = gate_logits_or_null;
-  p.out = out; p.out_f32 = out_is_f32;
-  p.B = B; p.D = D; p.H = H; p.W = W; p.Cout = Cout; p.relu = relu;
-  p.n_tiles = Cout / N; p.HT = ceil_div(H, TH); p.WT = ceil_div(W, TW);
-  p.DC = D; p.n_dc = 1; p.items = 0;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual_s2d_or_null);
+  p.out = out; p.out_f32 = out_is_f32; p.cout_valid = Cout;
+  p.B = B; p.relu = relu;
+  p.n_tiles = ceil_div(Cout, N);
+  p.DC = 1; p.n_dc = 1; p.items = 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (Cin == 32) return launch_s1<32, 32, 4, 27>(tm, p, st);
-  if (Cin == 64) return launch_s1<64, 32, 4, 27>(tm, p, st);
-  return launch_s1<128, 128, 3, 2>(tm, p, st);
+  CUtensorMap tm;
+  int rc;
+  if (kind == 2) {
+    p.D = D / 2; p.H = H / 2; p.W = W / 2;
+    rc = make_act_tmap(&tm, in_blocked, p.W, p.H, p.D, (long long)B * 8 * (Cin / 8), 4 * (Cin / 8));
+  } else {
+    p.D = D; p.H = H; p.W = W;
+    rc = make_act_tmap(&tm, in_blocked, W, H, D, (long long)B * (Cin / 8), Cin / 8);
+  }
+  if (rc != SS_OK) return rc;
+  p.HT = ceil_div(p.H, TH); p.WT = ceil_div(p.W, TW);
+  switch (kind) {
+    case 0:
+      if (Cin == 32) return launch_s1<32, 32, 4, 27, 27>(tm, p, st);
+      if (Cin == 64) return launch_s1<64, 32, 4, 27, 27>(tm, p, st);
+      return launch_s1<128, 128, 3, 2, 27>(tm, p, st);
+    case 1:
+      if (Cin == 32) return launch_s1<32, 32, 4, 1, 1>(tm, p, st);
+      return launch_s1<64, 64, 4, 1, 1>(tm, p, st);
+    case 2:
+      if (Cin == 32) return launch_s2<32, 64, 2, 27>(tm, p, st);
+      return launch_s2<64, 128, 2, 2>(tm, p, st);
+    default:
+      if (Cin == 128) return launch_t2<128, 64, 3, 2>(tm, p, st);
+      return launch_t2<64, 32, 3, 27>(tm, p, st);
+  }
 }
 
-extern "C" int ss_to_blocked_bf16(const float* in_ncdhw, void* out_blocked, int B, int C, int D, int H, int W, void* stream) {
+extern "C" int ss_to_blocked_bf16(const float* in_ncdhw, void* out_blocked, int B, int C, int D, int H, int W, int s2d, void* stream) {
   SS_REQUIRE(in_ncdhw && out_blocked && B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "ss_to_blocked_bf16: bad argument");
   SS_REQUIRE(C % 8 == 0, "ss_to_blocked_bf16: C=%d must be a multiple of 8", C);
+  SS_REQUIRE(!s2d || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "ss_to_blocked_bf16: phase-split layout needs even dims");
   SS_UNSUPPORTED(C / 8 > 65535 || B > 65535, "ss_to_blocked_bf16: grid dimension exceeds 65535");
   const size_t S = (size_t)D * H * W;
   to_blocked_kernel<<<dim3((unsigned)ceil_div64(S, 256), C / 8, B), 256, 0, (cudaStream_t)stream>>>(
-      in_ncdhw, reinterpret_cast<uint4*>(out_blocked), C, S);
+      in_ncdhw, reinterpret_cast<uint4*>(out_blocked), C, D, H, W, s2d);
   SS_CHECK_LAUNCH("ss_to_blocked_bf16");
   return SS_OK;
 }
@@ -387,5 +822,16 @@ extern "C" int ss_from_blocked_bf16(const void* in_blocked, float* out_ncdhw, in
   from_blocked_kernel<<<dim3((unsigned)ceil_div64(S, 256), C / 8, B), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(in_blocked), out_ncdhw, C, S);
   SS_CHECK_LAUNCH("ss_from_blocked_bf16");
+  return SS_OK;
+}
+
+extern "C" int ss_blocked_to_s2d(const void* in_blocked, void* out_s2d, int B, int C, int D, int H, int W, void* stream) {
+  SS_REQUIRE(in_blocked && out_s2d && B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "ss_blocked_to_s2d: bad argument");
+  SS_REQUIRE(C % 8 == 0 && D % 2 == 0 && H % 2 == 0 && W % 2 == 0, "ss_blocked_to_s2d: C %% 8 == 0 and even dims required");
+  SS_UNSUPPORTED(C / 8 > 65535 || B > 65535, "ss_blocked_to_s2d: grid dimension exceeds 65535");
+  const size_t S = (size_t)D * H * W;
+  blocked_to_s2d_kernel<<<dim3((unsigned)ceil_div64(S, 256), C / 8, B), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(in_blocked), reinterpret_cast<uint4*>(out_s2d), C / 8, D, H, W);
+  SS_CHECK_LAUNCH("ss_blocked_to_s2d");
   return SS_OK;
 }

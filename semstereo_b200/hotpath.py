@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from . import ops_tc as tc
 
 TOPK = 24  # SemStereo.py:301
 
@@ -166,12 +167,16 @@ class DisparityHotPath(nn.Module):
             raise NotImplementedError("DisparityHotPath is inference-only (eval-mode BatchNorm is folded)")
         c = {}
 
+        bf16 = self.precision == "bf16"
+
         def conv(name, convmod, bn, transposed=False):
             w = convmod.weight.detach().float()
-            c[name + ".w"] = ops.pack_conv3d_weight(w, transposed)
-            if (self.precision == "bf16" and not transposed and tuple(w.shape[2:]) == (3, 3, 3) and convmod.stride == (1, 1, 1)
-                    and ops.conv3d_tc_ntile(w.shape[1], w.shape[0]) > 0):
-                c[name + ".wtc"] = ops.pack_conv3d_weight_tc(w)
+            if bf16:      # tensor-core packing: kind from the layer geometry
+                k, st = convmod.kernel_size[0], convmod.stride[0]
+                kind = tc.T2 if transposed else (tc.K1 if k == 1 else (tc.S2 if st == 2 else tc.S1))
+                c[name + ".tc"] = tc.pack_weight(w, kind)
+            else:
+                c[name + ".w"] = ops.pack_conv3d_weight(w, transposed)
             if bn is not None:
                 c[name + ".scale"], c[name + ".shift"] = bn_affine(bn)
 
@@ -191,7 +196,10 @@ class DisparityHotPath(nn.Module):
         for cl in ("classif_att_", "classif"):
             m = getattr(self, cl)
             conv(cl + ".0", m[0][0], m[0][1])
-            c[cl + ".2.w"] = m[2].weight.detach().float().contiguous()
+            if bf16:
+                c[cl + ".2.tc"] = tc.pack_weight(m[2].weight.detach().float(), tc.S1)      # Cout 1 zero-padded to the 32-wide tile
+            else:
+                c[cl + ".2.w"] = m[2].weight.detach().float().contiguous()
         conv("concat_stem", self.concat_stem.conv, self.concat_stem.bn)
         for ca in ("corr_feature_att_8", "concat_feature_att_4"):
             m = getattr(self, ca).im_att
@@ -214,11 +222,37 @@ class DisparityHotPath(nn.Module):
             return self._conv_impl(c, name, x, k, stride, relu, transposed, residual, gate)
 
     def _conv_impl(self, c, name, x, k, stride, relu, transposed, residual, gate):
-        if name + ".wtc" in c and residual is None:
-            return ops.conv3d_tc(ops.to_blocked_bf16(x), c[name + ".wtc"], c.get(name + ".scale"), c.get(name + ".shift"), gate,
-                                 relu=relu, out_f32=True)
         return ops.conv3d_f32(x, c[name + ".w"], c.get(name + ".scale"), c.get(name + ".shift"), residual, gate,
                               k=k, stride=stride, transposed=transposed, relu=relu)
+
+    # ---- bf16 tensor-core flavour: activations stay in the blocked / phase-split bf16 layouts between the layers ----
+    def _tc(self, c, name, kind, x, cout, relu=True, gate=None, residual=None, out_f32=False):
+        with ops.label(name):
+            return tc.conv3d_tc(kind, x, c[name + ".tc"], cout, c.get(name + ".scale"), c.get(name + ".shift"), gate, residual,
+                                relu=relu, out_f32=out_f32)
+
+    def _hourglass_tc(self, c, hg, x_s2d):
+        """hourglass.forward (SemStereo.py:134-143) on tensor cores.  x_s2d: phase-split bf16 (B,8,4,D/2,H/2,W/2,8); returns
+        blocked bf16 (B,4,D,H,W,8).  The redir 1x1 convs run position-wise on the phase-split tensors and come back as the
+        residual of the transposed layers, which add it before their ReLU."""
+        block = getattr(self, hg).block
+        c1 = self._tc(c, hg + ".conv1", tc.S2, x_s2d, 64)
+        c2 = self._tc(c, hg + ".conv2", tc.S1, c1, 64)
+        with ops.label("layout"):
+            c2s = tc.blocked_to_s2d(c2)
+        c3 = self._tc(c, hg + ".conv3", tc.S2, c2s, 128)
+        c4 = self._tc(c, hg + ".conv4", tc.S1, c3, 128, out_f32=True)
+        c4 = ops.window_attention3d(c4, c[hg + ".wqkv_t"], c[hg + ".bqkv"], c[hg + ".wo_t"], c[hg + ".bo"], block, 16)
+        with ops.label("layout"):
+            c4b = tc.to_blocked_bf16(c4)
+        r2 = self._tc(c, hg + ".redir2", tc.K1, tc.s2d_as_batch(c2s), 64, relu=False).view(c2s.shape)
+        c5 = self._tc(c, hg + ".conv5", tc.T2, c4b, 64, residual=r2)
+        r1 = self._tc(c, hg + ".redir1", tc.K1, tc.s2d_as_batch(x_s2d), 32, relu=False).view(x_s2d.shape)
+        return self._tc(c, hg + ".conv6", tc.T2, c5, 32, residual=r1)
+
+    def _classifier_tc(self, c, cl, xb):
+        y = self._tc(c, cl + ".0", tc.S1, xb, 32)
+        return self._tc(c, cl + ".2", tc.S1, y, 1, relu=False, out_f32=True)
 
     def _hourglass(self, c, hg, x):
         """hourglass.forward (SemStereo.py:134-143): residual adds and ReLUs ride in the deconv epilogues."""
@@ -246,8 +280,13 @@ class DisparityHotPath(nn.Module):
         # --- attention branch @1/8 (SemStereo.py:273-278) ---
         corr = ops.gwc_volume(f8_l, f8_r, m8, 32, signed=self.signed, norm=True)
         vol = ops.patch_gate(corr, c["patch.w"], self._gate_logits(c, "corr_feature_att_8", f8_l))
-        vol = self._hourglass(c, "hourglass_att", vol)
-        cost_att = self._classifier(c, "classif_att_", vol)
+        if self.precision == "bf16":
+            with ops.label("layout"):
+                vol = tc.to_blocked_bf16(vol, s2d=True)
+            cost_att = self._classifier_tc(c, "classif_att_", self._hourglass_tc(c, "hourglass_att", vol))
+        else:
+            vol = self._hourglass(c, "hourglass_att", vol)
+            cost_att = self._classifier(c, "classif_att_", vol)
         # --- statistics, propagation, top-k @1/4 (SemStereo.py:279-310) ---
         dmin = float(-m4) if self.signed else 0.0
         att_up, mu, gate = ops.att_stats(cost_att, self.beta.data, self.gamma.data, dmin)
@@ -261,9 +300,18 @@ class DisparityHotPath(nn.Module):
             return out
         # --- sparse concat volume + aggregation (SemStereo.py:314-324) ---
         volume = ops.sparse_concat_volume(cf_l, cf_r, disp_topk, att_topk)
-        v = self._conv(c, "concat_stem", volume, gate=self._gate_logits(c, "concat_feature_att_4", f4_l))
-        v = self._hourglass(c, "hourglass", v)
-        cost = self._classifier(c, "classif", v)
+        gate4 = self._gate_logits(c, "concat_feature_att_4", f4_l)
+        if self.precision == "bf16":
+            with ops.label("layout"):
+                vb = tc.to_blocked_bf16(volume)
+            v = self._tc(c, "concat_stem", tc.S1, vb, 32, gate=gate4)
+            with ops.label("layout"):
+                v = tc.blocked_to_s2d(v)
+            cost = self._classifier_tc(c, "classif", self._hourglass_tc(c, "hourglass", v))
+        else:
+            v = self._conv(c, "concat_stem", volume, gate=gate4)
+            v = self._hourglass(c, "hourglass", v)
+            cost = self._classifier(c, "classif", v)
         pred = ops.regression_topk(cost.squeeze(1), disp_topk, 2)
         out.update(cost=cost, pred=pred)
         if keep:

@@ -334,61 +334,3 @@ def spatial_transformer_grid(x, y, disp_samples, want_x_rep=True):
     _call("ss_spatial_transformer_grid", dev, _ptr(x), _ptr(y), _ptr(disp_samples), _ptr(yw), _ptr(xr), B, C, K, H, W)
     return yw, xr
 
-
-# ---- K4 tensor-core mode (tcgen05): bf16 "blocked channels" activations [B][C/8][D][H][W][8] ---------------------------
-def _require_blocked(t):
-    if not t.is_cuda:
-        raise RuntimeError("semstereo_b200 kernels need CUDA tensors: there is no CPU fallback on this path")
-    if t.dtype != torch.bfloat16 or t.dim() != 6 or t.shape[-1] != 8 or not t.is_contiguous():
-        raise ValueError("expected a contiguous bf16 blocked tensor (B, C/8, D, H, W, 8)")
-    return t.device
-
-
-def to_blocked_bf16(x):
-    dev = _require_cuda(x)
-    B, C, D, H, W = x.shape
-    out = torch.empty((B, C // 8, D, H, W, 8), device=dev, dtype=torch.bfloat16)
-    _call("ss_to_blocked_bf16", dev, _ptr(x), _ptr(out), B, C, D, H, W)
-    return out
-
-
-def from_blocked_bf16(xb):
-    dev = _require_blocked(xb)
-    B, C8, D, H, W, _ = xb.shape
-    out = torch.empty((B, C8 * 8, D, H, W), device=dev, dtype=torch.float32)
-    _call("ss_from_blocked_bf16", dev, _ptr(xb), _ptr(out), B, C8 * 8, D, H, W)
-    return out
-
-
-def conv3d_tc_ntile(cin, cout):
-    return _lib.load().ss_conv3d_tc_ntile(int(cin), int(cout))
-
-
-def pack_conv3d_weight_tc(w):
-    """(Cout,Cin,3,3,3) fp32 -> bf16 [Cout/N][27][Cin/8][N][8] (N = the kernel's Cout tile)."""
-    cout, cin = w.shape[:2]
-    n = conv3d_tc_ntile(cin, cout)
-    if n == 0:
-        raise NotImplementedError(f"conv3d_tc: (Cin={cin}, Cout={cout}) has no tensor-core configuration")
-    t = w.permute(2, 3, 4, 1, 0).reshape(27, cin // 8, 8, cout // n, n)      # (tap, chunk, c8, ntile, n)
-    return t.permute(3, 0, 1, 4, 2).contiguous().to(torch.bfloat16)
-
-
-def conv3d_tc(xb, w_tc, scale=None, shift=None, gate_logits=None, relu=False, out_f32=False):
-    dev = _require_blocked(xb)
-    _require_cuda(*[t for t in (scale, shift, gate_logits) if t is not None] or [torch.empty(0, device=dev)])
-    B, C8, D, H, W, _ = xb.shape
-    cin = C8 * 8
-    ntiles, taps, c8w, n, _ = w_tc.shape
-    cout = ntiles * n
-    if w_tc.dtype != torch.bfloat16 or taps != 27 or c8w != C8 or n != conv3d_tc_ntile(cin, cout) or not w_tc.is_contiguous():
-        raise ValueError("conv3d_tc: weight must come from pack_conv3d_weight_tc for this (Cin, Cout)")
-    if gate_logits is not None and tuple(gate_logits.shape) != (B, cout, H, W):
-        raise ValueError("conv3d_tc: gate logits must be (B,Cout,H,W)")
-    if out_f32:
-        out = torch.empty((B, cout, D, H, W), device=dev, dtype=torch.float32)
-    else:
-        out = torch.empty((B, cout // 8, D, H, W, 8), device=dev, dtype=torch.bfloat16)
-    _call("ss_conv3d_tc", dev, _ptr(xb), _ptr(w_tc), _ptr(scale), _ptr(shift), _ptr(gate_logits), _ptr(out), int(out_f32),
-          B, cin, cout, D, H, W, int(relu))
-    return out

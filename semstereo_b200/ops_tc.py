@@ -1,0 +1,107 @@
+"""Wrappers for the tensor-core (tcgen05 / TMEM / TMA) 3-D convolutions and their bf16 "blocked channels" layouts.
+
+Layouts (bf16): blocked  = (B, C/8, D, H, W, 8);  phase-split ("s2d") = (B, 8, C/8, D/2, H/2, W/2, 8) with
+phase = 4*(d&1) + 2*(h&1) + (w&1).  See include/semstereo_b200.h and csrc/conv3d_tc.cu.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .ops import _call, _ptr, _require_cuda
+
+S1, K1, S2, T2 = 0, 1, 2, 3          # layer kinds of ss_conv3d_tc
+
+
+def _require_bf16(t, ndim):
+    if not t.is_cuda:
+        raise RuntimeError("semstereo_b200 kernels need CUDA tensors: there is no CPU fallback on this path")
+    if t.dtype != torch.bfloat16 or t.dim() != ndim or t.shape[-1] != 8 or not t.is_contiguous():
+        raise ValueError(f"expected a contiguous bf16 tensor with {ndim} dims and 8 innermost channels")
+    return t.device
+
+
+def to_blocked_bf16(x, s2d=False):
+    dev = _require_cuda(x)
+    B, C, D, H, W = x.shape
+    shape = (B, 8, C // 8, D // 2, H // 2, W // 2, 8) if s2d else (B, C // 8, D, H, W, 8)
+    out = torch.empty(shape, device=dev, dtype=torch.bfloat16)
+    _call("ss_to_blocked_bf16", dev, _ptr(x), _ptr(out), B, C, D, H, W, int(s2d))
+    return out
+
+
+def from_blocked_bf16(xb):
+    dev = _require_bf16(xb, 6)
+    B, C8, D, H, W, _ = xb.shape
+    out = torch.empty((B, C8 * 8, D, H, W), device=dev, dtype=torch.float32)
+    _call("ss_from_blocked_bf16", dev, _ptr(xb), _ptr(out), B, C8 * 8, D, H, W)
+    return out
+
+
+def blocked_to_s2d(xb):
+    dev = _require_bf16(xb, 6)
+    B, C8, D, H, W, _ = xb.shape
+    out = torch.empty((B, 8, C8, D // 2, H // 2, W // 2, 8), device=dev, dtype=torch.bfloat16)
+    _call("ss_blocked_to_s2d", dev, _ptr(xb), _ptr(out), B, C8 * 8, D, H, W)
+    return out
+
+
+def s2d_as_batch(xs):
+    """View a phase-split tensor as a blocked tensor with batch B*8 (position-wise layers do not care)."""
+    B, P, C8, D, H, W, _ = xs.shape
+    return xs.view(B * P, C8, D, H, W, 8)
+
+
+def ntile(kind, cin, cout):
+    return _lib.load().ss_conv3d_tc_ntile(int(kind), int(cin), int(cout))
+
+
+def pack_weight(w, kind):
+    """fp32 conv weight -> bf16 [ceil(Cout/N)][taps][Cin/8][N][8], Cout zero-padded to the kernel's tile N.
+    w: (Cout,Cin,k,k,k) for kinds S1/K1/S2, ConvTranspose3d (Cin,Cout,3,3,3) for T2."""
+    if kind == T2:
+        w = w.permute(1, 0, 2, 3, 4)                                   # -> (Cout, Cin, kd, kh, kw), taps index the weight directly
+    cout, cin = w.shape[:2]
+    taps = w.shape[2] * w.shape[3] * w.shape[4]
+    n = ntile(kind, cin, cout)
+    if n == 0:
+        raise NotImplementedError(f"conv3d_tc: kind {kind} with (Cin={cin}, Cout={cout}) has no tensor-core configuration")
+    nt = -(-cout // n)
+    wp = w.new_zeros((nt * n, cin, taps))
+    wp[:cout] = w.reshape(cout, cin, taps)
+    t = wp.reshape(nt, n, cin // 8, 8, taps).permute(0, 4, 2, 1, 3)     # (ntile, tap, chunk, n, c8)
+    return t.contiguous().to(torch.bfloat16)
+
+
+def conv3d_tc(kind, xb, w_tc, cout, scale=None, shift=None, gate_logits=None, residual_s2d=None, relu=False, out_f32=False):
+    """xb: blocked (kinds S1, K1, T2) or phase-split (kind S2) bf16 input.  Returns bf16 blocked or fp32 NCDHW."""
+    if kind == S2:
+        dev = _require_bf16(xb, 7)
+        B, _, C8, D2, H2, W2, _ = xb.shape
+        D, H, W = 2 * D2, 2 * H2, 2 * W2
+        Do, Ho, Wo = D2, H2, W2
+    else:
+        dev = _require_bf16(xb, 6)
+        B, C8, D, H, W, _ = xb.shape
+        Do, Ho, Wo = (2 * D, 2 * H, 2 * W) if kind == T2 else (D, H, W)
+    cin = C8 * 8
+    n = ntile(kind, cin, cout)
+    taps = 1 if kind == K1 else 27
+    if n == 0 or w_tc.dtype != torch.bfloat16 or tuple(w_tc.shape) != (-(-cout // n), taps, C8, n, 8) or not w_tc.is_contiguous():
+        raise ValueError("conv3d_tc: weight must come from pack_weight(w, kind) for this layer")
+    for t in (scale, shift, gate_logits):
+        if t is not None:
+            _require_cuda(t)
+    if gate_logits is not None and tuple(gate_logits.shape) != (B, cout, Ho, Wo):
+        raise ValueError("conv3d_tc: gate logits must be (B,Cout,Ho,Wo)")
+    if residual_s2d is not None:
+        _require_bf16(residual_s2d, 7)
+        if kind != T2 or tuple(residual_s2d.shape) != (B, 8, cout // 8, D, H, W, 8):
+            raise ValueError("conv3d_tc: residual must be phase-split (B,8,Cout/8,D,H,W,8) at the transposed layer's input dims")
+    if out_f32:
+        out = torch.empty((B, cout, Do, Ho, Wo), device=dev, dtype=torch.float32)
+    else:
+        out = torch.empty((B, cout // 8, Do, Ho, Wo, 8), device=dev, dtype=torch.bfloat16)
+    _call("ss_conv3d_tc", dev, int(kind), _ptr(xb), _ptr(w_tc), _ptr(scale), _ptr(shift), _ptr(gate_logits), _ptr(residual_s2d),
+          _ptr(out), int(out_f32), B, cin, cout, D, H, W, int(relu))
+    return out

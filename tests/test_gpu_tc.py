@@ -1,6 +1,6 @@
-"""Tensor-core (tcgen05/TMEM/TMA) conv3d vs torch fp32 conv on bf16-rounded operands.  Tolerance: the kernel accumulates in
-fp32, so against an fp32 conv of the SAME bf16-rounded inputs/weights only summation order and the bf16 rounding of the
-output differ: |err| <= 2^-8 * |y| + 1e-3 (bf16 output) or 1e-3 * max|y| (fp32 output)."""
+"""Tensor-core (tcgen05/TMEM/TMA) 3-D convolutions vs torch fp32 convs on bf16-rounded operands.
+The kernels accumulate in fp32, so against an fp32 conv of the SAME bf16-rounded inputs/weights only the summation order and
+the bf16 rounding of the output differ: |err| <= 2^-8*|y| + 2e-3*max|y| (bf16 output), 2e-3*max|y| (fp32 output)."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -9,25 +9,46 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 if torch.cuda.is_available():
-    from semstereo_b200 import ops
+    from semstereo_b200 import ops_tc as tc
 
 
 def bf(t):
     return t.to(torch.bfloat16).float()
 
 
-def test_blocked_roundtrip():
-    x = torch.randn(2, 32, 3, 5, 7, generator=torch.Generator().manual_seed(0))
-    xb = ops.to_blocked_bf16(x.to(DEV))
-    assert tuple(xb.shape) == (2, 4, 3, 5, 7, 8)
-    assert torch.equal(xb.cpu().float(), bf(x).view(2, 4, 8, 3, 5, 7).permute(0, 1, 3, 4, 5, 2))
-    assert torch.equal(ops.from_blocked_bf16(xb).cpu(), bf(x))
+def s2d_ref(x):
+    """(B,C,D,H,W) -> (B,8,C/8,D/2,H/2,W/2,8) phase-split blocked, reference permutation."""
+    B, C, D, H, W = x.shape
+    t = x.view(B, C // 8, 8, D // 2, 2, H // 2, 2, W // 2, 2).permute(0, 4, 6, 8, 1, 3, 5, 7, 2)
+    return t.reshape(B, 8, C // 8, D // 2, H // 2, W // 2, 8)
 
 
-@pytest.mark.parametrize("Cin,Cout,B,D,H,W", [(32, 32, 1, 4, 16, 8), (32, 32, 2, 5, 20, 12), (64, 32, 1, 6, 32, 24), (64, 64, 1, 4, 16, 16),
-                                              (128, 128, 1, 4, 8, 8), (128, 128, 2, 6, 16, 16), (64, 32, 1, 24, 64, 64), (32, 32, 1, 16, 128, 128)])
+def check(got, ref, bf16_out):
+    tol = 2e-3 * ref.abs().max().item() + (2.0 ** -8) * ref.abs() * (1 if bf16_out else 0) + 1e-4
+    bad = ((got - ref).abs() > tol).float().mean().item()
+    assert bad == 0.0, f"{bad:.4%} of outputs outside tolerance; max err {(got - ref).abs().max().item():.4f}"
+
+
+def test_layout_converters():
+    x = torch.randn(2, 32, 4, 6, 8, generator=torch.Generator().manual_seed(0))
+    xb = tc.to_blocked_bf16(x.to(DEV))
+    assert tuple(xb.shape) == (2, 4, 4, 6, 8, 8)
+    assert torch.equal(xb.cpu().float(), bf(x).view(2, 4, 8, 4, 6, 8).permute(0, 1, 3, 4, 5, 2))
+    assert torch.equal(tc.from_blocked_bf16(xb).cpu(), bf(x))
+    xs = tc.to_blocked_bf16(x.to(DEV), s2d=True)
+    assert torch.equal(xs.cpu().float(), s2d_ref(bf(x)))
+    assert torch.equal(tc.blocked_to_s2d(xb).cpu(), xs.cpu())
+
+
+S1_CASES = [(32, 32, 1, 4, 16, 8), (32, 32, 2, 5, 20, 12), (64, 32, 1, 6, 32, 24), (64, 64, 1, 4, 16, 16), (128, 128, 1, 4, 8, 8),
+            (128, 128, 2, 6, 16, 16), (64, 32, 1, 24, 64, 64), (32, 32, 1, 16, 128, 128), (32, 1, 1, 6, 16, 24)]
+
+
+@pytest.mark.parametrize("Cin,Cout,B,D,H,W", S1_CASES)
 @pytest.mark.parametrize("out_f32", [False, True])
-def test_conv3d_tc_s1(Cin, Cout, B, D, H, W, out_f32):
+def test_conv_k3_s1(Cin, Cout, B, D, H, W, out_f32):
+    if Cout % 8 and not out_f32:
+        pytest.skip("bf16 blocked output needs Cout % 8 == 0")
     g = torch.Generator().manual_seed(Cin + Cout + D)
     x = torch.randn(B, Cin, D, H, W, generator=g)
     w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) / (27 * Cin) ** 0.5
@@ -35,13 +56,62 @@ def test_conv3d_tc_s1(Cin, Cout, B, D, H, W, out_f32):
     gate = torch.randn(B, Cout, H, W, generator=g)
     y = F.conv3d(bf(x), bf(w), None, padding=1)
     ref = F.relu(y * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)) * torch.sigmoid(gate).unsqueeze(2)
-    xb = ops.to_blocked_bf16(x.to(DEV))
-    wt = ops.pack_conv3d_weight_tc(w).to(DEV)
-    out = ops.conv3d_tc(xb, wt, scale.to(DEV), shift.to(DEV), gate.to(DEV), relu=True, out_f32=out_f32)
+    xb = tc.to_blocked_bf16(x.to(DEV))
+    wt = tc.pack_weight(w, tc.S1).to(DEV)
+    out = tc.conv3d_tc(tc.S1, xb, wt, Cout, scale.to(DEV), shift.to(DEV), gate.to(DEV), relu=True, out_f32=out_f32)
     torch.cuda.synchronize()
-    got = out.cpu() if out_f32 else ops.from_blocked_bf16(out).cpu()
-    tol = 1e-3 * ref.abs().max().item() + (0 if out_f32 else 1) * (2.0 ** -8) * ref.abs()
-    bad = ((got - ref).abs() > tol + 1e-3).float().mean().item()
-    assert bad == 0.0, f"{bad:.4%} of outputs outside tolerance; max err {(got - ref).abs().max().item():.4f}"
-    plain = ops.conv3d_tc(xb, wt, out_f32=True)
-    assert (plain.cpu() - y).abs().max().item() <= 2e-3 * max(1.0, y.abs().max().item())
+    check(out.cpu() if out_f32 else tc.from_blocked_bf16(out).cpu(), ref, not out_f32)
+    plain = tc.conv3d_tc(tc.S1, xb, wt, Cout, out_f32=True)
+    check(plain.cpu(), y, False)
+
+
+@pytest.mark.parametrize("C,B,D,H,W", [(32, 2, 4, 16, 24), (64, 1, 6, 20, 12)])
+def test_conv_k1(C, B, D, H, W):
+    g = torch.Generator().manual_seed(C + D)
+    x = torch.randn(B, C, D, H, W, generator=g)
+    w = torch.randn(C, C, 1, 1, 1, generator=g) / C ** 0.5
+    scale, shift = torch.rand(C, generator=g) + 0.5, 0.3 * torch.randn(C, generator=g)
+    ref = F.conv3d(bf(x), bf(w)) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)
+    out = tc.conv3d_tc(tc.K1, tc.to_blocked_bf16(x.to(DEV)), tc.pack_weight(w, tc.K1).to(DEV), C, scale.to(DEV), shift.to(DEV))
+    check(tc.from_blocked_bf16(out).cpu(), ref, True)
+    # position-wise layer on a phase-split tensor viewed as batch*8 keeps the phase-split layout
+    xs = tc.to_blocked_bf16(x.to(DEV), s2d=True)
+    outs = tc.conv3d_tc(tc.K1, tc.s2d_as_batch(xs), tc.pack_weight(w, tc.K1).to(DEV), C, scale.to(DEV), shift.to(DEV))
+    assert torch.equal(outs.view(xs.shape).cpu(), tc.blocked_to_s2d(out).cpu())
+
+
+@pytest.mark.parametrize("Cin,Cout,B,D,H,W", [(32, 64, 1, 4, 16, 16), (32, 64, 2, 8, 40, 24), (64, 128, 1, 4, 32, 16), (64, 128, 2, 12, 16, 32),
+                                              (32, 64, 1, 24, 64, 64)])
+@pytest.mark.parametrize("out_f32", [False, True])
+def test_conv_k3_s2(Cin, Cout, B, D, H, W, out_f32):
+    g = torch.Generator().manual_seed(Cin + Cout + D + 1)
+    x = torch.randn(B, Cin, D, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) / (27 * Cin) ** 0.5
+    scale, shift = torch.rand(Cout, generator=g) + 0.5, 0.3 * torch.randn(Cout, generator=g)
+    ref = F.relu(F.conv3d(bf(x), bf(w), None, stride=2, padding=1) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
+    xs = tc.to_blocked_bf16(x.to(DEV), s2d=True)
+    out = tc.conv3d_tc(tc.S2, xs, tc.pack_weight(w, tc.S2).to(DEV), Cout, scale.to(DEV), shift.to(DEV), relu=True, out_f32=out_f32)
+    torch.cuda.synchronize()
+    check(out.cpu() if out_f32 else tc.from_blocked_bf16(out).cpu(), ref, not out_f32)
+
+
+@pytest.mark.parametrize("Cin,Cout,B,D,H,W", [(128, 64, 1, 2, 16, 8), (128, 64, 2, 3, 20, 12), (64, 32, 1, 4, 16, 16), (64, 32, 2, 6, 24, 40),
+                                              (64, 32, 1, 12, 64, 64)])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_conv_transposed(Cin, Cout, B, D, H, W, with_res):
+    g = torch.Generator().manual_seed(Cin + Cout + D + 2)
+    x = torch.randn(B, Cin, D, H, W, generator=g)
+    w = torch.randn(Cin, Cout, 3, 3, 3, generator=g) / (27 * Cin / 8) ** 0.5
+    scale, shift = torch.rand(Cout, generator=g) + 0.5, 0.3 * torch.randn(Cout, generator=g)
+    y = F.conv_transpose3d(bf(x), bf(w), None, stride=2, padding=1, output_padding=1)
+    res = torch.randn(y.shape, generator=g)
+    ref = y * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)
+    rs = None
+    if with_res:
+        ref = ref + bf(res)
+        rs = tc.to_blocked_bf16(res.to(DEV), s2d=True)
+    ref = F.relu(ref)
+    out = tc.conv3d_tc(tc.T2, tc.to_blocked_bf16(x.to(DEV)), tc.pack_weight(w, tc.T2).to(DEV), Cout, scale.to(DEV), shift.to(DEV),
+                       residual_s2d=rs, relu=True)
+    torch.cuda.synchronize()
+    check(tc.from_blocked_bf16(out).cpu(), ref, True)
