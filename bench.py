@@ -222,14 +222,29 @@ def main():
     h2d = sum(v.numel() * 4 for v in host.values())
     d2h = out_host.numel() * 4
     barrier()
+    # public API: HostPipeline (double-buffered: the H2D of step i+1 overlaps the compute of step i; every step copies all
+    # eight input tensors from pinned host memory and reads pred_up back to pinned host memory)
+    from semstereo_b200.pipeline import HostPipeline
+
+    def gather(o):
+        if world > 1:
+            tdist.all_gather_into_tensor(gathered, o)
+        return o
+
+    pipe = HostPipeline(model, depth=2, post=gather)
+    for _ in pipe.run(host for _ in range(2)):      # warm the staging buffers
+        pass
+    barrier()
+    t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for _ in range(a.steps):
-        cur = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        out_host.copy_(step(cur), non_blocking=True)
+    for res_host in pipe.run(host for _ in range(a.steps)):
+        pass
     f1.record()
     barrier()
-    ms_e2e = f0.elapsed_time(f1)
+    ms_e2e = max(f0.elapsed_time(f1), 0.0)
+    ms_e2e_wall = (time.perf_counter() - t0) * 1e3
+    ms_e2e = max(ms_e2e, ms_e2e_wall)               # device events and host wall clock agree up to launch latency; keep the larger
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms_total, ms_e2e], device=dev)

@@ -79,9 +79,19 @@ SS_API int ss_blocked_to_s2d(const void* in_blocked, void* out_s2d, int B, int C
  * N = ss_conv3d_tc_ntile(kind,Cin,Cout) (0 = unsupported), Cout zero-padded to a multiple of N, tap = (kd*3+kh)*3+kw (kind 3:
  * of the ConvTranspose3d weight (Cin,Cout,kd,kh,kw)).  out: bf16 blocked (Cout % 8 == 0) or fp32 NCDHW with Cout channels. */
 SS_API int ss_conv3d_tc_ntile(int kind, int Cin, int Cout);
+/* gate_blocked: sigmoid(channelAtt logits) as fp32 (B,Cout/8,Ho,Wo,8) from ss_gate_sigmoid_blocked.
+ * out_mode 0: bf16 blocked, 1: fp32 NCDHW, 2: bf16 phase-split blocked (kinds 0-2, even output dims). */
 SS_API int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight_packed, const float* scale_or_null,
-                        const float* shift_or_null, const float* gate_logits_or_null, const void* residual_s2d_or_null, void* out,
-                        int out_is_f32, int B, int Cin, int Cout, int D, int H, int W, int relu, void* stream);
+                        const float* shift_or_null, const float* gate_blocked_or_null, const void* residual_s2d_or_null, void* out,
+                        int out_mode, int B, int Cin, int Cout, int D, int H, int W, int relu, void* stream);
+/* Producers of the blocked layouts (bf16 mode never materialises the fp32 volumes):
+ * sigmoid(gate logits (B,C,H,W)) -> fp32 (B,C/8,H,W,8);  `patch` conv * gate (SemStereo.py:274-276) -> phase-split bf16;
+ * concat_volume_generator * att_topk (SemStereo.py:241-244,318) -> blocked bf16 (B,2C/8,K,H,W,8). */
+SS_API int ss_gate_sigmoid_blocked(const float* gate_logits, float* out_blocked, int B, int C, int H, int W, void* stream);
+SS_API int ss_patch_gate_blocked(const float* volume, const float* patch_w, const float* gate_logits, void* out_s2d, int B, int G, int D,
+                                 int H, int W, void* stream);
+SS_API int ss_sparse_concat_volume_blocked(const float* cf_l, const float* cf_r, const float* disp_topk, const float* att_topk_or_null,
+                                           void* volume_blocked, int B, int C, int K, int H, int W, void* stream);
 
 /* ---- K5: windowed 3-D attention --------------------------------------------------------------------- */
 /* attention_block.forward (submodule_other.py:805-837) for window-divisible D,H,W.  wqkv_t = qkv_3d.weight^T [C][3C],

@@ -30,6 +30,9 @@ SIGNATURES = {
     "ss_to_blocked_bf16": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ss_from_blocked_bf16": [_P, _P, _I, _I, _I, _I, _I, _P],
     "ss_blocked_to_s2d": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "ss_gate_sigmoid_blocked": [_P, _P, _I, _I, _I, _I, _P],
+    "ss_patch_gate_blocked": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "ss_sparse_concat_volume_blocked": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "ss_conv3d_tc_ntile": [_I, _I, _I],
     "ss_conv3d_tc": [_I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "ss_window_attention3d": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],

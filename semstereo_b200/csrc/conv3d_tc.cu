@@ -19,7 +19,7 @@
 //        2o-1+k is (phase 1, o-1), (phase 0, o), (phase 1, o) for k = 0,1,2, so every tap is a dense half-resolution tile.
 //   t2 : ConvTranspose3d k3 s2 p1 op1 as 8 sub-pixel output phases (1/2/4/8 taps each, no zero insertion); the hourglass
 //        skip connection (redir conv output, stored phase-split) is added in the epilogue before the ReLU.
-// Epilogue: y = acc*scale[co] + shift[co] (+ residual) -> ReLU -> * sigmoid(gate[b,co,h,w]) -> bf16 blocked or fp32 NCDHW.
+// Epilogue: y = acc*scale[co] + shift[co] (+ residual) -> ReLU -> * gate[b,co,h,w] -> bf16 blocked / phase-split, or fp32 NCDHW.
 #include "tc_common.cuh"
 
 namespace {
@@ -31,10 +31,10 @@ struct TcP {
   const __nv_bfloat16* w;         // [n_tiles][TAPS][CIN/8][N][8]
   const float* scale;             // [Cout] or null
   const float* shift;             // [Cout] or null
-  const float* gate;              // (B,Cout,OH,OW) logits or null
+  const float* gate;              // sigmoid(gate logits) as fp32 blocked (B,Cout/8,OH,OW,8), or null
   const __nv_bfloat16* residual;  // t2 only: phase-split blocked [B][8][Cout/8][D][H][W][8], or null
   void* out;
-  int out_f32;                    // 0: bf16 blocked, 1: fp32 NCDHW
+  int out_mode;                   // 0: bf16 blocked, 1: fp32 NCDHW, 2: bf16 phase-split blocked
   int cout_valid;                 // channels actually stored (Cout = n_tiles*N may be zero-padded), also the channel count of out
   int B, D, H, W;                 // tile space: output dims (s1, s2) / input dims (t2)
   int relu;
@@ -75,22 +75,34 @@ __device__ __forceinline__ void epilogue_store32(const TcP& p, float (&v)[32], c
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(fmaf(v[i], sc[i], sh[i]), lo);
   }
   const size_t OHW = (size_t)OH * OW;
-  if (p.gate) {                       // branch hoisted out of the channel loop: 32 independent loads in flight
-    const float* gp = p.gate + ((size_t)b * p.cout_valid + co0) * OHW + (size_t)oh * OW + ow;
-    float gl[32];
+  if (p.gate) {                       // pre-activated gate, fp32 blocked (B,Cout/8,OH,OW,8): two 128-bit loads per chunk
+    const float4* gp = reinterpret_cast<const float4*>(p.gate) + (((size_t)b * (p.cout_valid / 8) + co0 / 8) * OHW + (size_t)oh * OW + ow) * 2;
+    float4 g[8];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) gl[i] = (co0 + i < p.cout_valid) ? __ldg(gp + (size_t)i * OHW) : 0.0f;
+    for (int c8 = 0; c8 < 4; ++c8) {
+      const bool ok = co0 + 8 * c8 < p.cout_valid;
+      g[2 * c8] = ok ? __ldg(gp + (size_t)c8 * OHW * 2) : make_float4(1.f, 1.f, 1.f, 1.f);
+      g[2 * c8 + 1] = ok ? __ldg(gp + (size_t)c8 * OHW * 2 + 1) : make_float4(1.f, 1.f, 1.f, 1.f);
+    }
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] *= sigmoidf_(gl[i]);
+    for (int q = 0; q < 8; ++q) { v[4 * q] *= g[q].x; v[4 * q + 1] *= g[q].y; v[4 * q + 2] *= g[q].z; v[4 * q + 3] *= g[q].w; }
   }
   const size_t sp = ((size_t)od * OH + oh) * OW + ow, OS = (size_t)OD * OHW;
-  if (p.out_f32) {
+  if (p.out_mode == 1) {
     float* o = reinterpret_cast<float*>(p.out) + ((size_t)b * p.cout_valid + co0) * OS + sp;
 #pragma unroll
     for (int i = 0; i < 32; ++i)
       if (co0 + i < p.cout_valid) o[(size_t)i * OS] = v[i];
   } else {
-    uint4* o = reinterpret_cast<uint4*>(p.out) + ((size_t)b * (p.cout_valid / 8) + co0 / 8) * OS + sp;
+    uint4* o;
+    size_t cs = OS;                   // chunk stride in uint4
+    if (p.out_mode == 0) o = reinterpret_cast<uint4*>(p.out) + ((size_t)b * (p.cout_valid / 8) + co0 / 8) * OS + sp;
+    else {                            // phase-split: [B][8][C/8][OD/2][OH/2][OW/2]
+      const int phase = ((od & 1) << 2) | ((oh & 1) << 1) | (ow & 1);
+      cs = OS >> 3;
+      o = reinterpret_cast<uint4*>(p.out) + (((size_t)b * 8 + phase) * (p.cout_valid / 8) + co0 / 8) * cs +
+          ((size_t)(od >> 1) * (OH >> 1) + (oh >> 1)) * (OW >> 1) + (ow >> 1);
+    }
 #pragma unroll
     for (int c8 = 0; c8 < 4; ++c8) {
       if (co0 + 8 * c8 >= p.cout_valid) break;
@@ -99,7 +111,7 @@ __device__ __forceinline__ void epilogue_store32(const TcP& p, float (&v)[32], c
       q.y = tc::pack_bf16x2(v[8 * c8 + 2], v[8 * c8 + 3]);
       q.z = tc::pack_bf16x2(v[8 * c8 + 4], v[8 * c8 + 5]);
       q.w = tc::pack_bf16x2(v[8 * c8 + 6], v[8 * c8 + 7]);
-      o[(size_t)c8 * OS] = q;
+      o[(size_t)c8 * cs] = q;
     }
   }
 }
@@ -753,8 +765,8 @@ extern "C" int ss_conv3d_tc_ntile(int kind, int Cin, int Cout) {
 
 // D,H,W are the INPUT dims of the layer (kind 2: of the full-resolution input, all even; the tensor itself is phase-split).
 extern "C" int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight_packed, const float* scale_or_null,
-                            const float* shift_or_null, const float* gate_logits_or_null, const void* residual_s2d_or_null, void* out,
-                            int out_is_f32, int B, int Cin, int Cout, int D, int H, int W, int relu, void* stream) {
+                            const float* shift_or_null, const float* gate_blocked_or_null, const void* residual_s2d_or_null, void* out,
+                            int out_mode, int B, int Cin, int Cout, int D, int H, int W, int relu, void* stream) {
   SS_REQUIRE(in_blocked && weight_packed && out, "ss_conv3d_tc: null pointer");
   SS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && Cout > 0, "ss_conv3d_tc: non-positive dimension");
   const int N = ss_conv3d_tc_ntile(kind, Cin, Cout);
@@ -762,14 +774,19 @@ extern "C" int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight
   SS_REQUIRE((reinterpret_cast<uintptr_t>(in_blocked) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(weight_packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual_s2d_or_null) & 15) == 0,
              "ss_conv3d_tc: pointers must be 16-byte aligned");
-  SS_REQUIRE(out_is_f32 || Cout % 8 == 0, "ss_conv3d_tc: a bf16 blocked output needs Cout %% 8 == 0");
+  SS_REQUIRE(out_mode >= 0 && out_mode <= 2, "ss_conv3d_tc: out_mode must be 0, 1 or 2");
+  SS_REQUIRE(out_mode == 1 || Cout % 8 == 0, "ss_conv3d_tc: a bf16 blocked output needs Cout %% 8 == 0");
+  SS_REQUIRE(!gate_blocked_or_null || Cout % 8 == 0, "ss_conv3d_tc: the blocked gate needs Cout %% 8 == 0");
+  SS_REQUIRE(out_mode != 2 || (kind != 3 && ((kind == 2 ? D / 2 : D) % 2 == 0) && ((kind == 2 ? H / 2 : H) % 2 == 0) &&
+                               ((kind == 2 ? W / 2 : W) % 2 == 0)),
+             "ss_conv3d_tc: phase-split output needs even output dims and is not available for the transposed layer");
   SS_REQUIRE(kind == 3 || !residual_s2d_or_null, "ss_conv3d_tc: the residual input exists only for the transposed layer");
   SS_REQUIRE(kind != 2 || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "ss_conv3d_tc: stride-2 layer needs even input dims");
   TcP p;
   p.w = reinterpret_cast<const __nv_bfloat16*>(weight_packed);
-  p.scale = scale_or_null; p.shift = shift_or_null; p.gate = gate_logits_or_null;
+  p.scale = scale_or_null; p.shift = shift_or_null; p.gate = gate_blocked_or_null;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual_s2d_or_null);
-  p.out = out; p.out_f32 = out_is_f32; p.cout_valid = Cout;
+  p.out = out; p.out_mode = out_mode; p.cout_valid = Cout;
   p.B = B; p.relu = relu;
   p.n_tiles = ceil_div(Cout, N);
   p.DC = 1; p.n_dc = 1; p.items = 0;

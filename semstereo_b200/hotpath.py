@@ -226,10 +226,10 @@ class DisparityHotPath(nn.Module):
                               k=k, stride=stride, transposed=transposed, relu=relu)
 
     # ---- bf16 tensor-core flavour: activations stay in the blocked / phase-split bf16 layouts between the layers ----
-    def _tc(self, c, name, kind, x, cout, relu=True, gate=None, residual=None, out_f32=False):
+    def _tc(self, c, name, kind, x, cout, relu=True, gate=None, residual=None, out_mode=tc.BLOCKED):
         with ops.label(name):
             return tc.conv3d_tc(kind, x, c[name + ".tc"], cout, c.get(name + ".scale"), c.get(name + ".shift"), gate, residual,
-                                relu=relu, out_f32=out_f32)
+                                relu=relu, out_mode=out_mode)
 
     def _hourglass_tc(self, c, hg, x_s2d):
         """hourglass.forward (SemStereo.py:134-143) on tensor cores.  x_s2d: phase-split bf16 (B,8,4,D/2,H/2,W/2,8); returns
@@ -237,11 +237,9 @@ class DisparityHotPath(nn.Module):
         residual of the transposed layers, which add it before their ReLU."""
         block = getattr(self, hg).block
         c1 = self._tc(c, hg + ".conv1", tc.S2, x_s2d, 64)
-        c2 = self._tc(c, hg + ".conv2", tc.S1, c1, 64)
-        with ops.label("layout"):
-            c2s = tc.blocked_to_s2d(c2)
+        c2s = self._tc(c, hg + ".conv2", tc.S1, c1, 64, out_mode=tc.S2D)         # written phase-split for conv3 / redir2
         c3 = self._tc(c, hg + ".conv3", tc.S2, c2s, 128)
-        c4 = self._tc(c, hg + ".conv4", tc.S1, c3, 128, out_f32=True)
+        c4 = self._tc(c, hg + ".conv4", tc.S1, c3, 128, out_mode=tc.F32)
         c4 = ops.window_attention3d(c4, c[hg + ".wqkv_t"], c[hg + ".bqkv"], c[hg + ".wo_t"], c[hg + ".bo"], block, 16)
         with ops.label("layout"):
             c4b = tc.to_blocked_bf16(c4)
@@ -252,7 +250,7 @@ class DisparityHotPath(nn.Module):
 
     def _classifier_tc(self, c, cl, xb):
         y = self._tc(c, cl + ".0", tc.S1, xb, 32)
-        return self._tc(c, cl + ".2", tc.S1, y, 1, relu=False, out_f32=True)
+        return self._tc(c, cl + ".2", tc.S1, y, 1, relu=False, out_mode=tc.F32)
 
     def _hourglass(self, c, hg, x):
         """hourglass.forward (SemStereo.py:134-143): residual adds and ReLUs ride in the deconv epilogues."""
@@ -279,12 +277,12 @@ class DisparityHotPath(nn.Module):
         out = {}
         # --- attention branch @1/8 (SemStereo.py:273-278) ---
         corr = ops.gwc_volume(f8_l, f8_r, m8, 32, signed=self.signed, norm=True)
-        vol = ops.patch_gate(corr, c["patch.w"], self._gate_logits(c, "corr_feature_att_8", f8_l))
+        gate8 = self._gate_logits(c, "corr_feature_att_8", f8_l)
         if self.precision == "bf16":
-            with ops.label("layout"):
-                vol = tc.to_blocked_bf16(vol, s2d=True)
+            vol = tc.patch_gate_blocked(corr, c["patch.w"], gate8)
             cost_att = self._classifier_tc(c, "classif_att_", self._hourglass_tc(c, "hourglass_att", vol))
         else:
+            vol = ops.patch_gate(corr, c["patch.w"], gate8)
             vol = self._hourglass(c, "hourglass_att", vol)
             cost_att = self._classifier(c, "classif_att_", vol)
         # --- statistics, propagation, top-k @1/4 (SemStereo.py:279-310) ---
@@ -299,16 +297,13 @@ class DisparityHotPath(nn.Module):
         if self.att_weights_only:
             return out
         # --- sparse concat volume + aggregation (SemStereo.py:314-324) ---
-        volume = ops.sparse_concat_volume(cf_l, cf_r, disp_topk, att_topk)
         gate4 = self._gate_logits(c, "concat_feature_att_4", f4_l)
         if self.precision == "bf16":
-            with ops.label("layout"):
-                vb = tc.to_blocked_bf16(volume)
-            v = self._tc(c, "concat_stem", tc.S1, vb, 32, gate=gate4)
-            with ops.label("layout"):
-                v = tc.blocked_to_s2d(v)
+            volume = tc.sparse_concat_volume_blocked(cf_l, cf_r, disp_topk, att_topk)      # (B,8,24,H/4,W/4,8) bf16
+            v = self._tc(c, "concat_stem", tc.S1, volume, 32, gate=tc.gate_sigmoid_blocked(gate4), out_mode=tc.S2D)
             cost = self._classifier_tc(c, "classif", self._hourglass_tc(c, "hourglass", v))
         else:
+            volume = ops.sparse_concat_volume(cf_l, cf_r, disp_topk, att_topk)
             v = self._conv(c, "concat_stem", volume, gate=gate4)
             v = self._hourglass(c, "hourglass", v)
             cost = self._classifier(c, "classif", v)

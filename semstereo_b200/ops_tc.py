@@ -73,8 +73,42 @@ def pack_weight(w, kind):
     return t.contiguous().to(torch.bfloat16)
 
 
-def conv3d_tc(kind, xb, w_tc, cout, scale=None, shift=None, gate_logits=None, residual_s2d=None, relu=False, out_f32=False):
-    """xb: blocked (kinds S1, K1, T2) or phase-split (kind S2) bf16 input.  Returns bf16 blocked or fp32 NCDHW."""
+def gate_sigmoid_blocked(gate_logits):
+    """sigmoid of the channelAtt logits (B,C,H,W) as fp32 (B,C/8,H,W,8): what the conv epilogue multiplies with."""
+    dev = _require_cuda(gate_logits)
+    B, C, H, W = gate_logits.shape
+    out = torch.empty((B, C // 8, H, W, 8), device=dev, dtype=torch.float32)
+    _call("ss_gate_sigmoid_blocked", dev, _ptr(gate_logits), _ptr(out), B, C, H, W)
+    return out
+
+
+def patch_gate_blocked(volume, patch_w, gate_logits):
+    """`patch` depthwise conv * sigmoid(gate) written straight into the phase-split bf16 layout the stride-2 layer reads."""
+    dev = _require_cuda(volume, patch_w, gate_logits)
+    B, G, D, H, W = volume.shape
+    if patch_w.numel() != G * 9 or tuple(gate_logits.shape) != (B, G, H, W):
+        raise ValueError("patch_gate_blocked: patch weight (G,9) and gate logits (B,G,H,W) expected")
+    out = torch.empty((B, 8, G // 8, D // 2, H // 2, W // 2, 8), device=dev, dtype=torch.bfloat16)
+    _call("ss_patch_gate_blocked", dev, _ptr(volume), _ptr(patch_w), _ptr(gate_logits), _ptr(out), B, G, D, H, W)
+    return out
+
+
+def sparse_concat_volume_blocked(cf_l, cf_r, disp_topk, att_topk=None):
+    dev = _require_cuda(cf_l, cf_r, disp_topk, att_topk)
+    B, C, H, W = cf_l.shape
+    K = disp_topk.shape[1]
+    if cf_r.shape != cf_l.shape or tuple(disp_topk.shape) != (B, K, H, W):
+        raise ValueError("sparse_concat_volume_blocked: shape mismatch")
+    out = torch.empty((B, 2 * C // 8, K, H, W, 8), device=dev, dtype=torch.bfloat16)
+    _call("ss_sparse_concat_volume_blocked", dev, _ptr(cf_l), _ptr(cf_r), _ptr(disp_topk), _ptr(att_topk), _ptr(out), B, C, K, H, W)
+    return out
+
+
+BLOCKED, F32, S2D = 0, 1, 2          # out_mode of ss_conv3d_tc
+
+
+def conv3d_tc(kind, xb, w_tc, cout, scale=None, shift=None, gate_blocked=None, residual_s2d=None, relu=False, out_mode=BLOCKED):
+    """xb: blocked (kinds S1, K1, T2) or phase-split (kind S2) bf16 input.  Returns bf16 blocked / phase-split or fp32 NCDHW."""
     if kind == S2:
         dev = _require_bf16(xb, 7)
         B, _, C8, D2, H2, W2, _ = xb.shape
@@ -89,19 +123,21 @@ def conv3d_tc(kind, xb, w_tc, cout, scale=None, shift=None, gate_logits=None, re
     taps = 1 if kind == K1 else 27
     if n == 0 or w_tc.dtype != torch.bfloat16 or tuple(w_tc.shape) != (-(-cout // n), taps, C8, n, 8) or not w_tc.is_contiguous():
         raise ValueError("conv3d_tc: weight must come from pack_weight(w, kind) for this layer")
-    for t in (scale, shift, gate_logits):
+    for t in (scale, shift, gate_blocked):
         if t is not None:
             _require_cuda(t)
-    if gate_logits is not None and tuple(gate_logits.shape) != (B, cout, Ho, Wo):
-        raise ValueError("conv3d_tc: gate logits must be (B,Cout,Ho,Wo)")
+    if gate_blocked is not None and tuple(gate_blocked.shape) != (B, cout // 8, Ho, Wo, 8):
+        raise ValueError("conv3d_tc: gate must be fp32 (B,Cout/8,Ho,Wo,8) from gate_sigmoid_blocked")
     if residual_s2d is not None:
         _require_bf16(residual_s2d, 7)
         if kind != T2 or tuple(residual_s2d.shape) != (B, 8, cout // 8, D, H, W, 8):
             raise ValueError("conv3d_tc: residual must be phase-split (B,8,Cout/8,D,H,W,8) at the transposed layer's input dims")
-    if out_f32:
+    if out_mode == F32:
         out = torch.empty((B, cout, Do, Ho, Wo), device=dev, dtype=torch.float32)
+    elif out_mode == S2D:
+        out = torch.empty((B, 8, cout // 8, Do // 2, Ho // 2, Wo // 2, 8), device=dev, dtype=torch.bfloat16)
     else:
         out = torch.empty((B, cout // 8, Do, Ho, Wo, 8), device=dev, dtype=torch.bfloat16)
-    _call("ss_conv3d_tc", dev, int(kind), _ptr(xb), _ptr(w_tc), _ptr(scale), _ptr(shift), _ptr(gate_logits), _ptr(residual_s2d),
-          _ptr(out), int(out_f32), B, cin, cout, D, H, W, int(relu))
+    _call("ss_conv3d_tc", dev, int(kind), _ptr(xb), _ptr(w_tc), _ptr(scale), _ptr(shift), _ptr(gate_blocked), _ptr(residual_s2d),
+          _ptr(out), int(out_mode), B, cin, cout, D, H, W, int(relu))
     return out

@@ -1,0 +1,73 @@
+"""HostPipeline — the end-to-end entry point for callers whose stereo-pair features live in HOST memory.
+
+Every batch is copied host->device on a dedicated copy stream into one of `depth` device staging sets, the hot path runs on
+the compute stream, and the disparity is copied device->host into a pinned result buffer.  Stage i+1's H2D overlaps stage i's
+compute (CUDA events order the two streams; nothing synchronises the host until a result is consumed).  This is what replaces
+the reference's `.cuda()` copies + forward + `.cpu()` in `test_us3d.py:95-102`.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, Iterator
+
+import torch
+
+ORDER = ("f8_l", "f8_r", "f4_l", "f4_r", "cf_l", "cf_r", "spx_pred", "pred_label")
+
+
+class HostPipeline:
+    def __init__(self, path, depth: int = 2, post=None):
+        """path: a DisparityHotPath on a CUDA device.  post(device_result) -> device tensor to return (e.g. an all-gather)."""
+        self.path, self.depth, self.post = path, depth, post
+        self.dev = next(path.parameters()).device
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        self.key = "pred_att_up" if path.att_weights_only else "pred_up"
+        self._stage = [None] * depth          # device staging sets
+        self._host_out = [None] * depth       # pinned result buffers
+        self._copied = [torch.cuda.Event() for _ in range(depth)]
+        self._consumed = [torch.cuda.Event() for _ in range(depth)]
+        self._done = [torch.cuda.Event() for _ in range(depth)]
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _staging(self, i, batch):
+        st = self._stage[i]
+        if st is None or any(st[k].shape != batch[k].shape for k in ORDER):
+            st = {k: torch.empty(batch[k].shape, dtype=torch.float32, device=self.dev) for k in ORDER}
+            self._stage[i] = st
+        return st
+
+    def run(self, batches: Iterable[Dict[str, torch.Tensor]]) -> Iterator[torch.Tensor]:
+        """Yields one pinned host tensor (B,H,W) per input batch, in order.  The yielded tensor is reused `depth` batches
+        later: copy it if it must outlive that."""
+        compute = torch.cuda.current_stream(self.dev)
+        pending = []                           # slots whose result has not been yielded yet
+        n = 0
+        for batch in batches:
+            i = n % self.depth
+            if len(pending) == self.depth:     # slot i is about to be reused: hand out its result first
+                j = pending.pop(0)
+                self._done[j].synchronize()
+                yield self._host_out[j]
+            st = self._staging(i, batch)
+            with torch.cuda.stream(self.copy_stream):
+                if n >= self.depth:
+                    self.copy_stream.wait_event(self._consumed[i])     # compute of the previous tenant has read the staging set
+                for k in ORDER:
+                    st[k].copy_(batch[k], non_blocking=True)
+                self._copied[i].record(self.copy_stream)
+            self.h2d_bytes += sum(batch[k].numel() * 4 for k in ORDER)
+            compute.wait_event(self._copied[i])
+            out = self.path(*[st[k] for k in ORDER])[self.key]
+            self._consumed[i].record(compute)
+            if self.post is not None:
+                out = self.post(out)
+            if self._host_out[i] is None or self._host_out[i].shape != out.shape:
+                self._host_out[i] = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+            self._host_out[i].copy_(out, non_blocking=True)
+            self.d2h_bytes += out.numel() * out.element_size()
+            self._done[i].record(compute)
+            pending.append(i)
+            n += 1
+        for j in pending:
+            self._done[j].synchronize()
+            yield self._host_out[j]

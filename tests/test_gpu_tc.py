@@ -58,11 +58,18 @@ def test_conv_k3_s1(Cin, Cout, B, D, H, W, out_f32):
     ref = F.relu(y * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)) * torch.sigmoid(gate).unsqueeze(2)
     xb = tc.to_blocked_bf16(x.to(DEV))
     wt = tc.pack_weight(w, tc.S1).to(DEV)
-    out = tc.conv3d_tc(tc.S1, xb, wt, Cout, scale.to(DEV), shift.to(DEV), gate.to(DEV), relu=True, out_f32=out_f32)
+    gb = tc.gate_sigmoid_blocked(gate.to(DEV)) if Cout % 8 == 0 else None
+    if gb is None:
+        ref = F.relu(y * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
+    out = tc.conv3d_tc(tc.S1, xb, wt, Cout, scale.to(DEV), shift.to(DEV), gb, relu=True, out_mode=tc.F32 if out_f32 else tc.BLOCKED)
     torch.cuda.synchronize()
     check(out.cpu() if out_f32 else tc.from_blocked_bf16(out).cpu(), ref, not out_f32)
-    plain = tc.conv3d_tc(tc.S1, xb, wt, Cout, out_f32=True)
+    plain = tc.conv3d_tc(tc.S1, xb, wt, Cout, out_mode=tc.F32)
     check(plain.cpu(), y, False)
+    if Cout % 8 == 0 and D % 2 == 0 and H % 2 == 0 and W % 2 == 0:      # phase-split output == permutation of the blocked one
+        a = tc.conv3d_tc(tc.S1, xb, wt, Cout, scale.to(DEV), shift.to(DEV), relu=True, out_mode=tc.S2D)
+        b = tc.blocked_to_s2d(tc.conv3d_tc(tc.S1, xb, wt, Cout, scale.to(DEV), shift.to(DEV), relu=True))
+        assert torch.equal(a.cpu(), b.cpu())
 
 
 @pytest.mark.parametrize("C,B,D,H,W", [(32, 2, 4, 16, 24), (64, 1, 6, 20, 12)])
@@ -90,9 +97,31 @@ def test_conv_k3_s2(Cin, Cout, B, D, H, W, out_f32):
     scale, shift = torch.rand(Cout, generator=g) + 0.5, 0.3 * torch.randn(Cout, generator=g)
     ref = F.relu(F.conv3d(bf(x), bf(w), None, stride=2, padding=1) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
     xs = tc.to_blocked_bf16(x.to(DEV), s2d=True)
-    out = tc.conv3d_tc(tc.S2, xs, tc.pack_weight(w, tc.S2).to(DEV), Cout, scale.to(DEV), shift.to(DEV), relu=True, out_f32=out_f32)
+    out = tc.conv3d_tc(tc.S2, xs, tc.pack_weight(w, tc.S2).to(DEV), Cout, scale.to(DEV), shift.to(DEV), relu=True,
+                       out_mode=tc.F32 if out_f32 else tc.BLOCKED)
     torch.cuda.synchronize()
     check(out.cpu() if out_f32 else tc.from_blocked_bf16(out).cpu(), ref, not out_f32)
+
+
+def test_blocked_producers():
+    from oracle import ops as oo
+    from semstereo_b200 import ops
+    from semstereo_b200.params import make_params
+    p = make_params(seed=4)
+    g = torch.Generator().manual_seed(5)
+    vol, logits = torch.randn(2, 32, 6, 10, 20, generator=g), torch.randn(2, 32, 10, 20, generator=g)
+    ref = torch.sigmoid(logits).unsqueeze(2) * oo.patch_conv(vol, p)
+    got = tc.patch_gate_blocked(vol.to(DEV), p["patch.weight"].reshape(32, 9).to(DEV), logits.to(DEV))
+    assert torch.equal(got.cpu(), tc.to_blocked_bf16(ops.patch_gate(vol.to(DEV), p["patch.weight"].reshape(32, 9).to(DEV), logits.to(DEV)), s2d=True).cpu())
+    assert (got.cpu().float() - s2d_ref(ref)).abs().max() <= 2e-2
+    gb = tc.gate_sigmoid_blocked(logits.to(DEV)).cpu()
+    assert (gb - torch.sigmoid(logits).view(2, 4, 8, 10, 20).permute(0, 1, 3, 4, 2)).abs().max() <= 1e-6
+    cfl, cfr = torch.randn(2, 32, 9, 20, generator=g), torch.randn(2, 32, 9, 20, generator=g)
+    d = torch.randint(-6, 7, (2, 24, 9, 20), generator=g).float()
+    a = torch.rand(2, 24, 9, 20, generator=g)
+    v32 = ops.sparse_concat_volume(cfl.to(DEV), cfr.to(DEV), d.to(DEV), a.to(DEV))
+    vb = tc.sparse_concat_volume_blocked(cfl.to(DEV), cfr.to(DEV), d.to(DEV), a.to(DEV))
+    assert torch.equal(vb.cpu(), tc.to_blocked_bf16(v32).cpu())
 
 
 @pytest.mark.parametrize("Cin,Cout,B,D,H,W", [(128, 64, 1, 2, 16, 8), (128, 64, 2, 3, 20, 12), (64, 32, 1, 4, 16, 16), (64, 32, 2, 6, 24, 40),

@@ -27,7 +27,7 @@ for B in (1, 8):
         w = tc.pack_weight(torch.randn(*wshape) / (taps * ci) ** 0.5, kind).to(dev)
         sc, sh = torch.ones(co, device=dev), torch.zeros(co, device=dev)
         f32 = co % 8 != 0
-        run = lambda: tc.conv3d_tc(kind, x, w, co, sc, sh, relu=True, out_f32=f32)
+        run = lambda: tc.conv3d_tc(kind, x, w, co, sc, sh, relu=True, out_mode=tc.F32 if f32 else tc.BLOCKED)
         for _ in range(3):
             run()
         ts = []
