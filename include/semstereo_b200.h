@@ -100,6 +100,12 @@ SS_API int ss_window_attention3d(const float* x, const float* wqkv_t, const floa
                                  float* out, int B, int C, int D, int H, int W, int bd, int bh, int bw, int num_heads,
                                  void* stream);
 
+/* Tensor-core mode: the qkv Linear and the final 1x1x1 conv run as ss_conv3d_tc kind 1 layers (Cin=128 -> 384 / 128, bias as
+ * shift); this is the softmax(q k^T * scale) v core in between on the blocked layout, where head h is channel chunk h:
+ * qkv (B,48,D,H,W,8) bf16 -> out (B,16,D,H,W,8) bf16. */
+SS_API int ss_window_attention_core_blocked(const void* qkv_blocked, void* out_blocked, int B, int C, int D, int H, int W, int bd,
+                                            int bh, int bw, int num_heads, void* stream);
+
 /* ---- K6/K7/K8: attention statistics, sample strength, top-k selection -------------------------------- */
 /* F.interpolate(trilinear, x2) -> softmax(dim=1) -> disparity_regression -> disparity_variance -> sigmoid(beta+gamma*var)
  * (SemStereo.py:279-287).  cost_att (B,1,D8,H8,W8) -> att_up (B,2*D8,2*H8,2*W8) logits, mu (B,2H8,2W8), gate (B,1,2H8,2W8).

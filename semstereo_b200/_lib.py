@@ -30,6 +30,7 @@ SIGNATURES = {
     "ss_to_blocked_bf16": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ss_from_blocked_bf16": [_P, _P, _I, _I, _I, _I, _I, _P],
     "ss_blocked_to_s2d": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "ss_window_attention_core_blocked": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "ss_gate_sigmoid_blocked": [_P, _P, _I, _I, _I, _I, _P],
     "ss_patch_gate_blocked": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "ss_sparse_concat_volume_blocked": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],

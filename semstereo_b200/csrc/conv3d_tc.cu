@@ -750,6 +750,7 @@ extern "C" int ss_conv3d_tc_ntile(int kind, int Cin, int Cout) {
       return 0;
     case 1:
       if ((Cin == 32 && Cout == 32) || (Cin == 64 && Cout == 64)) return Cout;
+      if (Cin == 128 && (Cout == 128 || Cout == 384)) return 128;      // attention_block: qkv Linear and final 1x1x1 conv
       return 0;
     case 2:
       if (Cin == 32 && Cout == 64) return 64;
@@ -809,7 +810,8 @@ extern "C" int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight
       return launch_s1<128, 128, 3, 2, 27>(tm, p, st);
     case 1:
       if (Cin == 32) return launch_s1<32, 32, 4, 1, 1>(tm, p, st);
-      return launch_s1<64, 64, 4, 1, 1>(tm, p, st);
+      if (Cin == 64) return launch_s1<64, 64, 4, 1, 1>(tm, p, st);
+      return launch_s1<128, 128, 4, 1, 1>(tm, p, st);
     case 2:
       if (Cin == 32) return launch_s2<32, 64, 2, 27>(tm, p, st);
       return launch_s2<64, 128, 2, 2>(tm, p, st);

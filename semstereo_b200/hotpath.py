@@ -193,6 +193,11 @@ class DisparityHotPath(nn.Module):
             c[hg + ".bqkv"] = a.qkv_3d.bias.detach().float().contiguous()
             c[hg + ".wo_t"] = a.final1x1.weight.detach().float().reshape(a.final1x1.out_channels, -1).t().contiguous()
             c[hg + ".bo"] = a.final1x1.bias.detach().float().contiguous()
+            if bf16:
+                c[hg + ".attn_qkv.tc"] = tc.pack_weight(a.qkv_3d.weight.detach().float().reshape(384, 128, 1, 1, 1), tc.K1)
+                c[hg + ".attn_qkv.shift"] = c[hg + ".bqkv"]
+                c[hg + ".attn_out.tc"] = tc.pack_weight(a.final1x1.weight.detach().float(), tc.K1)
+                c[hg + ".attn_out.shift"] = c[hg + ".bo"]
         for cl in ("classif_att_", "classif"):
             m = getattr(self, cl)
             conv(cl + ".0", m[0][0], m[0][1])
@@ -239,10 +244,13 @@ class DisparityHotPath(nn.Module):
         c1 = self._tc(c, hg + ".conv1", tc.S2, x_s2d, 64)
         c2s = self._tc(c, hg + ".conv2", tc.S1, c1, 64, out_mode=tc.S2D)         # written phase-split for conv3 / redir2
         c3 = self._tc(c, hg + ".conv3", tc.S2, c2s, 128)
-        c4 = self._tc(c, hg + ".conv4", tc.S1, c3, 128, out_mode=tc.F32)
-        c4 = ops.window_attention3d(c4, c[hg + ".wqkv_t"], c[hg + ".bqkv"], c[hg + ".wo_t"], c[hg + ".bo"], block, 16)
-        with ops.label("layout"):
-            c4b = tc.to_blocked_bf16(c4)
+        c4 = self._tc(c, hg + ".conv4", tc.S1, c3, 128)
+        # attention_block (submodule_other.py:805-837): qkv Linear and final 1x1x1 conv as tensor-core 1x1 layers (bias = shift),
+        # the per-(window, head) softmax core in between; a head is one channel chunk of the blocked layout
+        qkv = self._tc(c, hg + ".attn_qkv", tc.K1, c4, 384, relu=False)
+        with ops.label(hg + ".attn_core"):
+            att = tc.window_attention_core(qkv, block, 16)
+        c4b = self._tc(c, hg + ".attn_out", tc.K1, att, 128, relu=False)
         r2 = self._tc(c, hg + ".redir2", tc.K1, tc.s2d_as_batch(c2s), 64, relu=False).view(c2s.shape)
         c5 = self._tc(c, hg + ".conv5", tc.T2, c4b, 64, residual=r2)
         r1 = self._tc(c, hg + ".redir1", tc.K1, tc.s2d_as_batch(x_s2d), 32, relu=False).view(x_s2d.shape)

@@ -104,6 +104,18 @@ def sparse_concat_volume_blocked(cf_l, cf_r, disp_topk, att_topk=None):
     return out
 
 
+def window_attention_core(qkv_blocked, block, num_heads=16):
+    """softmax(q k^T * hd^-0.5) v per (window, head) on the blocked layout: (B,48,D,H,W,8) -> (B,16,D,H,W,8)."""
+    dev = _require_bf16(qkv_blocked, 6)
+    B, C3, D, H, W, _ = qkv_blocked.shape
+    if C3 % 3:
+        raise ValueError("window_attention_core: qkv must have 3*C/8 channel chunks")
+    out = torch.empty((B, C3 // 3, D, H, W, 8), device=dev, dtype=torch.bfloat16)
+    _call("ss_window_attention_core_blocked", dev, _ptr(qkv_blocked), _ptr(out), B, (C3 // 3) * 8, D, H, W,
+          int(block[0]), int(block[1]), int(block[2]), int(num_heads))
+    return out
+
+
 BLOCKED, F32, S2D = 0, 1, 2          # out_mode of ss_conv3d_tc
 
 
