@@ -10,6 +10,10 @@
 // register tile: one 128-bit load of the left row and three of the right row feed 32 FMAs.
 #include "common.cuh"
 
+// volumes_tma.cu: 0 = done, 1 = shape not eligible for the TMA path, <0 = error
+int ss_gwc_volume_tma(const float* left, const float* right, float* volume, int B, int C, int H, int W, int maxdisp, int num_groups,
+                      int flags, cudaStream_t stream);
+
 namespace {
 
 struct GwcParams {
@@ -169,6 +173,10 @@ extern "C" int ss_gwc_volume(const float* left, const float* right, float* volum
   SS_REQUIRE(left && right && volume, "ss_gwc_volume: null pointer");
   SS_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && maxdisp > 0 && num_groups > 0, "ss_gwc_volume: non-positive dimension");
   SS_REQUIRE(C % num_groups == 0, "ss_gwc_volume: C=%d not divisible by num_groups=%d", C, num_groups);
+  {  // TMA-staged fast path (volumes_tma.cu) for 16-byte-aligned rows; everything else takes the generic kernel below
+    const int rc = ss_gwc_volume_tma(left, right, volume, B, C, H, W, maxdisp, num_groups, flags, (cudaStream_t)stream);
+    if (rc <= 0) return rc;
+  }
   const bool sgn = flags & 1;
   GwcParams p;
   p.L = left; p.R = right; p.out = volume;
