@@ -77,9 +77,21 @@ def hbm_bytes(H, W, maxdisp, signed=True):
         "ss_sample_strength": 4 * (2 * 128 * p4 + 2 * p4 + 5 * p4),
         "ss_topk_select": 4 * (nb * p4 + 5 * p4 + 2 * 24 * p4 + p4),
         "ss_sparse_concat_volume": 4 * (2 * 32 * p4 + 2 * 24 * p4 + 64 * 24 * p4),
+        "ss_patch_gate_blocked": 4 * (32 * d8 * p8 + 32 * p8) + 2 * 32 * d8 * p8,          # fp32 volume + gate in, bf16 out
+        "ss_sparse_concat_volume_blocked": 4 * (2 * 32 * p4 + 2 * 24 * p4) + 2 * 64 * 24 * p4,   # bf16 volume out
         "ss_regression_topk": 4 * (2 * 24 * p4 + p4),
         "ss_ssr_upsample": 4 * (p4 + 12 * p1 + p1),
     }
+
+
+def ncu_traffic(kernel, precision, batch):
+    """DRAM bytes (read + write) per launch of `kernel` from the committed `ncu --set full` capture (profiles/r01_traffic.json:
+    bytes per stereo pair, measured at the batch stated there), scaled to this run's batch; None when no capture exists."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(p):
+        return None
+    ent = json.load(open(p)).get(precision, {}).get(kernel)
+    return None if ent is None else int(ent["dram_bytes_per_pair"] * batch)
 
 
 class ClockSampler:
@@ -122,7 +134,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference(H, W, maxdisp, steps, warmup, signed=True):
+def cpu_reference(H, W, maxdisp, steps, warmup, signed=True, att_only=False):
     """The reference algorithm's CPU path (oracle port of SemStereo.forward:273-324; efficient closed forms, so it is
     FASTER than the reference's own Python-loop volume builder — a conservative baseline).  Each step = one pair."""
     from oracle import hotpath as oh
@@ -133,7 +145,7 @@ def cpu_reference(H, W, maxdisp, steps, warmup, signed=True):
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        oh.forward(p, inp, maxdisp, signed=signed)
+        oh.forward(p, inp, maxdisp, signed=signed, att_weights_only=att_only)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     return times
@@ -153,15 +165,27 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="bf16: k3 s1 3-D convs on tcgen05 tensor cores (BASELINE config #3); fp32: index-exact parity mode")
+    ap.add_argument("--variant", default="us3d", choices=["us3d", "whu"],
+                    help="us3d: SemStereo, signed, 1024x1024, maxdisp 64 (configs #1/#3); whu: SemStereo_WHU + submodule_.py, unsigned, "
+                         "384x768, maxdisp 128 (config #4)")
+    ap.add_argument("--att-only", action="store_true", help="attention_weights_only forward (the forward half of config #5)")
     a = ap.parse_args()
+    signed = a.variant == "us3d"
+    if a.variant == "whu":
+        if a.height == 1024 and a.width == 1024:
+            a.height, a.width = 384, 768
+        if a.maxdisp == 64:
+            a.maxdisp = 128
     H, W, md = a.height, a.width, a.maxdisp
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    workload = f"SemStereo disparity hot path (SemStereo.forward:273-324), {H}x{W} US3D-shaped pairs, maxdisp {md}, signed"
+    workload = (f"{'SemStereo' if signed else 'SemStereo_WHU'} disparity hot path (forward:273-324), {H}x{W} "
+                f"{'US3D' if signed else 'WHU'}-shaped pairs, maxdisp {md}, {'signed' if signed else 'unsigned'}"
+                f"{', attention_weights_only' if a.att_only else ''}")
 
     if a.impl == "reference":
         if rank != 0:
             return
-        times = cpu_reference(H, W, md, a.steps, min(a.warmup, 1))
+        times = cpu_reference(H, W, md, a.steps, min(a.warmup, 1), signed, a.att_only)
         ms = 1e3 * sum(times) / len(times)
         v = 1e3 / ms
         print(json.dumps({
@@ -182,7 +206,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     B = a.batch
-    model = DisparityHotPath(md, False, True, precision=a.precision)
+    model = DisparityHotPath(md, a.att_only, signed, precision=a.precision)
+    okey = "pred_att_up" if a.att_only else "pred_up"
     model.load_state_dict(make_params(seed=1, peaked=20.0), strict=True)
     model = model.to(dev)
     host = {k: v.pin_memory() for k, v in make_inputs(100 + rank, B, H, W).items()}
@@ -191,7 +216,7 @@ def main():
     gathered = torch.empty((world * B, H, W), device=dev) if world > 1 else None
 
     def step(inputs):
-        o = model(*[inputs[k] for k in ORDER])["pred_up"]
+        o = model(*[inputs[k] for k in ORDER])[okey]
         if world > 1:
             tdist.all_gather_into_tensor(gathered, o)
         return o
@@ -259,7 +284,7 @@ def main():
     durs = rec.durations_ms()
     per_step = {k: sum(v) / a.steps for k, v in durs.items()}
     total_k = sum(per_step.values())
-    flops, nbytes = conv_layers(H, W, md), hbm_bytes(H, W, md)
+    flops, nbytes = conv_layers(H, W, md, signed), hbm_bytes(H, W, md, signed)
     kernels = []
     for name, ms in sorted(per_step.items(), key=lambda kv: -kv[1]):
         launches = len(durs[name]) / a.steps
@@ -274,9 +299,11 @@ def main():
     dom = next(k for k in kernels if "bound" in k)
     roof = {"kernel": dom["name"], "bound": dom["bound"], "achieved": dom["achieved"],
             "peak": pk["tf_sust"] if dom["bound"] == "tensor" else pk["hbm"], "unit": dom["unit"], "frac": dom["frac"],
-            "traffic": None, "peak_source": pk["src"] + (" (sustained bf16 cuBLAS)" if dom["bound"] == "tensor" else " (copy)"),
-            "note": ("tcgen05 bf16 implicit GEMM (k3 s1 layers); stride-2 / transposed / 1x1 layers still on the fp32 pipe"
-                     if a.precision == "bf16" else "fp32-accurate FFMA mode; fraction is against the bf16 tensor peak")}
+            "traffic": ncu_traffic(dom["name"], a.precision, B),
+            "peak_source": pk["src"] + (" (sustained bf16 cuBLAS)" if dom["bound"] == "tensor" else " (copy)"),
+            "note": ("tcgen05 bf16 implicit GEMM, fp32 accumulation in TMEM; achieved = Table-A FLOPs of the layer x batch / CUDA-event "
+                     "time of the launch inside the timed region" if a.precision == "bf16"
+                     else "fp32-accurate FFMA mode; fraction is against the bf16 tensor peak")}
     value = world * B * a.steps / (ms_total * 1e-3)
     e2e_v = world * B * a.steps / (ms_e2e * 1e-3)
     res = {"metric": "stereo pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -288,7 +315,7 @@ def main():
            "e2e": {"value": e2e_v, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps},
            "gpu_launches": rec.count, "clocks": clocks, "roofline": roof, "kernels": kernels}
     if world == 1 and not a.no_cpu_baseline:
-        times = cpu_reference(H, W, md, a.cpu_steps, 1)
+        times = cpu_reference(H, W, md, a.cpu_steps, 1, signed, a.att_only)
         res["cpu_baseline"] = {"value": len(times) / sum(times), "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
                                "sample": f"{len(times)} pairs at {H}x{W} through oracle/hotpath.py (torch CPU fp32), 1 warm-up"}
     print(json.dumps(res))

@@ -55,63 +55,92 @@ __global__ void __launch_bounds__(128) sparse_concat_kernel(const float* __restr
   float* ol = out + ((size_t)b * 2 * C * K + k) * HW + pix;
   float* orr = ol + (size_t)C * K * HW;
   for (int c = 0; c < C; ++c) {
-    const float* plane = rp + (size_t)c * HW;
-    float r = __ldg(plane + q.o00) * q.w00 + __ldg(plane + q.o01) * q.w01 + __ldg(plane + q.o10) * q.w10 +
-              __ldg(plane + q.o11) * q.w11;
+    const float r = bilin_fetch(rp + (size_t)c * HW, q);
     __stcs(ol + (size_t)c * K * HW, a * __ldg(lp + (size_t)c * HW));
     __stcs(orr + (size_t)c * K * HW, a * r);
   }
 }
 
-// out[b,co,p] = act(scale[co] * sum_ci W[co,ci] * in[b,ci,p] + shift[co]);  tile 128 pixels x 32 couts, K chunk 16
+// out[b,co,p] = act(scale[co] * sum_ci W[co,ci] * in[b,ci,p] + shift[co]).  Tile = 128 pixels x BN couts, K chunk 16, register
+// double buffering of the global loads; thread tile = 4 pixels x (BN/8) couts (warp-uniform couts -> weight reads broadcast).
+template <int BN>
 __global__ void __launch_bounds__(256) pointwise_conv2d_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                                const float* __restrict__ scale, const float* __restrict__ shift,
                                                                float* __restrict__ out, int Cin, int Cout, int P, int relu) {
-  __shared__ __align__(16) float As[16][128];
-  __shared__ __align__(16) float Ws[16][32];
+  constexpr int TN = BN / 8;
+  __shared__ __align__(16) float As[2][16][128];
+  __shared__ __align__(16) float Ws[2][16][BN];
   const int b = blockIdx.z;
-  const int p0 = blockIdx.x * 128, co0 = blockIdx.y * 32;
-  const int tp = threadIdx.x & 31, tc = threadIdx.x >> 5;   // 32 pixel-quads x 8 cout-quads
+  const int p0 = blockIdx.x * 128, co0 = blockIdx.y * BN;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* ib = in + (size_t)b * Cin * P;
-  float acc[4][4];
+  float acc[4][TN];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+  float a_reg[8], w_reg[(16 * BN) / 256];
+  const int ap = threadIdx.x & 127, ak0 = threadIdx.x >> 7;           // A gather: pixel, first k row (step 2)
+  auto load = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + ak0 + 2 * j;
+      a_reg[j] = (k < Cin && p0 + ap < P) ? __ldg(ib + (size_t)k * P + p0 + ap) : 0.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < (16 * BN) / 256; ++j) {
+      const int i = threadIdx.x + j * 256, c = i >> 4, k = i & 15;
+      w_reg[j] = (k0 + k < Cin && co0 + c < Cout) ? __ldg(w + (size_t)(co0 + c) * Cin + k0 + k) : 0.0f;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) As[buf][ak0 + 2 * j][ap] = a_reg[j];
+#pragma unroll
+    for (int j = 0; j < (16 * BN) / 256; ++j) {
+      const int i = threadIdx.x + j * 256, c = i >> 4, k = i & 15;
+      Ws[buf][k][c] = w_reg[j];
+    }
+  };
+  load(0);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
   for (int k0 = 0; k0 < Cin; k0 += 16) {
-    for (int i = threadIdx.x; i < 16 * 128; i += 256) {
-      const int k = i >> 7, p = i & 127;
-      As[k][p] = (k0 + k < Cin && p0 + p < P) ? __ldg(ib + (size_t)(k0 + k) * P + p0 + p) : 0.0f;
-    }
-    for (int i = threadIdx.x; i < 16 * 32; i += 256) {
-      const int c = i >> 4, k = i & 15;
-      Ws[k][c] = (k0 + k < Cin && co0 + c < Cout) ? __ldg(w + (size_t)(co0 + c) * Cin + k0 + k) : 0.0f;
-    }
-    __syncthreads();
+    const bool more = k0 + 16 < Cin;
+    if (more) load(k0 + 16);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[k][4 * tp]);
-      const float4 ww = *reinterpret_cast<const float4*>(&Ws[k][4 * tc]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {ww.x, ww.y, ww.z, ww.w};
+      const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][4 * lane]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      float wv[TN];
+#pragma unroll
+      for (int j = 0; j < TN; j += 4) {
+        const float4 ww = *reinterpret_cast<const float4*>(&Ws[buf][k][warp * TN + j]);
+        wv[j] = ww.x; wv[j + 1] = ww.y; wv[j + 2] = ww.z; wv[j + 3] = ww.w;
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
     }
+    if (more) stash(buf ^ 1);
     __syncthreads();
+    buf ^= 1;
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int co = co0 + 4 * tc + j;
+  for (int j = 0; j < TN; ++j) {
+    const int co = co0 + warp * TN + j;
     if (co >= Cout) continue;
     const float s = scale ? __ldg(scale + co) : 1.0f, t = shift ? __ldg(shift + co) : 0.0f;
+    float v[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int p = p0 + 4 * tp + i;
-      if (p >= P) continue;
-      float v = fmaf(acc[i][j], s, t);
-      out[((size_t)b * Cout + co) * P + p] = relu ? fmaxf(v, 0.0f) : v;
-    }
+    for (int i = 0; i < 4; ++i) { v[i] = fmaf(acc[i][j], s, t); if (relu) v[i] = fmaxf(v[i], 0.0f); }
+    float* o = out + ((size_t)b * Cout + co) * P + p0 + 4 * lane;
+    if ((P & 3) == 0 && p0 + 4 * lane + 3 < P) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    else
+      for (int i = 0; i < 4; ++i)
+        if (p0 + 4 * lane + i < P) o[i] = v[i];
   }
 }
 
@@ -144,8 +173,12 @@ extern "C" int ss_pointwise_conv2d(const float* in, const float* weight, const f
   SS_REQUIRE(in && weight && out, "ss_pointwise_conv2d: null pointer");
   SS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && P > 0, "ss_pointwise_conv2d: non-positive dimension");
   SS_UNSUPPORTED(B > 65535 || ceil_div(Cout, 32) > 65535, "ss_pointwise_conv2d: grid dimension exceeds 65535");
-  pointwise_conv2d_kernel<<<dim3(ceil_div(P, 128), ceil_div(Cout, 32), B), 256, 0, (cudaStream_t)stream>>>(
-      in, weight, scale_or_null, shift_or_null, out, Cin, Cout, P, relu);
+  if (Cout >= 64)
+    pointwise_conv2d_kernel<64><<<dim3(ceil_div(P, 128), ceil_div(Cout, 64), B), 256, 0, (cudaStream_t)stream>>>(
+        in, weight, scale_or_null, shift_or_null, out, Cin, Cout, P, relu);
+  else
+    pointwise_conv2d_kernel<32><<<dim3(ceil_div(P, 128), ceil_div(Cout, 32), B), 256, 0, (cudaStream_t)stream>>>(
+        in, weight, scale_or_null, shift_or_null, out, Cin, Cout, P, relu);
   SS_CHECK_LAUNCH("ss_pointwise_conv2d");
   return SS_OK;
 }

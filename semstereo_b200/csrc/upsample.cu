@@ -23,80 +23,98 @@ __device__ __forceinline__ void lin4(int dst, int n_in, int& i0, int& i1, float&
   l0 = 1.0f - l1;
 }
 
+__device__ __forceinline__ float sel3(float v0, float v1, float v2, int idx, int i0, int i1) {
+  return idx == i0 ? v0 : (idx == i1 ? v1 : v2);
+}
+
+// One thread = 4 consecutive full-res pixels (one low-res column x): the 3x6 upsampled neighbourhood is built from 18
+// low-res loads, spx / label / output move as 128-bit vectors.  The arithmetic per pixel is unchanged.
 template <int NC>
-__global__ void __launch_bounds__(256) ssr_upsample_kernel(const float* __restrict__ depth_low, const float* __restrict__ spx,
+__global__ void __launch_bounds__(128) ssr_upsample_kernel(const float* __restrict__ depth_low, const float* __restrict__ spx,
                                                            const float* __restrict__ label, float* __restrict__ out,
                                                            const SsrPacked<NC> P, int h, int w) {
   const int H = 4 * h, W = 4 * w;
-  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;          // low-res column
   const int Y = blockIdx.y, b = blockIdx.z;
-  if (X >= W) return;
+  if (x >= w) return;
+  const int X0 = 4 * x;
   const float* dl = depth_low + (size_t)b * h * w;
-  // bilinear x4 of the low-res disparity at the 3x3 full-res neighbourhood (zero outside: the conv pads BN output)
-  float v[9], centre = 0.0f;
+  const int cx0 = max(x - 1, 0), cx1 = x, cx2 = min(x + 1, w - 1);
+  // bilinear x4 of the low-res disparity on rows Y-1..Y+1, columns X0-1..X0+4 (zero outside: the conv pads the BN output)
+  float v[3][6], centre[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int dy = -1; dy <= 1; ++dy) {
-    const int yy = Y + dy;
+  for (int r = 0; r < 3; ++r) {
+    const int yy = Y + r - 1;
+    const bool yin = yy >= 0 && yy < H;
     int y0 = 0, y1 = 0;
     float hy0 = 0.f, hy1 = 0.f;
-    const bool yin = yy >= 0 && yy < H;
     if (yin) lin4(yy, h, y0, y1, hy0, hy1);
+    const float a0 = __ldg(dl + y0 * w + cx0), a1 = __ldg(dl + y0 * w + cx1), a2 = __ldg(dl + y0 * w + cx2);
+    const float c0 = __ldg(dl + y1 * w + cx0), c1 = __ldg(dl + y1 * w + cx1), c2 = __ldg(dl + y1 * w + cx2);
 #pragma unroll
-    for (int dx = -1; dx <= 1; ++dx) {
-      const int xx = X + dx;
+    for (int j = 0; j < 6; ++j) {
+      const int xx = X0 - 1 + j;
       float val = 0.0f;
       if (yin && xx >= 0 && xx < W) {
         int x0, x1;
         float wx0, wx1;
         lin4(xx, w, x0, x1, wx0, wx1);
-        const float up = hy0 * (wx0 * __ldg(dl + y0 * w + x0) + wx1 * __ldg(dl + y0 * w + x1)) +
-                         hy1 * (wx0 * __ldg(dl + y1 * w + x0) + wx1 * __ldg(dl + y1 * w + x1));
-        if (dy == 0 && dx == 0) centre = up;
+        const float up = hy0 * (wx0 * sel3(a0, a1, a2, x0, cx0, cx1) + wx1 * sel3(a0, a1, a2, x1, cx0, cx1)) +
+                         hy1 * (wx0 * sel3(c0, c1, c2, x0, cx0, cx1) + wx1 * sel3(c0, c1, c2, x1, cx0, cx1));
+        if (r == 1 && j >= 1 && j <= 4) centre[j - 1] = up;
         val = fmaf(P.a0, up, P.b0);
       }
-      v[(dy + 1) * 3 + dx + 1] = val;
+      v[r][j] = val;
     }
   }
-  const size_t HW = (size_t)H * W, pix = (size_t)Y * W + X;
-  float sp[NC], lab[NC];
-  float m = -INFINITY;
+  const size_t HW = (size_t)H * W, pix = (size_t)Y * W + X0;
+  float sp[NC][4], lab[NC][4];
 #pragma unroll
   for (int i = 0; i < NC; ++i) {
-    sp[i] = __ldcs(spx + ((size_t)b * NC + i) * HW + pix);
-    lab[i] = __ldcs(label + ((size_t)b * NC + i) * HW + pix);
-    m = fmaxf(m, lab[i]);
+    const float4 s4 = __ldcs(reinterpret_cast<const float4*>(spx + ((size_t)b * NC + i) * HW + pix));
+    const float4 l4 = __ldcs(reinterpret_cast<const float4*>(label + ((size_t)b * NC + i) * HW + pix));
+    sp[i][0] = s4.x; sp[i][1] = s4.y; sp[i][2] = s4.z; sp[i][3] = s4.w;
+    lab[i][0] = l4.x; lab[i][1] = l4.y; lab[i][2] = l4.z; lab[i][3] = l4.w;
   }
-  float sum = 0.0f;
+  float o[4];
 #pragma unroll
-  for (int i = 0; i < NC; ++i) { lab[i] = expf(lab[i] - m); sum += lab[i]; }
-  float in1[NC], g1[NC], g2[NC];
+  for (int px = 0; px < 4; ++px) {
+    float m = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < NC; ++i) in1[i] = (lab[i] / sum) * sp[i];
+    for (int i = 0; i < NC; ++i) m = fmaxf(m, lab[i][px]);
+    float e[NC], sum = 0.0f;
 #pragma unroll
-  for (int j = 0; j < NC; ++j) {
-    float a = P.b1[j];
+    for (int i = 0; i < NC; ++i) { e[i] = expf(lab[i][px] - m); sum += e[i]; }
+    float in1[NC], g1[NC], g2[NC];
 #pragma unroll
-    for (int i = 0; i < NC; ++i) a = fmaf(P.w1[j][i], in1[i], a);
-    g1[j] = sigmoidf_(fmaf(P.s1[j], a, P.t1[j]));
+    for (int i = 0; i < NC; ++i) in1[i] = (e[i] / sum) * sp[i][px];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      float a = P.b1[j];
+#pragma unroll
+      for (int i = 0; i < NC; ++i) a = fmaf(P.w1[j][i], in1[i], a);
+      g1[j] = sigmoidf_(fmaf(P.s1[j], a, P.t1[j]));
+    }
+#pragma unroll
+    for (int i = 0; i < NC; ++i) in1[i] = g1[i] * sp[i][px];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      float a = P.b2[j];
+#pragma unroll
+      for (int i = 0; i < NC; ++i) a = fmaf(P.w2[j][i], in1[i], a);
+      g2[j] = sigmoidf_(fmaf(P.sb2[j], a, P.tb2[j]));
+    }
+    float res = P.b3;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      float a = P.bc[j];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) a = fmaf(P.wc[j][t], v[t / 3][px + t % 3], a);
+      res = fmaf(P.w3[j], fmaf(P.s2[j], a, P.t2[j]) * g2[j], res);
+    }
+    o[px] = centre[px] + res;
   }
-#pragma unroll
-  for (int i = 0; i < NC; ++i) in1[i] = g1[i] * sp[i];
-#pragma unroll
-  for (int j = 0; j < NC; ++j) {
-    float a = P.b2[j];
-#pragma unroll
-    for (int i = 0; i < NC; ++i) a = fmaf(P.w2[j][i], in1[i], a);
-    g2[j] = sigmoidf_(fmaf(P.sb2[j], a, P.tb2[j]));
-  }
-  float res = P.b3;
-#pragma unroll
-  for (int j = 0; j < NC; ++j) {
-    float a = P.bc[j];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) a = fmaf(P.wc[j][t], v[t], a);
-    res = fmaf(P.w3[j], fmaf(P.s2[j], a, P.t2[j]) * g2[j], res);
-  }
-  out[(size_t)b * HW + pix] = centre + res;
+  *reinterpret_cast<float4*>(out + (size_t)b * HW + pix) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 __global__ void __launch_bounds__(256) context_upsample_kernel(const float* __restrict__ depth_low, const float* __restrict__ upw,
@@ -134,7 +152,9 @@ extern "C" int ss_ssr_upsample(const float* depth_low, const float* spx, const f
   SsrPacked<6> P;
   static_assert(sizeof(P) == 189 * sizeof(float), "packed SSR layout");
   memcpy(&P, packed_host, sizeof(P));
-  ssr_upsample_kernel<6><<<dim3(ceil_div(4 * w, 256), 4 * h, B), 256, 0, (cudaStream_t)stream>>>(depth_low, spx, label, out, P, h, w);
+  SS_REQUIRE(((reinterpret_cast<uintptr_t>(spx) | reinterpret_cast<uintptr_t>(label) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+             "ss_ssr_upsample: spx, label and out must be 16-byte aligned");
+  ssr_upsample_kernel<6><<<dim3(ceil_div(w, 128), 4 * h, B), 128, 0, (cudaStream_t)stream>>>(depth_low, spx, label, out, P, h, w);
   SS_CHECK_LAUNCH("ss_ssr_upsample");
   return SS_OK;
 }

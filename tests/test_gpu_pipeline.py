@@ -1,0 +1,27 @@
+"""HostPipeline (pinned host -> device staging on a copy stream -> hot path -> pinned host) returns what direct calls return."""
+import pytest
+import torch
+
+from semstereo_b200.params import make_inputs, make_params
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ORDER = ("f8_l", "f8_r", "f4_l", "f4_r", "cf_l", "cf_r", "spx_pred", "pred_label")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_pipeline_matches_direct_calls(precision):
+    from semstereo_b200.hotpath import DisparityHotPath
+    from semstereo_b200.pipeline import HostPipeline
+    m = DisparityHotPath(64, False, True, precision=precision)
+    m.load_state_dict(make_params(seed=1, peaked=20.0), strict=True)
+    m = m.to(DEV)
+    batches = [{k: v.pin_memory() for k, v in make_inputs(30 + i, 1, 128, 128).items()} for i in range(5)]
+    direct = [m(*[b[k].to(DEV) for k in ORDER])["pred_up"].cpu() for b in batches]
+    pipe = HostPipeline(m, depth=2)
+    got = [o.clone() for o in pipe.run(batches)]
+    assert len(got) == len(direct)
+    for a, b in zip(got, direct):
+        assert torch.equal(a, b)
+    assert pipe.h2d_bytes == 5 * sum(v.numel() * 4 for v in batches[0].values())
+    assert pipe.d2h_bytes == 5 * direct[0].numel() * 4
