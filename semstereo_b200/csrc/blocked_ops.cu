@@ -57,35 +57,43 @@ __global__ void __launch_bounds__(128) patch_gate_blocked_kernel(const float* __
   out[(((size_t)b * 8 + phase) * G8 + chunk) * S8 + ((size_t)(d >> 1) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)] = q;
 }
 
-// out blocked bf16 (B, 2C/8, K, H, W, 8): chunks [0, C/8) = cf_l * a_k ; [C/8, 2C/8) = bilinear(cf_r, x - d_k) * a_k
+// out blocked bf16 (B, 2C/8, K, H, W, 8): chunks [0, C/8) = cf_l * a_k ; [C/8, 2C/8) = bilinear(cf_r, x - d_k) * a_k.
+// One thread = one pixel, all K samples: the left chunk is loaded once per 8 channels and reused by the K samples; the right
+// reads of consecutive samples (ascending disparity) fall in the same few cache lines.
 __global__ void __launch_bounds__(128) sparse_concat_blocked_kernel(const float* __restrict__ cf_l, const float* __restrict__ cf_r,
                                                                     const float* __restrict__ disp, const float* __restrict__ att,
                                                                     uint4* __restrict__ out, int C, int K, int H, int W) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= W) return;
-  const int y = blockIdx.y % H, k = blockIdx.y / H, b = blockIdx.z;
+  const int y = blockIdx.y, b = blockIdx.z;
   const size_t HW = (size_t)H * W, pix = (size_t)y * W + x;
-  const float d = __ldg(disp + ((size_t)b * K + k) * HW + pix);
-  const float a = att ? __ldg(att + ((size_t)b * K + k) * HW + pix) : 1.0f;
-  const Bilin q = make_bilin(warp_coord((float)x - d, (float)(W - 1)), warp_coord((float)y, (float)(H - 1)), H, W);
+  const float iy = warp_coord((float)y, (float)(H - 1));
   const float* lp = cf_l + (size_t)b * C * HW + pix;
   const float* rp = cf_r + (size_t)b * C * HW;
+  const float* dp = disp + (size_t)b * K * HW + pix;
+  const float* ap = att ? att + (size_t)b * K * HW + pix : nullptr;
   const int C8 = C >> 3;
-  uint4* ob = out + (((size_t)b * 2 * C8) * K + k) * HW + pix;      // chunk stride = K*HW
-  const size_t cs = (size_t)K * HW;
+  const size_t cs = (size_t)K * HW;                                   // chunk stride (uint4)
+  uint4* ob = out + ((size_t)b * 2 * C8) * cs + pix;
   for (int c8 = 0; c8 < C8; ++c8) {
-    float l[8], r[8];
+    float l[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = c8 * 8 + i;
-      l[i] = a * __ldg(lp + (size_t)c * HW);
-      r[i] = a * bilin_fetch(rp + (size_t)c * HW, q);
+    for (int i = 0; i < 8; ++i) l[i] = __ldg(lp + (size_t)(c8 * 8 + i) * HW);
+    const float* rc = rp + (size_t)c8 * 8 * HW;
+    for (int k = 0; k < K; ++k) {
+      const float d = __ldg(dp + (size_t)k * HW);
+      const float a = ap ? __ldg(ap + (size_t)k * HW) : 1.0f;
+      const Bilin q = make_bilin(warp_coord((float)x - d, (float)(W - 1)), iy, H, W);
+      float r[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = a * bilin_fetch(rc + (size_t)i * HW, q);
+      uint4 ql, qr;
+      ql.x = tc::pack_bf16x2(a * l[0], a * l[1]); ql.y = tc::pack_bf16x2(a * l[2], a * l[3]);
+      ql.z = tc::pack_bf16x2(a * l[4], a * l[5]); ql.w = tc::pack_bf16x2(a * l[6], a * l[7]);
+      qr.x = tc::pack_bf16x2(r[0], r[1]); qr.y = tc::pack_bf16x2(r[2], r[3]); qr.z = tc::pack_bf16x2(r[4], r[5]); qr.w = tc::pack_bf16x2(r[6], r[7]);
+      __stcs(ob + (size_t)c8 * cs + (size_t)k * HW, ql);
+      __stcs(ob + (size_t)(C8 + c8) * cs + (size_t)k * HW, qr);
     }
-    uint4 ql, qr;
-    ql.x = tc::pack_bf16x2(l[0], l[1]); ql.y = tc::pack_bf16x2(l[2], l[3]); ql.z = tc::pack_bf16x2(l[4], l[5]); ql.w = tc::pack_bf16x2(l[6], l[7]);
-    qr.x = tc::pack_bf16x2(r[0], r[1]); qr.y = tc::pack_bf16x2(r[2], r[3]); qr.z = tc::pack_bf16x2(r[4], r[5]); qr.w = tc::pack_bf16x2(r[6], r[7]);
-    __stcs(ob + (size_t)c8 * cs, ql);
-    __stcs(ob + (size_t)(C8 + c8) * cs, qr);
   }
 }
 
@@ -119,8 +127,8 @@ extern "C" int ss_sparse_concat_volume_blocked(const float* cf_l, const float* c
   SS_REQUIRE(cf_l && cf_r && disp_topk && volume_blocked, "ss_sparse_concat_volume_blocked: null pointer");
   SS_REQUIRE(B > 0 && C > 0 && K > 0 && H > 1 && W > 1, "ss_sparse_concat_volume_blocked: bad dimension");
   SS_REQUIRE(C % 8 == 0, "ss_sparse_concat_volume_blocked: C=%d must be a multiple of 8", C);
-  SS_UNSUPPORTED((int64_t)K * H > 65535 || B > 65535, "ss_sparse_concat_volume_blocked: grid dimension exceeds 65535");
-  sparse_concat_blocked_kernel<<<dim3(ceil_div(W, 128), K * H, B), 128, 0, (cudaStream_t)stream>>>(
+  SS_UNSUPPORTED(H > 65535 || B > 65535, "ss_sparse_concat_volume_blocked: grid dimension exceeds 65535");
+  sparse_concat_blocked_kernel<<<dim3(ceil_div(W, 128), H, B), 128, 0, (cudaStream_t)stream>>>(
       cf_l, cf_r, disp_topk, att_topk_or_null, reinterpret_cast<uint4*>(volume_blocked), C, K, H, W);
   SS_CHECK_LAUNCH("ss_sparse_concat_volume_blocked");
   return SS_OK;

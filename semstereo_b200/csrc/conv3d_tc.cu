@@ -51,14 +51,12 @@ __device__ __forceinline__ void decode_item(const TcP& p, int s, int& b, int& h0
 }
 
 // Applies the fused epilogue to 32 consecutive output channels (co0 ...) of one voxel and stores them.
-// (od,oh,ow) / (OD,OH,OW): output voxel and output dims.  res: this voxel's residual chunk co0/8 (chunk stride res_cs uint4).
+// (od,oh,ow) / (OD,OH,OW): output voxel and output dims.  r: the 4 residual chunks of these channels, already loaded (the
+// loads are issued BEFORE the wait on the accumulator so their latency hides behind the MMAs), or nullptr.
 __device__ __forceinline__ void epilogue_store32(const TcP& p, float (&v)[32], const float* sc, const float* sh, int co0, int b, int od,
-                                                 int oh, int ow, int OD, int OH, int OW, const uint4* res, size_t res_cs) {
+                                                 int oh, int ow, int OD, int OH, int OW, const uint4* r) {
   const float lo = p.relu ? 0.0f : -INFINITY;
-  if (res) {
-    uint4 r[4];
-#pragma unroll
-    for (int c8 = 0; c8 < 4; ++c8) r[c8] = __ldg(res + (size_t)c8 * res_cs);
+  if (r) {
 #pragma unroll
     for (int c8 = 0; c8 < 4; ++c8) {
       const uint32_t u[4] = {r[c8].x, r[c8].y, r[c8].z, r[c8].w};
@@ -294,7 +292,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_const
             tc::mbar_arrive(&acc_empty[as]);
           }
           if (!valid || nt * N + j * 32 >= p.cout_valid) continue;
-          epilogue_store32(p, v, s_scale + j * 32, s_shift + j * 32, nt * N + j * 32, b, d_out, h, w, p.D, p.H, p.W, nullptr, 0);
+          epilogue_store32(p, v, s_scale + j * 32, s_shift + j * 32, nt * N + j * 32, b, d_out, h, w, p.D, p.H, p.W, nullptr);
         }
       }
     }
@@ -436,7 +434,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s2_kernel(const __grid_const
             tc::mbar_arrive(&acc_empty[as]);
           }
           if (!valid || nt * N + j * 32 >= p.cout_valid) continue;
-          epilogue_store32(p, v, s_scale + j * 32, s_shift + j * 32, nt * N + j * 32, b, d_out, h, w, p.D, p.H, p.W, nullptr, 0);
+          epilogue_store32(p, v, s_scale + j * 32, s_shift + j * 32, nt * N + j * 32, b, d_out, h, w, p.D, p.H, p.W, nullptr);
         }
       }
     }
@@ -448,18 +446,29 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s2_kernel(const __grid_const
 // t2: ConvTranspose3d k3 s2 p1 op1.  Tile space = INPUT voxels; output voxel 2i+p per dim:  p=0: tap k=1 from input i;
 // p=1: tap k=0 from input i+1 and tap k=2 from input i.  Per input depth i the 8 output phases are 8 accumulators in a row.
 // =====================================================================================================================
-template <int CIN, int N, int NS, int NWS>
-__global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_constant__ CUtensorMap tmA, const TcP p) {
+// RS = depth of the ring that prefetches the skip-connection tiles (one TH x TW x N tile per output phase) by TMA: the layer
+// is memory-heavy (it reads a full-resolution residual and writes a full-resolution output per 27/8 taps of math), and 128
+// epilogue threads issuing just-in-time loads cannot keep enough bytes in flight; the ring keeps RS tiles ahead.
+template <int CIN, int N, int NS, int NWS, int RS>
+__global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                              const __grid_constant__ CUtensorMap tmRes, const TcP p) {
   constexpr bool kResident = (NWS == 27);
+  constexpr uint32_t RTILE = (N / 8) * TH * TW * 16;          // bytes of one residual tile
   constexpr uint32_t SLICE = (CIN / 8) * TILE_B;
   constexpr uint32_t TAPB = CIN * N * 2;
   constexpr int KS = CIN / 16;
   constexpr uint32_t LBO_A = TILE_B, SBO_A = WW * 16, LBO_B = N * 16, SBO_B = 128;
   constexpr uint32_t TMEM_COLS = tmem_cols_for(2 * N);
   constexpr uint32_t IDESC = tc::make_idesc_bf16(128, N);
+  __shared__ __align__(8) uint64_t res_full[RS], res_empty[RS];
+  if (threadIdx.x == 0) {      // made visible to the async proxy by the fence in the prologue (same thread)
+    for (int i = 0; i < RS; ++i) { tc::mbar_init(&res_full[i], 1); tc::mbar_init(&res_empty[i], 128); }
+  }
   TC_KERNEL_PROLOGUE(NS, NWS, kResident)
   uint8_t* Abase = smem;
   uint8_t* Wbase = smem + NS * SLICE;
+  uint8_t* Rbase = Wbase + NWS * TAPB;
+  const bool has_res = p.residual != nullptr;
 
   // tap (shift, k) lists of one dimension for output parity q: q=0 -> {(0,1)}, q=1 -> {(1,0),(0,2)}
   auto ntaps = [](int q) { return q ? 2 : 1; };
@@ -508,6 +517,20 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_const
           }
       }
     }
+  } else if (warp == 2 && lane == 0 && has_res) {
+    // ===== skip-connection producer: one dense [N/8][TH][TW][16 B] tile of the phase-split residual per output phase =====
+    uint32_t r = 0;
+    for (int s = cta_s; s < p.items; s += cta_stride) {
+      int b, h0, w0, dlo, dhi;
+      decode_item(p, s, b, h0, w0, dlo, dhi);
+      for (int i = dlo; i < dhi; ++i)
+        for (int ph8 = 0; ph8 < 8; ++ph8, ++r) {
+          const uint32_t slot = r % RS;
+          tc::mbar_wait(&res_empty[slot], ((r / RS) & 1) ^ 1);
+          tc::mbar_expect_tx(&res_full[slot], RTILE);
+          tc::tma_load_4d(Rbase + slot * RTILE, &tmRes, &res_full[slot], w0 * 8, h0, i, (b * 8 + ph8) * (p.cout_valid / 8) + nt * (N / 8));
+        }
+    }
   } else if (warp == 1) {
     const bool leader = tc::elect_one();
     const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(Abase), LBO_A), a_hi = tc::desc_hi(SBO_A);
@@ -523,7 +546,9 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_const
         tc::mbar_wait(&a_full[slot0], (gs0 / NS) & 1);
         if (i + 1 <= din1) tc::mbar_wait(&a_full[slot1], ((gs0 + 1) / NS) & 1);
         tc::fence_after_sync();
-#pragma unroll 1
+        // fully unrolled over the 8 output phases and their taps: every tap index / operand offset is an immediate, so the
+        // issuing warp spends ~3 instructions per MMA (a rolled loop made this layer issue-bound at 4x the MMA time)
+#pragma unroll
         for (int ph8 = 0; ph8 < 8; ++ph8, ++acc_it) {
           const int pd = ph8 >> 2, ph = (ph8 >> 1) & 1, pw = ph8 & 1;
           const uint32_t as = acc_it & 1;
@@ -531,11 +556,14 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_const
           tc::fence_after_sync();
           const uint32_t tmem_d = tmem_base + as * N;
           uint32_t accumulate = 0;
+#pragma unroll
           for (int td = 0; td < ntaps(pd); ++td) {
             const int sd = tap_shift(pd, td);
             if (i + sd >= p.D) continue;
             const uint32_t a_lo = a_lo0 + (sd ? slot1 : slot0) * (SLICE >> 4);
+#pragma unroll
             for (int th = 0; th < ntaps(ph); ++th)
+#pragma unroll
               for (int tw = 0; tw < ntaps(pw); ++tw) {
                 const int tap = tap_k(pd, td) * 9 + tap_k(ph, th) * 3 + tap_k(pw, tw);
                 const uint32_t a_off = (uint32_t)(tap_shift(ph, th) * WW + tap_shift(pw, tw));     // 16-byte units
@@ -584,9 +612,19 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_const
         for (int ph8 = 0; ph8 < 8; ++ph8, ++acc_it) {
           const int pd = ph8 >> 2, ph = (ph8 >> 1) & 1, pw = ph8 & 1;
           const uint32_t as = acc_it & 1;
+          uint4 rpre[N / 32][4];                       // skip-connection chunks of this thread's voxel, from the TMA ring
+          const bool use_res = has_res;
+          if (has_res) {
+            const uint32_t slot = acc_it % RS;
+            tc::mbar_wait(&res_full[slot], (acc_it / RS) & 1);
+            const uint4* rt = reinterpret_cast<const uint4*>(Rbase + slot * RTILE) + m;      // [chunk][TH*TW] uint4
+#pragma unroll
+            for (int q = 0; q < N / 8; ++q) rpre[q / 4][q % 4] = rt[q * (TH * TW)];
+            tc::mbar_arrive(&res_empty[slot]);
+          }
           tc::mbar_wait(&acc_full[as], (acc_it >> 1) & 1);
           tc::fence_after_sync();
-#pragma unroll 1
+#pragma unroll
           for (int j = 0; j < N / 32; ++j) {
             float v[32];
             tc::tmem_ld32(tmem_base + ((uint32_t)(e * 32) << 16) + as * N + j * 32, v);
@@ -596,12 +634,8 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_const
             }
             const int co0 = nt * N + j * 32;
             if (!valid || co0 >= p.cout_valid) continue;
-            const uint4* res = nullptr;
-            if (p.residual)
-              res = reinterpret_cast<const uint4*>(p.residual) + (((size_t)b * 8 + ph8) * (p.cout_valid / 8) + co0 / 8) * S_in +
-                    ((size_t)i * p.H + h) * p.W + w;
             epilogue_store32(p, v, s_scale + j * 32, s_shift + j * 32, co0, b, 2 * i + pd, 2 * h + ph, 2 * w + pw, 2 * p.D, 2 * p.H,
-                             2 * p.W, res, S_in);
+                             2 * p.W, use_res ? rpre[j] : nullptr);
           }
         }
     }
@@ -679,11 +713,9 @@ int make_act_tmap(CUtensorMap* tm, const void* base, int W, int H, int D, long l
   return SS_OK;
 }
 
-// Picks the depth chunk (balances waves against the halo slices every chunk re-reads), sizes the grid, launches.
-template <typename K>
-int launch_tc(K kernel, size_t smem, const CUtensorMap& tm, TcP p, double halo_cost, cudaStream_t st, const char* name) {
-  SS_CUDA(ss_allow_smem(kernel, smem));
-  int grid = ss_num_sms();
+// Picks the depth chunk (balances waves against the halo slices every chunk re-reads) and sizes the persistent grid.
+void plan_tc(TcP& p, double halo_cost, int& grid) {
+  grid = ss_num_sms();
   grid -= grid % p.n_tiles;
   if (grid < p.n_tiles) grid = p.n_tiles;
   const int spatial = p.B * p.HT * p.WT;
@@ -700,6 +732,13 @@ int launch_tc(K kernel, size_t smem, const CUtensorMap& tm, TcP p, double halo_c
   p.items = spatial * p.n_dc;
   const long long total = (long long)p.items * p.n_tiles;
   if (total < grid) grid = (int)total;
+}
+
+template <typename K>
+int launch_tc(K kernel, size_t smem, const CUtensorMap& tm, TcP p, double halo_cost, cudaStream_t st, const char* name) {
+  SS_CUDA(ss_allow_smem(kernel, smem));
+  int grid;
+  plan_tc(p, halo_cost, grid);
   kernel<<<grid, 256, smem, st>>>(tm, p);
   SS_CHECK_LAUNCH(name);
   return SS_OK;
@@ -717,11 +756,34 @@ int launch_s2(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
   static_assert(smem <= 227 * 1024 - 2048, "shared memory budget");
   return launch_tc(conv3d_tc_s2_kernel<CIN, N, NS, NWS>, smem, tm, p, 0.4, st, "ss_conv3d_tc(s2)");
 }
-template <int CIN, int N, int NS, int NWS>
+template <int CIN, int N, int NS, int NWS, int RS>
 int launch_t2(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
-  constexpr size_t smem = (size_t)NS * (CIN / 8) * TILE_B + (size_t)NWS * CIN * N * 2;
+  constexpr size_t smem = (size_t)NS * (CIN / 8) * TILE_B + (size_t)NWS * CIN * N * 2 + (size_t)RS * (N / 8) * TH * TW * 16;
   static_assert(smem <= 227 * 1024 - 2048, "shared memory budget");
-  return launch_tc(conv3d_tc_t2_kernel<CIN, N, NS, NWS>, smem, tm, p, 0.3, st, "ss_conv3d_tc(t2)");
+  CUtensorMap tmr = tm;                      // placeholder when there is no residual (never dereferenced then)
+  if (p.residual) {                          // phase-split residual: dims (W*8, H, D, B*8*Cout/8), dense TW x TH tiles
+    ss_encode_tiled_fn enc = ss_get_encode_tiled();
+    if (!enc) return SS_ERR_CUDA;
+    cuuint64_t dims[4] = {(cuuint64_t)p.W * 8, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.B * 8 * (p.cout_valid / 8)};
+    cuuint64_t strides[3] = {(cuuint64_t)p.W * 16, (cuuint64_t)p.H * p.W * 16, (cuuint64_t)p.D * p.H * p.W * 16};
+    cuuint32_t box[4] = {(cuuint32_t)TW * 8, (cuuint32_t)TH, 1u, (cuuint32_t)(N / 8)};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(p.residual), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      ss_set_error("cuTensorMapEncodeTiled(residual) failed with CUresult %d", (int)r);
+      return SS_ERR_CUDA;
+    }
+  }
+  auto kernel = conv3d_tc_t2_kernel<CIN, N, NS, NWS, RS>;
+  SS_CUDA(ss_allow_smem(kernel, smem));
+  TcP q = p;
+  int grid;
+  plan_tc(q, 0.3, grid);
+  kernel<<<grid, 256, smem, st>>>(tm, tmr, q);
+  SS_CHECK_LAUNCH("ss_conv3d_tc(t2)");
+  return SS_OK;
 }
 
 }  // namespace
@@ -816,8 +878,8 @@ extern "C" int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight
       if (Cin == 32) return launch_s2<32, 64, 2, 27>(tm, p, st);
       return launch_s2<64, 128, 2, 2>(tm, p, st);
     default:
-      if (Cin == 128) return launch_t2<128, 64, 3, 2>(tm, p, st);
-      return launch_t2<64, 32, 3, 27>(tm, p, st);
+      if (Cin == 128) return launch_t2<128, 64, 3, 2, 2>(tm, p, st);
+      return launch_t2<64, 32, 3, 27, 4>(tm, p, st);
   }
 }
 

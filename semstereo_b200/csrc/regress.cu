@@ -89,31 +89,66 @@ __global__ void __launch_bounds__(128) att_stats_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// K7: block = (64 pixels) x (5 hypotheses)
+// K7: block = (64 pixels) x (5 hypotheses).  Per 16-channel chunk the left row tile and the two right rows the bilinear
+// taps can touch (floor(iy) and floor(iy)+1 are the same for the whole image row) are staged in shared memory with coalesced
+// loads, including a +-PAD column window around the tile; the 5 x 4 corner reads per channel then hit shared memory.
+// A hypothesis whose corners fall outside the staged window (|disparity| > PAD-2) reads global memory instead.
 // ---------------------------------------------------------------------------------------------
+constexpr int SS_TX = 64, SS_PAD = 24, SS_WW = SS_TX + 2 * SS_PAD, SS_CK = 16;
+
 __global__ void __launch_bounds__(320) sample_strength_kernel(const float* __restrict__ fl, const float* __restrict__ fr,
                                                               const float* __restrict__ mu, const float* __restrict__ gate,
                                                               float* __restrict__ strength, int B, int C, int H, int W) {
-  __shared__ float logit[5][64];
-  const int tx = threadIdx.x, s = threadIdx.y;
-  const int x = blockIdx.x * 64 + tx, y = blockIdx.y, b = blockIdx.z;
+  __shared__ float logit[5][SS_TX];
+  __shared__ float Ls[SS_CK][SS_TX];
+  __shared__ float Rs[SS_CK][2][SS_WW];
+  const int tx = threadIdx.x, s = threadIdx.y, tid = s * SS_TX + tx;
+  const int x0 = blockIdx.x * SS_TX, x = x0 + tx, y = blockIdx.y, b = blockIdx.z;
   const size_t HW = (size_t)H * W;
-  if (x < W) {
+  const float iy = warp_coord((float)y, (float)(H - 1));
+  const int y0 = (int)floorf(iy);                                  // uniform over the row
+  const bool active = x < W;
+  float d = 0.0f, g = 0.0f;
+  if (active) {
     const int ty = min(max(y + kPropDy[s], 0), H - 1), txx = min(max(x + kPropDx[s], 0), W - 1);
-    const float d = __ldg(mu + (size_t)b * HW + (size_t)ty * W + txx);
-    const float g = __ldg(gate + (size_t)b * HW + (size_t)ty * W + txx);
-    const float ix = warp_coord((float)x - d, (float)(W - 1));
-    const float iy = warp_coord((float)y, (float)(H - 1));
-    const Bilin q = make_bilin(ix, iy, H, W);
-    const float* lp = fl + (size_t)b * C * HW + (size_t)y * W + x;
-    const float* rp = fr + (size_t)b * C * HW;
-    float acc = 0.0f;
-#pragma unroll 4
-    for (int c = 0; c < C; ++c) acc += __ldg(lp + (size_t)c * HW) * bilin_fetch(rp + (size_t)c * HW, q);
-    logit[s][tx] = (acc / (float)C) * g;
+    d = __ldg(mu + (size_t)b * HW + (size_t)ty * W + txx);
+    g = __ldg(gate + (size_t)b * HW + (size_t)ty * W + txx);
   }
+  const Bilin q = make_bilin(warp_coord((float)x - d, (float)(W - 1)), iy, H, W);
+  // column of the west corners inside the staged window; both corners must be inside to use it
+  const float fx0 = floorf(warp_coord((float)x - d, (float)(W - 1)));
+  const float jf = fx0 - (float)(x0 - SS_PAD);
+  const bool in_win = jf >= 0.0f && jf <= (float)(SS_WW - 2);
+  const int j0 = in_win ? (int)jf : 0;
+  const float* lb = fl + (size_t)b * C * HW + (size_t)y * W;
+  const float* rb = fr + (size_t)b * C * HW;
+  float acc = 0.0f;
+  for (int c0 = 0; c0 < C; c0 += SS_CK) {
+    for (int i = tid; i < SS_CK * SS_TX; i += 320) {
+      const int c = i / SS_TX, j = i - c * SS_TX;
+      Ls[c][j] = (c0 + c < C && x0 + j < W) ? __ldg(lb + (size_t)(c0 + c) * HW + x0 + j) : 0.0f;
+    }
+    for (int i = tid; i < SS_CK * 2 * SS_WW; i += 320) {
+      const int c = i / (2 * SS_WW), r = (i / SS_WW) & 1, j = i % SS_WW;
+      const int xx = x0 - SS_PAD + j, yy = y0 + r;
+      Rs[c][r][j] = (c0 + c < C && xx >= 0 && xx < W && yy >= 0 && yy < H) ? __ldg(rb + (size_t)(c0 + c) * HW + (size_t)yy * W + xx) : 0.0f;
+    }
+    __syncthreads();
+    if (active) {
+      const int nc = min(SS_CK, C - c0);
+      if (in_win) {
+#pragma unroll 4
+        for (int c = 0; c < nc; ++c)
+          acc += Ls[c][tx] * (((Rs[c][0][j0] * q.w00 + Rs[c][0][j0 + 1] * q.w01) + Rs[c][1][j0] * q.w10) + Rs[c][1][j0 + 1] * q.w11);
+      } else {
+        for (int c = 0; c < nc; ++c) acc += Ls[c][tx] * bilin_fetch(rb + (size_t)(c0 + c) * HW, q);
+      }
+    }
+    __syncthreads();
+  }
+  if (active) logit[s][tx] = (acc / (float)C) * g;
   __syncthreads();
-  if (x < W) {
+  if (active) {
     float m = logit[0][tx];
 #pragma unroll
     for (int i = 1; i < 5; ++i) m = fmaxf(m, logit[i][tx]);

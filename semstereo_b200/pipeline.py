@@ -34,6 +34,9 @@ class HostPipeline:
         if st is None or any(st[k].shape != batch[k].shape for k in ORDER):
             st = {k: torch.empty(batch[k].shape, dtype=torch.float32, device=self.dev) for k in ORDER}
             self._stage[i] = st
+            # the caching allocator may hand out blocks that kernels already queued on the compute stream still use
+            # (stream-ordered reuse): order the first copy into a fresh staging set after that work, once
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.dev))
         return st
 
     def run(self, batches: Iterable[Dict[str, torch.Tensor]]) -> Iterator[torch.Tensor]:
