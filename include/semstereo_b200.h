@@ -84,6 +84,11 @@ SS_API int ss_conv3d_tc_ntile(int kind, int Cin, int Cout);
 SS_API int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight_packed, const float* scale_or_null,
                         const float* shift_or_null, const float* gate_blocked_or_null, const void* residual_s2d_or_null, void* out,
                         int out_mode, int B, int Cin, int Cout, int D, int H, int W, int relu, void* stream);
+/* nn.Conv3d(32, 1, 3, padding=1, bias=False) classifier heads (SemStereo.py:230,234) with the taps as the GEMM's N dimension:
+ * in_blocked bf16 (B,4,D,H,W,8); weight_packed bf16 [4][32][8] = weight[0][chunk*8+c8][tap] (27 taps, rows 27..31 zero);
+ * out fp32 (B,1,D,H,W). */
+SS_API int ss_conv3d_tc_head(const void* in_blocked, const void* weight_packed, float* out, int B, int Cin, int D, int H, int W,
+                             void* stream);
 /* Producers of the blocked layouts (bf16 mode never materialises the fp32 volumes):
  * sigmoid(gate logits (B,C,H,W)) -> fp32 (B,C/8,H,W,8);  `patch` conv * gate (SemStereo.py:274-276) -> phase-split bf16;
  * concat_volume_generator * att_topk (SemStereo.py:241-244,318) -> blocked bf16 (B,2C/8,K,H,W,8). */

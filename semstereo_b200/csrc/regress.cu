@@ -94,14 +94,15 @@ __global__ void __launch_bounds__(128) att_stats_kernel(const float* __restrict_
 // loads, including a +-PAD column window around the tile; the 5 x 4 corner reads per channel then hit shared memory.
 // A hypothesis whose corners fall outside the staged window (|disparity| > PAD-2) reads global memory instead.
 // ---------------------------------------------------------------------------------------------
-constexpr int SS_TX = 64, SS_PAD = 24, SS_WW = SS_TX + 2 * SS_PAD, SS_CK = 16;
+constexpr int SS_TX = 64, SS_PAD = 24, SS_WW = SS_TX + 2 * SS_PAD, SS_CK = 32;
 
 __global__ void __launch_bounds__(320) sample_strength_kernel(const float* __restrict__ fl, const float* __restrict__ fr,
                                                               const float* __restrict__ mu, const float* __restrict__ gate,
                                                               float* __restrict__ strength, int B, int C, int H, int W) {
   __shared__ float logit[5][SS_TX];
-  __shared__ float Ls[SS_CK][SS_TX];
-  __shared__ float Rs[SS_CK][2][SS_WW];
+  __shared__ __align__(16) float Ls[SS_CK][SS_TX];
+  __shared__ __align__(16) float Rs[SS_CK][2][SS_WW];
+  const bool vec4 = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(fl) | reinterpret_cast<uintptr_t>(fr)) & 15) == 0;
   const int tx = threadIdx.x, s = threadIdx.y, tid = s * SS_TX + tx;
   const int x0 = blockIdx.x * SS_TX, x = x0 + tx, y = blockIdx.y, b = blockIdx.z;
   const size_t HW = (size_t)H * W;
@@ -124,14 +125,31 @@ __global__ void __launch_bounds__(320) sample_strength_kernel(const float* __res
   const float* rb = fr + (size_t)b * C * HW;
   float acc = 0.0f;
   for (int c0 = 0; c0 < C; c0 += SS_CK) {
-    for (int i = tid; i < SS_CK * SS_TX; i += 320) {
-      const int c = i / SS_TX, j = i - c * SS_TX;
-      Ls[c][j] = (c0 + c < C && x0 + j < W) ? __ldg(lb + (size_t)(c0 + c) * HW + x0 + j) : 0.0f;
-    }
-    for (int i = tid; i < SS_CK * 2 * SS_WW; i += 320) {
-      const int c = i / (2 * SS_WW), r = (i / SS_WW) & 1, j = i % SS_WW;
-      const int xx = x0 - SS_PAD + j, yy = y0 + r;
-      Rs[c][r][j] = (c0 + c < C && xx >= 0 && xx < W && yy >= 0 && yy < H) ? __ldg(rb + (size_t)(c0 + c) * HW + (size_t)yy * W + xx) : 0.0f;
+    if (vec4) {        // rows are 16-byte aligned: stage with 128-bit loads (x0 and x0 - PAD are multiples of 4)
+      for (int i = tid; i < SS_CK * (SS_TX / 4); i += 320) {
+        const int c = i / (SS_TX / 4), j = (i - c * (SS_TX / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + c < C && x0 + j < W) v = __ldg(reinterpret_cast<const float4*>(lb + (size_t)(c0 + c) * HW + x0 + j));
+        *reinterpret_cast<float4*>(&Ls[c][j]) = v;
+      }
+      for (int i = tid; i < SS_CK * 2 * (SS_WW / 4); i += 320) {
+        const int c = i / (2 * (SS_WW / 4)), r = (i / (SS_WW / 4)) & 1, j = (i % (SS_WW / 4)) * 4;
+        const int xx = x0 - SS_PAD + j, yy = y0 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + c < C && xx >= 0 && xx < W && yy >= 0 && yy < H)
+          v = __ldg(reinterpret_cast<const float4*>(rb + (size_t)(c0 + c) * HW + (size_t)yy * W + xx));
+        *reinterpret_cast<float4*>(&Rs[c][r][j]) = v;
+      }
+    } else {
+      for (int i = tid; i < SS_CK * SS_TX; i += 320) {
+        const int c = i / SS_TX, j = i - c * SS_TX;
+        Ls[c][j] = (c0 + c < C && x0 + j < W) ? __ldg(lb + (size_t)(c0 + c) * HW + x0 + j) : 0.0f;
+      }
+      for (int i = tid; i < SS_CK * 2 * SS_WW; i += 320) {
+        const int c = i / (2 * SS_WW), r = (i / SS_WW) & 1, j = i % SS_WW;
+        const int xx = x0 - SS_PAD + j, yy = y0 + r;
+        Rs[c][r][j] = (c0 + c < C && xx >= 0 && xx < W && yy >= 0 && yy < H) ? __ldg(rb + (size_t)(c0 + c) * HW + (size_t)yy * W + xx) : 0.0f;
+      }
     }
     __syncthreads();
     if (active) {

@@ -202,7 +202,7 @@ class DisparityHotPath(nn.Module):
             m = getattr(self, cl)
             conv(cl + ".0", m[0][0], m[0][1])
             if bf16:
-                c[cl + ".2.tc"] = tc.pack_weight(m[2].weight.detach().float(), tc.S1)      # Cout 1 zero-padded to the 32-wide tile
+                c[cl + ".2.tc"] = tc.pack_head_weight(m[2].weight.detach().float())          # taps-as-N head kernel
             else:
                 c[cl + ".2.w"] = m[2].weight.detach().float().contiguous()
         conv("concat_stem", self.concat_stem.conv, self.concat_stem.bn)
@@ -258,7 +258,8 @@ class DisparityHotPath(nn.Module):
 
     def _classifier_tc(self, c, cl, xb):
         y = self._tc(c, cl + ".0", tc.S1, xb, 32)
-        return self._tc(c, cl + ".2", tc.S1, y, 1, relu=False, out_mode=tc.F32)
+        with ops.label(cl + ".2"):
+            return tc.conv3d_tc_head(y, c[cl + ".2.tc"])
 
     def _hourglass(self, c, hg, x):
         """hourglass.forward (SemStereo.py:134-143): residual adds and ReLUs ride in the deconv epilogues."""
