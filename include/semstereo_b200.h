@@ -80,10 +80,15 @@ SS_API int ss_blocked_to_s2d(const void* in_blocked, void* out_s2d, int B, int C
  * of the ConvTranspose3d weight (Cin,Cout,kd,kh,kw)).  out: bf16 blocked (Cout % 8 == 0) or fp32 NCDHW with Cout channels. */
 SS_API int ss_conv3d_tc_ntile(int kind, int Cin, int Cout);
 /* gate_blocked: sigmoid(channelAtt logits) as fp32 (B,Cout/8,Ho,Wo,8) from ss_gate_sigmoid_blocked.
- * out_mode 0: bf16 blocked, 1: fp32 NCDHW, 2: bf16 phase-split blocked (kinds 0-2, even output dims). */
+ * out_mode 0: bf16 blocked, 1: fp32 NCDHW, 2: bf16 phase-split blocked (kinds 0-2, even output dims).
+ * skip_weight (kind 3 only): when given, residual_s2d is the INPUT of the hourglass' 1x1 redir conv (phase-split, Cout
+ * channels) and skip_weight its weight as bf16 [Cout/8][Cout][8] with the redir BatchNorm scale folded in; the redir conv then
+ * runs as one more GEMM tap inside the layer (the caller folds the layer's own BN scale into weight_packed, passes no scale
+ * and the sum of the two BN shifts as shift). */
 SS_API int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight_packed, const float* scale_or_null,
-                        const float* shift_or_null, const float* gate_blocked_or_null, const void* residual_s2d_or_null, void* out,
-                        int out_mode, int B, int Cin, int Cout, int D, int H, int W, int relu, void* stream);
+                        const float* shift_or_null, const float* gate_blocked_or_null, const void* residual_s2d_or_null,
+                        const void* skip_weight_or_null, void* out, int out_mode, int B, int Cin, int Cout, int D, int H, int W,
+                        int relu, void* stream);
 /* nn.Conv3d(32, 1, 3, padding=1, bias=False) classifier heads (SemStereo.py:230,234) with the taps as the GEMM's N dimension:
  * in_blocked bf16 (B,4,D,H,W,8); weight_packed bf16 [4][32][8] = weight[0][chunk*8+c8][tap] (27 taps, rows 27..31 zero);
  * out fp32 (B,1,D,H,W). */

@@ -33,6 +33,8 @@ struct TcP {
   const float* shift;             // [Cout] or null
   const float* gate;              // sigmoid(gate logits) as fp32 blocked (B,Cout/8,OH,OW,8), or null
   const __nv_bfloat16* residual;  // t2 only: phase-split blocked [B][8][Cout/8][D][H][W][8], or null
+  const __nv_bfloat16* skip_w;    // t2 only: when set, `residual` is the INPUT of the 1x1 skip conv and this is its weight
+                                  // [N/8][N][8] (BN scale folded in): the skip conv runs as one more GEMM tap on the staged tile
   void* out;
   int out_mode;                   // 0: bf16 blocked, 1: fp32 NCDHW, 2: bf16 phase-split blocked
   int cout_valid;                 // channels actually stored (Cout = n_tiles*N may be zero-padded), also the channel count of out
@@ -460,15 +462,19 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_const
   constexpr uint32_t LBO_A = TILE_B, SBO_A = WW * 16, LBO_B = N * 16, SBO_B = 128;
   constexpr uint32_t TMEM_COLS = tmem_cols_for(2 * N);
   constexpr uint32_t IDESC = tc::make_idesc_bf16(128, N);
-  __shared__ __align__(8) uint64_t res_full[RS], res_empty[RS];
+  __shared__ __align__(8) uint64_t res_full[RS], res_empty[RS], skip_full;
+  constexpr uint32_t SKIPB = N * N * 2;                       // bytes of the fused 1x1 skip weight
   if (threadIdx.x == 0) {      // made visible to the async proxy by the fence in the prologue (same thread)
-    for (int i = 0; i < RS; ++i) { tc::mbar_init(&res_full[i], 1); tc::mbar_init(&res_empty[i], 128); }
+    for (int i = 0; i < RS; ++i) { tc::mbar_init(&res_full[i], 1); tc::mbar_init(&res_empty[i], p.skip_w ? 1 : 128); }
+    tc::mbar_init(&skip_full, 1);
   }
   TC_KERNEL_PROLOGUE(NS, NWS, kResident)
   uint8_t* Abase = smem;
   uint8_t* Wbase = smem + NS * SLICE;
   uint8_t* Rbase = Wbase + NWS * TAPB;
+  uint8_t* Sbase = Rbase + RS * RTILE;
   const bool has_res = p.residual != nullptr;
+  const bool fuse_skip = p.skip_w != nullptr;
 
   // tap (shift, k) lists of one dimension for output parity q: q=0 -> {(0,1)}, q=1 -> {(1,0),(0,2)}
   auto ntaps = [](int q) { return q ? 2 : 1; };
@@ -519,6 +525,10 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_const
     }
   } else if (warp == 2 && lane == 0 && has_res) {
     // ===== skip-connection producer: one dense [N/8][TH][TW][16 B] tile of the phase-split residual per output phase =====
+    if (fuse_skip && cta_s < p.items) {
+      tc::mbar_expect_tx(&skip_full, SKIPB);
+      tc::bulk_load(Sbase, p.skip_w, SKIPB, &skip_full);
+    }
     uint32_t r = 0;
     for (int s = cta_s; s < p.items; s += cta_stride) {
       int b, h0, w0, dlo, dhi;
@@ -536,6 +546,9 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_const
     const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(Abase), LBO_A), a_hi = tc::desc_hi(SBO_A);
     const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(Wbase), LBO_B), b_hi = tc::desc_hi(SBO_B);
     if (kResident && cta_s < p.items) tc::mbar_wait(&w_full[0], 0);
+    if (fuse_skip && cta_s < p.items) tc::mbar_wait(&skip_full, 0);
+    const uint32_t r_lo0 = tc::desc_lo(tc::smem_u32(Rbase), TH * TW * 16), r_hi = tc::desc_hi(128);
+    const uint32_t s_lo0 = tc::desc_lo(tc::smem_u32(Sbase), LBO_B);
     uint32_t g_base = 0, acc_it = 0, wc = 0;
     for (int s = cta_s; s < p.items; s += cta_stride) {
       int b, h0, w0, dlo, dhi;
@@ -588,6 +601,18 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_const
                 if (!kResident) ++wc;
               }
           }
+          if (fuse_skip) {          // the 1x1 skip conv: the TMA-staged tile of its input is one more K-major A operand (K = N)
+            const uint32_t rslot = acc_it % RS;
+            tc::mbar_wait(&res_full[rslot], (acc_it / RS) & 1);
+            tc::fence_after_sync();
+            if (leader) {
+#pragma unroll
+              for (int ks = 0; ks < N / 16; ++ks)
+                tc::mma_bf16_lohi(tmem_d, r_lo0 + rslot * (RTILE >> 4) + (uint32_t)(ks * 2 * TH * TW), r_hi,
+                                  s_lo0 + (uint32_t)(ks * 2 * LBO_B) / 16, b_hi, IDESC, 1);
+              tc::mma_commit(&res_empty[rslot]);
+            }
+          }
           if (leader) tc::mma_commit(&acc_full[as]);
           __syncwarp();
         }
@@ -613,8 +638,8 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_const
           const int pd = ph8 >> 2, ph = (ph8 >> 1) & 1, pw = ph8 & 1;
           const uint32_t as = acc_it & 1;
           uint4 rpre[N / 32][4];                       // skip-connection chunks of this thread's voxel, from the TMA ring
-          const bool use_res = has_res;
-          if (has_res) {
+          const bool use_res = has_res && !fuse_skip;
+          if (use_res) {
             const uint32_t slot = acc_it % RS;
             tc::mbar_wait(&res_full[slot], (acc_it / RS) & 1);
             const uint4* rt = reinterpret_cast<const uint4*>(Rbase + slot * RTILE) + m;      // [chunk][TH*TW] uint4
@@ -758,7 +783,7 @@ int launch_s2(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
 }
 template <int CIN, int N, int NS, int NWS, int RS>
 int launch_t2(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
-  constexpr size_t smem = (size_t)NS * (CIN / 8) * TILE_B + (size_t)NWS * CIN * N * 2 + (size_t)RS * (N / 8) * TH * TW * 16;
+  constexpr size_t smem = (size_t)NS * (CIN / 8) * TILE_B + (size_t)NWS * CIN * N * 2 + (size_t)RS * (N / 8) * TH * TW * 16 + (size_t)N * N * 2;
   static_assert(smem <= 227 * 1024 - 2048, "shared memory budget");
   CUtensorMap tmr = tm;                      // placeholder when there is no residual (never dereferenced then)
   if (p.residual) {                          // phase-split residual: dims (W*8, H, D, B*8*Cout/8), dense TW x TH tiles
@@ -828,8 +853,8 @@ extern "C" int ss_conv3d_tc_ntile(int kind, int Cin, int Cout) {
 
 // D,H,W are the INPUT dims of the layer (kind 2: of the full-resolution input, all even; the tensor itself is phase-split).
 extern "C" int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight_packed, const float* scale_or_null,
-                            const float* shift_or_null, const float* gate_blocked_or_null, const void* residual_s2d_or_null, void* out,
-                            int out_mode, int B, int Cin, int Cout, int D, int H, int W, int relu, void* stream) {
+                            const float* shift_or_null, const float* gate_blocked_or_null, const void* residual_s2d_or_null,
+                            const void* skip_weight_or_null, void* out, int out_mode, int B, int Cin, int Cout, int D, int H, int W, int relu, void* stream) {
   SS_REQUIRE(in_blocked && weight_packed && out, "ss_conv3d_tc: null pointer");
   SS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && Cout > 0, "ss_conv3d_tc: non-positive dimension");
   const int N = ss_conv3d_tc_ntile(kind, Cin, Cout);
@@ -844,11 +869,14 @@ extern "C" int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight
                                ((kind == 2 ? W / 2 : W) % 2 == 0)),
              "ss_conv3d_tc: phase-split output needs even output dims and is not available for the transposed layer");
   SS_REQUIRE(kind == 3 || !residual_s2d_or_null, "ss_conv3d_tc: the residual input exists only for the transposed layer");
+  SS_REQUIRE(!skip_weight_or_null || (residual_s2d_or_null && Cout == N && (reinterpret_cast<uintptr_t>(skip_weight_or_null) & 15) == 0),
+             "ss_conv3d_tc: a fused skip conv needs its phase-split input as `residual` and Cout == the layer's tile");
   SS_REQUIRE(kind != 2 || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "ss_conv3d_tc: stride-2 layer needs even input dims");
   TcP p;
   p.w = reinterpret_cast<const __nv_bfloat16*>(weight_packed);
   p.scale = scale_or_null; p.shift = shift_or_null; p.gate = gate_blocked_or_null;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual_s2d_or_null);
+  p.skip_w = reinterpret_cast<const __nv_bfloat16*>(skip_weight_or_null);
   p.out = out; p.out_mode = out_mode; p.cout_valid = Cout;
   p.B = B; p.relu = relu;
   p.n_tiles = ceil_div(Cout, N);

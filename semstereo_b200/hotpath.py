@@ -188,6 +188,15 @@ class DisparityHotPath(nn.Module):
             conv(f"{hg}.conv6", m.conv6[0], m.conv6[1], True)
             conv(f"{hg}.redir1", m.redir1[0], m.redir1[1])
             conv(f"{hg}.redir2", m.redir2[0], m.redir2[1])
+            if bf16:
+                for dc, rd in (("conv5", "redir2"), ("conv6", "redir1")):
+                    deconv, dbn = getattr(m, dc)[0], getattr(m, dc)[1]
+                    rconv, rbn = getattr(m, rd)[0], getattr(m, rd)[1]
+                    ds, dt = bn_affine(dbn)
+                    rs, rt = bn_affine(rbn)
+                    c[f"{hg}.{dc}.ftc"] = tc.pack_weight(deconv.weight.detach().float() * ds.view(1, -1, 1, 1, 1), tc.T2)
+                    c[f"{hg}.{dc}.skipw"] = tc.pack_skip_weight(rconv.weight.detach().float(), rs)
+                    c[f"{hg}.{dc}.fshift"] = (dt + rt).contiguous()
             a = m.attention_block
             c[hg + ".wqkv_t"] = a.qkv_3d.weight.detach().float().t().contiguous()
             c[hg + ".bqkv"] = a.qkv_3d.bias.detach().float().contiguous()
@@ -251,10 +260,14 @@ class DisparityHotPath(nn.Module):
         with ops.label(hg + ".attn_core"):
             att = tc.window_attention_core(qkv, block, 16)
         c4b = self._tc(c, hg + ".attn_out", tc.K1, att, 128, relu=False)
-        r2 = self._tc(c, hg + ".redir2", tc.K1, tc.s2d_as_batch(c2s), 64, relu=False).view(c2s.shape)
-        c5 = self._tc(c, hg + ".conv5", tc.T2, c4b, 64, residual=r2)
-        r1 = self._tc(c, hg + ".redir1", tc.K1, tc.s2d_as_batch(x_s2d), 32, relu=False).view(x_s2d.shape)
-        return self._tc(c, hg + ".conv6", tc.T2, c5, 32, residual=r1)
+        # conv5/conv6 (transposed) with the redir2/redir1 1x1 skip convs fused in as one more GEMM tap on the TMA-staged skip
+        # tile (BN scales folded into both weights, shifts summed): relu(bn(deconv(x)) + bn(redir(skip)))  (SemStereo.py:141-142)
+        with ops.label(hg + ".conv5"):
+            c5 = tc.conv3d_tc(tc.T2, c4b, c[hg + ".conv5.ftc"], 64, None, c[hg + ".conv5.fshift"], residual_s2d=c2s,
+                              skip_weight=c[hg + ".conv5.skipw"], relu=True)
+        with ops.label(hg + ".conv6"):
+            return tc.conv3d_tc(tc.T2, c5, c[hg + ".conv6.ftc"], 32, None, c[hg + ".conv6.fshift"], residual_s2d=x_s2d,
+                                skip_weight=c[hg + ".conv6.skipw"], relu=True)
 
     def _classifier_tc(self, c, cl, xb):
         y = self._tc(c, cl + ".0", tc.S1, xb, 32)

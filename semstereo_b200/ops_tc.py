@@ -139,7 +139,15 @@ def conv3d_tc_head(xb, w_head):
 BLOCKED, F32, S2D = 0, 1, 2          # out_mode of ss_conv3d_tc
 
 
-def conv3d_tc(kind, xb, w_tc, cout, scale=None, shift=None, gate_blocked=None, residual_s2d=None, relu=False, out_mode=BLOCKED):
+def pack_skip_weight(w, scale):
+    """1x1x1 redir conv weight (C,C,1,1,1) with its BN scale folded in -> bf16 [C/8][C][8] (K-major rows = output channels)."""
+    c = w.shape[0]
+    t = (w.reshape(c, c) * scale.reshape(c, 1)).reshape(c, c // 8, 8).permute(1, 0, 2)      # (chunk, cout, c8)
+    return t.contiguous().to(torch.bfloat16)
+
+
+def conv3d_tc(kind, xb, w_tc, cout, scale=None, shift=None, gate_blocked=None, residual_s2d=None, relu=False, out_mode=BLOCKED,
+              skip_weight=None):
     """xb: blocked (kinds S1, K1, T2) or phase-split (kind S2) bf16 input.  Returns bf16 blocked / phase-split or fp32 NCDHW."""
     if kind == S2:
         dev = _require_bf16(xb, 7)
@@ -170,6 +178,9 @@ def conv3d_tc(kind, xb, w_tc, cout, scale=None, shift=None, gate_blocked=None, r
         out = torch.empty((B, 8, cout // 8, Do // 2, Ho // 2, Wo // 2, 8), device=dev, dtype=torch.bfloat16)
     else:
         out = torch.empty((B, cout // 8, Do, Ho, Wo, 8), device=dev, dtype=torch.bfloat16)
+    if skip_weight is not None and (residual_s2d is None or skip_weight.dtype != torch.bfloat16
+                                    or tuple(skip_weight.shape) != (cout // 8, cout, 8) or not skip_weight.is_contiguous()):
+        raise ValueError("conv3d_tc: skip_weight must come from pack_skip_weight and needs the skip input as residual_s2d")
     _call("ss_conv3d_tc", dev, int(kind), _ptr(xb), _ptr(w_tc), _ptr(scale), _ptr(shift), _ptr(gate_blocked), _ptr(residual_s2d),
-          _ptr(out), int(out_mode), B, cin, cout, D, H, W, int(relu))
+          _ptr(skip_weight), _ptr(out), int(out_mode), B, cin, cout, D, H, W, int(relu))
     return out

@@ -155,3 +155,23 @@ def test_conv_head_taps_as_n(B, D, H, W):
     out = tc.conv3d_tc_head(tc.to_blocked_bf16(x.to(DEV)), tc.pack_head_weight(w).to(DEV))
     torch.cuda.synchronize()
     check(out.cpu(), ref, False)
+
+
+@pytest.mark.parametrize("Cin,Cout,B,D,H,W", [(128, 64, 1, 2, 16, 8), (64, 32, 2, 4, 24, 16), (64, 32, 1, 12, 64, 64)])
+def test_conv_transposed_with_fused_skip_conv(Cin, Cout, B, D, H, W):
+    """relu(bn(deconv(x)) + bn(redir(skip))) with the 1x1 redir conv fused into the transposed layer (SemStereo.py:141-142)."""
+    g = torch.Generator().manual_seed(Cin + D + 7)
+    x = torch.randn(B, Cin, D, H, W, generator=g)
+    skip = torch.randn(B, Cout, 2 * D, 2 * H, 2 * W, generator=g)
+    w = torch.randn(Cin, Cout, 3, 3, 3, generator=g) / (27 * Cin / 8) ** 0.5
+    wr = torch.randn(Cout, Cout, 1, 1, 1, generator=g) / Cout ** 0.5
+    s1, t1 = torch.rand(Cout, generator=g) + 0.5, 0.3 * torch.randn(Cout, generator=g)
+    s2, t2 = torch.rand(Cout, generator=g) + 0.5, 0.3 * torch.randn(Cout, generator=g)
+    wf = w * s1.view(1, -1, 1, 1, 1)
+    wrf = wr * s2.view(-1, 1, 1, 1, 1)
+    ref = F.relu(F.conv_transpose3d(bf(x), bf(wf), None, stride=2, padding=1, output_padding=1) + F.conv3d(bf(skip), bf(wrf))
+                 + (t1 + t2).view(1, -1, 1, 1, 1))
+    out = tc.conv3d_tc(tc.T2, tc.to_blocked_bf16(x.to(DEV)), tc.pack_weight(wf, tc.T2).to(DEV), Cout, None, (t1 + t2).to(DEV),
+                       residual_s2d=tc.to_blocked_bf16(skip.to(DEV), s2d=True), skip_weight=tc.pack_skip_weight(wr, s2).to(DEV), relu=True)
+    torch.cuda.synchronize()
+    check(tc.from_blocked_bf16(out).cpu(), ref, True)
