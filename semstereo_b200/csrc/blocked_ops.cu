@@ -58,42 +58,85 @@ __global__ void __launch_bounds__(128) patch_gate_blocked_kernel(const float* __
 }
 
 // out blocked bf16 (B, 2C/8, K, H, W, 8): chunks [0, C/8) = cf_l * a_k ; [C/8, 2C/8) = bilinear(cf_r, x - d_k) * a_k.
-// One thread = one pixel, all K samples: the left chunk is loaded once per 8 channels and reused by the K samples; the right
-// reads of consecutive samples (ascending disparity) fall in the same few cache lines.
+// One CTA = one image row x 64 pixels, thread (pixel, half of the samples).  The left tile and the two right rows the bilinear
+// taps can touch (floor(iy), floor(iy)+1: the same for the whole row) are staged once in shared memory with a +-PAD column
+// window (128-bit loads); every (sample, channel) corner read then hits shared memory.  Samples whose corners leave the
+// window (|disparity| > PAD-2) read global memory instead.
+constexpr int SC_TX = 64, SC_PAD = 24, SC_WW = SC_TX + 2 * SC_PAD, SC_C = 32;
+
 __global__ void __launch_bounds__(128) sparse_concat_blocked_kernel(const float* __restrict__ cf_l, const float* __restrict__ cf_r,
                                                                     const float* __restrict__ disp, const float* __restrict__ att,
                                                                     uint4* __restrict__ out, int C, int K, int H, int W) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= W) return;
-  const int y = blockIdx.y, b = blockIdx.z;
+  __shared__ __align__(16) float Ls[SC_C][SC_TX];
+  __shared__ __align__(16) float Rs[SC_C][2][SC_WW];
+  const int tx = threadIdx.x & (SC_TX - 1), half = threadIdx.x >> 6, tid = threadIdx.x;
+  const int x0 = blockIdx.x * SC_TX, x = x0 + tx, y = blockIdx.y, b = blockIdx.z;
   const size_t HW = (size_t)H * W, pix = (size_t)y * W + x;
   const float iy = warp_coord((float)y, (float)(H - 1));
-  const float* lp = cf_l + (size_t)b * C * HW + pix;
-  const float* rp = cf_r + (size_t)b * C * HW;
-  const float* dp = disp + (size_t)b * K * HW + pix;
-  const float* ap = att ? att + (size_t)b * K * HW + pix : nullptr;
+  const int y0 = (int)floorf(iy);
+  const float* lb = cf_l + (size_t)b * C * HW + (size_t)y * W;
+  const float* rb = cf_r + (size_t)b * C * HW;
+  const bool vec4 = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(cf_l) | reinterpret_cast<uintptr_t>(cf_r)) & 15) == 0;
   const int C8 = C >> 3;
   const size_t cs = (size_t)K * HW;                                   // chunk stride (uint4)
-  uint4* ob = out + ((size_t)b * 2 * C8) * cs + pix;
-  for (int c8 = 0; c8 < C8; ++c8) {
-    float l[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) l[i] = __ldg(lp + (size_t)(c8 * 8 + i) * HW);
-    const float* rc = rp + (size_t)c8 * 8 * HW;
-    for (int k = 0; k < K; ++k) {
-      const float d = __ldg(dp + (size_t)k * HW);
-      const float a = ap ? __ldg(ap + (size_t)k * HW) : 1.0f;
-      const Bilin q = make_bilin(warp_coord((float)x - d, (float)(W - 1)), iy, H, W);
-      float r[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) r[i] = a * bilin_fetch(rc + (size_t)i * HW, q);
-      uint4 ql, qr;
-      ql.x = tc::pack_bf16x2(a * l[0], a * l[1]); ql.y = tc::pack_bf16x2(a * l[2], a * l[3]);
-      ql.z = tc::pack_bf16x2(a * l[4], a * l[5]); ql.w = tc::pack_bf16x2(a * l[6], a * l[7]);
-      qr.x = tc::pack_bf16x2(r[0], r[1]); qr.y = tc::pack_bf16x2(r[2], r[3]); qr.z = tc::pack_bf16x2(r[4], r[5]); qr.w = tc::pack_bf16x2(r[6], r[7]);
-      __stcs(ob + (size_t)c8 * cs + (size_t)k * HW, ql);
-      __stcs(ob + (size_t)(C8 + c8) * cs + (size_t)k * HW, qr);
+  for (int c0 = 0; c0 < C; c0 += SC_C) {
+    if (vec4) {
+      for (int i = tid; i < SC_C * (SC_TX / 4); i += 128) {
+        const int c = i / (SC_TX / 4), j = (i - c * (SC_TX / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + c < C && x0 + j < W) v = __ldg(reinterpret_cast<const float4*>(lb + (size_t)(c0 + c) * HW + x0 + j));
+        *reinterpret_cast<float4*>(&Ls[c][j]) = v;
+      }
+      for (int i = tid; i < SC_C * 2 * (SC_WW / 4); i += 128) {
+        const int c = i / (2 * (SC_WW / 4)), r = (i / (SC_WW / 4)) & 1, j = (i % (SC_WW / 4)) * 4;
+        const int xx = x0 - SC_PAD + j, yy = y0 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + c < C && xx >= 0 && xx < W && yy >= 0 && yy < H)
+          v = __ldg(reinterpret_cast<const float4*>(rb + (size_t)(c0 + c) * HW + (size_t)yy * W + xx));
+        *reinterpret_cast<float4*>(&Rs[c][r][j]) = v;
+      }
+    } else {
+      for (int i = tid; i < SC_C * SC_TX; i += 128) {
+        const int c = i / SC_TX, j = i - c * SC_TX;
+        Ls[c][j] = (c0 + c < C && x0 + j < W) ? __ldg(lb + (size_t)(c0 + c) * HW + x0 + j) : 0.0f;
+      }
+      for (int i = tid; i < SC_C * 2 * SC_WW; i += 128) {
+        const int c = i / (2 * SC_WW), r = (i / SC_WW) & 1, j = i % SC_WW;
+        const int xx = x0 - SC_PAD + j, yy = y0 + r;
+        Rs[c][r][j] = (c0 + c < C && xx >= 0 && xx < W && yy >= 0 && yy < H) ? __ldg(rb + (size_t)(c0 + c) * HW + (size_t)yy * W + xx) : 0.0f;
+      }
     }
+    __syncthreads();
+    if (x < W) {
+      const int nch = min(SC_C, C - c0) >> 3;                         // 8-channel chunks staged
+      for (int k = half; k < K; k += 2) {
+        const float d = __ldg(disp + ((size_t)b * K + k) * HW + pix);
+        const float a = att ? __ldg(att + ((size_t)b * K + k) * HW + pix) : 1.0f;
+        const float ix = warp_coord((float)x - d, (float)(W - 1));
+        const Bilin q = make_bilin(ix, iy, H, W);
+        const float jf = floorf(ix) - (float)(x0 - SC_PAD);
+        const bool in_win = jf >= 0.0f && jf <= (float)(SC_WW - 2);
+        const int j0 = in_win ? (int)jf : 0;
+        uint4* ob = out + ((size_t)b * 2 * C8 + (c0 >> 3)) * cs + (size_t)k * HW + pix;
+        for (int c8 = 0; c8 < nch; ++c8) {
+          float l[8], r[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int c = c8 * 8 + i;
+            l[i] = a * Ls[c][tx];
+            const float rv = in_win ? (((Rs[c][0][j0] * q.w00 + Rs[c][0][j0 + 1] * q.w01) + Rs[c][1][j0] * q.w10) + Rs[c][1][j0 + 1] * q.w11)
+                                    : bilin_fetch(rb + (size_t)(c0 + c) * HW, q);
+            r[i] = a * rv;
+          }
+          uint4 ql, qr;
+          ql.x = tc::pack_bf16x2(l[0], l[1]); ql.y = tc::pack_bf16x2(l[2], l[3]); ql.z = tc::pack_bf16x2(l[4], l[5]); ql.w = tc::pack_bf16x2(l[6], l[7]);
+          qr.x = tc::pack_bf16x2(r[0], r[1]); qr.y = tc::pack_bf16x2(r[2], r[3]); qr.z = tc::pack_bf16x2(r[4], r[5]); qr.w = tc::pack_bf16x2(r[6], r[7]);
+          __stcs(ob + (size_t)c8 * cs, ql);
+          __stcs(ob + (size_t)(C8 + c8) * cs, qr);
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -128,7 +171,7 @@ extern "C" int ss_sparse_concat_volume_blocked(const float* cf_l, const float* c
   SS_REQUIRE(B > 0 && C > 0 && K > 0 && H > 1 && W > 1, "ss_sparse_concat_volume_blocked: bad dimension");
   SS_REQUIRE(C % 8 == 0, "ss_sparse_concat_volume_blocked: C=%d must be a multiple of 8", C);
   SS_UNSUPPORTED(H > 65535 || B > 65535, "ss_sparse_concat_volume_blocked: grid dimension exceeds 65535");
-  sparse_concat_blocked_kernel<<<dim3(ceil_div(W, 128), H, B), 128, 0, (cudaStream_t)stream>>>(
+  sparse_concat_blocked_kernel<<<dim3(ceil_div(W, SC_TX), H, B), 128, 0, (cudaStream_t)stream>>>(
       cf_l, cf_r, disp_topk, att_topk_or_null, reinterpret_cast<uint4*>(volume_blocked), C, K, H, W);
   SS_CHECK_LAUNCH("ss_sparse_concat_volume_blocked");
   return SS_OK;

@@ -895,8 +895,8 @@ extern "C" int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight
   p.HT = ceil_div(p.H, TH); p.WT = ceil_div(p.W, TW);
   switch (kind) {
     case 0:
-      if (Cin == 32) return launch_s1<32, 32, 4, 27, 27>(tm, p, st);
-      if (Cin == 64) return launch_s1<64, 32, 4, 27, 27>(tm, p, st);
+      if (Cin == 32) return launch_s1<32, 32, 8, 27, 27>(tm, p, st);
+      if (Cin == 64) return launch_s1<64, 32, 5, 27, 27>(tm, p, st);
       return launch_s1<128, 128, 3, 2, 27>(tm, p, st);
     case 1:
       if (Cin == 32) return launch_s1<32, 32, 4, 1, 1>(tm, p, st);
