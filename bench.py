@@ -134,14 +134,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference(H, W, maxdisp, steps, warmup, signed=True, att_only=False):
+def drop_cf(inp, external_cf):
+    """Default workload: concat_feature(f4_*) (SemStereo.py:314-315) runs INSIDE the path, so cf_l / cf_r are not inputs."""
+    return inp if external_cf else {k: v for k, v in inp.items() if k not in ("cf_l", "cf_r")}
+
+
+def cpu_reference(H, W, maxdisp, steps, warmup, signed=True, att_only=False, external_cf=False):
     """The reference algorithm's CPU path (oracle port of SemStereo.forward:273-324; efficient closed forms, so it is
     FASTER than the reference's own Python-loop volume builder — a conservative baseline).  Each step = one pair."""
     from oracle import hotpath as oh
     from semstereo_b200.params import make_inputs, make_params
     torch.set_num_threads(os.cpu_count() or 1)
     p = make_params(seed=1, peaked=20.0)
-    inp = make_inputs(3, 1, H, W)
+    inp = drop_cf(make_inputs(3, 1, H, W), external_cf)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
@@ -169,6 +174,8 @@ def main():
                     help="us3d: SemStereo, signed, 1024x1024, maxdisp 64 (configs #1/#3); whu: SemStereo_WHU + submodule_.py, unsigned, "
                          "384x768, maxdisp 128 (config #4)")
     ap.add_argument("--att-only", action="store_true", help="attention_weights_only forward (the forward half of config #5)")
+    ap.add_argument("--external-cf", action="store_true",
+                    help="hand concat_feature(f4_*) in as inputs (round-1 boundary) instead of computing it inside the path")
     a = ap.parse_args()
     signed = a.variant == "us3d"
     if a.variant == "whu":
@@ -180,12 +187,13 @@ def main():
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     workload = (f"{'SemStereo' if signed else 'SemStereo_WHU'} disparity hot path (forward:273-324), {H}x{W} "
                 f"{'US3D' if signed else 'WHU'}-shaped pairs, maxdisp {md}, {'signed' if signed else 'unsigned'}"
-                f"{', attention_weights_only' if a.att_only else ''}")
+                f"{', attention_weights_only' if a.att_only else ''}"
+                f"{'' if a.external_cf or a.att_only else ', concat_feature (:314-315) computed inside the path'}")
 
     if a.impl == "reference":
         if rank != 0:
             return
-        times = cpu_reference(H, W, md, a.steps, min(a.warmup, 1), signed, a.att_only)
+        times = cpu_reference(H, W, md, a.steps, min(a.warmup, 1), signed, a.att_only, a.external_cf)
         ms = 1e3 * sum(times) / len(times)
         v = 1e3 / ms
         print(json.dumps({
@@ -210,13 +218,13 @@ def main():
     okey = "pred_att_up" if a.att_only else "pred_up"
     model.load_state_dict(make_params(seed=1, peaked=20.0), strict=True)
     model = model.to(dev)
-    host = {k: v.pin_memory() for k, v in make_inputs(100 + rank, B, H, W).items()}
+    host = {k: v.pin_memory() for k, v in drop_cf(make_inputs(100 + rank, B, H, W), a.external_cf and not a.att_only).items()}
     devin = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
     out_host = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
     gathered = torch.empty((world * B, H, W), device=dev) if world > 1 else None
 
     def step(inputs):
-        o = model(*[inputs[k] for k in ORDER])[okey]
+        o = model(*[inputs.get(k) for k in ORDER])[okey]
         if world > 1:
             tdist.all_gather_into_tensor(gathered, o)
         return o
@@ -315,7 +323,7 @@ def main():
            "e2e": {"value": e2e_v, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps},
            "gpu_launches": rec.count, "clocks": clocks, "roofline": roof, "kernels": kernels}
     if world == 1 and not a.no_cpu_baseline:
-        times = cpu_reference(H, W, md, a.cpu_steps, 1, signed, a.att_only)
+        times = cpu_reference(H, W, md, a.cpu_steps, 1, signed, a.att_only, a.external_cf)
         res["cpu_baseline"] = {"value": len(times) / sum(times), "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
                                "sample": f"{len(times)} pairs at {H}x{W} through oracle/hotpath.py (torch CPU fp32), 1 warm-up"}
     print(json.dumps(res))

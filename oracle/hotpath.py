@@ -104,7 +104,9 @@ def forward(p, inp, maxdisp, signed=True, att_weights_only=False, keep=False):
     out["pred_att_up"] = ops.ssr_upsample(sel["pred_att"].unsqueeze(1), inp["spx_pred"], inp["pred_label"], p)
     if att_weights_only:
         return out
-    volume = sparse_concat_volume(inp["cf_l"], inp["cf_r"], sel["disp_topk"], sel["att_topk"])
+    cf_l = inp["cf_l"] if inp.get("cf_l") is not None else ops.concat_feature(f4_l, p)        # SemStereo.py:314-315
+    cf_r = inp["cf_r"] if inp.get("cf_r") is not None else ops.concat_feature(f4_r, p)
+    volume = sparse_concat_volume(cf_l, cf_r, sel["disp_topk"], sel["att_topk"])
     cost = aggregation_branch(p, volume, f4_l)
     pred = ops.regression_topk(cost.squeeze(1), sel["disp_topk"], 2)
     out.update(cost=cost, pred=pred)

@@ -358,3 +358,10 @@ def channel_att_logits(im, p, prefix):
 def channel_att(cv, im, p, prefix):
     """channelAtt.forward (SemStereo.py:98-103): sigmoid(gate)[:, :, None] * cv."""
     return torch.sigmoid(channel_att_logits(im, p, prefix)).unsqueeze(2) * cv
+
+
+def concat_feature(f4, p, prefix="concat_feature"):
+    """concat_feature (SemStereo.py:221-223, called at :314-315): BasicConv 3x3 (conv+BN+ReLU) -> Conv2d 3x3 (no bias)."""
+    y = F.conv2d(f4, p[prefix + ".0.conv.weight"], None, padding=1)
+    y = F.relu(_bn(y, p, prefix + ".0.bn"))
+    return F.conv2d(y, p[prefix + ".1.weight"], None, padding=1)

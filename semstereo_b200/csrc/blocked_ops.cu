@@ -30,23 +30,32 @@ __global__ void __launch_bounds__(128) patch_gate_blocked_kernel(const float* __
   const int y = blockIdx.y % H, d = blockIdx.y / H;
   const int G8 = G >> 3, chunk = blockIdx.z % G8, b = blockIdx.z / G8;
   const size_t HW = (size_t)H * W;
+  // branch-free 3x3: out-of-range taps read a clamped address and get weight 0, so all 72 loads of the 8 groups can be in flight
+  int yo[3], xo[3];
+  float ym[3], xm[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int yy = y + k - 1, xx = x + k - 1;
+    ym[k] = (yy >= 0 && yy < H) ? 1.0f : 0.0f;
+    xm[k] = (xx >= 0 && xx < W) ? 1.0f : 0.0f;
+    yo[k] = min(max(yy, 0), H - 1) * W;
+    xo[k] = min(max(xx, 0), W - 1);
+  }
   float f[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int g = chunk * 8 + i;
     const float* plane = vol + (((size_t)b * G + g) * D + d) * HW;
+    float v[9];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) v[ky * 3 + kx] = __ldg(plane + yo[ky] + xo[kx]);
     float acc = 0.0f;
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yy = y + ky - 1;
-      if (yy < 0 || yy >= H) continue;
+    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int xx = x + kx - 1;
-        if (xx < 0 || xx >= W) continue;
-        acc = fmaf(__ldg(w + g * 9 + ky * 3 + kx), __ldg(plane + (size_t)yy * W + xx), acc);
-      }
-    }
+      for (int kx = 0; kx < 3; ++kx) acc = fmaf(__ldg(w + g * 9 + ky * 3 + kx) * (ym[ky] * xm[kx]), v[ky * 3 + kx], acc);
     f[i] = sigmoidf_(__ldg(gate + ((size_t)b * G + g) * HW + (size_t)y * W + x)) * acc;
   }
   uint4 q;

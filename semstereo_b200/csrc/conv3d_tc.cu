@@ -155,7 +155,8 @@ constexpr uint32_t tmem_cols_for(int n2) { return n2 <= 32 ? 32 : n2 <= 64 ? 64 
 template <int CIN, int N, int NS, int NWS, int TAPS>
 __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_constant__ CUtensorMap tmA, const TcP p) {
   constexpr bool kResident = (NWS == TAPS);
-  constexpr bool k3 = (TAPS == 27);
+  constexpr bool k3 = (TAPS == 27);            // taps along the depth axis
+  constexpr bool kHW3 = (TAPS >= 9);           // 3x3 in-plane taps (TAPS == 9: a 2-D 3x3 conv on a depth-1 volume)
   constexpr uint32_t SLICE = (CIN / 8) * TILE_B;
   constexpr uint32_t TAPB = CIN * N * 2;
   constexpr int KS = CIN / 16;
@@ -195,14 +196,14 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_const
         int b, h0, w0, dlo, dhi;
         decode_item(p, s, b, h0, w0, dlo, dhi);
         for (int d_out = dlo; d_out < dhi; ++d_out)
-          for (int kd = 0; kd < 3; ++kd) {
+          for (int kd = (k3 ? 0 : 1); kd < (k3 ? 3 : 2); ++kd) {
             const int d_in = d_out + kd - 1;
             if (d_in < 0 || d_in >= p.D) continue;
-            for (int t9 = 0; t9 < 9; ++t9, ++wc) {
+            for (int t9 = (kHW3 ? 0 : 4); t9 < (kHW3 ? 9 : 5); ++t9, ++wc) {
               const uint32_t slot = wc % NWS;
               tc::mbar_wait(&w_empty[slot], ((wc / NWS) & 1) ^ 1);
               tc::mbar_expect_tx(&w_full[slot], TAPB);
-              tc::bulk_load(Wbase + slot * TAPB, wsrc + (size_t)(kd * 9 + t9) * TAPB, TAPB, &w_full[slot]);
+              tc::bulk_load(Wbase + slot * TAPB, wsrc + (size_t)(k3 ? kd * 9 + t9 : (kHW3 ? t9 : 0)) * TAPB, TAPB, &w_full[slot]);
             }
           }
       }
@@ -233,10 +234,10 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_const
           tc::fence_after_sync();
           const uint32_t a_lo = a_lo0 + slot * (SLICE >> 4);
 #pragma unroll
-          for (int t9 = (k3 ? 0 : 4); t9 < (k3 ? 9 : 5); ++t9) {
+          for (int t9 = (kHW3 ? 0 : 4); t9 < (kHW3 ? 9 : 5); ++t9) {
             const int kh = t9 / 3, kw = t9 - 3 * kh;
             uint32_t b_lo, wslot = 0;
-            if (kResident) b_lo = b_lo0 + (uint32_t)(k3 ? kd * 9 + t9 : 0) * (TAPB >> 4);
+            if (kResident) b_lo = b_lo0 + (uint32_t)(k3 ? kd * 9 + t9 : (kHW3 ? t9 : 0)) * (TAPB >> 4);
             else {
               wslot = wc % NWS;
               tc::mbar_wait(&w_full[wslot], (wc / NWS) & 1);
@@ -827,7 +828,8 @@ ss_encode_tiled_fn ss_get_encode_tiled() {
   return fn;
 }
 
-// kind: 0 = Conv3d k3 s1, 1 = Conv3d k1, 2 = Conv3d k3 s2 (phase-split input), 3 = ConvTranspose3d k3 s2 p1 op1.
+// kind: 0 = Conv3d k3 s1, 1 = Conv3d k1, 2 = Conv3d k3 s2 (phase-split input), 3 = ConvTranspose3d k3 s2 p1 op1,
+//       4 = Conv2d k3 s1 p1 on a depth-1 volume (9 in-plane taps).
 // Returns the Cout tile N the kernel uses (weights are packed [ceil(Cout/N)][taps][Cin/8][N][8]); 0 = unsupported.
 extern "C" int ss_conv3d_tc_ntile(int kind, int Cin, int Cout) {
   switch (kind) {
@@ -844,6 +846,10 @@ extern "C" int ss_conv3d_tc_ntile(int kind, int Cin, int Cout) {
       if (Cin == 64 && Cout == 128) return 128;
       return 0;
     case 3:
+      if (Cin == 128 && Cout == 64) return 64;
+      if (Cin == 64 && Cout == 32) return 32;
+      return 0;
+    case 4:                                        // concat_feature (SemStereo.py:221-223): 128 -> 64 -> 32 at 1/4 resolution
       if (Cin == 128 && Cout == 64) return 64;
       if (Cin == 64 && Cout == 32) return 32;
       return 0;
@@ -872,6 +878,8 @@ extern "C" int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight
   SS_REQUIRE(!skip_weight_or_null || (residual_s2d_or_null && Cout == N && (reinterpret_cast<uintptr_t>(skip_weight_or_null) & 15) == 0),
              "ss_conv3d_tc: a fused skip conv needs its phase-split input as `residual` and Cout == the layer's tile");
   SS_REQUIRE(kind != 2 || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "ss_conv3d_tc: stride-2 layer needs even input dims");
+  SS_REQUIRE(kind != 4 || D == 1, "ss_conv3d_tc: the 2-D layer (kind 4) takes a depth-1 volume");
+  SS_REQUIRE(kind >= 0 && kind <= 4, "ss_conv3d_tc: unknown kind %d", kind);
   TcP p;
   p.w = reinterpret_cast<const __nv_bfloat16*>(weight_packed);
   p.scale = scale_or_null; p.shift = shift_or_null; p.gate = gate_blocked_or_null;
@@ -905,6 +913,9 @@ extern "C" int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight
     case 2:
       if (Cin == 32) return launch_s2<32, 64, 2, 27>(tm, p, st);
       return launch_s2<64, 128, 2, 2>(tm, p, st);
+    case 4:
+      if (Cin == 128) return launch_s1<128, 64, 3, 2, 9>(tm, p, st);
+      return launch_s1<64, 32, 4, 9, 9>(tm, p, st);
     default:
       if (Cin == 128) return launch_t2<128, 64, 3, 2, 2>(tm, p, st);
       return launch_t2<64, 32, 3, 27, 4>(tm, p, st);

@@ -76,7 +76,7 @@ class ShardedHotPath:
         order = ("f8_l", "f8_r", "f4_l", "f4_r", "cf_l", "cf_r", "spx_pred", "pred_label")
         if not presharded:
             global_batch = inputs[order[0]].shape[0]
-            inputs = {k: shard(inputs[k], self.rank, self.world) for k in order}
-        out = self.path(*[inputs[k] for k in order])
+            inputs = {k: shard(inputs[k], self.rank, self.world) for k in order if inputs.get(k) is not None}
+        out = self.path(*[inputs.get(k) for k in order])
         key = "pred_att_up" if self.path.att_weights_only else "pred_up"
         return gather_batch(out[key], global_batch, self.group)

@@ -130,6 +130,9 @@ class DisparityHotPath(nn.Module):
         self.classif = nn.Sequential(_convbn3d(32, 32, 3, 1, 1), nn.ReLU(), nn.Conv3d(32, 1, 3, 1, 1, bias=False))
         self.concat_stem = _ConvBN(nn.Conv3d(64, 32, 3, 1, 1, bias=False), nn.BatchNorm3d(32))
         self.ssr_upsample = _SSRParams(num_classes)
+        # concat_feature (SemStereo.py:221-223): used when the caller does not supply cf_l / cf_r
+        self.concat_feature = nn.Sequential(_ConvBN(nn.Conv2d(128, 64, 3, 1, 1, bias=False), nn.BatchNorm2d(64)),
+                                            nn.Conv2d(64, 32, 3, 1, 1, bias=False))
         self._cache = None
         self.eval()
         for p in self.parameters():
@@ -221,12 +224,32 @@ class DisparityHotPath(nn.Module):
             c[ca + ".s0"], c[ca + ".t0"] = bn_affine(m[0].bn)
             c[ca + ".w1"] = m[1].weight.detach().float().reshape(m[1].out_channels, -1).contiguous()
             c[ca + ".b1"] = m[1].bias.detach().float().contiguous()
+        cf0, cf1 = self.concat_feature[0], self.concat_feature[1]
+        c["cf0.scale"], c["cf0.shift"] = bn_affine(cf0.bn)
+        if bf16:
+            c["cf0.tc"] = tc.pack_weight(cf0.conv.weight.detach().float(), tc.C2D)
+            c["cf1.tc"] = tc.pack_weight(cf1.weight.detach().float(), tc.C2D)
+        else:      # fp32 mode: the 2-D 3x3 conv as the centre depth plane of a 3x3x3 kernel on a depth-1 volume
+            for name, w in (("cf0", cf0.conv.weight), ("cf1", cf1.weight)):
+                w3 = w.detach().float().new_zeros((w.shape[0], w.shape[1], 3, 3, 3))
+                w3[:, :, 1] = w.detach().float()
+                c[name + ".w"] = ops.pack_conv3d_weight(w3)
         c["patch.w"] = self.patch.weight.detach().float().reshape(32, 9).contiguous()
         c["ssr"] = pack_ssr(self.ssr_upsample)
         self._cache = c
         return c
 
     # ------------------------------------------------------------------------------------------
+    def _concat_feature(self, c, f4):
+        """concat_feature(features[1]) (SemStereo.py:314-315): (B,128,H/4,W/4) -> (B,32,H/4,W/4) fp32."""
+        with ops.label("concat_feature"):
+            x = f4.unsqueeze(2)
+            if self.precision == "bf16":
+                y = tc.conv3d_tc(tc.C2D, tc.to_blocked_bf16(x), c["cf0.tc"], 64, c["cf0.scale"], c["cf0.shift"], relu=True)
+                return tc.conv3d_tc(tc.C2D, y, c["cf1.tc"], 32, out_mode=tc.F32).squeeze(2)
+            y = ops.conv3d_f32(x, c["cf0.w"], c["cf0.scale"], c["cf0.shift"], k=3, relu=True)
+            return ops.conv3d_f32(y, c["cf1.w"], k=3).squeeze(2)
+
     def _gate_logits(self, c, name, im):
         y = ops.pointwise_conv2d(im, c[name + ".w0"], c[name + ".s0"], c[name + ".t0"], relu=True)
         return ops.pointwise_conv2d(y, c[name + ".w1"], None, c[name + ".b1"], relu=False)
@@ -294,6 +317,7 @@ class DisparityHotPath(nn.Module):
 
     @torch.no_grad()
     def forward(self, f8_l, f8_r, f4_l, f4_r, cf_l, cf_r, spx_pred, pred_label, keep: bool = False):
+        """cf_l / cf_r may be None: concat_feature(f4_*) is then computed here (tensor cores in bf16 mode)."""
         c = self._packed()
         m8, m4 = self.maxdisp // 8, self.maxdisp // 4
         out = {}
@@ -319,6 +343,10 @@ class DisparityHotPath(nn.Module):
         if self.att_weights_only:
             return out
         # --- sparse concat volume + aggregation (SemStereo.py:314-324) ---
+        if cf_l is None:
+            cf_l = self._concat_feature(c, f4_l)
+        if cf_r is None:
+            cf_r = self._concat_feature(c, f4_r)
         gate4 = self._gate_logits(c, "concat_feature_att_4", f4_l)
         if self.precision == "bf16":
             volume = tc.sparse_concat_volume_blocked(cf_l, cf_r, disp_topk, att_topk)      # (B,8,24,H/4,W/4,8) bf16

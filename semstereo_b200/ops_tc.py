@@ -10,7 +10,7 @@ import torch
 from . import _lib
 from .ops import _call, _ptr, _require_cuda
 
-S1, K1, S2, T2 = 0, 1, 2, 3          # layer kinds of ss_conv3d_tc
+S1, K1, S2, T2, C2D = 0, 1, 2, 3, 4   # layer kinds of ss_conv3d_tc (C2D: Conv2d 3x3 on a depth-1 volume)
 
 
 def _require_bf16(t, ndim):
@@ -61,6 +61,8 @@ def pack_weight(w, kind):
     w: (Cout,Cin,k,k,k) for kinds S1/K1/S2, ConvTranspose3d (Cin,Cout,3,3,3) for T2."""
     if kind == T2:
         w = w.permute(1, 0, 2, 3, 4)                                   # -> (Cout, Cin, kd, kh, kw), taps index the weight directly
+    if kind == C2D:
+        w = w.reshape(w.shape[0], w.shape[1], 1, 3, 3)                 # Conv2d (Cout,Cin,3,3): 9 in-plane taps
     cout, cin = w.shape[:2]
     taps = w.shape[2] * w.shape[3] * w.shape[4]
     n = ntile(kind, cin, cout)
@@ -160,7 +162,7 @@ def conv3d_tc(kind, xb, w_tc, cout, scale=None, shift=None, gate_blocked=None, r
         Do, Ho, Wo = (2 * D, 2 * H, 2 * W) if kind == T2 else (D, H, W)
     cin = C8 * 8
     n = ntile(kind, cin, cout)
-    taps = 1 if kind == K1 else 27
+    taps = 1 if kind == K1 else (9 if kind == C2D else 27)
     if n == 0 or w_tc.dtype != torch.bfloat16 or tuple(w_tc.shape) != (-(-cout // n), taps, C8, n, 8) or not w_tc.is_contiguous():
         raise ValueError("conv3d_tc: weight must come from pack_weight(w, kind) for this layer")
     for t in (scale, shift, gate_blocked):

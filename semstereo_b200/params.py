@@ -67,6 +67,11 @@ def hotpath_param_shapes(num_classes: int = 6) -> "OrderedDict[str, tuple]":
         _bn(d, f"ssr_upsample.{k}.1", nc)
     d["ssr_upsample.conv3.weight"] = (1, nc, 1, 1)
     d["ssr_upsample.conv3.bias"] = (1,)
+    # concat_feature (SemStereo.py:221-223): the 2-D convs that feed the sparse concat volume -- first step of the widening into
+    # SURVEY section 8(f) rank 1.  Appended LAST so the seeded values of every tensor above are unchanged.
+    d["concat_feature.0.conv.weight"] = (64, 128, 3, 3)
+    _bn(d, "concat_feature.0.bn", 64)
+    d["concat_feature.1.weight"] = (32, 64, 3, 3)
     return d
 
 

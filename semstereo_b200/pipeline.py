@@ -31,8 +31,9 @@ class HostPipeline:
 
     def _staging(self, i, batch):
         st = self._stage[i]
-        if st is None or any(st[k].shape != batch[k].shape for k in ORDER):
-            st = {k: torch.empty(batch[k].shape, dtype=torch.float32, device=self.dev) for k in ORDER}
+        keys = [k for k in ORDER if batch.get(k) is not None]          # cf_l / cf_r are optional (computed on the device if absent)
+        if st is None or set(st) != set(keys) or any(st[k].shape != batch[k].shape for k in keys):
+            st = {k: torch.empty(batch[k].shape, dtype=torch.float32, device=self.dev) for k in keys}
             self._stage[i] = st
             # the caching allocator may hand out blocks that kernels already queued on the compute stream still use
             # (stream-ordered reuse): order the first copy into a fresh staging set after that work, once
@@ -55,12 +56,12 @@ class HostPipeline:
             with torch.cuda.stream(self.copy_stream):
                 if n >= self.depth:
                     self.copy_stream.wait_event(self._consumed[i])     # compute of the previous tenant has read the staging set
-                for k in ORDER:
+                for k in st:
                     st[k].copy_(batch[k], non_blocking=True)
                 self._copied[i].record(self.copy_stream)
-            self.h2d_bytes += sum(batch[k].numel() * 4 for k in ORDER)
+            self.h2d_bytes += sum(batch[k].numel() * 4 for k in st)
             compute.wait_event(self._copied[i])
-            out = self.path(*[st[k] for k in ORDER])[self.key]
+            out = self.path(*[st.get(k) for k in ORDER])[self.key]
             self._consumed[i].record(compute)
             if self.post is not None:
                 out = self.post(out)

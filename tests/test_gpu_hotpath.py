@@ -10,6 +10,7 @@ import pytest
 import torch
 
 from oracle import hotpath as oh
+from oracle import ops as oo
 from semstereo_b200.params import make_inputs, make_params
 
 pytestmark = pytest.mark.gpu
@@ -142,3 +143,24 @@ def test_full_size_properties():
     # att_weights_only is a strict prefix of the full path
     out_a = run(build(64, True, True, 20.0), inp, keep=False)
     assert torch.equal(out_a["pred_att_up"], out["pred_att_up"])
+
+
+def test_concat_feature_inside_the_path():
+    """cf_l / cf_r omitted: concat_feature(f4_*) (SemStereo.py:314-315) is computed on the device; same result as handing the
+    oracle's concat features in, and the whole path still matches the oracle run that computes them itself."""
+    p = make_params(seed=9, peaked=20.0, gamma=0.1)
+    inp = make_inputs(11, 1, 128, 128)
+    m = DisparityHotPath(64, False, True)
+    m.load_state_dict(p, strict=True)
+    m = m.to(DEV)
+    cf = m._concat_feature(m._packed(), inp["f4_l"].to(DEV)).cpu()
+    cf_ref = oo.concat_feature(inp["f4_l"], p)
+    assert maxerr(cf, cf_ref) <= 1e-4 * max(1.0, cf_ref.abs().max().item())
+    inp_nocf = {k: v for k, v in inp.items() if k not in ("cf_l", "cf_r")}
+    ref = oh.forward(p, inp_nocf, 64, signed=True, keep=True)
+    out = m(*[inp_nocf[k].to(DEV) if k in inp_nocf else None for k in ORDER], keep=True)
+    torch.cuda.synchronize()
+    out = {k: v.cpu() for k, v in out.items() if v is not None}
+    assert bool((out["ind_k"] == ref["ind_k"]).all())
+    assert maxerr(out["volume"], ref["volume"]) <= 1e-4 * max(1.0, ref["volume"].abs().max().item())
+    assert maxerr(out["cost"], ref["cost"]) <= 2e-2

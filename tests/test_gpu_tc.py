@@ -175,3 +175,22 @@ def test_conv_transposed_with_fused_skip_conv(Cin, Cout, B, D, H, W):
                        residual_s2d=tc.to_blocked_bf16(skip.to(DEV), s2d=True), skip_weight=tc.pack_skip_weight(wr, s2).to(DEV), relu=True)
     torch.cuda.synchronize()
     check(tc.from_blocked_bf16(out).cpu(), ref, True)
+
+
+@pytest.mark.parametrize("Cin,Cout,B,H,W", [(128, 64, 1, 16, 8), (128, 64, 2, 40, 24), (64, 32, 1, 32, 32), (64, 32, 2, 20, 44),
+                                            (128, 64, 1, 256, 256)])
+def test_conv2d_3x3(Cin, Cout, B, H, W):
+    """kind 4: a 2-D 3x3 convolution (concat_feature, SemStereo.py:221-223) as a depth-1 volume with 9 taps."""
+    g = torch.Generator().manual_seed(Cin + H)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5
+    scale, shift = torch.rand(Cout, generator=g) + 0.5, 0.3 * torch.randn(Cout, generator=g)
+    y = F.conv2d(bf(x), bf(w), None, padding=1)
+    ref = F.relu(y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    xb = tc.to_blocked_bf16(x.unsqueeze(2).to(DEV))
+    wt = tc.pack_weight(w, tc.C2D).to(DEV)
+    out = tc.conv3d_tc(tc.C2D, xb, wt, Cout, scale.to(DEV), shift.to(DEV), relu=True)
+    plain = tc.conv3d_tc(tc.C2D, xb, wt, Cout, out_mode=tc.F32)
+    torch.cuda.synchronize()
+    check(tc.from_blocked_bf16(out).cpu().squeeze(2), ref, True)
+    check(plain.cpu().squeeze(2), y, False)
