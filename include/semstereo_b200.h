@@ -74,6 +74,8 @@ SS_API int ss_from_blocked_bf16(const void* in_blocked, float* out_ncdhw, int B,
 SS_API int ss_blocked_to_s2d(const void* in_blocked, void* out_s2d, int B, int C, int D, int H, int W, void* stream);
 /* The 3-D layers of the hourglass stack (same layers as ss_conv3d_f32) + folded eval-BN + residual + ReLU + channelAtt gate.
  * kind 4: Conv2d k3 s1 p1 on a depth-1 volume (D = 1, 9 taps) -- the two convs of `concat_feature` (SemStereo.py:221-223, 314-315).
+ * kind 5: Conv3d k3 s1 p1 for narrow layers (Cout == 32 or 64, Cin 32 / 64) with the three depth taps folded into the GEMM N:
+ *         weight_packed is [9 in-plane taps][Cin/8][3*Cout (j*Cout + co, kd = 2 - j)][8]; same results as kind 0.
  * kind 0: Conv3d k3 s1 p1;  1: Conv3d k1;  2: Conv3d k3 s2 p1 (input tensor phase-split);  3: ConvTranspose3d k3 s2 p1 op1
  * (residual_s2d: the skip tensor in phase-split layout at OUTPUT resolution, added before the ReLU; SemStereo.py:141-142).
  * D,H,W: input dims of the layer (kind 2: of the un-split input).  weight_packed: bf16 [ceil(Cout/N)][taps][Cin/8][N][8],

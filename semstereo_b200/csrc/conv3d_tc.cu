@@ -117,9 +117,10 @@ __device__ __forceinline__ void epilogue_store32(const TcP& p, float (&v)[32], c
 }
 
 // Common prologue: barriers, TMEM, folded-BN staging.
-#define TC_KERNEL_PROLOGUE(NSLOTS, NWSLOTS, RESIDENT)                                                                      \
+#define TC_KERNEL_PROLOGUE(NSLOTS, NWSLOTS, RESIDENT) TC_KERNEL_PROLOGUE_N(NSLOTS, NWSLOTS, RESIDENT, 2)
+#define TC_KERNEL_PROLOGUE_N(NSLOTS, NWSLOTS, RESIDENT, NACC)                                                              \
   extern __shared__ __align__(1024) uint8_t smem[];                                                                        \
-  __shared__ __align__(8) uint64_t a_full[NSLOTS], a_empty[NSLOTS], w_full[NWSLOTS], w_empty[NWSLOTS], acc_full[2], acc_empty[2]; \
+  __shared__ __align__(8) uint64_t a_full[NSLOTS], a_empty[NSLOTS], w_full[NWSLOTS], w_empty[NWSLOTS], acc_full[NACC], acc_empty[NACC]; \
   __shared__ uint32_t tmem_base_s;                                                                                         \
   __shared__ float s_scale[N], s_shift[N];                                                                                 \
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;                                                              \
@@ -133,7 +134,7 @@ __device__ __forceinline__ void epilogue_store32(const TcP& p, float (&v)[32], c
     tc::prefetch_tmap(&tmA);                                                                                               \
     for (int i = 0; i < NSLOTS; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1); }                      \
     for (int i = 0; i < ((RESIDENT) ? 1 : NWSLOTS); ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }  \
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }                     \
+    for (int i = 0; i < NACC; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }                  \
     tc::fence_barrier_init();                                                                                              \
   }                                                                                                                        \
   if (warp == 2) tc::tmem_alloc(&tmem_base_s, TMEM_COLS);                                                                  \
@@ -296,6 +297,169 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_const
           }
           if (!valid || nt * N + j * 32 >= p.cout_valid) continue;
           epilogue_store32(p, v, s_scale + j * 32, s_shift + j * 32, nt * N + j * 32, b, d_out, h, w, p.D, p.H, p.W, nullptr);
+        }
+      }
+    }
+  }
+  TC_KERNEL_EPILOGUE()
+}
+
+// =====================================================================================================================
+// s1f: Conv3d k3 s1 p1 for the narrow layers (Cout = 32 / 64) with the three DEPTH taps folded into the GEMM's N.
+// An N = 32 MMA reads 4 KB of A and 1 KB of B from shared memory for 128x32x16 MACs, so the shared-memory read port (not the
+// tensor pipe) bounds it.  Here ONE MMA of N = 3*Cout multiplies an in-plane tap of an input slice by the weights of all three
+// depth taps: column block j of the product belongs to output depth d_in - 1 + j (kd = 2 - j).  The accumulators of
+// consecutive output depths are consecutive column blocks of a ring over all 512 TMEM columns, so the three partial
+// products land directly in the three accumulators they belong to: 3x fewer MMAs and 3x fewer A bytes per MAC; every input
+// slice is used exactly once.  One instruction carries one accumulate flag, so blocks are ALWAYS accumulated into and the
+// epilogue warps write zeros back (tcgen05.st) into a block after draining it.  Where the three blocks wrap around the ring
+// (or the depth range is cut by the volume / chunk boundary) the MMA is split into two narrower ones / narrowed.
+// Weights: [9 in-plane taps][CIN/8][3*N (j*N + co)][8].
+// =====================================================================================================================
+template <int CIN, int N, int NS, int NWS>
+__global__ void __launch_bounds__(256, 1) conv3d_tc_s1f_kernel(const __grid_constant__ CUtensorMap tmA, const TcP p) {
+  constexpr bool kResident = (NWS == 9);
+  constexpr uint32_t SLICE = (CIN / 8) * TILE_B;
+  constexpr uint32_t TAPB = CIN * 3 * N * 2;
+  constexpr int KS = CIN / 16;
+  constexpr uint32_t LBO_A = TILE_B, SBO_A = WW * 16, LBO_B = 3 * N * 16, SBO_B = 128;
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t NB = 512 / N;                     // accumulator blocks in the TMEM ring
+  TC_KERNEL_PROLOGUE_N(NS, NWS, kResident, NB)
+  uint8_t* Abase = smem;
+  uint8_t* Wbase = smem + NS * SLICE;
+  if (warp >= 4) {                                     // all accumulator blocks start out zero
+#pragma unroll 1
+    for (uint32_t c = 0; c < 512; c += 32) tc::tmem_zero32(tmem_base + ((uint32_t)((warp - 4) * 32) << 16) + c);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+
+  if (warp == 0 && lane == 0) {
+    // ===== input-slice producer =====
+    uint32_t g = 0;
+    for (int s = cta_s; s < p.items; s += cta_stride) {
+      int b, h0, w0, dlo, dhi;
+      decode_item(p, s, b, h0, w0, dlo, dhi);
+      const int din0 = max(dlo - 1, 0), din1 = min(dhi, p.D - 1);
+      for (int d_in = din0; d_in <= din1; ++d_in, ++g) {
+        const uint32_t slot = g % NS;
+        tc::mbar_wait(&a_empty[slot], ((g / NS) & 1) ^ 1);
+        tc::mbar_expect_tx(&a_full[slot], SLICE);
+        tc::tma_load_4d(Abase + slot * SLICE, &tmA, &a_full[slot], (w0 - 1) * 8, h0 - 1, d_in, b * (CIN / 8));
+      }
+    }
+  } else if (warp == 3 && lane == 0) {
+    // ===== weight producer =====
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w);
+    if (kResident) {
+      if (cta_s < p.items) {
+        tc::mbar_expect_tx(&w_full[0], 9 * TAPB);
+        for (int t9 = 0; t9 < 9; ++t9) tc::bulk_load(Wbase + t9 * TAPB, wsrc + (size_t)t9 * TAPB, TAPB, &w_full[0]);
+      }
+    } else {
+      uint32_t wc = 0;
+      for (int s = cta_s; s < p.items; s += cta_stride) {
+        int b, h0, w0, dlo, dhi;
+        decode_item(p, s, b, h0, w0, dlo, dhi);
+        const int din0 = max(dlo - 1, 0), din1 = min(dhi, p.D - 1);
+        for (int d_in = din0; d_in <= din1; ++d_in)
+          for (int t9 = 0; t9 < 9; ++t9, ++wc) {
+            const uint32_t slot = wc % NWS;
+            tc::mbar_wait(&w_empty[slot], ((wc / NWS) & 1) ^ 1);
+            tc::mbar_expect_tx(&w_full[slot], TAPB);
+            tc::bulk_load(Wbase + slot * TAPB, wsrc + (size_t)t9 * TAPB, TAPB, &w_full[slot]);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const bool leader = tc::elect_one();
+    const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(Abase), LBO_A), a_hi = tc::desc_hi(SBO_A);
+    const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(Wbase), LBO_B), b_hi = tc::desc_hi(SBO_B);
+    if (kResident && cta_s < p.items) tc::mbar_wait(&w_full[0], 0);
+    uint32_t g = 0, wc = 0;
+    uint32_t acc_base = 0;       // unwrapped ring index of the accumulator of (this item, dlo)
+    uint32_t acquired = 0;       // accumulator blocks handed to the MMAs so far (unwrapped)
+    for (int s = cta_s; s < p.items; s += cta_stride) {
+      int b, h0, w0, dlo, dhi;
+      decode_item(p, s, b, h0, w0, dlo, dhi);
+      const int din0 = max(dlo - 1, 0), din1 = min(dhi, p.D - 1);
+#pragma unroll 1
+      for (int d_in = din0; d_in <= din1; ++d_in, ++g) {
+        const int j0 = max(0, dlo - d_in + 1), j1 = min(3, dhi - d_in + 1);       // column blocks [j0, j1) exist
+        const uint32_t u0 = acc_base + (uint32_t)(d_in - 1 + j0 - dlo), nb = (uint32_t)(j1 - j0);
+        while (acquired < u0 + nb) {
+          tc::mbar_wait(&acc_empty[acquired % NB], ((acquired / NB) & 1) ^ 1);
+          ++acquired;
+        }
+        const uint32_t slot = g % NS;
+        tc::mbar_wait(&a_full[slot], (g / NS) & 1);
+        tc::fence_after_sync();
+        const uint32_t blk = u0 % NB, n1 = min(nb, NB - blk), n2 = nb - n1;
+        const uint32_t id1 = n1 == 1 ? tc::make_idesc_bf16(128, N) : n1 == 2 ? tc::make_idesc_bf16(128, 2 * N) : tc::make_idesc_bf16(128, 3 * N);
+        const uint32_t id2 = n2 == 1 ? tc::make_idesc_bf16(128, N) : tc::make_idesc_bf16(128, 2 * N);
+        const uint32_t d1 = tmem_base + blk * N, d2 = tmem_base;
+        const uint32_t a_lo = a_lo0 + slot * (SLICE >> 4);
+        const uint32_t brow1 = (uint32_t)j0 * (N / 8) * (SBO_B >> 4), brow2 = (uint32_t)(j0 + n1) * (N / 8) * (SBO_B >> 4);
+#pragma unroll
+        for (int t9 = 0; t9 < 9; ++t9) {
+          const int kh = t9 / 3, kw = t9 - 3 * kh;
+          uint32_t b_lo, wslot = 0;
+          if (kResident) b_lo = b_lo0 + (uint32_t)t9 * (TAPB >> 4);
+          else {
+            wslot = wc % NWS;
+            tc::mbar_wait(&w_full[wslot], (wc / NWS) & 1);
+            tc::fence_after_sync();
+            b_lo = b_lo0 + wslot * (TAPB >> 4);
+          }
+          if (leader) {
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+              const uint32_t a = a_lo + (uint32_t)((kh * WW + kw) * 16 + ks * 2 * LBO_A) / 16;
+              const uint32_t bb = b_lo + (uint32_t)(ks * 2 * LBO_B) / 16;
+              tc::mma_bf16_lohi(d1, a, a_hi, bb + brow1, b_hi, id1, 1u);
+              if (n2) tc::mma_bf16_lohi(d2, a, a_hi, bb + brow2, b_hi, id2, 1u);
+            }
+            if (!kResident) tc::mma_commit(&w_empty[wslot]);
+          }
+          if (!kResident) ++wc;
+        }
+        if (leader) {
+          tc::mma_commit(&a_empty[slot]);
+          if (d_in - 1 >= dlo) tc::mma_commit(&acc_full[(acc_base + (uint32_t)(d_in - 1 - dlo)) % NB]);
+          if (d_in == din1 && din1 == dhi - 1) tc::mma_commit(&acc_full[(acc_base + (uint32_t)(d_in - dlo)) % NB]);
+        }
+        __syncwarp();
+      }
+      acc_base += (uint32_t)(dhi - dlo);
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    const int e = warp - 4, m = e * 32 + lane, hh = m >> 3, ww = m & 7;
+    uint32_t u = 0;
+    for (int s = cta_s; s < p.items; s += cta_stride) {
+      int b, h0, w0, dlo, dhi;
+      decode_item(p, s, b, h0, w0, dlo, dhi);
+      const int h = h0 + hh, w = w0 + ww;
+      const bool valid = h < p.H && w < p.W;
+      for (int d_out = dlo; d_out < dhi; ++d_out, ++u) {
+        const uint32_t blk = u % NB;
+        tc::mbar_wait(&acc_full[blk], (u / NB) & 1);
+        tc::fence_after_sync();
+#pragma unroll 1
+        for (int j = 0; j < N / 32; ++j) {
+          float v[32];
+          const uint32_t ta = tmem_base + ((uint32_t)(e * 32) << 16) + blk * N + j * 32;
+          tc::tmem_ld32(ta, v);
+          tc::tmem_zero32(ta);
+          if (j == N / 32 - 1) {            // block drained and zeroed: hand it back before the stores
+            tc::fence_before_sync();
+            tc::mbar_arrive(&acc_empty[blk]);
+          }
+          if (!valid) continue;
+          epilogue_store32(p, v, s_scale + j * 32, s_shift + j * 32, j * 32, b, d_out, h, w, p.D, p.H, p.W, nullptr);
         }
       }
     }
@@ -777,6 +941,12 @@ int launch_s1(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
   return launch_tc(conv3d_tc_s1_kernel<CIN, N, NS, NWS, TAPS>, smem, tm, p, TAPS == 27 ? 0.35 : 0.0, st, "ss_conv3d_tc(s1)");
 }
 template <int CIN, int N, int NS, int NWS>
+int launch_s1f(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
+  constexpr size_t smem = (size_t)NS * (CIN / 8) * TILE_B + (size_t)NWS * CIN * 3 * N * 2;
+  static_assert(smem <= 227 * 1024 - 2048, "shared memory budget");
+  return launch_tc(conv3d_tc_s1f_kernel<CIN, N, NS, NWS>, smem, tm, p, 1.4, st, "ss_conv3d_tc(s1f)");
+}
+template <int CIN, int N, int NS, int NWS>
 int launch_s2(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
   constexpr size_t smem = (size_t)NS * 4 * (CIN / 8) * TILE_B + (size_t)NWS * CIN * N * 2;
   static_assert(smem <= 227 * 1024 - 2048, "shared memory budget");
@@ -829,7 +999,8 @@ ss_encode_tiled_fn ss_get_encode_tiled() {
 }
 
 // kind: 0 = Conv3d k3 s1, 1 = Conv3d k1, 2 = Conv3d k3 s2 (phase-split input), 3 = ConvTranspose3d k3 s2 p1 op1,
-//       4 = Conv2d k3 s1 p1 on a depth-1 volume (9 in-plane taps).
+//       4 = Conv2d k3 s1 p1 on a depth-1 volume (9 in-plane taps),
+//       5 = Conv3d k3 s1 with the depth taps folded into N (Cout == N in {32, 64}; weights [9][Cin/8][3N][8]).
 // Returns the Cout tile N the kernel uses (weights are packed [ceil(Cout/N)][taps][Cin/8][N][8]); 0 = unsupported.
 extern "C" int ss_conv3d_tc_ntile(int kind, int Cin, int Cout) {
   switch (kind) {
@@ -852,6 +1023,9 @@ extern "C" int ss_conv3d_tc_ntile(int kind, int Cin, int Cout) {
     case 4:                                        // concat_feature (SemStereo.py:221-223): 128 -> 64 -> 32 at 1/4 resolution
       if (Cin == 128 && Cout == 64) return 64;
       if (Cin == 64 && Cout == 32) return 32;
+      return 0;
+    case 5:
+      if ((Cin == 32 || Cin == 64) && (Cout == 32 || Cout == 64)) return Cout;
       return 0;
   }
   return 0;
@@ -879,7 +1053,7 @@ extern "C" int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight
              "ss_conv3d_tc: a fused skip conv needs its phase-split input as `residual` and Cout == the layer's tile");
   SS_REQUIRE(kind != 2 || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "ss_conv3d_tc: stride-2 layer needs even input dims");
   SS_REQUIRE(kind != 4 || D == 1, "ss_conv3d_tc: the 2-D layer (kind 4) takes a depth-1 volume");
-  SS_REQUIRE(kind >= 0 && kind <= 4, "ss_conv3d_tc: unknown kind %d", kind);
+  SS_REQUIRE(kind >= 0 && kind <= 5, "ss_conv3d_tc: unknown kind %d", kind);
   TcP p;
   p.w = reinterpret_cast<const __nv_bfloat16*>(weight_packed);
   p.scale = scale_or_null; p.shift = shift_or_null; p.gate = gate_blocked_or_null;
@@ -916,6 +1090,11 @@ extern "C" int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight
     case 4:
       if (Cin == 128) return launch_s1<128, 64, 3, 2, 9>(tm, p, st);
       return launch_s1<64, 32, 4, 9, 9>(tm, p, st);
+    case 5:
+      if (Cin == 32 && Cout == 32) return launch_s1f<32, 32, 6, 9>(tm, p, st);
+      if (Cin == 64 && Cout == 32) return launch_s1f<64, 32, 4, 9>(tm, p, st);
+      if (Cin == 32 && Cout == 64) return launch_s1f<32, 64, 6, 9>(tm, p, st);
+      return launch_s1f<64, 64, 4, 4>(tm, p, st);
     default:
       if (Cin == 128) return launch_t2<128, 64, 3, 2, 2>(tm, p, st);
       return launch_t2<64, 32, 3, 27, 4>(tm, p, st);

@@ -125,6 +125,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Writes zeros to 32 consecutive TMEM columns of this warp's 32 lanes and waits for the store to land.
+__device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
+  const uint32_t z = 0;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      :: "r"(taddr), "r"(z)
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // ---- descriptors ------------------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, K-major, no swizzle ("interleave" canonical layout, in 16-byte units:
 // ((8,n),2):((1,SBO),LBO)): a core matrix is 8 rows x 16 bytes stored contiguously (128 B); SBO = byte distance between

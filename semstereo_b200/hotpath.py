@@ -177,6 +177,9 @@ class DisparityHotPath(nn.Module):
             if bf16:      # tensor-core packing: kind from the layer geometry
                 k, st = convmod.kernel_size[0], convmod.stride[0]
                 kind = tc.T2 if transposed else (tc.K1 if k == 1 else (tc.S2 if st == 2 else tc.S1))
+                if kind == tc.S1 and tc.ntile(tc.S1F, w.shape[1], w.shape[0]) == w.shape[0]:
+                    kind = tc.S1F          # narrow layers: depth taps folded into the GEMM N (csrc/conv3d_tc.cu, s1f)
+                c[name + ".kind"] = kind
                 c[name + ".tc"] = tc.pack_weight(w, kind)
             else:
                 c[name + ".w"] = ops.pack_conv3d_weight(w, transposed)
@@ -265,7 +268,7 @@ class DisparityHotPath(nn.Module):
     # ---- bf16 tensor-core flavour: activations stay in the blocked / phase-split bf16 layouts between the layers ----
     def _tc(self, c, name, kind, x, cout, relu=True, gate=None, residual=None, out_mode=tc.BLOCKED):
         with ops.label(name):
-            return tc.conv3d_tc(kind, x, c[name + ".tc"], cout, c.get(name + ".scale"), c.get(name + ".shift"), gate, residual,
+            return tc.conv3d_tc(c.get(name + ".kind", kind), x, c[name + ".tc"], cout, c.get(name + ".scale"), c.get(name + ".shift"), gate, residual,
                                 relu=relu, out_mode=out_mode)
 
     def _hourglass_tc(self, c, hg, x_s2d):

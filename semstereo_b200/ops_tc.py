@@ -10,7 +10,7 @@ import torch
 from . import _lib
 from .ops import _call, _ptr, _require_cuda
 
-S1, K1, S2, T2, C2D = 0, 1, 2, 3, 4   # layer kinds of ss_conv3d_tc (C2D: Conv2d 3x3 on a depth-1 volume)
+S1, K1, S2, T2, C2D, S1F = 0, 1, 2, 3, 4, 5   # layer kinds of ss_conv3d_tc (C2D: Conv2d 3x3 on a depth-1 volume; S1F: S1 with depth taps folded into N)
 
 
 def _require_bf16(t, ndim):
@@ -63,6 +63,13 @@ def pack_weight(w, kind):
         w = w.permute(1, 0, 2, 3, 4)                                   # -> (Cout, Cin, kd, kh, kw), taps index the weight directly
     if kind == C2D:
         w = w.reshape(w.shape[0], w.shape[1], 1, 3, 3)                 # Conv2d (Cout,Cin,3,3): 9 in-plane taps
+    if kind == S1F:
+        # depth taps folded into N: [9 in-plane taps][Cin/8][3*Cout (j*Cout + co, kd = 2 - j)][8]
+        cout, cin = w.shape[:2]
+        if ntile(kind, cin, cout) != cout:
+            raise NotImplementedError(f"conv3d_tc: kind {kind} with (Cin={cin}, Cout={cout}) has no tensor-core configuration")
+        t = w.flip(2).reshape(cout, cin // 8, 8, 3, 9).permute(4, 1, 3, 0, 2)        # (t9, chunk, j, co, c8)
+        return t.reshape(9, cin // 8, 3 * cout, 8).contiguous().to(torch.bfloat16)
     cout, cin = w.shape[:2]
     taps = w.shape[2] * w.shape[3] * w.shape[4]
     n = ntile(kind, cin, cout)
@@ -163,7 +170,8 @@ def conv3d_tc(kind, xb, w_tc, cout, scale=None, shift=None, gate_blocked=None, r
     cin = C8 * 8
     n = ntile(kind, cin, cout)
     taps = 1 if kind == K1 else (9 if kind == C2D else 27)
-    if n == 0 or w_tc.dtype != torch.bfloat16 or tuple(w_tc.shape) != (-(-cout // n), taps, C8, n, 8) or not w_tc.is_contiguous():
+    wshape = (9, C8, 3 * cout, 8) if kind == S1F else (-(-cout // max(n, 1)), taps, C8, n, 8)
+    if n == 0 or w_tc.dtype != torch.bfloat16 or tuple(w_tc.shape) != wshape or not w_tc.is_contiguous():
         raise ValueError("conv3d_tc: weight must come from pack_weight(w, kind) for this layer")
     for t in (scale, shift, gate_blocked):
         if t is not None:

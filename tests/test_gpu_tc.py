@@ -194,3 +194,26 @@ def test_conv2d_3x3(Cin, Cout, B, H, W):
     torch.cuda.synchronize()
     check(tc.from_blocked_bf16(out).cpu().squeeze(2), ref, True)
     check(plain.cpu().squeeze(2), y, False)
+
+
+@pytest.mark.parametrize("Cin,Cout,B,D,H,W", [(32, 32, 1, 4, 16, 8), (64, 32, 2, 5, 20, 12), (64, 32, 1, 24, 64, 64), (32, 32, 1, 16, 128, 128),
+                                              (32, 64, 1, 6, 16, 24), (64, 64, 1, 12, 32, 32), (64, 64, 2, 20, 40, 24), (64, 32, 1, 40, 16, 16),
+                                              (32, 32, 3, 1, 16, 16), (64, 32, 1, 2, 24, 8)])
+def test_conv_k3_s1_depth_folded(Cin, Cout, B, D, H, W):
+    """kind 5 (depth taps folded into N, TMEM accumulator ring) gives what kind 0 gives; D = 40 wraps the 16-block ring twice."""
+    g = torch.Generator().manual_seed(Cin + Cout + D)
+    x = torch.randn(B, Cin, D, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) / (27 * Cin) ** 0.5
+    scale, shift = torch.rand(Cout, generator=g) + 0.5, 0.3 * torch.randn(Cout, generator=g)
+    gate = torch.randn(B, Cout, H, W, generator=g)
+    y = F.conv3d(bf(x), bf(w), None, padding=1)
+    ref = F.relu(y * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)) * torch.sigmoid(gate).unsqueeze(2)
+    xb = tc.to_blocked_bf16(x.to(DEV))
+    wt = tc.pack_weight(w, tc.S1F).to(DEV)
+    gb = tc.gate_sigmoid_blocked(gate.to(DEV))
+    for _ in range(2):          # twice: the second launch must not depend on TMEM state left by the first
+        out = tc.conv3d_tc(tc.S1F, xb, wt, Cout, scale.to(DEV), shift.to(DEV), gb, relu=True)
+        plain = tc.conv3d_tc(tc.S1F, xb, wt, Cout, out_mode=tc.F32)
+        torch.cuda.synchronize()
+        check(tc.from_blocked_bf16(out).cpu(), ref, True)
+        check(plain.cpu(), y, False)

@@ -11,7 +11,11 @@ LAYERS = [("concat_stem", tc.S1, 64, 32, 24, 256, 256), ("classif.0", tc.S1, 32,
           ("hourglass.conv3", tc.S2, 64, 128, 12, 128, 128), ("hourglass.conv4", tc.S1, 128, 128, 6, 64, 64),
           ("hourglass.conv5", tc.T2, 128, 64, 6, 64, 64), ("hourglass.conv6", tc.T2, 64, 32, 12, 128, 128),
           ("hourglass.redir1", tc.K1, 32, 32, 24, 256, 256), ("hourglass.redir2", tc.K1, 64, 64, 12, 128, 128),
-          ("classif_att_.0", tc.S1, 32, 32, 16, 128, 128), ("hourglass_att.conv2", tc.S1, 64, 64, 8, 64, 64)]
+          ("classif_att_.0", tc.S1, 32, 32, 16, 128, 128), ("hourglass_att.conv2", tc.S1, 64, 64, 8, 64, 64),
+          ("concat_stem[folded]", tc.S1F, 64, 32, 24, 256, 256), ("classif.0[folded]", tc.S1F, 32, 32, 24, 256, 256),
+          ("hourglass.conv2[folded]", tc.S1F, 64, 64, 12, 128, 128), ("classif_att_.0[folded]", tc.S1F, 32, 32, 16, 128, 128)]
+if len(sys.argv) > 1:
+    LAYERS = [l for l in LAYERS if any(a in l[0] for a in sys.argv[1:])]
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 res = []
 for B in (1, 8):
