@@ -81,6 +81,7 @@ def hbm_bytes(H, W, maxdisp, signed=True):
         "ss_sparse_concat_volume_blocked": 4 * (2 * 32 * p4 + 2 * 24 * p4) + 2 * 64 * 24 * p4,   # bf16 volume out
         "ss_regression_topk": 4 * (2 * 24 * p4 + p4),
         "ss_ssr_upsample": 4 * (p4 + 12 * p1 + p1),
+        "ss_ssr_upsample2": 4 * (2 * p4 + 12 * p1 + 2 * p1),      # two low-res maps in, spx + label once, two full-res maps out
     }
 
 

@@ -149,6 +149,10 @@ SS_API int ss_regression_topk(const float* cost, const float* disp_samples, floa
 SS_API int ss_ssr_param_count(int num_classes);
 SS_API int ss_ssr_upsample(const float* depth_low, const float* spx, const float* label, float* out, const float* packed_host, int B,
                            int h, int w, int num_classes, void* stream);
+/* The model's two SSR_upsample calls (SemStereo.py:312 pred_att, :324 pred; same spx / label) in one pass: the class gate is
+ * computed once per pixel.  out_a / out_b are bit-identical to two ss_ssr_upsample calls. */
+SS_API int ss_ssr_upsample2(const float* depth_low_a, const float* depth_low_b, const float* spx, const float* label, float* out_a,
+                            float* out_b, const float* packed_host, int B, int h, int w, int num_classes, void* stream);
 /* context_upsample (submodule_.py:311-323): depth_low (B,1,h,w), up_weights (B,9,4h,4w) -> out (B,4h,4w). */
 SS_API int ss_context_upsample(const float* depth_low, const float* up_weights, float* out, int B, int h, int w, void* stream);
 /* disparity_regression (submodule.py:164-170) / disparity_variance (:257-263): prob (B,D,H,W); dmin = value of bin 0. */

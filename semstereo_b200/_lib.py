@@ -45,6 +45,7 @@ SIGNATURES = {
     "ss_regression_topk": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "ss_ssr_param_count": [_I],
     "ss_ssr_upsample": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "ss_ssr_upsample2": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "ss_context_upsample": [_P, _P, _P, _I, _I, _I, _P],
     "ss_disparity_regression": [_P, _P, _I, _I, _I, _I, _F, _P],
     "ss_disparity_variance": [_P, _P, _P, _I, _I, _I, _I, _F, _P],

@@ -792,7 +792,6 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_const
   } else if (warp >= 4) {
     const int e = warp - 4, m = e * 32 + lane, hh = m >> 3, ww = m & 7;
     uint32_t acc_it = 0;
-    const size_t S_in = (size_t)p.D * p.H * p.W;
     for (int s = cta_s; s < p.items; s += cta_stride) {
       int b, h0, w0, dlo, dhi;
       decode_item(p, s, b, h0, w0, dlo, dhi);
@@ -1011,6 +1010,7 @@ extern "C" int ss_conv3d_tc_ntile(int kind, int Cin, int Cout) {
     case 1:
       if ((Cin == 32 && Cout == 32) || (Cin == 64 && Cout == 64)) return Cout;
       if (Cin == 128 && (Cout == 128 || Cout == 384)) return 128;      // attention_block: qkv Linear and final 1x1x1 conv
+      if ((Cin == 128 && Cout == 64) || (Cin == 64 && Cout == 32)) return Cout;   // channelAtt im_att at 1/4 res (SemStereo.py:93-95)
       return 0;
     case 2:
       if (Cin == 32 && Cout == 64) return 64;
@@ -1082,8 +1082,8 @@ extern "C" int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight
       return launch_s1<128, 128, 3, 2, 27>(tm, p, st);
     case 1:
       if (Cin == 32) return launch_s1<32, 32, 4, 1, 1>(tm, p, st);
-      if (Cin == 64) return launch_s1<64, 64, 4, 1, 1>(tm, p, st);
-      return launch_s1<128, 128, 4, 1, 1>(tm, p, st);
+      if (Cin == 64) return N == 64 ? launch_s1<64, 64, 4, 1, 1>(tm, p, st) : launch_s1<64, 32, 4, 1, 1>(tm, p, st);
+      return N == 128 ? launch_s1<128, 128, 4, 1, 1>(tm, p, st) : launch_s1<128, 64, 4, 1, 1>(tm, p, st);
     case 2:
       if (Cin == 32) return launch_s2<32, 64, 2, 27>(tm, p, st);
       return launch_s2<64, 128, 2, 2>(tm, p, st);

@@ -29,42 +29,50 @@ __device__ __forceinline__ float sel3(float v0, float v1, float v2, int idx, int
 
 // One thread = 4 consecutive full-res pixels (one low-res column x): the 3x6 upsampled neighbourhood is built from 18
 // low-res loads, spx / label / output move as 128-bit vectors.  The arithmetic per pixel is unchanged.
-template <int NC>
-__global__ void __launch_bounds__(128) ssr_upsample_kernel(const float* __restrict__ depth_low, const float* __restrict__ spx,
-                                                           const float* __restrict__ label, float* __restrict__ out,
+// ND = 2 upsamples two low-res disparity maps (pred_att and pred, SemStereo.py:312 and :324) in one pass: the class-probability
+// gate g2 depends only on spx / label, so both maps share its loads and its 12 sigmoids + softmax per pixel.
+template <int NC, int ND>
+__global__ void __launch_bounds__(128) ssr_upsample_kernel(const float* __restrict__ depth_low_a, const float* __restrict__ depth_low_b,
+                                                           const float* __restrict__ spx, const float* __restrict__ label,
+                                                           float* __restrict__ out_a, float* __restrict__ out_b,
                                                            const SsrPacked<NC> P, int h, int w) {
   const int H = 4 * h, W = 4 * w;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;          // low-res column
   const int Y = blockIdx.y, b = blockIdx.z;
   if (x >= w) return;
   const int X0 = 4 * x;
-  const float* dl = depth_low + (size_t)b * h * w;
   const int cx0 = max(x - 1, 0), cx1 = x, cx2 = min(x + 1, w - 1);
   // bilinear x4 of the low-res disparity on rows Y-1..Y+1, columns X0-1..X0+4 (zero outside: the conv pads the BN output)
-  float v[3][6], centre[4] = {0.f, 0.f, 0.f, 0.f};
+  float v[ND][3][6], centre[ND][4];
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int yy = Y + r - 1;
-    const bool yin = yy >= 0 && yy < H;
-    int y0 = 0, y1 = 0;
-    float hy0 = 0.f, hy1 = 0.f;
-    if (yin) lin4(yy, h, y0, y1, hy0, hy1);
-    const float a0 = __ldg(dl + y0 * w + cx0), a1 = __ldg(dl + y0 * w + cx1), a2 = __ldg(dl + y0 * w + cx2);
-    const float c0 = __ldg(dl + y1 * w + cx0), c1 = __ldg(dl + y1 * w + cx1), c2 = __ldg(dl + y1 * w + cx2);
+  for (int n = 0; n < ND; ++n) {
+    const float* dl = (n == 0 ? depth_low_a : depth_low_b) + (size_t)b * h * w;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      const int xx = X0 - 1 + j;
-      float val = 0.0f;
-      if (yin && xx >= 0 && xx < W) {
-        int x0, x1;
-        float wx0, wx1;
-        lin4(xx, w, x0, x1, wx0, wx1);
-        const float up = hy0 * (wx0 * sel3(a0, a1, a2, x0, cx0, cx1) + wx1 * sel3(a0, a1, a2, x1, cx0, cx1)) +
-                         hy1 * (wx0 * sel3(c0, c1, c2, x0, cx0, cx1) + wx1 * sel3(c0, c1, c2, x1, cx0, cx1));
-        if (r == 1 && j >= 1 && j <= 4) centre[j - 1] = up;
-        val = fmaf(P.a0, up, P.b0);
+    for (int j = 0; j < 4; ++j) centre[n][j] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int yy = Y + r - 1;
+      const bool yin = yy >= 0 && yy < H;
+      int y0 = 0, y1 = 0;
+      float hy0 = 0.f, hy1 = 0.f;
+      if (yin) lin4(yy, h, y0, y1, hy0, hy1);
+      const float a0 = __ldg(dl + y0 * w + cx0), a1 = __ldg(dl + y0 * w + cx1), a2 = __ldg(dl + y0 * w + cx2);
+      const float c0 = __ldg(dl + y1 * w + cx0), c1 = __ldg(dl + y1 * w + cx1), c2 = __ldg(dl + y1 * w + cx2);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int xx = X0 - 1 + j;
+        float val = 0.0f;
+        if (yin && xx >= 0 && xx < W) {
+          int x0, x1;
+          float wx0, wx1;
+          lin4(xx, w, x0, x1, wx0, wx1);
+          const float up = hy0 * (wx0 * sel3(a0, a1, a2, x0, cx0, cx1) + wx1 * sel3(a0, a1, a2, x1, cx0, cx1)) +
+                           hy1 * (wx0 * sel3(c0, c1, c2, x0, cx0, cx1) + wx1 * sel3(c0, c1, c2, x1, cx0, cx1));
+          if (r == 1 && j >= 1 && j <= 4) centre[n][j - 1] = up;
+          val = fmaf(P.a0, up, P.b0);
+        }
+        v[n][r][j] = val;
       }
-      v[r][j] = val;
     }
   }
   const size_t HW = (size_t)H * W, pix = (size_t)Y * W + X0;
@@ -76,7 +84,7 @@ __global__ void __launch_bounds__(128) ssr_upsample_kernel(const float* __restri
     sp[i][0] = s4.x; sp[i][1] = s4.y; sp[i][2] = s4.z; sp[i][3] = s4.w;
     lab[i][0] = l4.x; lab[i][1] = l4.y; lab[i][2] = l4.z; lab[i][3] = l4.w;
   }
-  float o[4];
+  float o[ND][4];
 #pragma unroll
   for (int px = 0; px < 4; ++px) {
     float m = -INFINITY;
@@ -104,17 +112,21 @@ __global__ void __launch_bounds__(128) ssr_upsample_kernel(const float* __restri
       for (int i = 0; i < NC; ++i) a = fmaf(P.w2[j][i], in1[i], a);
       g2[j] = sigmoidf_(fmaf(P.sb2[j], a, P.tb2[j]));
     }
-    float res = P.b3;
 #pragma unroll
-    for (int j = 0; j < NC; ++j) {
-      float a = P.bc[j];
+    for (int n = 0; n < ND; ++n) {
+      float res = P.b3;
 #pragma unroll
-      for (int t = 0; t < 9; ++t) a = fmaf(P.wc[j][t], v[t / 3][px + t % 3], a);
-      res = fmaf(P.w3[j], fmaf(P.s2[j], a, P.t2[j]) * g2[j], res);
+      for (int j = 0; j < NC; ++j) {
+        float a = P.bc[j];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) a = fmaf(P.wc[j][t], v[n][t / 3][px + t % 3], a);
+        res = fmaf(P.w3[j], fmaf(P.s2[j], a, P.t2[j]) * g2[j], res);
+      }
+      o[n][px] = centre[n][px] + res;
     }
-    o[px] = centre[px] + res;
   }
-  *reinterpret_cast<float4*>(out + (size_t)b * HW + pix) = make_float4(o[0], o[1], o[2], o[3]);
+  *reinterpret_cast<float4*>(out_a + (size_t)b * HW + pix) = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
+  if (ND == 2) *reinterpret_cast<float4*>(out_b + (size_t)b * HW + pix) = make_float4(o[ND - 1][0], o[ND - 1][1], o[ND - 1][2], o[ND - 1][3]);
 }
 
 __global__ void __launch_bounds__(256) context_upsample_kernel(const float* __restrict__ depth_low, const float* __restrict__ upw,
@@ -143,20 +155,36 @@ __global__ void __launch_bounds__(256) context_upsample_kernel(const float* __re
 // `packed` is a HOST array of ss_ssr_param_count(num_classes) floats in the order of SsrPacked (see include/semstereo_b200.h).
 extern "C" int ss_ssr_param_count(int num_classes) { return 2 + num_classes * (9 + 1 + 2 + 2 * (num_classes + 3) + 1) + 1; }
 
-extern "C" int ss_ssr_upsample(const float* depth_low, const float* spx, const float* label, float* out, const float* packed_host,
-                               int B, int h, int w, int num_classes, void* stream) {
-  SS_REQUIRE(depth_low && spx && label && out && packed_host, "ss_ssr_upsample: null pointer");
-  SS_REQUIRE(B > 0 && h > 0 && w > 0, "ss_ssr_upsample: non-positive dimension");
-  SS_UNSUPPORTED(num_classes != 6, "ss_ssr_upsample: num_classes=%d unsupported (the model's spx head has 6 channels)", num_classes);
-  SS_UNSUPPORTED(4 * h > 65535 || B > 65535, "ss_ssr_upsample: grid dimension exceeds 65535");
+static int ssr_launch(const float* da, const float* db, const float* spx, const float* label, float* oa, float* ob, const float* packed_host,
+                      int B, int h, int w, int num_classes, void* stream, const char* name) {
+  SS_REQUIRE(da && spx && label && oa && packed_host && (!db == !ob), "%s: null pointer", name);
+  SS_REQUIRE(B > 0 && h > 0 && w > 0, "%s: non-positive dimension", name);
+  SS_UNSUPPORTED(num_classes != 6, "%s: num_classes=%d unsupported (the model's spx head has 6 channels)", name, num_classes);
+  SS_UNSUPPORTED(4 * h > 65535 || B > 65535, "%s: grid dimension exceeds 65535", name);
   SsrPacked<6> P;
   static_assert(sizeof(P) == 189 * sizeof(float), "packed SSR layout");
   memcpy(&P, packed_host, sizeof(P));
-  SS_REQUIRE(((reinterpret_cast<uintptr_t>(spx) | reinterpret_cast<uintptr_t>(label) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
-             "ss_ssr_upsample: spx, label and out must be 16-byte aligned");
-  ssr_upsample_kernel<6><<<dim3(ceil_div(w, 128), 4 * h, B), 128, 0, (cudaStream_t)stream>>>(depth_low, spx, label, out, P, h, w);
-  SS_CHECK_LAUNCH("ss_ssr_upsample");
+  SS_REQUIRE(((reinterpret_cast<uintptr_t>(spx) | reinterpret_cast<uintptr_t>(label) | reinterpret_cast<uintptr_t>(oa) |
+               reinterpret_cast<uintptr_t>(ob)) & 15) == 0,
+             "%s: spx, label and out must be 16-byte aligned", name);
+  const dim3 grid(ceil_div(w, 128), 4 * h, B);
+  if (db) ssr_upsample_kernel<6, 2><<<grid, 128, 0, (cudaStream_t)stream>>>(da, db, spx, label, oa, ob, P, h, w);
+  else ssr_upsample_kernel<6, 1><<<grid, 128, 0, (cudaStream_t)stream>>>(da, da, spx, label, oa, oa, P, h, w);
+  SS_CHECK_LAUNCH(name);
   return SS_OK;
+}
+
+extern "C" int ss_ssr_upsample(const float* depth_low, const float* spx, const float* label, float* out, const float* packed_host,
+                               int B, int h, int w, int num_classes, void* stream) {
+  return ssr_launch(depth_low, nullptr, spx, label, out, nullptr, packed_host, B, h, w, num_classes, stream, "ss_ssr_upsample");
+}
+
+// Two low-res maps through the same SSR_upsample module in one pass (the model calls it at SemStereo.py:312 and :324 with the
+// same spx / label): out_a = ssr(depth_low_a), out_b = ssr(depth_low_b), each bit-identical to the single-map call.
+extern "C" int ss_ssr_upsample2(const float* depth_low_a, const float* depth_low_b, const float* spx, const float* label, float* out_a,
+                                float* out_b, const float* packed_host, int B, int h, int w, int num_classes, void* stream) {
+  SS_REQUIRE(depth_low_b && out_b, "ss_ssr_upsample2: null pointer");
+  return ssr_launch(depth_low_a, depth_low_b, spx, label, out_a, out_b, packed_host, B, h, w, num_classes, stream, "ss_ssr_upsample2");
 }
 
 extern "C" int ss_context_upsample(const float* depth_low, const float* up_weights, float* out, int B, int h, int w, void* stream) {

@@ -227,6 +227,10 @@ class DisparityHotPath(nn.Module):
             c[ca + ".s0"], c[ca + ".t0"] = bn_affine(m[0].bn)
             c[ca + ".w1"] = m[1].weight.detach().float().reshape(m[1].out_channels, -1).contiguous()
             c[ca + ".b1"] = m[1].bias.detach().float().contiguous()
+            w0, w1 = m[0].conv.weight.detach().float(), m[1].weight.detach().float()
+            if bf16 and tc.ntile(tc.K1, w0.shape[1], w0.shape[0]) and tc.ntile(tc.K1, w1.shape[1], w1.shape[0]):
+                c[ca + ".tc0"] = tc.pack_weight(w0.unsqueeze(2), tc.K1)          # (Cout,Cin,1,1) -> (Cout,Cin,1,1,1)
+                c[ca + ".tc1"] = tc.pack_weight(w1.unsqueeze(2), tc.K1)
         cf0, cf1 = self.concat_feature[0], self.concat_feature[1]
         c["cf0.scale"], c["cf0.shift"] = bn_affine(cf0.bn)
         if bf16:
@@ -243,17 +247,24 @@ class DisparityHotPath(nn.Module):
         return c
 
     # ------------------------------------------------------------------------------------------
-    def _concat_feature(self, c, f4):
+    def _concat_feature(self, c, f4, f4_blocked=None):
         """concat_feature(features[1]) (SemStereo.py:314-315): (B,128,H/4,W/4) -> (B,32,H/4,W/4) fp32."""
         with ops.label("concat_feature"):
             x = f4.unsqueeze(2)
             if self.precision == "bf16":
-                y = tc.conv3d_tc(tc.C2D, tc.to_blocked_bf16(x), c["cf0.tc"], 64, c["cf0.scale"], c["cf0.shift"], relu=True)
+                xb = f4_blocked if f4_blocked is not None else tc.to_blocked_bf16(x)
+                y = tc.conv3d_tc(tc.C2D, xb, c["cf0.tc"], 64, c["cf0.scale"], c["cf0.shift"], relu=True)
                 return tc.conv3d_tc(tc.C2D, y, c["cf1.tc"], 32, out_mode=tc.F32).squeeze(2)
             y = ops.conv3d_f32(x, c["cf0.w"], c["cf0.scale"], c["cf0.shift"], k=3, relu=True)
             return ops.conv3d_f32(y, c["cf1.w"], k=3).squeeze(2)
 
-    def _gate_logits(self, c, name, im):
+    def _gate_logits(self, c, name, im, im_blocked=None):
+        """channelAtt.im_att (SemStereo.py:93-95): 1x1 conv + BN + ReLU -> 1x1 conv + bias.  With a blocked bf16 copy of the image
+        features at hand (bf16 mode, 1/4 resolution) both 1x1 convs run on the tensor cores."""
+        if im_blocked is not None and (name + ".tc0") in c:
+            with ops.label(name):
+                y = tc.conv3d_tc(tc.K1, im_blocked, c[name + ".tc0"], c[name + ".tc0"].shape[3], c[name + ".s0"], c[name + ".t0"], relu=True)
+                return tc.conv3d_tc(tc.K1, y, c[name + ".tc1"], 32, None, c[name + ".b1"], out_mode=tc.F32).squeeze(2)
         y = ops.pointwise_conv2d(im, c[name + ".w0"], c[name + ".s0"], c[name + ".t0"], relu=True)
         return ops.pointwise_conv2d(y, c[name + ".w1"], None, c[name + ".b1"], relu=False)
 
@@ -342,15 +353,16 @@ class DisparityHotPath(nn.Module):
         out.update(cost_att=cost_att, pred_att=pred_att, disp_topk=disp_topk, att_topk=att_topk)
         if keep:
             out.update(corr_volume=corr, att_weights=att_up, pred_att0=mu, var_gate=gate, strength=strength, ind_k=ind_k, prob=prob)
-        out["pred_att_up"] = ops.ssr_upsample(pred_att.unsqueeze(1), spx_pred, pred_label, c["ssr"])
         if self.att_weights_only:
+            out["pred_att_up"] = ops.ssr_upsample(pred_att.unsqueeze(1), spx_pred, pred_label, c["ssr"])
             return out
         # --- sparse concat volume + aggregation (SemStereo.py:314-324) ---
+        f4l_b = tc.to_blocked_bf16(f4_l.unsqueeze(2)) if self.precision == "bf16" else None    # feeds concat_feature and the gate convs
         if cf_l is None:
-            cf_l = self._concat_feature(c, f4_l)
+            cf_l = self._concat_feature(c, f4_l, f4l_b)
         if cf_r is None:
             cf_r = self._concat_feature(c, f4_r)
-        gate4 = self._gate_logits(c, "concat_feature_att_4", f4_l)
+        gate4 = self._gate_logits(c, "concat_feature_att_4", f4_l, f4l_b)
         if self.precision == "bf16":
             volume = tc.sparse_concat_volume_blocked(cf_l, cf_r, disp_topk, att_topk)      # (B,8,24,H/4,W/4,8) bf16
             v = self._tc(c, "concat_stem", tc.S1, volume, 32, gate=tc.gate_sigmoid_blocked(gate4), out_mode=tc.S2D)
@@ -364,7 +376,8 @@ class DisparityHotPath(nn.Module):
         out.update(cost=cost, pred=pred)
         if keep:
             out["volume"] = volume
-        out["pred_up"] = ops.ssr_upsample(pred, spx_pred, pred_label, c["ssr"])
+        # both SSR_upsample calls of the model (:312 on pred_att, :324 on pred) share spx / label: one pass
+        out["pred_att_up"], out["pred_up"] = ops.ssr_upsample2(pred_att.unsqueeze(1), pred, spx_pred, pred_label, c["ssr"])
         return out
 
     def as_model_outputs(self, out, pred_label):

@@ -275,6 +275,22 @@ def ssr_upsample(depth_low, spx, label, packed_host):
     return out
 
 
+def ssr_upsample2(depth_low_a, depth_low_b, spx, label, packed_host):
+    """Both SSR_upsample calls of the model (SemStereo.py:312, :324) in one pass; returns (out_a, out_b)."""
+    dev = _require_cuda(depth_low_a, depth_low_b, spx, label)
+    B, one, h, w = depth_low_a.shape
+    nc = spx.shape[1]
+    if one != 1 or depth_low_b.shape != depth_low_a.shape or tuple(spx.shape) != (B, nc, 4 * h, 4 * w) or label.shape != spx.shape:
+        raise ValueError("ssr_upsample2: depth_low_a/b (B,1,h,w), weights/pred_label (B,nc,4h,4w)")
+    if packed_host.is_cuda or packed_host.dtype != torch.float32 or packed_host.numel() != ssr_param_count(nc):
+        raise ValueError("ssr_upsample2: packed parameters must be a CPU float32 tensor of ss_ssr_param_count() elements")
+    out_a = torch.empty((B, 4 * h, 4 * w), device=dev, dtype=torch.float32)
+    out_b = torch.empty_like(out_a)
+    _call("ss_ssr_upsample2", dev, _ptr(depth_low_a), _ptr(depth_low_b), _ptr(spx), _ptr(label), _ptr(out_a), _ptr(out_b),
+          ctypes.c_void_p(packed_host.contiguous().data_ptr()), B, h, w, nc)
+    return out_a, out_b
+
+
 def context_upsample(depth_low, up_weights):
     dev = _require_cuda(depth_low, up_weights)
     B, one, h, w = depth_low.shape

@@ -225,3 +225,19 @@ def test_error_behaviour():
                                torch.zeros(128, 128, device=DEV), torch.zeros(128, device=DEV), (4, 4, 4))
     with pytest.raises(RuntimeError):
         ops.gwc_volume(torch.zeros(1, 8, 4, 8), torch.zeros(1, 8, 4, 8), 2, 2)   # CPU tensors: no fallback
+
+
+def test_ssr_upsample2_equals_two_calls():
+    """The fused two-map SSR_upsample (SemStereo.py:312 + :324) is bit-identical to two single-map calls."""
+    from semstereo_b200.hotpath import DisparityHotPath, pack_ssr
+    from semstereo_b200.params import make_params
+    m = DisparityHotPath(64, False, True)
+    m.load_state_dict(make_params(seed=4), strict=True)
+    packed = pack_ssr(m.ssr_upsample)
+    g = torch.Generator().manual_seed(8)
+    B, h, w = 2, 24, 40
+    da, db = (8 * torch.randn(B, 1, h, w, generator=g)).to(DEV), (8 * torch.randn(B, 1, h, w, generator=g)).to(DEV)
+    spx, lab = torch.randn(B, 6, 4 * h, 4 * w, generator=g).to(DEV), (2 * torch.randn(B, 6, 4 * h, 4 * w, generator=g)).to(DEV)
+    oa, ob = ops.ssr_upsample2(da, db, spx, lab, packed)
+    assert torch.equal(oa, ops.ssr_upsample(da, spx, lab, packed))
+    assert torch.equal(ob, ops.ssr_upsample(db, spx, lab, packed))
