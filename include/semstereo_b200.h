@@ -97,6 +97,24 @@ SS_API int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight_pac
  * out fp32 (B,1,D,H,W). */
 SS_API int ss_conv3d_tc_head(const void* in_blocked, const void* weight_packed, float* out, int B, int Cin, int D, int H, int W,
                              void* stream);
+/* 2-D decoder convolutions around the path (FeatUp / Conv2x, models/submodule.py:119-161; segmenthead,
+ * :31-52; chal_*, spx*, models/SemStereo.py:207-216) on tcgen05 tensor cores.  Activations bf16 blocked (B,C/8,H,W,8).
+ * mode 0: Conv2d 3x3 s1 p1; mode 1: Conv2d 1x1; mode 2: ConvTranspose2d k4 s2 p1 (H,W = input dims, output 2H x 2W).
+ * The input is the channel concat [in0 (C0) | in1 (C1)] (torch.cat((x, rem), 1), submodule.py:155) without materialising it;
+ * in1 may be NULL with C1 = 0; C0 and C1 must be multiples of 64.  y = conv * scale[co] + shift[co] (folded BN / bias) -> ReLU.
+ * N = ss_conv2d_tc_ntile(mode, C0+C1, Cout) (0 = unsupported).  weight_packed (bf16), cb = 64-channel block of the concat:
+ *   modes 0/1: [ceil(Cout/N)][ncb][taps][8][N][8] = w[nt*N+n][cb*64+chunk*8+c][tap]            (Cout zero-padded)
+ *   mode 2   : [ceil(Cout/N)][ncb][9 slabs], slab s = [8][rows_s][8] with rows = (phase, n) over the output phases the input
+ *              shift feeds: shifts (0,0),(-1,0),(+1,0),(0,-1),(0,+1),(-1,-1),(-1,+1),(+1,-1),(+1,+1) feed phases
+ *              {0,1,2,3},{0,1},{2,3},{0,2},{1,3},{0},{1},{2},{3} (phase = 2*(oh&1) + (ow&1)); tap k(phase bit, shift):
+ *              k(0,0)=1, k(0,-1)=3, k(1,0)=2, k(1,+1)=0; value w_convT[cb*64+chunk*8+c][nt*N+n][k_h][k_w].
+ * out_mode 0: bf16 blocked, 1: fp32 NCHW. */
+SS_API int ss_conv2d_tc_ntile(int mode, int Cin, int Cout);
+SS_API int ss_conv2d_tc(int mode, const void* in0_blocked, int C0, const void* in1_blocked_or_null, int C1, const void* weight_packed,
+                        const float* scale_or_null, const float* shift_or_null, void* out, int out_mode, int B, int Cout, int H, int W,
+                        int relu, void* stream);
+/* F.interpolate(scale 2, bilinear, align_corners=False) of `planes` fp32 (h,w) planes (segmenthead, submodule.py:46-51). */
+SS_API int ss_bilinear_up2(const float* in, float* out, int planes, int h, int w, void* stream);
 /* Producers of the blocked layouts (bf16 mode never materialises the fp32 volumes):
  * sigmoid(gate logits (B,C,H,W)) -> fp32 (B,C/8,H,W,8);  `patch` conv * gate (SemStereo.py:274-276) -> phase-split bf16;
  * concat_volume_generator * att_topk (SemStereo.py:241-244,318) -> blocked bf16 (B,2C/8,K,H,W,8). */

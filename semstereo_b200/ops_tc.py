@@ -194,3 +194,98 @@ def conv3d_tc(kind, xb, w_tc, cout, scale=None, shift=None, gate_blocked=None, r
     _call("ss_conv3d_tc", dev, int(kind), _ptr(xb), _ptr(w_tc), _ptr(scale), _ptr(shift), _ptr(gate_blocked), _ptr(residual_s2d),
           _ptr(skip_weight), _ptr(out), int(out_mode), B, cin, cout, D, H, W, int(relu))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 2-D decoder convolutions (csrc/conv2d_tc.cu): blocked bf16 (B, C/8, H, W, 8)
+# ---------------------------------------------------------------------------------------------------------------------
+CONV3, CONV1, DECONV4 = 0, 1, 2      # modes of ss_conv2d_tc
+_DECONV_SLABS = (((0, 0), (0, 1, 2, 3)), ((-1, 0), (0, 1)), ((1, 0), (2, 3)), ((0, -1), (0, 2)), ((0, 1), (1, 3)),
+                 ((-1, -1), (0,)), ((-1, 1), (1,)), ((1, -1), (2,)), ((1, 1), (3,)))
+_DECONV_TAP = {(0, 0): 1, (0, -1): 3, (1, 0): 2, (1, 1): 0}       # (output phase bit, input shift) -> kernel index
+
+
+def to_blocked2d(x):
+    """fp32 NCHW -> bf16 (B, C/8, H, W, 8)."""
+    B, C, H, W = x.shape
+    return to_blocked_bf16(x.unsqueeze(2)).view(B, C // 8, H, W, 8)
+
+
+def from_blocked2d(xb):
+    B, C8, H, W, _ = xb.shape
+    return from_blocked_bf16(xb.view(B, C8, 1, H, W, 8)).squeeze(2)
+
+
+def ntile2d(mode, cin, cout):
+    return _lib.load().ss_conv2d_tc_ntile(int(mode), int(cin), int(cout))
+
+
+def pack_weight2d(w, mode):
+    """Conv2d weight (Cout,Cin,k,k) for CONV3 / CONV1, ConvTranspose2d weight (Cin,Cout,4,4) for DECONV4 -> the bf16 layout
+    ss_conv2d_tc documents (include/semstereo_b200.h)."""
+    w = w.detach().float()
+    if mode == DECONV4:
+        cin, cout = w.shape[:2]
+        n = ntile2d(mode, cin, cout)
+        if n == 0 or tuple(w.shape[2:]) != (4, 4):
+            raise NotImplementedError(f"conv2d_tc: no tensor-core configuration for ConvTranspose2d {tuple(w.shape)}")
+        nt, ncb = -(-cout // n), cin // 64
+        wp = w.new_zeros((cin, nt * n, 4, 4))
+        wp[:, :cout] = w
+        wp = wp.reshape(ncb, 8, 8, nt, n, 4, 4)                                    # (cb, chunk, c, nt, n, kh, kw)
+        slabs = []
+        for (sh, sw), phases in _DECONV_SLABS:
+            rows = [wp[..., _DECONV_TAP[(ph >> 1, sh)], _DECONV_TAP[(ph & 1, sw)]] for ph in phases]      # each (cb,chunk,c,nt,n)
+            r = torch.stack(rows, 4)                                               # (cb, chunk, c, nt, phase, n)
+            slabs.append(r.permute(3, 0, 1, 4, 5, 2).reshape(nt, ncb, 8 * len(phases) * n * 8))   # (nt, cb, [chunk][phase*n][c])
+        return torch.cat(slabs, 2).contiguous().to(torch.bfloat16)                 # (nt, ncb, 16*n*64)
+    cout, cin = w.shape[:2]
+    taps = w.shape[2] * w.shape[3]
+    n = ntile2d(mode, cin, cout)
+    if n == 0 or taps != (9 if mode == CONV3 else 1):
+        raise NotImplementedError(f"conv2d_tc: no tensor-core configuration for Conv2d {tuple(w.shape)} in mode {mode}")
+    nt, ncb = -(-cout // n), cin // 64
+    wp = w.new_zeros((nt * n, cin, taps))
+    wp[:cout] = w.reshape(cout, cin, taps)
+    t = wp.reshape(nt, n, ncb, 8, 8, taps).permute(0, 2, 5, 3, 1, 4)                 # (nt, cb, tap, chunk, n, c)
+    return t.contiguous().to(torch.bfloat16)
+
+
+def conv2d_tc(mode, x0, w_packed, cout, scale=None, shift=None, relu=False, out_f32=False, x1=None):
+    """x0 (and optionally x1, concatenated after it along channels) blocked bf16 (B,C/8,H,W,8).  Returns blocked bf16
+    (B,Cout/8,OH,OW,8) or fp32 NCHW; OH,OW = H,W (conv) or 2H,2W (DECONV4)."""
+    dev = _require_bf16(x0, 5)
+    B, C80, H, W, _ = x0.shape
+    c0, c1 = C80 * 8, 0
+    if x1 is not None:
+        _require_bf16(x1, 5)
+        if x1.shape[0] != B or tuple(x1.shape[2:4]) != (H, W):
+            raise ValueError("conv2d_tc: the two inputs of the channel concat must agree in batch and spatial size")
+        c1 = x1.shape[1] * 8
+    n = ntile2d(mode, c0 + c1, cout)
+    if n == 0 or c0 % 64 or c1 % 64:
+        raise NotImplementedError(f"conv2d_tc: mode {mode} with Cin=({c0},{c1}), Cout={cout} has no tensor-core configuration")
+    nt, ncb = -(-cout // n), (c0 + c1) // 64
+    want = (nt, ncb, 16 * n * 64) if mode == DECONV4 else (nt, ncb, 9 if mode == CONV3 else 1, 8, n, 8)
+    if w_packed.dtype != torch.bfloat16 or tuple(w_packed.shape) != want or not w_packed.is_contiguous():
+        raise ValueError("conv2d_tc: weight must come from pack_weight2d(w, mode) for this layer")
+    for t in (scale, shift):
+        if t is not None:
+            _require_cuda(t)
+    OH, OW = (2 * H, 2 * W) if mode == DECONV4 else (H, W)
+    if out_f32:
+        out = torch.empty((B, cout, OH, OW), device=dev, dtype=torch.float32)
+    else:
+        out = torch.empty((B, cout // 8, OH, OW, 8), device=dev, dtype=torch.bfloat16)
+    _call("ss_conv2d_tc", dev, int(mode), _ptr(x0), c0, _ptr(x1), c1, _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(out),
+          int(out_f32), B, cout, H, W, int(relu))
+    return out
+
+
+def bilinear_up2(x):
+    """F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False) for fp32 NCHW."""
+    dev = _require_cuda(x)
+    B, C, h, w = x.shape
+    out = torch.empty((B, C, 2 * h, 2 * w), device=dev, dtype=torch.float32)
+    _call("ss_bilinear_up2", dev, _ptr(x), _ptr(out), B * C, h, w)
+    return out
