@@ -115,6 +115,10 @@ SS_API int ss_conv2d_tc(int mode, const void* in0_blocked, int C0, const void* i
                         int relu, void* stream);
 /* F.interpolate(scale 2, bilinear, align_corners=False) of `planes` fp32 (h,w) planes (segmenthead, submodule.py:46-51). */
 SS_API int ss_bilinear_up2(const float* in, float* out, int planes, int h, int w, void* stream);
+/* segmenthead.conv2 (submodule.py:36,44): Conv2d 1x1 + bias, Cout <= 8, from blocked bf16 (B,C/8,H,W,8) to fp32 (B,Cout,H,W);
+ * weight fp32 [Cout][C]. */
+SS_API int ss_pointwise_blocked_small(const void* in_blocked, const float* weight, const float* bias_or_null, float* out, int B, int C,
+                                      int Cout, int H, int W, void* stream);
 /* Producers of the blocked layouts (bf16 mode never materialises the fp32 volumes):
  * sigmoid(gate logits (B,C,H,W)) -> fp32 (B,C/8,H,W,8);  `patch` conv * gate (SemStereo.py:274-276) -> phase-split bf16;
  * concat_volume_generator * att_topk (SemStereo.py:241-244,318) -> blocked bf16 (B,2C/8,K,H,W,8). */

@@ -39,6 +39,7 @@ SIGNATURES = {
     "ss_conv2d_tc_ntile": [_I, _I, _I],
     "ss_conv2d_tc": [_I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ss_bilinear_up2": [_P, _P, _I, _I, _I, _P],
+    "ss_pointwise_blocked_small": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "ss_conv3d_tc": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "ss_window_attention3d": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "ss_att_stats": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],

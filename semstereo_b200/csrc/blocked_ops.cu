@@ -185,3 +185,46 @@ extern "C" int ss_sparse_concat_volume_blocked(const float* cf_l, const float* c
   SS_CHECK_LAUNCH("ss_sparse_concat_volume_blocked");
   return SS_OK;
 }
+
+// segmenthead.conv2 (models/submodule.py:36,44): Conv2d 1x1 with bias from the blocked bf16 activation (B,C/8,H,W,8) to a few
+// fp32 NCHW channels (Cout <= 8).  One thread per pixel; weights in shared memory; 16-byte channel-chunk loads.
+namespace {
+template <int CO>
+__global__ void __launch_bounds__(256) pointwise_blocked_small_kernel(const uint4* __restrict__ in, const float* __restrict__ w,
+                                                                      const float* __restrict__ bias, float* __restrict__ out, int C,
+                                                                      int cout, size_t P) {
+  extern __shared__ float sw[];                 // [CO][C]
+  for (int i = threadIdx.x; i < CO * C; i += blockDim.x) sw[i] = (i / C) < cout ? __ldg(w + i) : 0.0f;
+  __syncthreads();
+  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (pix >= P) return;
+  float acc[CO];
+#pragma unroll
+  for (int o = 0; o < CO; ++o) acc[o] = (bias && o < cout) ? __ldg(bias + o) : 0.0f;
+  for (int c8 = 0; c8 < C / 8; ++c8) {
+    const uint4 q = __ldg(in + ((size_t)b * (C / 8) + c8) * P + pix);
+    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { x[2 * i] = __uint_as_float(u[i] << 16); x[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
+#pragma unroll
+    for (int o = 0; o < CO; ++o)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[o] = fmaf(sw[o * C + c8 * 8 + i], x[i], acc[o]);
+  }
+  for (int o = 0; o < cout; ++o) out[((size_t)b * cout + o) * P + pix] = acc[o];
+}
+}  // namespace
+
+extern "C" int ss_pointwise_blocked_small(const void* in_blocked, const float* weight, const float* bias_or_null, float* out, int B, int C,
+                                          int Cout, int H, int W, void* stream) {
+  SS_REQUIRE(in_blocked && weight && out, "ss_pointwise_blocked_small: null pointer");
+  SS_REQUIRE(B > 0 && C > 0 && Cout > 0 && H > 0 && W > 0 && C % 8 == 0, "ss_pointwise_blocked_small: bad dimension");
+  SS_UNSUPPORTED(Cout > 8 || C > 512 || B > 65535, "ss_pointwise_blocked_small: Cout=%d (max 8) / C=%d (max 512) unsupported", Cout, C);
+  const size_t P = (size_t)H * W;
+  pointwise_blocked_small_kernel<8><<<dim3((unsigned)ceil_div64(P, 256), B), 256, 8 * C * sizeof(float), (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(in_blocked), weight, bias_or_null, out, C, Cout, P);
+  SS_CHECK_LAUNCH("ss_pointwise_blocked_small");
+  return SS_OK;
+}

@@ -289,3 +289,16 @@ def bilinear_up2(x):
     out = torch.empty((B, C, 2 * h, 2 * w), device=dev, dtype=torch.float32)
     _call("ss_bilinear_up2", dev, _ptr(x), _ptr(out), B * C, h, w)
     return out
+
+
+def pointwise_blocked_small(xb, weight, bias=None):
+    """Conv2d 1x1 (Cout <= 8) from blocked bf16 (B,C/8,H,W,8) to fp32 NCHW -- segmenthead.conv2."""
+    dev = _require_bf16(xb, 5)
+    _require_cuda(weight, bias)
+    B, C8, H, W, _ = xb.shape
+    cout = weight.shape[0]
+    if weight.numel() != cout * C8 * 8 or (bias is not None and bias.numel() != cout):
+        raise ValueError("pointwise_blocked_small: weight (Cout,C[,1,1]) and bias (Cout,) expected")
+    out = torch.empty((B, cout, H, W), device=dev, dtype=torch.float32)
+    _call("ss_pointwise_blocked_small", dev, _ptr(xb), _ptr(weight), _ptr(bias), _ptr(out), B, C8 * 8, cout, H, W)
+    return out

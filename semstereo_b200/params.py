@@ -137,3 +137,84 @@ def make_inputs(seed: int, B: int, H: int, W: int, num_classes: int = 6, max_shi
     lab = 2.0 * torch.randn(B, num_classes, H, W, generator=g)
     return dict(f8_l=f8_l, f8_r=f8_r, f4_l=f4_l, f4_r=f4_r, cf_l=cf_l, cf_r=cf_r,
                 spx_pred=spx.contiguous(), pred_label=lab.contiguous())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 2-D decoder around the path: FeatUp, segmentheads, chal_*, spx* (models/SemStereo.py:59-86, 196-216)
+# ---------------------------------------------------------------------------------------------------------------------
+BACKBONE_CHANS = (64, 128, 256, 384, 512)      # x2, x4, x8, x16, x32 of `Feature` (SemStereo.py:33-56)
+CHANS = (128, 256, 512, 768, 512)              # after FeatUp (SemStereo.py:196)
+CHANS2 = (64, 128, 256, 384, 256)              # after chal_* (SemStereo.py:197)
+
+
+def _conv2x(d, pre, cin, cout):
+    """Conv2x(cin, cout, deconv=True, concat=True) (models/submodule.py:119-146)."""
+    d[pre + ".conv1.conv.weight"] = (cin, cout, 4, 4)            # ConvTranspose2d layout (Cin, Cout, kH, kW)
+    _bn(d, pre + ".conv1.bn", cout)
+    d[pre + ".conv2.conv.weight"] = (2 * cout, 2 * cout, 3, 3)
+    _bn(d, pre + ".conv2.bn", 2 * cout)
+
+
+def decoder_param_shapes(num_classes: int = 6) -> "OrderedDict[str, tuple]":
+    d: "OrderedDict[str, tuple]" = OrderedDict()
+    bc = BACKBONE_CHANS
+    _conv2x(d, "feature_up.deconv32_16", bc[4], bc[3])
+    _conv2x(d, "feature_up.deconv16_8", bc[3] * 2, bc[2])
+    _conv2x(d, "feature_up.deconv8_4", bc[2] * 2, bc[1])
+    _conv2x(d, "feature_up.deconv4_2", bc[1] * 2, bc[0])
+    for h in ("head_l", "head_r"):
+        d[h + ".conv1.conv.weight"] = (CHANS[0] // 4, CHANS[0], 3, 3)
+        _bn(d, h + ".conv1.bn", CHANS[0] // 4)
+        d[h + ".conv2.weight"] = (num_classes, CHANS[0] // 4, 1, 1)
+        d[h + ".conv2.bias"] = (num_classes,)
+    d["spx2.0.weight"] = (CHANS2[0] * 2, 6, 4, 4)
+    d["spx2.0.bias"] = (6,)
+    _conv2x(d, "spx4_2", CHANS2[1] * 2, CHANS2[0])
+    _conv2x(d, "spx8_4", CHANS2[2] * 2, CHANS2[1])
+    _conv2x(d, "spx16_8", CHANS2[3] * 2, CHANS2[2])
+    _conv2x(d, "spx32_16", CHANS2[4], CHANS2[3])
+    for i in range(5):
+        d[f"chal_{i}.0.weight"] = (CHANS2[i], CHANS[i], 1, 1)
+        d[f"chal_{i}.0.bias"] = (CHANS2[i],)
+        _bn(d, f"chal_{i}.1", CHANS2[i])
+    return d
+
+
+def make_decoder_params(seed: int = 2) -> "OrderedDict[str, torch.Tensor]":
+    """Seeded parameters of the 2-D decoder (same recipe as make_params: unit-gain weights, non-trivial BN statistics)."""
+    g = torch.Generator().manual_seed(seed)
+    p: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for name, shape in decoder_param_shapes().items():
+        if name.endswith("running_var"):
+            t = torch.rand(shape, generator=g) + 0.5
+        elif name.endswith("running_mean"):
+            t = 0.1 * torch.randn(shape, generator=g)
+        elif len(shape) == 1 and name.endswith(".weight"):
+            t = torch.rand(shape, generator=g) + 0.5
+        elif len(shape) == 1:
+            t = 0.1 * torch.randn(shape, generator=g)
+        else:
+            fan_in = shape[0] * 4 if shape[-1] == 4 else shape[1] * shape[2] * shape[3]      # k4 s2 deconv: 4 taps hit each output
+            t = (torch.rand(shape, generator=g) * 2 - 1) * (3.0 / fan_in) ** 0.5
+        p[name] = t.contiguous()
+    return p
+
+
+def make_backbone_features(seed: int, B: int, H: int, W: int, max_shift: int = 3):
+    """Seeded stand-ins for `Feature` outputs [x2, x4, x8, x16, x32] of the left and right image (CPU fp32): right = left shifted
+    along x by a row-block-dependent amount plus noise, like make_inputs."""
+    assert H % 128 == 0 and W % 128 == 0, "H and W must be multiples of 128"
+    g = torch.Generator().manual_seed(seed)
+    fl, fr = [], []
+    for c, s in zip(BACKBONE_CHANS, (2, 4, 8, 16, 32)):
+        h, w = H // s, W // s
+        l = torch.randn(B, c, h, w, generator=g)
+        r = torch.empty_like(l)
+        for i in range(4):
+            sft = ((i % (2 * max_shift + 1)) - max_shift) * max(1, 8 // s)
+            ys = slice(i * h // 4, (i + 1) * h // 4)
+            r[:, :, ys] = torch.roll(l[:, :, ys], shifts=-sft, dims=-1)
+        r = r + 0.25 * torch.randn(B, c, h, w, generator=g)
+        fl.append(l.contiguous())
+        fr.append(r.contiguous())
+    return fl, fr

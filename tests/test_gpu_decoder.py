@@ -1,0 +1,86 @@
+"""Decoder2D / StereoHead (bf16 tensor-core 2-D decoder + disparity path) vs the CPU oracle (oracle/decoder.py, pinned to the
+reference's own modules by tests/golden/decoder_us3d.npz) and vs that golden directly.  bf16 operands, fp32 accumulation:
+tolerances are statistical and stated here; the per-layer arithmetic is checked exactly in test_gpu_conv2d.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import decoder as od
+from oracle import hotpath as oh
+from semstereo_b200.params import make_backbone_features, make_decoder_params, make_params
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+if torch.cuda.is_available():
+    from semstereo_b200.decoder import Decoder2D, StereoHead
+
+
+def params():
+    p = dict(make_params(seed=1, peaked=20.0))
+    p.update(make_decoder_params(seed=2))
+    return p
+
+
+def rel(got, ref):
+    d = (got.double() - ref.double()).abs()
+    return d.max().item() / ref.abs().max().item(), d.mean().item() / ref.abs().mean().item()
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 128, 128), (2, 128, 256)])
+def test_decoder_against_oracle(B, H, W):
+    p = params()
+    fl, fr = make_backbone_features(7, B, H, W)
+    ref = od.forward(p, fl, fr)
+    m = Decoder2D()
+    m.load_state_dict(p, strict=True)
+    m = m.to(DEV)
+    out = m([t.to(DEV) for t in fl], [t.to(DEV) for t in fr], right_label=True)
+    torch.cuda.synchronize()
+    for k in ("f4_l", "f4_r", "f8_l", "f8_r", "spx_pred", "pred_label", "pred_label_r"):
+        got = out[k].cpu()
+        assert got.shape == ref[k].shape, k
+        rmax, rmean = rel(got, ref[k])
+        print(f"\n[decoder bf16] {k}: max err / max|ref| = {rmax:.4f}, mean err / mean|ref| = {rmean:.4f}")
+        assert rmax <= 4e-2 and rmean <= 1.5e-2, (k, rmax, rmean)
+    assert torch.equal(tc_from_blocked(out["f4_l_blocked"]), out["f4_l"].cpu())
+
+
+def tc_from_blocked(xb):
+    from semstereo_b200 import ops_tc as tc
+    return tc.from_blocked2d(xb).cpu()
+
+
+def test_decoder_against_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "decoder_us3d.npz"))
+    p = params()
+    fl, fr = make_backbone_features(7, 1, 128, 128)
+    m = Decoder2D()
+    m.load_state_dict(p, strict=True)
+    out = m.to(DEV)([t.to(DEV) for t in fl], [t.to(DEV) for t in fr], right_label=True)
+    for k in ("f4_l", "f8_r", "spx_pred", "pred_label", "pred_label_r"):
+        rmax, rmean = rel(out[k].cpu(), torch.from_numpy(g[k]))
+        assert rmax <= 4e-2 and rmean <= 1.5e-2, (k, rmax, rmean)
+
+
+def test_stereo_head_against_oracle():
+    """Backbone pyramids -> full-resolution disparity: decoder + path on the GPU vs oracle decoder + oracle path."""
+    p = params()
+    fl, fr = make_backbone_features(7, 1, 128, 256)
+    d = od.forward(p, fl, fr)
+    ref = oh.forward(p, {k: d[k] for k in ("f8_l", "f8_r", "f4_l", "f4_r", "spx_pred", "pred_label")}, 64, signed=True, keep=True)
+    m = StereoHead(64)
+    m.load_state_dict(p, strict=True)
+    assert set(m.state_dict()) >= set(p)
+    out = m.to(DEV)([t.to(DEV) for t in fl], [t.to(DEV) for t in fr], keep=True)
+    torch.cuda.synchronize()
+    agree = (out["ind_k"].cpu() == ref["ind_k"]).all(dim=2).float().mean().item()
+    e = (out["pred_up"].cpu() - ref["pred_up"]).abs().flatten()
+    print(f"\n[stereo head bf16] top-24 set agreement {agree:.4f}; pred_up median {e.median():.4f} p90 {e.quantile(0.9):.4f} "
+          f"max {e.max():.3f} (1/4-res px)")
+    assert agree >= 0.85
+    assert e.median().item() <= 0.06 and e.quantile(0.9).item() <= 0.8
+    disp, label = m.as_model_outputs(out)
+    assert tuple(disp[0].shape) == (1, 128, 256) and tuple(label.shape) == (1, 6, 128, 256)

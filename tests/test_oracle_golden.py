@@ -108,3 +108,25 @@ def test_hotpath_matches_reference_forward(golden_dir, name, maxdisp, signed, pe
             close(out["cost"], g["cost"], 2e-3 * peaked, "cost")
             close(out["pred_up"], g["pred_up"], 1e-3, "pred_up")
             close(out["pred_up"] * 4, g["model_out"], 4e-3, "model_out")
+
+
+def test_decoder_oracle_matches_reference_modules(golden_dir):
+    """oracle/decoder.py (+ oracle/hotpath.py after it) vs the reference's own FeatUp / segmenthead / chal_* / spx* modules and
+    its final disparity (tests/golden/decoder_us3d.npz, written by oracle/make_golden_decoder.py from /root/reference)."""
+    from oracle import decoder as od
+    from semstereo_b200.params import make_backbone_features, make_decoder_params
+    g = np.load(os.path.join(golden_dir, "decoder_us3d.npz"))
+    p = dict(make_params(seed=1, peaked=20.0))
+    p.update(make_decoder_params(seed=2))
+    fl, fr = make_backbone_features(7, 1, 128, 128)
+    out = od.forward(p, fl, fr)
+    for k in ("f4_l", "f4_r", "f8_l", "f8_r", "spx_pred", "pred_label", "pred_label_r"):
+        ref = torch.from_numpy(g[k])
+        assert (out[k] - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item()), k
+    up = od.feat_up(p, fl)
+    for k, i, st in (("x2_up", 0, 8), ("x4_up", 1, 8), ("x16_up", 3, 16)):
+        ref = torch.from_numpy(g[k])
+        assert (up[i][:, ::st] - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item()), k
+    full = oh.forward(p, {k: out[k] for k in ("f8_l", "f8_r", "f4_l", "f4_r", "spx_pred", "pred_label")}, 64, signed=True)
+    diff = (full["pred_up"] * 4 - torch.from_numpy(g["model_disp"])).abs()
+    assert diff.median().item() <= 1e-3 and (diff > 1e-2).float().mean().item() <= 0.02     # top-k ties may flip isolated pixels
