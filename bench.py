@@ -65,6 +65,23 @@ def conv_layers(H, W, maxdisp, signed=True):
     return out
 
 
+def decoder_layers(H, W):
+    """label -> FLOPs per LAUNCH and image of the 2-D decoder convs (models/SemStereo.py:59-86, 196-216)."""
+    px = lambda s: (H // s) * (W // s)      # noqa: E731
+    out = {}
+    for pre, table in (("feature_up.", (("deconv32_16", 512, 384, 16), ("deconv16_8", 768, 256, 8), ("deconv8_4", 512, 128, 4),
+                                        ("deconv4_2", 256, 64, 2))),
+                       ("", (("spx32_16", 256, 384, 16), ("spx16_8", 768, 256, 8), ("spx8_4", 512, 128, 4), ("spx4_2", 256, 64, 2)))):
+        for name, ci, co, s in table:
+            out[pre + name + ".conv1"] = 2 * px(s) * ci * co * 4            # k4 s2 transposed: 4 taps per output pixel
+            out[pre + name + ".conv2"] = 2 * px(s) * (2 * co) * (2 * co) * 9
+    for i, (ci, co) in enumerate(((128, 64), (256, 128), (512, 256), (768, 384), (512, 256))):
+        out[f"chal_{i}"] = 2 * px(2 << i) * ci * co
+    out["head_l"] = out["head_r"] = 2 * px(2) * (128 * 32 * 9 + 32 * 6)
+    out["spx2"] = 2 * px(1) * 128 * 6 * 4
+    return out
+
+
 def hbm_bytes(H, W, maxdisp, signed=True):
     """label -> algorithmic bytes (fp32 in + out) of the memory-bound launches, per pair."""
     p8, p4, p1 = (H // 8) * (W // 8), (H // 4) * (W // 4), H * W
@@ -140,7 +157,7 @@ def drop_cf(inp, external_cf):
     return inp if external_cf else {k: v for k, v in inp.items() if k not in ("cf_l", "cf_r")}
 
 
-def cpu_reference(H, W, maxdisp, steps, warmup, signed=True, att_only=False, external_cf=False):
+def cpu_reference(H, W, maxdisp, steps, warmup, signed=True, att_only=False, external_cf=False, stage="path"):
     """The reference algorithm's CPU path (oracle port of SemStereo.forward:273-324; efficient closed forms, so it is
     FASTER than the reference's own Python-loop volume builder — a conservative baseline).  Each step = one pair."""
     from oracle import hotpath as oh
@@ -148,9 +165,18 @@ def cpu_reference(H, W, maxdisp, steps, warmup, signed=True, att_only=False, ext
     torch.set_num_threads(os.cpu_count() or 1)
     p = make_params(seed=1, peaked=20.0)
     inp = drop_cf(make_inputs(3, 1, H, W), external_cf)
+    if stage == "head":
+        from oracle import decoder as od
+        from semstereo_b200.params import make_backbone_features, make_decoder_params
+        p = dict(p)
+        p.update(make_decoder_params(seed=2))
+        fl, fr = make_backbone_features(3, 1, H, W)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
+        if stage == "head":
+            d = od.forward(p, fl, fr, right_label=False)
+            inp = {k: d[k] for k in ("f8_l", "f8_r", "f4_l", "f4_r", "spx_pred", "pred_label")}
         oh.forward(p, inp, maxdisp, signed=signed, att_weights_only=att_only)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
@@ -175,6 +201,9 @@ def main():
                     help="us3d: SemStereo, signed, 1024x1024, maxdisp 64 (configs #1/#3); whu: SemStereo_WHU + submodule_.py, unsigned, "
                          "384x768, maxdisp 128 (config #4)")
     ap.add_argument("--att-only", action="store_true", help="attention_weights_only forward (the forward half of config #5)")
+    ap.add_argument("--stage", default="path", choices=["path", "head"],
+                    help="path: the disparity hot path (forward:273-324, BASELINE north_star; default).  head: everything after the "
+                         "backbone (forward:249-346): the 2-D decoder (SURVEY 8(f) rank 1) + the path; inputs are the backbone pyramids")
     ap.add_argument("--external-cf", action="store_true",
                     help="hand concat_feature(f4_*) in as inputs (round-1 boundary) instead of computing it inside the path")
     a = ap.parse_args()
@@ -186,7 +215,11 @@ def main():
             a.maxdisp = 128
     H, W, md = a.height, a.width, a.maxdisp
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    workload = (f"{'SemStereo' if signed else 'SemStereo_WHU'} disparity hot path (forward:273-324), {H}x{W} "
+    head = a.stage == "head"
+    if head and (a.att_only or a.precision != "bf16" or not signed):
+        raise SystemExit("--stage head runs the US3D model, full forward, bf16")
+    workload = (f"{'SemStereo' if signed else 'SemStereo_WHU'} "
+                f"{'decoder + disparity path = everything after the backbone (forward:249-346)' if head else 'disparity hot path (forward:273-324)'}, {H}x{W} "
                 f"{'US3D' if signed else 'WHU'}-shaped pairs, maxdisp {md}, {'signed' if signed else 'unsigned'}"
                 f"{', attention_weights_only' if a.att_only else ''}"
                 f"{'' if a.external_cf or a.att_only else ', concat_feature (:314-315) computed inside the path'}")
@@ -194,7 +227,7 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        times = cpu_reference(H, W, md, a.steps, min(a.warmup, 1), signed, a.att_only, a.external_cf)
+        times = cpu_reference(H, W, md, a.steps, min(a.warmup, 1), signed, a.att_only, a.external_cf, a.stage)
         ms = 1e3 * sum(times) / len(times)
         v = 1e3 / ms
         print(json.dumps({
@@ -215,17 +248,30 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     B = a.batch
-    model = DisparityHotPath(md, a.att_only, signed, precision=a.precision)
     okey = "pred_att_up" if a.att_only else "pred_up"
-    model.load_state_dict(make_params(seed=1, peaked=20.0), strict=True)
+    if head:
+        from semstereo_b200.decoder import StereoHead
+        from semstereo_b200.params import make_backbone_features, make_decoder_params
+        model = StereoHead(md)
+        sd = dict(make_params(seed=1, peaked=20.0))
+        sd.update(make_decoder_params(seed=2))
+        model.load_state_dict(sd, strict=True)
+        fl, fr = make_backbone_features(100 + rank, B, H, W)
+        host = {f"l{i}": t.pin_memory() for i, t in enumerate(fl)}
+        host.update({f"r{i}": t.pin_memory() for i, t in enumerate(fr)})
+        call = lambda st: model([st[f"l{i}"] for i in range(5)], [st[f"r{i}"] for i in range(5)])[okey]      # noqa: E731
+    else:
+        model = DisparityHotPath(md, a.att_only, signed, precision=a.precision)
+        model.load_state_dict(make_params(seed=1, peaked=20.0), strict=True)
+        host = {k: v.pin_memory() for k, v in drop_cf(make_inputs(100 + rank, B, H, W), a.external_cf and not a.att_only).items()}
+        call = lambda st: model(*[st.get(k) for k in ORDER])[okey]      # noqa: E731
     model = model.to(dev)
-    host = {k: v.pin_memory() for k, v in drop_cf(make_inputs(100 + rank, B, H, W), a.external_cf and not a.att_only).items()}
     devin = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
     out_host = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
     gathered = torch.empty((world * B, H, W), device=dev) if world > 1 else None
 
     def step(inputs):
-        o = model(*[inputs.get(k) for k in ORDER])[okey]
+        o = call(inputs)
         if world > 1:
             tdist.all_gather_into_tensor(gathered, o)
         return o
@@ -265,7 +311,7 @@ def main():
             tdist.all_gather_into_tensor(gathered, o)
         return o
 
-    pipe = HostPipeline(model, depth=2, post=gather)
+    pipe = HostPipeline(model, depth=2, post=gather, keys=tuple(host), call=call)
     for _ in pipe.run(host for _ in range(2)):      # warm the staging buffers
         pass
     barrier()
@@ -294,12 +340,13 @@ def main():
     per_step = {k: sum(v) / a.steps for k, v in durs.items()}
     total_k = sum(per_step.values())
     flops, nbytes = conv_layers(H, W, md, signed), hbm_bytes(H, W, md, signed)
+    dflops = decoder_layers(H, W) if head else {}
     kernels = []
     for name, ms in sorted(per_step.items(), key=lambda kv: -kv[1]):
         launches = len(durs[name]) / a.steps
         ent = {"name": name, "ms_per_step": round(ms, 4), "share": round(ms / total_k, 4), "launches_per_step": launches}
-        if name in flops:
-            ach = flops[name] * B / (ms * 1e-3) / 1e12
+        if name in flops or name in dflops:
+            ach = (flops[name] if name in flops else dflops[name] * launches) * B / (ms * 1e-3) / 1e12
             ent.update(bound="tensor", achieved=round(ach, 3), unit="TFLOP/s", frac=round(ach / pk["tf_sust"], 5))
         elif name in nbytes:
             ach = nbytes[name] * B * launches / (ms * 1e-3) / 1e9
@@ -319,14 +366,15 @@ def main():
            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if a.precision == "bf16" else "f32",
            "data": "synthetic", "config": {"workload": workload, "pairs_per_gpu_per_step": B, "global_pairs_per_step": world * B,
                                            "l2": "per-step inputs (1.3 GB at batch 8) exceed the 126 MB L2", "parallelism": f"dp{world}",
-                                           "precision_mode": ("bf16 operands / fp32 accumulation in the k3 s1 3-D convs, fp32 elsewhere"
+                                           "precision_mode": ("bf16 operands / fp32 accumulation on the tensor cores for every 3-D conv, the window attention, concat_feature"
+                                                              " and (stage head) the 2-D decoder; fp32 elsewhere"
                                                               if a.precision == "bf16" else "fp32 everywhere (FFMA 3-D convs)")},
            "e2e": {"value": e2e_v, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps},
            "gpu_launches": rec.count, "clocks": clocks, "roofline": roof, "kernels": kernels}
     if world == 1 and not a.no_cpu_baseline:
-        times = cpu_reference(H, W, md, a.cpu_steps, 1, signed, a.att_only, a.external_cf)
+        times = cpu_reference(H, W, md, a.cpu_steps, 1, signed, a.att_only, a.external_cf, a.stage)
         res["cpu_baseline"] = {"value": len(times) / sum(times), "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
-                               "sample": f"{len(times)} pairs at {H}x{W} through oracle/hotpath.py (torch CPU fp32), 1 warm-up"}
+                               "sample": f"{len(times)} pairs at {H}x{W} through {'oracle/decoder.py + ' if head else ''}oracle/hotpath.py (torch CPU fp32), 1 warm-up"}
     print(json.dumps(res))
     if world > 1:
         tdist.destroy_process_group()

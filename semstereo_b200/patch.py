@@ -1,0 +1,45 @@
+"""patch_model — model-level drop-in: keep the reference model object (and its timm backbone `model.feature`)
+and run everything after the backbone (models/SemStereo.py:249-346) through the B200 kernels.
+
+    model = SemStereo(64, False, True, True, 6); model.load_state_dict(ckpt); model.cuda().eval()
+    patch_model(model)                     # model(left, right) now returns the same ([disp], pred_label) from the sm_100a path
+
+The reference forward is one monolithic function, so the patch rebinds `model.forward`; the parameters are read from
+`model.state_dict()` (same key names), nothing in the reference tree is modified.  Inference only: `model.train()` restores
+nothing and the patched forward raises in training mode (there is no silent fallback to the torch modules).
+"""
+from __future__ import annotations
+
+import types
+
+import torch
+
+from .decoder import StereoHead
+
+
+def patch_model(model, signed: bool | None = None):
+    for attr in ("feature", "maxdisp", "att_weights_only", "seg_if", "stereo_if", "num_classes"):
+        if not hasattr(model, attr):
+            raise ValueError(f"patch_model: the model has no attribute '{attr}' (expected a SemStereo / SemStereo_WHU instance)")
+    if not model.stereo_if:
+        raise NotImplementedError("patch_model: stereo_if=False (segmentation only) has no disparity path to accelerate")
+    if signed is None:
+        signed = not type(model).__name__.endswith("_WHU")      # SemStereo_WHU runs the unsigned submodule_.py
+    dev = next(model.parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("patch_model: move the model to a CUDA device first (there is no CPU fallback)")
+    head = StereoHead(model.maxdisp, model.att_weights_only, signed, model.num_classes)
+    head.load_state_dict(model.state_dict(), strict=True)
+    head = head.to(dev)
+
+    def forward(self, left, right):
+        if self.training:
+            raise NotImplementedError("patch_model: the B200 path is inference-only; call model.eval()")
+        with torch.no_grad():
+            out = head(list(self.feature(left)), list(self.feature(right)))
+            disp, label = head.as_model_outputs(out)
+        return (disp, label) if self.seg_if else disp       # SemStereo.py:340-346
+
+    model._b200_head = [head]                               # in a list: not registered as a sub-module (state_dict unchanged)
+    model.forward = types.MethodType(forward, model)
+    return model

@@ -15,12 +15,17 @@ ORDER = ("f8_l", "f8_r", "f4_l", "f4_r", "cf_l", "cf_r", "spx_pred", "pred_label
 
 
 class HostPipeline:
-    def __init__(self, path, depth: int = 2, post=None):
-        """path: a DisparityHotPath on a CUDA device.  post(device_result) -> device tensor to return (e.g. an all-gather)."""
-        self.path, self.depth, self.post = path, depth, post
+    def __init__(self, path, depth: int = 2, post=None, keys=ORDER, call=None):
+        """path: a DisparityHotPath (or, with `keys` / `call`, any module of this package, e.g. decoder.StereoHead) on a CUDA
+        device.  keys: the batch-dict entries staged on the device; call(staged_dict) -> device result tensor (default: the hot
+        path's full-resolution disparity).  post(device_result) -> device tensor to return (e.g. an all-gather)."""
+        self.path, self.depth, self.post, self.keys = path, depth, post, tuple(keys)
         self.dev = next(path.parameters()).device
         self.copy_stream = torch.cuda.Stream(self.dev)
-        self.key = "pred_att_up" if path.att_weights_only else "pred_up"
+        if call is None:
+            key = "pred_att_up" if path.att_weights_only else "pred_up"
+            call = lambda st: path(*[st.get(k) for k in ORDER])[key]          # noqa: E731
+        self.call = call
         self._stage = [None] * depth          # device staging sets
         self._host_out = [None] * depth       # pinned result buffers
         self._copied = [torch.cuda.Event() for _ in range(depth)]
@@ -31,7 +36,7 @@ class HostPipeline:
 
     def _staging(self, i, batch):
         st = self._stage[i]
-        keys = [k for k in ORDER if batch.get(k) is not None]          # cf_l / cf_r are optional (computed on the device if absent)
+        keys = [k for k in self.keys if batch.get(k) is not None]      # cf_l / cf_r are optional (computed on the device if absent)
         if st is None or set(st) != set(keys) or any(st[k].shape != batch[k].shape for k in keys):
             st = {k: torch.empty(batch[k].shape, dtype=torch.float32, device=self.dev) for k in keys}
             self._stage[i] = st
@@ -61,7 +66,7 @@ class HostPipeline:
                 self._copied[i].record(self.copy_stream)
             self.h2d_bytes += sum(batch[k].numel() * 4 for k in st)
             compute.wait_event(self._copied[i])
-            out = self.path(*[st.get(k) for k in ORDER])[self.key]
+            out = self.call(st)
             self._consumed[i].record(compute)
             if self.post is not None:
                 out = self.post(out)

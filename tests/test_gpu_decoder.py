@@ -84,3 +84,48 @@ def test_stereo_head_against_oracle():
     assert e.median().item() <= 0.06 and e.quantile(0.9).item() <= 0.8
     disp, label = m.as_model_outputs(out)
     assert tuple(disp[0].shape) == (1, 128, 256) and tuple(label.shape) == (1, 6, 128, 256)
+
+
+def test_patch_model_rebinds_forward():
+    """patch_model on a stand-in with the reference model's attribute surface (the reference tree is not on the GPU box):
+    backbone = its own torch module, everything after = StereoHead with the parameters read from model.state_dict()."""
+    import torch.nn as nn
+    from semstereo_b200.patch import patch_model
+    from semstereo_b200.params import BACKBONE_CHANS
+
+    class Backbone(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.convs = nn.ModuleList(nn.Conv2d(3, c, 1) for c in BACKBONE_CHANS)
+
+        def forward(self, x):
+            return [conv(torch.nn.functional.avg_pool2d(x, s)) for conv, s in zip(self.convs, (2, 4, 8, 16, 32))]
+
+    class StandIn(nn.Module):
+        def __init__(self, p):
+            super().__init__()
+            self.maxdisp, self.att_weights_only, self.seg_if, self.stereo_if, self.num_classes = 64, False, True, True, 6
+            self.feature = Backbone()
+            self.extra = nn.ParameterDict()
+            self._p = p
+
+        def state_dict(self, *a, **k):
+            sd = super().state_dict(*a, **k)
+            sd.update(self._p)
+            return sd
+
+    torch.manual_seed(0)
+    p = params()
+    model = StandIn(p).to(DEV).eval()
+    left, right = torch.randn(1, 3, 128, 128, device=DEV), torch.randn(1, 3, 128, 128, device=DEV)
+    patch_model(model)
+    disp, label = model(left, right)
+    head = StereoHead(64)
+    head.load_state_dict(p, strict=True)
+    head = head.to(DEV)
+    with torch.no_grad():
+        out = head(model.feature(left), model.feature(right))
+    assert torch.equal(disp[0], out["pred_up"] * 4) and torch.equal(label, out["pred_label"])
+    model.train()
+    with pytest.raises(NotImplementedError):
+        model(left, right)
