@@ -205,7 +205,8 @@ class StereoHead(nn.Module):
     @torch.no_grad()
     def forward(self, feat_l, feat_r, keep: bool = False, right_label: bool = False):
         d = self.decoder(feat_l, feat_r, right_label=right_label)
-        out = self.path(d["f8_l"], d["f8_r"], d["f4_l"], d["f4_r"], None, None, d["spx_pred"], d["pred_label"], keep=keep)
+        out = self.path(d["f8_l"], d["f8_r"], d["f4_l"], d["f4_r"], None, None, d["spx_pred"], d["pred_label"], keep=keep,
+                        f4_l_blocked=d["f4_l_blocked"])
         out["pred_label"] = d["pred_label"]
         if right_label:
             out["pred_label_r"] = d["pred_label_r"]

@@ -80,3 +80,69 @@ class ShardedHotPath:
         out = self.path(*[inputs.get(k) for k in order])
         key = "pred_att_up" if self.path.att_weights_only else "pred_up"
         return gather_batch(out[key], global_batch, self.group)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Large single images: row tiles with halos, tiles spread over the ranks ("large single images")
+# ---------------------------------------------------------------------------------------------------------------------
+TILE_UNIT = 128          # the path needs H % 128 == 0 and tile origins on the window-attention grid (128 px at 1/32 resolution)
+EXACT_HALO = 384         # >= the vertical receptive field of the whole path (~380 px)
+
+
+def plan_row_tiles(H: int, n_tiles: int, halo: int = EXACT_HALO):
+    """Splits H rows into `n_tiles` bands of whole 128-row units (as even as possible) and extends each band by `halo` rows on
+    the sides that are not image borders.  Epipolar lines are rows, so bands need no disparity halo, only the receptive-field
+    one.  Returns [(ext_lo, ext_hi, keep_lo, keep_hi)], all multiples of 128."""
+    if H % TILE_UNIT or halo % TILE_UNIT or halo < 0:
+        raise ValueError("plan_row_tiles: H and halo must be multiples of 128")
+    units = H // TILE_UNIT
+    if not (1 <= n_tiles <= units):
+        raise ValueError(f"plan_row_tiles: need 1 <= n_tiles <= H/128 = {units}")
+    base, extra = divmod(units, n_tiles)
+    tiles, lo = [], 0
+    for t in range(n_tiles):
+        hi = lo + (base + (1 if t < extra else 0)) * TILE_UNIT
+        tiles.append((max(0, lo - halo), min(H, hi + halo), lo, hi))
+        lo = hi
+    return tiles
+
+
+class TiledHotPath:
+    """Runs `path` on row bands of one large image batch and stitches the kept rows.  With a process group the bands are dealt
+    round-robin to the ranks and the stitched disparity is summed across ranks (every row is written by exactly one rank, the
+    others contribute zeros, so the sum is exact).  With halo >= EXACT_HALO no kept row can see a cut; what remains is the fp32
+    rounding of the reference's own grid normalisation (SpatialTransformer_grid divides by (H-1)/2 and multiplies back,
+    submodule.py:279-280, so its sampling rows depend on the tile height at the 1e-6 level): <= 1e-4 px in fp32 mode
+    (measured, tests/test_gpu_hotpath.py).  A smaller halo trades seam accuracy for less recomputation.  The reference has no
+    tiling at all (main_us3d.py feeds whole crops)."""
+
+    def __init__(self, path, n_tiles: int, halo: int = EXACT_HALO, group=None):
+        self.path, self.n_tiles, self.halo, self.group = path, n_tiles, halo, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def __call__(self, inputs: dict):
+        order = ("f8_l", "f8_r", "f4_l", "f4_r", "cf_l", "cf_r", "spx_pred", "pred_label")
+        H = inputs["spx_pred"].shape[-2]
+        key = "pred_att_up" if self.path.att_weights_only else "pred_up"
+        out = None
+        for t, (e0, e1, k0, k1) in enumerate(plan_row_tiles(H, self.n_tiles, self.halo)):
+            if t % self.world != self.rank:
+                continue
+            args = []
+            for k in order:
+                x = inputs.get(k)
+                if x is not None:
+                    s = H // x.shape[-2]                 # 8, 4 or 1
+                    x = x[..., e0 // s: e1 // s, :].contiguous()
+                args.append(x)
+            o = self.path(*args)[key]
+            if out is None:
+                out = o.new_zeros((o.shape[0], H, o.shape[-1]))
+            out[:, k0:k1] = o[:, k0 - e0: k1 - e0]
+        if out is None:                                    # more ranks than tiles
+            ref = inputs["spx_pred"]
+            out = ref.new_zeros((ref.shape[0], H, ref.shape[-1]))
+        if self.world > 1:
+            dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
+        return out

@@ -228,9 +228,9 @@ class DisparityHotPath(nn.Module):
             c[ca + ".w1"] = m[1].weight.detach().float().reshape(m[1].out_channels, -1).contiguous()
             c[ca + ".b1"] = m[1].bias.detach().float().contiguous()
             w0, w1 = m[0].conv.weight.detach().float(), m[1].weight.detach().float()
-            if bf16 and tc.ntile(tc.K1, w0.shape[1], w0.shape[0]) and tc.ntile(tc.K1, w1.shape[1], w1.shape[0]):
-                c[ca + ".tc0"] = tc.pack_weight(w0.unsqueeze(2), tc.K1)          # (Cout,Cin,1,1) -> (Cout,Cin,1,1,1)
-                c[ca + ".tc1"] = tc.pack_weight(w1.unsqueeze(2), tc.K1)
+            if bf16:
+                c[ca + ".tc0"] = tc.pack_weight2d(w0, tc.CONV1)
+                c[ca + ".tc1"] = tc.pack_weight2d(w1, tc.CONV1)
         cf0, cf1 = self.concat_feature[0], self.concat_feature[1]
         c["cf0.scale"], c["cf0.shift"] = bn_affine(cf0.bn)
         if bf16:
@@ -259,12 +259,14 @@ class DisparityHotPath(nn.Module):
             return ops.conv3d_f32(y, c["cf1.w"], k=3).squeeze(2)
 
     def _gate_logits(self, c, name, im, im_blocked=None):
-        """channelAtt.im_att (SemStereo.py:93-95): 1x1 conv + BN + ReLU -> 1x1 conv + bias.  With a blocked bf16 copy of the image
-        features at hand (bf16 mode, 1/4 resolution) both 1x1 convs run on the tensor cores."""
-        if im_blocked is not None and (name + ".tc0") in c:
+        """channelAtt.im_att (SemStereo.py:93-95): 1x1 conv + BN + ReLU -> 1x1 conv + bias.  bf16 mode: both 1x1 convs run on
+        the tensor cores (csrc/conv2d_tc.cu, mode CONV1) from a blocked bf16 copy of the image features."""
+        if self.precision == "bf16":
             with ops.label(name):
-                y = tc.conv3d_tc(tc.K1, im_blocked, c[name + ".tc0"], c[name + ".tc0"].shape[3], c[name + ".s0"], c[name + ".t0"], relu=True)
-                return tc.conv3d_tc(tc.K1, y, c[name + ".tc1"], 32, None, c[name + ".b1"], out_mode=tc.F32).squeeze(2)
+                B, C, H, W = im.shape
+                xb = im_blocked.view(B, C // 8, H, W, 8) if im_blocked is not None else tc.to_blocked2d(im)
+                y = tc.conv2d_tc(tc.CONV1, xb, c[name + ".tc0"], C // 2, c[name + ".s0"], c[name + ".t0"], relu=True)
+                return tc.conv2d_tc(tc.CONV1, y, c[name + ".tc1"], 32, None, c[name + ".b1"], out_f32=True)
         y = ops.pointwise_conv2d(im, c[name + ".w0"], c[name + ".s0"], c[name + ".t0"], relu=True)
         return ops.pointwise_conv2d(y, c[name + ".w1"], None, c[name + ".b1"], relu=False)
 
@@ -330,7 +332,7 @@ class DisparityHotPath(nn.Module):
             return ops.conv3d_cout1_f32(y, c[cl + ".2.w"])
 
     @torch.no_grad()
-    def forward(self, f8_l, f8_r, f4_l, f4_r, cf_l, cf_r, spx_pred, pred_label, keep: bool = False):
+    def forward(self, f8_l, f8_r, f4_l, f4_r, cf_l, cf_r, spx_pred, pred_label, keep: bool = False, f4_l_blocked=None):
         """cf_l / cf_r may be None: concat_feature(f4_*) is then computed here (tensor cores in bf16 mode)."""
         c = self._packed()
         m8, m4 = self.maxdisp // 8, self.maxdisp // 4
@@ -357,7 +359,10 @@ class DisparityHotPath(nn.Module):
             out["pred_att_up"] = ops.ssr_upsample(pred_att.unsqueeze(1), spx_pred, pred_label, c["ssr"])
             return out
         # --- sparse concat volume + aggregation (SemStereo.py:314-324) ---
-        f4l_b = tc.to_blocked_bf16(f4_l.unsqueeze(2)) if self.precision == "bf16" else None    # feeds concat_feature and the gate convs
+        f4l_b = None                            # bf16 blocked copy of f4_l: feeds concat_feature and the gate convs
+        if self.precision == "bf16":
+            f4l_b = (f4_l_blocked.view(f4_l.shape[0], 16, 1, *f4_l.shape[2:], 8) if f4_l_blocked is not None
+                     else tc.to_blocked_bf16(f4_l.unsqueeze(2)))
         if cf_l is None:
             cf_l = self._concat_feature(c, f4_l, f4l_b)
         if cf_r is None:

@@ -164,3 +164,22 @@ def test_concat_feature_inside_the_path():
     assert bool((out["ind_k"] == ref["ind_k"]).all())
     assert maxerr(out["volume"], ref["volume"]) <= 1e-4 * max(1.0, ref["volume"].abs().max().item())
     assert maxerr(out["cost"], ref["cost"]) <= 2e-2
+
+
+def test_row_tiles_with_receptive_field_halo_match_the_untiled_run():
+    """A 2048-row image as two 1024-row bands, origins on the 128-px window grid.  With 384-row halos (>= the path's vertical
+    receptive field) no kept row sees a cut: the stitched result equals the untiled one up to the fp32 rounding of the
+    reference's grid normalisation, which depends on the tile height (<= 1e-3 px, the north-star tolerance).  With a 128-row
+    halo the same holds for rows further than 384 px from the seam."""
+    from semstereo_b200.dist import TiledHotPath
+    m = build(64, True, False, 20.0)
+    inp = {k: v.to(DEV) for k, v in make_inputs(31, 1, 2048, 128).items()}
+    full = m(*[inp[k] for k in ORDER])["pred_up"]
+    tiled = TiledHotPath(m, n_tiles=2, halo=384)(inp)
+    assert float((tiled - full).abs().max()) <= 1e-3
+    approx = TiledHotPath(m, n_tiles=2, halo=128)(inp)
+    diff = (approx - full).abs()
+    away = torch.ones(2048, dtype=torch.bool, device=DEV)
+    away[1024 - 384: 1024 + 384] = False
+    assert float(diff[:, away].max()) <= 1e-3
+    print(f"\n[row tiles, halo 128] rows within 384 px of the seam: max |diff| {float(diff.max()):.4f}, mean {float(diff.mean()):.6f}")

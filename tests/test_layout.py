@@ -88,6 +88,17 @@ inp = {k: torch.randn(B, 3, 4, 5, generator=g) for k in names}
 full = FakePath()(*[inp[k] for k in names])["pred_up"]
 got = sd.ShardedHotPath(FakePath())(inp)
 assert got.shape == full.shape and torch.equal(got, full), (rank, got.shape)
+class RowPath:             # row-local stand-in: row tiles with any halo must reproduce the untiled result exactly
+    att_weights_only = False
+    def __call__(self, f8_l, f8_r, f4_l, f4_r, cf_l, cf_r, spx, lab):
+        up = lambda t, s: t.sum(1).repeat_interleave(s, 1).repeat_interleave(s, 2)
+        return {"pred_up": spx.sum(1) + up(f8_l, 8) + up(f4_r, 4) + lab.mean(1)}
+H, W = 640, 128
+inp2 = {k: torch.randn(1, 2, H // s, W // s, generator=g) for k, s in zip(names, (8, 8, 4, 4, 4, 4, 1, 1))}
+full2 = RowPath()(*[inp2[k] for k in names])["pred_up"]
+for n_tiles, halo in ((3, 128), (2, 0), (5, 256)):
+    got2 = sd.TiledHotPath(RowPath(), n_tiles=n_tiles, halo=halo)(inp2)
+    assert torch.equal(got2, full2), (rank, n_tiles, halo)
 dist.barrier(); dist.destroy_process_group()
 print("ok", rank)
 '''
@@ -112,3 +123,16 @@ def test_bench_reference_arm_small():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_plan_row_tiles():
+    from semstereo_b200.dist import plan_row_tiles
+    assert plan_row_tiles(1024, 2, 384) == [(0, 896, 0, 512), (128, 1024, 512, 1024)]
+    assert plan_row_tiles(1024, 1, 384) == [(0, 1024, 0, 1024)]
+    tiles = plan_row_tiles(2048, 3, 128)
+    assert [t[2:] for t in tiles] == [(0, 768), (768, 1408), (1408, 2048)]           # 6 + 5 + 5 units of 128 rows
+    assert all(e0 % 128 == 0 and e1 % 128 == 0 and e0 <= k0 < k1 <= e1 for e0, e1, k0, k1 in tiles)
+    with pytest.raises(ValueError):
+        plan_row_tiles(1000, 2)
+    with pytest.raises(ValueError):
+        plan_row_tiles(256, 3)
