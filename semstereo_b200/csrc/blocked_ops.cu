@@ -66,6 +66,64 @@ __global__ void __launch_bounds__(128) patch_gate_blocked_kernel(const float* __
   out[(((size_t)b * 8 + phase) * G8 + chunk) * S8 + ((size_t)(d >> 1) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)] = q;
 }
 
+// Same op, 4 consecutive x per thread (W % 4 == 0): each of the 3 rows is one aligned float4 plus its two neighbours, so a
+// thread issues 9 loads per group for 4 outputs instead of 36; the two x-parities of its outputs are two 32-byte runs.
+__global__ void __launch_bounds__(128) patch_gate_blocked_x4_kernel(const float* __restrict__ vol, const float* __restrict__ w,
+                                                                    const float* __restrict__ gate, uint4* __restrict__ out, int G, int D,
+                                                                    int H, int W) {
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (x >= W) return;
+  const int y = blockIdx.y % H, d = blockIdx.y / H;
+  const int G8 = G >> 3, chunk = blockIdx.z % G8, b = blockIdx.z / G8;
+  const size_t HW = (size_t)H * W;
+  int yo[3];
+  float ym[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int yy = y + k - 1;
+    ym[k] = (yy >= 0 && yy < H) ? 1.0f : 0.0f;
+    yo[k] = min(max(yy, 0), H - 1) * W;
+  }
+  const float lm = x > 0 ? 1.0f : 0.0f, rm = x + 4 < W ? 1.0f : 0.0f;
+  const int xl = max(x - 1, 0), xr = min(x + 4, W - 1);
+  float f[4][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int g = chunk * 8 + i;
+    const float* plane = vol + (((size_t)b * G + g) * D + d) * HW;
+    float wk[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wk[t] = __ldg(w + g * 9 + t);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const float4 c = __ldg(reinterpret_cast<const float4*>(plane + yo[ky] + x));
+      const float v[6] = {__ldg(plane + yo[ky] + xl) * lm, c.x, c.y, c.z, c.w, __ldg(plane + yo[ky] + xr) * rm};
+      const float w0 = wk[ky * 3] * ym[ky], w1 = wk[ky * 3 + 1] * ym[ky], w2 = wk[ky * 3 + 2] * ym[ky];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(w2, v[j + 2], fmaf(w1, v[j + 1], fmaf(w0, v[j], acc[j])));
+    }
+    const float4 gl = __ldg(reinterpret_cast<const float4*>(gate + ((size_t)b * G + g) * HW + (size_t)y * W + x));
+    f[0][i] = sigmoidf_(gl.x) * acc[0]; f[1][i] = sigmoidf_(gl.y) * acc[1];
+    f[2][i] = sigmoidf_(gl.z) * acc[2]; f[3][i] = sigmoidf_(gl.w) * acc[3];
+  }
+  const size_t S8 = (size_t)(D >> 1) * (H >> 1) * (W >> 1);
+  const size_t sp = ((size_t)(d >> 1) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
+  const int ph0 = ((d & 1) << 2) | ((y & 1) << 1);
+#pragma unroll
+  for (int pw = 0; pw < 2; ++pw) {
+    uint4* o = out + (((size_t)b * 8 + ph0 + pw) * G8 + chunk) * S8 + sp;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float* v = f[2 * j + pw];
+      uint4 q;
+      q.x = tc::pack_bf16x2(v[0], v[1]); q.y = tc::pack_bf16x2(v[2], v[3]);
+      q.z = tc::pack_bf16x2(v[4], v[5]); q.w = tc::pack_bf16x2(v[6], v[7]);
+      o[j] = q;
+    }
+  }
+}
+
 // out blocked bf16 (B, 2C/8, K, H, W, 8): chunks [0, C/8) = cf_l * a_k ; [C/8, 2C/8) = bilinear(cf_r, x - d_k) * a_k.
 // One CTA = one image row x 64 pixels, thread (pixel, half of the samples).  The left tile and the two right rows the bilinear
 // taps can touch (floor(iy), floor(iy)+1: the same for the whole row) are staged once in shared memory with a +-PAD column
@@ -168,8 +226,13 @@ extern "C" int ss_patch_gate_blocked(const float* volume, const float* patch_w, 
   SS_REQUIRE(B > 0 && G > 0 && D > 0 && H > 0 && W > 0, "ss_patch_gate_blocked: non-positive dimension");
   SS_REQUIRE(G % 8 == 0 && D % 2 == 0 && H % 2 == 0 && W % 2 == 0, "ss_patch_gate_blocked: G %% 8 == 0 and even D,H,W required");
   SS_UNSUPPORTED((int64_t)D * H > 65535 || (int64_t)B * (G / 8) > 65535, "ss_patch_gate_blocked: grid dimension exceeds 65535");
-  patch_gate_blocked_kernel<<<dim3(ceil_div(W, 128), D * H, B * (G / 8)), 128, 0, (cudaStream_t)stream>>>(
-      volume, patch_w, gate_logits, reinterpret_cast<uint4*>(out_s2d), G, D, H, W);
+  const bool x4 = W % 4 == 0 && ((reinterpret_cast<uintptr_t>(volume) | reinterpret_cast<uintptr_t>(gate_logits)) & 15) == 0;
+  if (x4)
+    patch_gate_blocked_x4_kernel<<<dim3(ceil_div(W / 4, 32), D * H, B * (G / 8)), 32, 0, (cudaStream_t)stream>>>(
+        volume, patch_w, gate_logits, reinterpret_cast<uint4*>(out_s2d), G, D, H, W);
+  else
+    patch_gate_blocked_kernel<<<dim3(ceil_div(W, 128), D * H, B * (G / 8)), 128, 0, (cudaStream_t)stream>>>(
+        volume, patch_w, gate_logits, reinterpret_cast<uint4*>(out_s2d), G, D, H, W);
   SS_CHECK_LAUNCH("ss_patch_gate_blocked");
   return SS_OK;
 }

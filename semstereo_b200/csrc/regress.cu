@@ -89,91 +89,127 @@ __global__ void __launch_bounds__(128) att_stats_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// K7: block = (64 pixels) x (5 hypotheses).  Per 16-channel chunk the left row tile and the two right rows the bilinear
-// taps can touch (floor(iy) and floor(iy)+1 are the same for the whole image row) are staged in shared memory with coalesced
-// loads, including a +-PAD column window around the tile; the 5 x 4 corner reads per channel then hit shared memory.
-// A hypothesis whose corners fall outside the staged window (|disparity| > PAD-2) reads global memory instead.
+// K7: block = 128 pixels of one image row, one thread per pixel and all 5 hypotheses.  Per 32-channel chunk the left row tile
+// and the right row are staged in shared memory (128-bit loads) with a +-PAD column window.  The bilinear weights factor into
+// an x and a y term and the y term is the same for the whole row (iy depends on y only), so the two right rows floor(iy),
+// floor(iy)+1 are blended while staging -- with the reference's fp32 coordinate round trip the second weight is exactly 0 on
+// ~75 % of the rows and that row is then not even loaded.  A hypothesis then costs 2 shared loads per channel instead of 4,
+// and the left value is read once for all 5.  Hypotheses whose corners leave the window (|disparity| > PAD-2) read global memory.
 // ---------------------------------------------------------------------------------------------
-constexpr int SS_TX = 64, SS_PAD = 24, SS_WW = SS_TX + 2 * SS_PAD, SS_CK = 32;
+constexpr int SS_TX = 128, SS_PAD = 24, SS_WW = SS_TX + 2 * SS_PAD, SS_CK = 32;
 
-__global__ void __launch_bounds__(320) sample_strength_kernel(const float* __restrict__ fl, const float* __restrict__ fr,
-                                                              const float* __restrict__ mu, const float* __restrict__ gate,
-                                                              float* __restrict__ strength, int B, int C, int H, int W) {
-  __shared__ float logit[5][SS_TX];
+__global__ void __launch_bounds__(SS_TX) sample_strength_kernel(const float* __restrict__ fl, const float* __restrict__ fr,
+                                                                const float* __restrict__ mu, const float* __restrict__ gate,
+                                                                float* __restrict__ strength, int B, int C, int H, int W) {
   __shared__ __align__(16) float Ls[SS_CK][SS_TX];
-  __shared__ __align__(16) float Rs[SS_CK][2][SS_WW];
+  __shared__ __align__(16) float Rc[SS_CK][SS_WW];
   const bool vec4 = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(fl) | reinterpret_cast<uintptr_t>(fr)) & 15) == 0;
-  const int tx = threadIdx.x, s = threadIdx.y, tid = s * SS_TX + tx;
+  const int tx = threadIdx.x;
   const int x0 = blockIdx.x * SS_TX, x = x0 + tx, y = blockIdx.y, b = blockIdx.z;
   const size_t HW = (size_t)H * W;
   const float iy = warp_coord((float)y, (float)(H - 1));
-  const int y0 = (int)floorf(iy);                                  // uniform over the row
+  const float fy0 = floorf(iy), fy1 = fy0 + 1.0f;
+  const bool vy0 = fy0 >= 0.0f && fy0 <= (float)(H - 1), vy1 = fy1 >= 0.0f && fy1 <= (float)(H - 1);
+  const float wy0 = vy0 ? fy1 - iy : 0.0f, wy1 = vy1 ? iy - fy0 : 0.0f;      // uniform over the row
+  const int y0 = vy0 ? (int)fy0 : 0, y1 = vy1 ? (int)fy1 : 0;
   const bool active = x < W;
-  float d = 0.0f, g = 0.0f;
-  if (active) {
-    const int ty = min(max(y + kPropDy[s], 0), H - 1), txx = min(max(x + kPropDx[s], 0), W - 1);
-    d = __ldg(mu + (size_t)b * HW + (size_t)ty * W + txx);
-    g = __ldg(gate + (size_t)b * HW + (size_t)ty * W + txx);
+  float g[5], wx0[5], wx1[5], ixs[5];
+  int j0[5];
+  bool in_win[5];
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    float d = 0.0f;
+    g[s] = 0.0f;
+    if (active) {
+      const int ty = min(max(y + kPropDy[s], 0), H - 1), txx = min(max(x + kPropDx[s], 0), W - 1);
+      d = __ldg(mu + (size_t)b * HW + (size_t)ty * W + txx);
+      g[s] = __ldg(gate + (size_t)b * HW + (size_t)ty * W + txx);
+    }
+    const float ix = warp_coord((float)x - d, (float)(W - 1));
+    ixs[s] = ix;
+    const float fx0 = floorf(ix), fx1 = fx0 + 1.0f;
+    const float jf = fx0 - (float)(x0 - SS_PAD);
+    in_win[s] = jf >= 0.0f && jf <= (float)(SS_WW - 2);      // both corners inside the staged window (zeros outside the image)
+    j0[s] = in_win[s] ? (int)jf : 0;
+    wx0[s] = in_win[s] ? fx1 - ix : 0.0f;         // out-of-window hypotheses add 0 in the staged loop and are done below
+    wx1[s] = in_win[s] ? ix - fx0 : 0.0f;
   }
-  const Bilin q = make_bilin(warp_coord((float)x - d, (float)(W - 1)), iy, H, W);
-  // column of the west corners inside the staged window; both corners must be inside to use it
-  const float fx0 = floorf(warp_coord((float)x - d, (float)(W - 1)));
-  const float jf = fx0 - (float)(x0 - SS_PAD);
-  const bool in_win = jf >= 0.0f && jf <= (float)(SS_WW - 2);
-  const int j0 = in_win ? (int)jf : 0;
   const float* lb = fl + (size_t)b * C * HW + (size_t)y * W;
   const float* rb = fr + (size_t)b * C * HW;
-  float acc = 0.0f;
+  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   for (int c0 = 0; c0 < C; c0 += SS_CK) {
-    if (vec4) {        // rows are 16-byte aligned: stage with 128-bit loads (x0 and x0 - PAD are multiples of 4)
-      for (int i = tid; i < SS_CK * (SS_TX / 4); i += 320) {
+    if (vec4) {        // rows are 16-byte aligned: x0 and x0 - PAD are multiples of 4
+      for (int i = tx; i < SS_CK * (SS_TX / 4); i += SS_TX) {
         const int c = i / (SS_TX / 4), j = (i - c * (SS_TX / 4)) * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c0 + c < C && x0 + j < W) v = __ldg(reinterpret_cast<const float4*>(lb + (size_t)(c0 + c) * HW + x0 + j));
         *reinterpret_cast<float4*>(&Ls[c][j]) = v;
       }
-      for (int i = tid; i < SS_CK * 2 * (SS_WW / 4); i += 320) {
-        const int c = i / (2 * (SS_WW / 4)), r = (i / (SS_WW / 4)) & 1, j = (i % (SS_WW / 4)) * 4;
-        const int xx = x0 - SS_PAD + j, yy = y0 + r;
+      for (int i = tx; i < SS_CK * (SS_WW / 4); i += SS_TX) {
+        const int c = i / (SS_WW / 4), j = (i - c * (SS_WW / 4)) * 4;
+        const int xx = x0 - SS_PAD + j;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c0 + c < C && xx >= 0 && xx < W && yy >= 0 && yy < H)
-          v = __ldg(reinterpret_cast<const float4*>(rb + (size_t)(c0 + c) * HW + (size_t)yy * W + xx));
-        *reinterpret_cast<float4*>(&Rs[c][r][j]) = v;
+        if (c0 + c < C && xx >= 0 && xx < W) {
+          const float* rp = rb + (size_t)(c0 + c) * HW + xx;
+          if (wy0 != 0.0f) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(rp + (size_t)y0 * W));
+            v = make_float4(a.x * wy0, a.y * wy0, a.z * wy0, a.w * wy0);
+          }
+          if (wy1 != 0.0f) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(rp + (size_t)y1 * W));
+            v.x = fmaf(a.x, wy1, v.x); v.y = fmaf(a.y, wy1, v.y); v.z = fmaf(a.z, wy1, v.z); v.w = fmaf(a.w, wy1, v.w);
+          }
+        }
+        *reinterpret_cast<float4*>(&Rc[c][j]) = v;
       }
     } else {
-      for (int i = tid; i < SS_CK * SS_TX; i += 320) {
+      for (int i = tx; i < SS_CK * SS_TX; i += SS_TX) {
         const int c = i / SS_TX, j = i - c * SS_TX;
         Ls[c][j] = (c0 + c < C && x0 + j < W) ? __ldg(lb + (size_t)(c0 + c) * HW + x0 + j) : 0.0f;
       }
-      for (int i = tid; i < SS_CK * 2 * SS_WW; i += 320) {
-        const int c = i / (2 * SS_WW), r = (i / SS_WW) & 1, j = i % SS_WW;
-        const int xx = x0 - SS_PAD + j, yy = y0 + r;
-        Rs[c][r][j] = (c0 + c < C && xx >= 0 && xx < W && yy >= 0 && yy < H) ? __ldg(rb + (size_t)(c0 + c) * HW + (size_t)yy * W + xx) : 0.0f;
+      for (int i = tx; i < SS_CK * SS_WW; i += SS_TX) {
+        const int c = i / SS_WW, j = i - c * SS_WW;
+        const int xx = x0 - SS_PAD + j;
+        float v = 0.0f;
+        if (c0 + c < C && xx >= 0 && xx < W) {
+          const float* rp = rb + (size_t)(c0 + c) * HW + xx;
+          if (wy0 != 0.0f) v = __ldg(rp + (size_t)y0 * W) * wy0;
+          if (wy1 != 0.0f) v = fmaf(__ldg(rp + (size_t)y1 * W), wy1, v);
+        }
+        Rc[c][j] = v;
       }
     }
     __syncthreads();
     if (active) {
       const int nc = min(SS_CK, C - c0);
-      if (in_win) {
 #pragma unroll 4
-        for (int c = 0; c < nc; ++c)
-          acc += Ls[c][tx] * (((Rs[c][0][j0] * q.w00 + Rs[c][0][j0 + 1] * q.w01) + Rs[c][1][j0] * q.w10) + Rs[c][1][j0 + 1] * q.w11);
-      } else {
-        for (int c = 0; c < nc; ++c) acc += Ls[c][tx] * bilin_fetch(rb + (size_t)(c0 + c) * HW, q);
+      for (int c = 0; c < nc; ++c) {
+        const float l = Ls[c][tx];
+#pragma unroll
+        for (int s = 0; s < 5; ++s) acc[s] = fmaf(l, fmaf(Rc[c][j0[s] + 1], wx1[s], Rc[c][j0[s]] * wx0[s]), acc[s]);
       }
     }
     __syncthreads();
   }
-  if (active) logit[s][tx] = (acc / (float)C) * g;
-  __syncthreads();
   if (active) {
-    float m = logit[0][tx];
 #pragma unroll
-    for (int i = 1; i < 5; ++i) m = fmaxf(m, logit[i][tx]);
-    float sum = 0.0f;
+    for (int s = 0; s < 5; ++s) {
+      if (in_win[s]) continue;                      // rare: wild disparity, corners outside the staged window
+      const Bilin q = make_bilin(ixs[s], iy, H, W);
+      float a = 0.0f;
+      for (int c = 0; c < C; ++c) a += __ldg(lb + (size_t)c * HW + x) * bilin_fetch(rb + (size_t)c * HW, q);
+      acc[s] = a;
+    }
+  }
+  if (active) {
+    float logit[5], m = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) sum += expf(logit[i][tx] - m);
-    strength[((size_t)b * 5 + s) * HW + (size_t)y * W + x] = expf(logit[s][tx] - m) / sum;
+    for (int s = 0; s < 5; ++s) { logit[s] = (acc[s] / (float)C) * g[s]; m = fmaxf(m, logit[s]); }
+    float e[5], sum = 0.0f;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) { e[s] = expf(logit[s] - m); sum += e[s]; }
+#pragma unroll
+    for (int s = 0; s < 5; ++s) strength[((size_t)b * 5 + s) * HW + (size_t)y * W + x] = e[s] / sum;
   }
 }
 
@@ -361,8 +397,8 @@ extern "C" int ss_sample_strength(const float* feat_l, const float* feat_r, cons
   SS_REQUIRE(feat_l && feat_r && mu && gate && strength, "ss_sample_strength: null pointer");
   SS_REQUIRE(B > 0 && C > 0 && H > 1 && W > 1, "ss_sample_strength: bad dimension");
   SS_GRID_LIMIT(H <= 65535 && B <= 65535, "ss_sample_strength");
-  dim3 grid(ceil_div(W, 64), H, B), block(64, 5);
-  sample_strength_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(feat_l, feat_r, mu, gate, strength, B, C, H, W);
+  dim3 grid(ceil_div(W, SS_TX), H, B);
+  sample_strength_kernel<<<grid, SS_TX, 0, (cudaStream_t)stream>>>(feat_l, feat_r, mu, gate, strength, B, C, H, W);
   SS_CHECK_LAUNCH("ss_sample_strength");
   return SS_OK;
 }

@@ -103,19 +103,20 @@ def test_conv_k3_s2(Cin, Cout, B, D, H, W, out_f32):
     check(out.cpu() if out_f32 else tc.from_blocked_bf16(out).cpu(), ref, not out_f32)
 
 
-def test_blocked_producers():
+@pytest.mark.parametrize("W", [20, 18, 128])          # W % 4 == 0 takes the 4-pixel-per-thread patch-gate kernel
+def test_blocked_producers(W):
     from oracle import ops as oo
     from semstereo_b200 import ops
     from semstereo_b200.params import make_params
     p = make_params(seed=4)
     g = torch.Generator().manual_seed(5)
-    vol, logits = torch.randn(2, 32, 6, 10, 20, generator=g), torch.randn(2, 32, 10, 20, generator=g)
+    vol, logits = torch.randn(2, 32, 6, 10, W, generator=g), torch.randn(2, 32, 10, W, generator=g)
     ref = torch.sigmoid(logits).unsqueeze(2) * oo.patch_conv(vol, p)
     got = tc.patch_gate_blocked(vol.to(DEV), p["patch.weight"].reshape(32, 9).to(DEV), logits.to(DEV))
     assert torch.equal(got.cpu(), tc.to_blocked_bf16(ops.patch_gate(vol.to(DEV), p["patch.weight"].reshape(32, 9).to(DEV), logits.to(DEV)), s2d=True).cpu())
     assert (got.cpu().float() - s2d_ref(ref)).abs().max() <= 2e-2
     gb = tc.gate_sigmoid_blocked(logits.to(DEV)).cpu()
-    assert (gb - torch.sigmoid(logits).view(2, 4, 8, 10, 20).permute(0, 1, 3, 4, 2)).abs().max() <= 1e-6
+    assert (gb - torch.sigmoid(logits).view(2, 4, 8, 10, W).permute(0, 1, 3, 4, 2)).abs().max() <= 1e-6
     cfl, cfr = torch.randn(2, 32, 9, 20, generator=g), torch.randn(2, 32, 9, 20, generator=g)
     d = torch.randint(-6, 7, (2, 24, 9, 20), generator=g).float()
     a = torch.rand(2, 24, 9, 20, generator=g)
