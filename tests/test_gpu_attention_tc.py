@@ -28,3 +28,19 @@ def test_attention_block_tc(block, D, H, W):
     torch.cuda.synchronize()
     err = (out.cpu() - ref).abs().max().item()
     assert err <= 3e-2 * ref.abs().max().item() + 1e-2, err
+
+
+@pytest.mark.parametrize("block,B,D,H,W", [((4, 4, 4), 2, 4, 8, 8), ((6, 4, 4), 1, 12, 8, 12), ((2, 4, 4), 1, 4, 8, 8)])
+def test_attention_core_vs_fp32_softmax(block, B, D, H, W):
+    """The softmax(q k^T / sqrt(8)) v core alone (mma.sync kernel for 64 / 96-token windows, fp32 kernel otherwise) against an
+    fp32 torch evaluation of the SAME bf16 q, k, v: differences = bf16 rounding of the probabilities and of the output."""
+    g = torch.Generator().manual_seed(sum(block) + D)
+    qkv = (1.5 * torch.randn(B, 384, D, H, W, generator=g)).to(torch.bfloat16).float()
+    got = tc.from_blocked_bf16(tc.window_attention_core(tc.to_blocked_bf16(qkv.to(DEV)), block, 16)).cpu()
+    bd, bh, bw = block
+    t = qkv.view(B, 3, 16, 8, D // bd, bd, H // bh, bh, W // bw, bw).permute(1, 0, 4, 6, 8, 2, 5, 7, 9, 3)
+    q, k, v = [x.reshape(B, D // bd, H // bh, W // bw, 16, bd * bh * bw, 8) for x in t]      # (..., head, token, hd)
+    att = torch.softmax(q @ k.transpose(-1, -2) * 8 ** -0.5, dim=-1) @ v
+    ref = att.view(B, D // bd, H // bh, W // bw, 16, bd, bh, bw, 8).permute(0, 4, 8, 1, 5, 2, 6, 3, 7).reshape(B, 128, D, H, W)
+    err = (got - ref).abs().max().item()
+    assert err <= 1.5e-2 * ref.abs().max().item(), err
