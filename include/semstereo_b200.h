@@ -93,7 +93,8 @@ SS_API int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight_pac
                         const void* skip_weight_or_null, void* out, int out_mode, int B, int Cin, int Cout, int D, int H, int W,
                         int relu, void* stream);
 /* nn.Conv3d(32, 1, 3, padding=1, bias=False) classifier heads (SemStereo.py:230,234) with the taps as the GEMM's N dimension:
- * in_blocked bf16 (B,4,D,H,W,8); weight_packed bf16 [4][32][8] = weight[0][chunk*8+c8][tap] (27 taps, rows 27..31 zero);
+ * in_blocked bf16 (B,4,D,H,W,8); weight_packed bf16 [4][48][8]: row j*16 + t9 of chunk c = weight[0][c*8+c8][kd = 2-j][t9]
+ * (t9 = kh*3+kw; rows with t9 >= 9 zero) -- the three depth taps are folded into N like kind 5 of ss_conv3d_tc;
  * out fp32 (B,1,D,H,W). */
 SS_API int ss_conv3d_tc_head(const void* in_blocked, const void* weight_packed, float* out, int B, int Cin, int D, int H, int W,
                              void* stream);

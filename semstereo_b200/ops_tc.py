@@ -126,19 +126,20 @@ def window_attention_core(qkv_blocked, block, num_heads=16):
 
 
 def pack_head_weight(w):
-    """(1,32,3,3,3) fp32 -> bf16 [4][32][8]: rows = taps (27 real, 5 zero), K-major chunks of 8 input channels."""
+    """(1,32,3,3,3) fp32 -> bf16 [4][48][8]: rows j*16 + t9 (depth tap kd = 2 - j, 9 in-plane taps + 7 zero rows), K-major chunks
+    of 8 input channels (csrc/conv3d_tc_head.cu)."""
     if tuple(w.shape) != (1, 32, 3, 3, 3):
         raise NotImplementedError("conv3d_tc_head: only Conv3d(32, 1, 3) is supported")
-    t = w.new_zeros((32, 32))                      # [c][tap]
-    t[:, :27] = w.reshape(32, 27)
-    return t.reshape(4, 8, 32).permute(0, 2, 1).contiguous().to(torch.bfloat16)
+    t = w.new_zeros((32, 3, 16))                   # [c][j][t9]
+    t[:, :, :9] = w[0].flip(1).reshape(32, 3, 9)
+    return t.reshape(4, 8, 48).permute(0, 2, 1).contiguous().to(torch.bfloat16)
 
 
 def conv3d_tc_head(xb, w_head):
     """Cout = 1 classifier head on the blocked layout: (B,4,D,H,W,8) bf16 -> (B,1,D,H,W) fp32."""
     dev = _require_bf16(xb, 6)
     B, C8, D, H, W, _ = xb.shape
-    if w_head.dtype != torch.bfloat16 or tuple(w_head.shape) != (4, 32, 8) or not w_head.is_contiguous():
+    if w_head.dtype != torch.bfloat16 or tuple(w_head.shape) != (4, 48, 8) or not w_head.is_contiguous():
         raise ValueError("conv3d_tc_head: weight must come from pack_head_weight")
     out = torch.empty((B, 1, D, H, W), device=dev, dtype=torch.float32)
     _call("ss_conv3d_tc_head", dev, _ptr(xb), _ptr(w_head), _ptr(out), B, C8 * 8, D, H, W)
