@@ -11,10 +11,11 @@
 // fetched ONCE per output tile column and reused by all its taps and by up to 3 output slices (depth-sliding ring).
 // GEMM tile: M = 128 voxels (16 h x 8 w of one depth slice), N = Cout tile, K = taps * Cin.
 //
-// Three kernels share the skeleton (persistent CTAs, 256 threads, 1 CTA/SM; warp 0 = TMA slice producer, warp 3 = weight
+// Four kernels share the skeleton (persistent CTAs, 256 threads, 1 CTA/SM; warp 0 = TMA slice producer, warp 3 = weight
 // producer (resident: all taps once; streamed: per-tap ring), warp 1 = MMA issuer (warp-uniform control flow, one elected
-// lane issues), warp 2 = TMEM allocator, warps 4-7 = epilogue; accumulators double-buffered in TMEM):
-//   s1 : Conv3d k3 s1 p1 (TAPS=27) and Conv3d k1 (TAPS=1).
+// lane issues), warp 2 = TMEM allocator, warps 4-7 = epilogue; accumulators double-buffered in TMEM, s1f: a 512-column ring):
+//   s1 : Conv3d k3 s1 p1 (TAPS=27), Conv3d k1 (TAPS=1), Conv2d 3x3 on a depth-1 volume (TAPS=9).
+//   s1f: Conv3d k3 s1 p1 for Cout = 32 / 64 with the three depth taps folded into the GEMM N (see the kernel's comment).
 //   s2 : Conv3d k3 s2 p1 on a phase-split ("s2d") input [B][8 phases (d,h,w parity)][C/8][D/2][H/2][W/2][8]: input index
 //        2o-1+k is (phase 1, o-1), (phase 0, o), (phase 1, o) for k = 0,1,2, so every tap is a dense half-resolution tile.
 //   t2 : ConvTranspose3d k3 s2 p1 op1 as 8 sub-pixel output phases (1/2/4/8 taps each, no zero insertion); the hourglass
