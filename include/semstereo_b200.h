@@ -92,6 +92,16 @@ SS_API int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight_pac
                         const float* shift_or_null, const float* gate_blocked_or_null, const void* residual_s2d_or_null,
                         const void* skip_weight_or_null, void* out, int out_mode, int B, int Cin, int Cout, int D, int H, int W,
                         int relu, void* stream);
+/* concat_volume_generator * att_topk -> concat_stem -> * sigmoid(gate) (SemStereo.py:241-244, 316-320) in ONE kernel: the sparse
+ * concat volume is produced tile by tile in shared memory as the GEMM's A operand and never written to HBM.
+ * cf_l / cf_r: bf16 blocked (B,4,H,W,8) = concat_feature(f4_*) (32 channels); disp_topk, att_topk: fp32 (B,K,H,W);
+ * samples must be the integer disparity bins dmin .. dmin+31 (disparity_sample_topk, :305; dmin = -(maxdisp/4) signed, 0 unsigned);
+ * weight_packed: concat_stem's Conv3d(64,32,3) weight in the kind-5 packing of ss_conv3d_tc; scale/shift: folded BN;
+ * gate_blocked: fp32 (B,4,H,W,8) pre-activated gate or NULL; out: (B,32,K,H,W) in out_mode 0 / 1 / 2 as ss_conv3d_tc. */
+SS_API int ss_concat_stem_fused(const void* cf_l_blocked, const void* cf_r_blocked, const float* disp_topk, const float* att_topk,
+                                const void* weight_packed, const float* scale_or_null, const float* shift_or_null,
+                                const float* gate_blocked_or_null, void* out, int out_mode, int B, int K, int H, int W, int dmin,
+                                int relu, void* stream);
 /* nn.Conv3d(32, 1, 3, padding=1, bias=False) classifier heads (SemStereo.py:230,234) with the taps as the GEMM's N dimension:
  * in_blocked bf16 (B,4,D,H,W,8); weight_packed bf16 [4][48][8]: row j*16 + t9 of chunk c = weight[0][c*8+c8][kd = 2-j][t9]
  * (t9 = kh*3+kw; rows with t9 >= 9 zero) -- the three depth taps are folded into N like kind 5 of ss_conv3d_tc;

@@ -36,6 +36,7 @@ SIGNATURES = {
     "ss_sparse_concat_volume_blocked": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "ss_conv3d_tc_ntile": [_I, _I, _I],
     "ss_conv3d_tc_head": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "ss_concat_stem_fused": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ss_conv2d_tc_ntile": [_I, _I, _I],
     "ss_conv2d_tc": [_I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ss_bilinear_up2": [_P, _P, _I, _I, _I, _P],

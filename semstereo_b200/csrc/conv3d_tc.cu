@@ -469,6 +469,234 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1f_kernel(const __grid_cons
 }
 
 // =====================================================================================================================
+// k9: concat_stem (Conv3d 64 -> 32 k3 s1 + BN + ReLU, gate) with the sparse concat volume generated INSIDE the kernel
+// (SemStereo.py:241-244, 316-319): the 403 MB/pair volume  V[c,k] = [cf_l[c] | cf_r[c](x - d_k)] * a_k  never exists in HBM.
+// Same GEMM as s1f<64,32> (depth taps folded into N, TMEM accumulator ring), but the A operand of input slice k is WRITTEN by
+// four producer warps instead of fetched by TMA: per work item one TMA round stages the bf16 cf_l halo tile and the cf_r rows
+// with a window wide enough for every disparity bin (41 px); the disp_topk / att_topk values of a thread's halo pixels are
+// prefetched from global memory one slice ahead; for each slice k the producers scale the left chunk and the
+// disparity-shifted right chunk of every halo pixel by a_k and store them in the [chunk][18x10 px][16 B] K-major layout the
+// MMAs read (generic-proxy stores -> fence.proxy.async -> mbarrier).  The weights stay resident (110 KB): shared memory is
+// the bottleneck resource of this layer, so nothing is streamed through it that does not have to be.
+// Out-of-image pixels have a_k = 0 and out-of-image right taps are 0 through the TMA zero fill: exactly the zero padding of
+// the convolution and of grid_sample.  Disparity samples are the integer bins dmin .. dmin+31 (disparity_sample_topk, :305);
+// the reference's bilinear weights differ from this integer shift by the 1e-6 of its fp32 grid round trip, below bf16 resolution.
+// =====================================================================================================================
+constexpr int K9_NS = 2, K9_RW = 41, K9_BINS = 32;
+constexpr uint32_t K9_SLICE = 8 * TILE_B, K9_TAPB = 64 * 96 * 2;
+constexpr uint32_t K9_OFF_W = K9_NS * K9_SLICE, K9_OFF_L = K9_OFF_W + 9 * K9_TAPB, K9_OFF_R = K9_OFF_L + 4 * HH * WW * 16,
+                   K9_SMEM = K9_OFF_R + 4 * HH * K9_RW * 16;
+static_assert(K9_OFF_L % 128 == 0 && K9_OFF_R % 128 == 0, "TMA destinations");
+static_assert(K9_SMEM <= 227 * 1024 - 2048, "shared memory budget");
+
+struct K9P {
+  TcP t;              // the conv part (w = s1f-packed weights [9][8][96][8]); t.D = number of samples K
+  const float* disp;  // (B,K,H,W) integer-valued samples
+  const float* att;   // (B,K,H,W)
+  int dmin;           // lowest disparity bin (-(maxdisp/4) signed, 0 unsigned); samples are integers in [dmin, dmin + 31]
+};
+
+__device__ __forceinline__ uint4 scale8(const uint4 q, float a) {
+  const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+  uint32_t r[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = tc::pack_bf16x2(__uint_as_float(u[i] << 16) * a, __uint_as_float(u[i] & 0xffff0000u) * a);
+  return make_uint4(r[0], r[1], r[2], r[3]);
+}
+
+__global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR,
+                                                                const K9P kp) {
+  constexpr int N = 32, KS = 4;
+  constexpr uint32_t LBO_A = TILE_B, SBO_A = WW * 16, LBO_B = 3 * N * 16, SBO_B = 128;
+  constexpr uint32_t NB = 512 / N;
+  const TcP& p = kp.t;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t a_full[K9_NS], a_empty[K9_NS], w_full, acc_full[NB], acc_empty[NB], st_full, st_empty;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_scale[N], s_shift[N];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta_s = blockIdx.x, cta_stride = gridDim.x;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    s_scale[i] = p.scale ? __ldg(p.scale + i) : 1.0f;
+    s_shift[i] = p.shift ? __ldg(p.shift + i) : 0.0f;
+  }
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&tmL); tc::prefetch_tmap(&tmR);
+    for (int i = 0; i < K9_NS; ++i) { tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1); }
+    tc::mbar_init(&w_full, 1);
+    for (uint32_t i = 0; i < NB; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
+    tc::mbar_init(&st_full, 1); tc::mbar_init(&st_empty, 128);
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc(&tmem_base_s, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+  if (warp >= 4 && warp < 8) {
+#pragma unroll 1
+    for (uint32_t c = 0; c < 512; c += 32) tc::tmem_zero32(tmem_base + ((uint32_t)((warp - 4) * 32) << 16) + c);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  uint8_t* Abase = smem;
+  uint8_t* Wbase = smem + K9_OFF_W;
+  const int dhi_bin = kp.dmin + K9_BINS - 1;                 // largest disparity a sample can take
+
+  if (warp == 0 && lane == 0) {
+    // ===== stager: per item, the cf_l tile, the cf_r window and the sample columns =====
+    uint32_t it = 0;
+    for (int s = cta_s; s < p.items; s += cta_stride, ++it) {
+      int b, h0, w0, dlo, dhi;
+      decode_item(p, s, b, h0, w0, dlo, dhi);
+      tc::mbar_wait(&st_empty, (it & 1) ^ 1);
+      tc::mbar_expect_tx(&st_full, K9_SMEM - K9_OFF_L);
+      tc::tma_load_4d(smem + K9_OFF_L, &tmL, &st_full, 0, w0 - 1, h0 - 1, b * 4);
+      tc::tma_load_4d(smem + K9_OFF_R, &tmR, &st_full, 0, w0 - 1 - dhi_bin, h0 - 1, b * 4);
+    }
+  } else if (warp == 3 && lane == 0) {
+    // ===== weights: resident, one bulk copy per tap =====
+    if (cta_s < p.items) {
+      tc::mbar_expect_tx(&w_full, 9 * K9_TAPB);
+      for (int t9 = 0; t9 < 9; ++t9)
+        tc::bulk_load(Wbase + t9 * K9_TAPB, reinterpret_cast<const uint8_t*>(p.w) + (size_t)t9 * K9_TAPB, K9_TAPB, &w_full);
+    }
+  } else if (warp >= 8) {
+    // ===== A producers: the slice k of the sparse concat volume for the 180 halo pixels =====
+    const int pt = threadIdx.x - 256;
+    const uint4* Ls = reinterpret_cast<const uint4*>(smem + K9_OFF_L);     // [4][180]
+    const uint4* Rs = reinterpret_cast<const uint4*>(smem + K9_OFF_R);     // [4][18][41]
+    const size_t HW = (size_t)p.H * p.W;
+    const int px1 = pt + 128;                                                // this thread's halo pixels: pt and (if < 180) pt + 128
+    const int r0 = pt / WW, c0 = pt - r0 * WW, r1 = px1 / WW, c1 = px1 - r1 * WW;
+    uint32_t g = 0, it = 0;
+    for (int s = cta_s; s < p.items; s += cta_stride, ++it) {
+      int b, h0, w0, dlo, dhi;
+      decode_item(p, s, b, h0, w0, dlo, dhi);
+      const int din0 = max(dlo - 1, 0), din1 = min(dhi, p.D - 1);
+      // sample values of this thread's pixels (a = 0 outside the image: the convolution's zero padding), one slice ahead
+      const int y0 = h0 - 1 + r0, x0 = w0 - 1 + c0, y1 = h0 - 1 + r1, x1 = w0 - 1 + c1;
+      const bool in0 = y0 >= 0 && y0 < p.H && x0 >= 0 && x0 < p.W;
+      const bool in1 = px1 < HH * WW && y1 >= 0 && y1 < p.H && x1 >= 0 && x1 < p.W;
+      const size_t o0 = (size_t)b * p.D * HW + (size_t)(in0 ? y0 : 0) * p.W + (in0 ? x0 : 0);
+      const size_t o1 = (size_t)b * p.D * HW + (size_t)(in1 ? y1 : 0) * p.W + (in1 ? x1 : 0);
+      float na0 = in0 ? __ldg(kp.att + o0 + (size_t)din0 * HW) : 0.0f, nd0 = in0 ? __ldg(kp.disp + o0 + (size_t)din0 * HW) : 0.0f;
+      float na1 = in1 ? __ldg(kp.att + o1 + (size_t)din0 * HW) : 0.0f, nd1 = in1 ? __ldg(kp.disp + o1 + (size_t)din0 * HW) : 0.0f;
+      tc::mbar_wait(&st_full, it & 1);
+#pragma unroll 1
+      for (int d_in = din0; d_in <= din1; ++d_in, ++g) {
+        const float a0 = na0, d0 = nd0, a1 = na1, d1 = nd1;
+        if (d_in < din1) {
+          const size_t ko = (size_t)(d_in + 1) * HW;
+          na0 = in0 ? __ldg(kp.att + o0 + ko) : 0.0f; nd0 = in0 ? __ldg(kp.disp + o0 + ko) : 0.0f;
+          na1 = in1 ? __ldg(kp.att + o1 + ko) : 0.0f; nd1 = in1 ? __ldg(kp.disp + o1 + ko) : 0.0f;
+        }
+        const uint32_t slot = g % K9_NS;
+        tc::mbar_wait(&a_empty[slot], ((g / K9_NS) & 1) ^ 1);
+        uint4* At = reinterpret_cast<uint4*>(Abase + slot * K9_SLICE);       // [8][180]
+#pragma unroll
+        for (int rep = 0; rep < 2; ++rep) {
+          const int px = rep ? px1 : pt, r = rep ? r1 : r0, c = rep ? c1 : c0;
+          if (px < HH * WW) {
+            const float a = rep ? a1 : a0;
+            int cs = c + dhi_bin - __float2int_rn(rep ? d1 : d0);
+            const bool ok = cs >= 0 && cs < K9_RW;                           // always true for samples in [dmin, dmin + 31]
+            cs = ok ? cs : 0;
+            const float ar = ok ? a : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              At[j * (HH * WW) + px] = scale8(Ls[j * (HH * WW) + px], a);
+              At[(4 + j) * (HH * WW) + px] = scale8(Rs[(j * HH + r) * K9_RW + cs], ar);
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic stores -> visible to the tensor core's reads
+        tc::mbar_arrive(&a_full[slot]);
+      }
+      tc::mbar_arrive(&st_empty);                                            // the staged item is no longer needed by this thread
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (as s1f, weights resident) =====
+    const bool leader = tc::elect_one();
+    const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(Abase), LBO_A), a_hi = tc::desc_hi(SBO_A);
+    const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(Wbase), LBO_B), b_hi = tc::desc_hi(SBO_B);
+    if (cta_s < p.items) tc::mbar_wait(&w_full, 0);
+    uint32_t g = 0, acc_base = 0, acquired = 0;
+    for (int s = cta_s; s < p.items; s += cta_stride) {
+      int b, h0, w0, dlo, dhi;
+      decode_item(p, s, b, h0, w0, dlo, dhi);
+      const int din0 = max(dlo - 1, 0), din1 = min(dhi, p.D - 1);
+#pragma unroll 1
+      for (int d_in = din0; d_in <= din1; ++d_in, ++g) {
+        const int j0 = max(0, dlo - d_in + 1), j1 = min(3, dhi - d_in + 1);
+        const uint32_t u0 = acc_base + (uint32_t)(d_in - 1 + j0 - dlo), nb = (uint32_t)(j1 - j0);
+        while (acquired < u0 + nb) {
+          tc::mbar_wait(&acc_empty[acquired % NB], ((acquired / NB) & 1) ^ 1);
+          ++acquired;
+        }
+        const uint32_t slot = g % K9_NS;
+        tc::mbar_wait(&a_full[slot], (g / K9_NS) & 1);
+        tc::fence_after_sync();
+        const uint32_t blk = u0 % NB, n1 = min(nb, NB - blk), n2 = nb - n1;
+        const uint32_t id1 = n1 == 1 ? tc::make_idesc_bf16(128, N) : n1 == 2 ? tc::make_idesc_bf16(128, 2 * N) : tc::make_idesc_bf16(128, 3 * N);
+        const uint32_t id2 = n2 == 1 ? tc::make_idesc_bf16(128, N) : tc::make_idesc_bf16(128, 2 * N);
+        const uint32_t d1 = tmem_base + blk * N, d2 = tmem_base;
+        const uint32_t a_lo = a_lo0 + slot * (K9_SLICE >> 4);
+        const uint32_t brow1 = (uint32_t)j0 * (N / 8) * (SBO_B >> 4), brow2 = (uint32_t)(j0 + n1) * (N / 8) * (SBO_B >> 4);
+#pragma unroll
+        for (int t9 = 0; t9 < 9; ++t9) {
+          const int kh = t9 / 3, kw = t9 - 3 * kh;
+          const uint32_t b_lo = b_lo0 + (uint32_t)t9 * (K9_TAPB >> 4);
+          if (leader) {
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+              const uint32_t a = a_lo + (uint32_t)((kh * WW + kw) * 16 + ks * 2 * LBO_A) / 16;
+              const uint32_t bb = b_lo + (uint32_t)(ks * 2 * LBO_B) / 16;
+              tc::mma_bf16_lohi(d1, a, a_hi, bb + brow1, b_hi, id1, 1u);
+              if (n2) tc::mma_bf16_lohi(d2, a, a_hi, bb + brow2, b_hi, id2, 1u);
+            }
+          }
+        }
+        if (leader) {
+          tc::mma_commit(&a_empty[slot]);
+          if (d_in - 1 >= dlo) tc::mma_commit(&acc_full[(acc_base + (uint32_t)(d_in - 1 - dlo)) % NB]);
+          if (d_in == din1 && din1 == dhi - 1) tc::mma_commit(&acc_full[(acc_base + (uint32_t)(d_in - dlo)) % NB]);
+        }
+        __syncwarp();
+      }
+      acc_base += (uint32_t)(dhi - dlo);
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (as s1f) =====
+    const int e = warp - 4, m = e * 32 + lane, hh = m >> 3, ww = m & 7;
+    uint32_t u = 0;
+    for (int s = cta_s; s < p.items; s += cta_stride) {
+      int b, h0, w0, dlo, dhi;
+      decode_item(p, s, b, h0, w0, dlo, dhi);
+      const int h = h0 + hh, w = w0 + ww;
+      const bool valid = h < p.H && w < p.W;
+      for (int d_out = dlo; d_out < dhi; ++d_out, ++u) {
+        const uint32_t blk = u % NB;
+        tc::mbar_wait(&acc_full[blk], (u / NB) & 1);
+        tc::fence_after_sync();
+        float v[32];
+        const uint32_t ta = tmem_base + ((uint32_t)(e * 32) << 16) + blk * N;
+        tc::tmem_ld32(ta, v);
+        tc::tmem_zero32(ta);
+        tc::fence_before_sync();
+        tc::mbar_arrive(&acc_empty[blk]);
+        if (!valid) continue;
+        epilogue_store32(p, v, s_scale, s_shift, 0, b, d_out, h, w, p.D, p.H, p.W, nullptr);
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// =====================================================================================================================
 // s2: Conv3d k3 s2 p1 on the phase-split input.  A staged slice = (d-phase pd, half-res depth d') = 4 (h,w)-phase halo tiles.
 // Per output depth d the slice uses are, in order: (1,d-1) [kd=0], (0,d) [kd=1], (1,d) [kd=2, kept for d+1's kd=0].
 // =====================================================================================================================
@@ -1100,6 +1328,58 @@ extern "C" int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight
       if (Cin == 128) return launch_t2<128, 64, 3, 2, 2>(tm, p, st);
       return launch_t2<64, 32, 3, 27, 4>(tm, p, st);
   }
+}
+
+// concat_stem with the sparse concat volume generated inside the kernel (k9 kernel above).
+extern "C" int ss_concat_stem_fused(const void* cf_l_blocked, const void* cf_r_blocked, const float* disp_topk, const float* att_topk,
+                                    const void* weight_packed, const float* scale_or_null, const float* shift_or_null,
+                                    const float* gate_blocked_or_null, void* out, int out_mode, int B, int K, int H, int W, int dmin,
+                                    int relu, void* stream) {
+  SS_REQUIRE(cf_l_blocked && cf_r_blocked && disp_topk && att_topk && weight_packed && out, "ss_concat_stem_fused: null pointer");
+  SS_REQUIRE(B > 0 && K > 0 && H > 0 && W > 0, "ss_concat_stem_fused: non-positive dimension");
+  SS_REQUIRE(out_mode >= 0 && out_mode <= 2, "ss_concat_stem_fused: out_mode must be 0, 1 or 2");
+  SS_REQUIRE(out_mode != 2 || (K % 2 == 0 && H % 2 == 0 && W % 2 == 0), "ss_concat_stem_fused: phase-split output needs even dims");
+  SS_REQUIRE(((reinterpret_cast<uintptr_t>(cf_l_blocked) | reinterpret_cast<uintptr_t>(cf_r_blocked) | reinterpret_cast<uintptr_t>(disp_topk) |
+               reinterpret_cast<uintptr_t>(att_topk) | reinterpret_cast<uintptr_t>(weight_packed) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+             "ss_concat_stem_fused: pointers must be 16-byte aligned");
+  ss_encode_tiled_fn enc = ss_get_encode_tiled();
+  if (!enc) return SS_ERR_CUDA;
+  K9P kp;
+  TcP& p = kp.t;
+  p.w = reinterpret_cast<const __nv_bfloat16*>(weight_packed);
+  p.scale = scale_or_null; p.shift = shift_or_null; p.gate = gate_blocked_or_null; p.residual = nullptr; p.skip_w = nullptr;
+  p.out = out; p.out_mode = out_mode; p.cout_valid = 32;
+  p.B = B; p.D = K; p.H = H; p.W = W; p.relu = relu;
+  p.n_tiles = 1; p.HT = ceil_div(H, TH); p.WT = ceil_div(W, TW);
+  p.DC = 1; p.n_dc = 1; p.items = 0;
+  kp.dmin = dmin; kp.disp = disp_topk; kp.att = att_topk;
+  CUtensorMap tmL, tmR;
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  auto encode = [&](CUtensorMap* tm, CUtensorMapDataType dt, const void* base, const cuuint64_t* dims, const cuuint64_t* strides,
+                    const cuuint32_t* box) -> int {
+    CUresult r = enc(tm, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      ss_set_error("ss_concat_stem_fused: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+      return SS_ERR_CUDA;
+    }
+    return SS_OK;
+  };
+  {
+    // (8 channels, x, y, chunk): a box dimension may not exceed 256 elements, so the 41-pixel window cannot be 328 bf16 in one dim
+    const cuuint64_t dims[4] = {8u, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * 4};
+    const cuuint64_t strides[3] = {16u, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+    const cuuint32_t boxl[4] = {8u, (cuuint32_t)WW, (cuuint32_t)HH, 4u}, boxr[4] = {8u, (cuuint32_t)K9_RW, (cuuint32_t)HH, 4u};
+    int rc = encode(&tmL, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, cf_l_blocked, dims, strides, boxl);
+    if (rc != SS_OK) return rc;
+    if ((rc = encode(&tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, cf_r_blocked, dims, strides, boxr)) != SS_OK) return rc;
+  }
+  SS_CUDA(ss_allow_smem(concat_stem_k9_kernel, K9_SMEM));
+  int grid;
+  plan_tc(p, 1.4, grid);
+  concat_stem_k9_kernel<<<grid, 384, K9_SMEM, (cudaStream_t)stream>>>(tmL, tmR, kp);
+  SS_CHECK_LAUNCH("ss_concat_stem_fused");
+  return SS_OK;
 }
 
 extern "C" int ss_to_blocked_bf16(const float* in_ncdhw, void* out_blocked, int B, int C, int D, int H, int W, int s2d, void* stream) {

@@ -247,13 +247,16 @@ class DisparityHotPath(nn.Module):
         return c
 
     # ------------------------------------------------------------------------------------------
-    def _concat_feature(self, c, f4, f4_blocked=None):
-        """concat_feature(features[1]) (SemStereo.py:314-315): (B,128,H/4,W/4) -> (B,32,H/4,W/4) fp32."""
+    def _concat_feature(self, c, f4, f4_blocked=None, blocked=False):
+        """concat_feature(features[1]) (SemStereo.py:314-315): (B,128,H/4,W/4) -> (B,32,H/4,W/4) fp32, or (bf16 mode, blocked=True)
+        the bf16 blocked (B,4,1,H/4,W/4,8) tensor the fused concat_stem kernel stages."""
         with ops.label("concat_feature"):
             x = f4.unsqueeze(2)
             if self.precision == "bf16":
                 xb = f4_blocked if f4_blocked is not None else tc.to_blocked_bf16(x)
                 y = tc.conv3d_tc(tc.C2D, xb, c["cf0.tc"], 64, c["cf0.scale"], c["cf0.shift"], relu=True)
+                if blocked:
+                    return tc.conv3d_tc(tc.C2D, y, c["cf1.tc"], 32)
                 return tc.conv3d_tc(tc.C2D, y, c["cf1.tc"], 32, out_mode=tc.F32).squeeze(2)
             y = ops.conv3d_f32(x, c["cf0.w"], c["cf0.scale"], c["cf0.shift"], k=3, relu=True)
             return ops.conv3d_f32(y, c["cf1.w"], k=3).squeeze(2)
@@ -363,12 +366,26 @@ class DisparityHotPath(nn.Module):
         if self.precision == "bf16":
             f4l_b = (f4_l_blocked.view(f4_l.shape[0], 16, 1, *f4_l.shape[2:], 8) if f4_l_blocked is not None
                      else tc.to_blocked_bf16(f4_l.unsqueeze(2)))
+        # bf16 mode without kept intermediates: the sparse concat volume is generated inside the concat_stem kernel (never in HBM)
+        nbins = (2 if self.signed else 1) * m4
+        fused = self.precision == "bf16" and not keep and nbins == 32 and f4_l.shape[-1] % 4 == 0
         if cf_l is None:
-            cf_l = self._concat_feature(c, f4_l, f4l_b)
+            cf_l = self._concat_feature(c, f4_l, f4l_b, blocked=fused)
+        elif fused:
+            cf_l = tc.to_blocked2d(cf_l)
         if cf_r is None:
-            cf_r = self._concat_feature(c, f4_r)
+            cf_r = self._concat_feature(c, f4_r, blocked=fused)
+        elif fused:
+            cf_r = tc.to_blocked2d(cf_r)
         gate4 = self._gate_logits(c, "concat_feature_att_4", f4_l, f4l_b)
-        if self.precision == "bf16":
+        if fused:
+            volume = None
+            gb = tc.gate_sigmoid_blocked(gate4)
+            with ops.label("concat_stem"):
+                v = tc.concat_stem_fused(cf_l, cf_r, disp_topk, att_topk, c["concat_stem.tc"], int(dmin), c["concat_stem.scale"],
+                                         c["concat_stem.shift"], gb, relu=True, out_mode=tc.S2D)
+            cost = self._classifier_tc(c, "classif", self._hourglass_tc(c, "hourglass", v))
+        elif self.precision == "bf16":
             volume = tc.sparse_concat_volume_blocked(cf_l, cf_r, disp_topk, att_topk)      # (B,8,24,H/4,W/4,8) bf16
             v = self._tc(c, "concat_stem", tc.S1, volume, 32, gate=tc.gate_sigmoid_blocked(gate4), out_mode=tc.S2D)
             cost = self._classifier_tc(c, "classif", self._hourglass_tc(c, "hourglass", v))

@@ -303,3 +303,34 @@ def pointwise_blocked_small(xb, weight, bias=None):
     out = torch.empty((B, cout, H, W), device=dev, dtype=torch.float32)
     _call("ss_pointwise_blocked_small", dev, _ptr(xb), _ptr(weight), _ptr(bias), _ptr(out), B, C8 * 8, cout, H, W)
     return out
+
+
+def concat_stem_fused(cf_l_b, cf_r_b, disp_topk, att_topk, w_s1f, dmin, scale=None, shift=None, gate_blocked=None, relu=True,
+                      out_mode=BLOCKED):
+    """concat_volume_generator * att_topk -> concat_stem (+ gate) with the volume produced inside the kernel (SemStereo.py:316-320).
+    cf_*_b: bf16 blocked (B,4,H,W,8) [or (B,4,1,H,W,8)]; disp_topk / att_topk fp32 (B,K,H,W) with integer samples in
+    [dmin, dmin+31]; w_s1f = pack_weight(concat_stem weight, S1F).  Returns (B,4,K,H,W,8) blocked / phase-split / fp32 (B,32,K,H,W)."""
+    cf_l_b = cf_l_b.view(cf_l_b.shape[0], 4, *cf_l_b.shape[-3:])
+    cf_r_b = cf_r_b.view(cf_r_b.shape[0], 4, *cf_r_b.shape[-3:])
+    dev = _require_bf16(cf_l_b, 5)
+    _require_bf16(cf_r_b, 5)
+    _require_cuda(disp_topk, att_topk, scale, shift, gate_blocked)
+    B, _, H, W, _ = cf_l_b.shape
+    K = disp_topk.shape[1]
+    if att_topk.dim() == 5 and att_topk.shape[1] == 1:          # the model's att_topk keeps the cost volume's channel dim (B,1,K,H,W)
+        att_topk = att_topk.squeeze(1)
+    if cf_r_b.shape != cf_l_b.shape or tuple(disp_topk.shape) != (B, K, H, W) or att_topk.shape != disp_topk.shape:
+        raise ValueError("concat_stem_fused: cf (B,4,H,W,8) and samples (B,K,H,W) expected")
+    if w_s1f.dtype != torch.bfloat16 or tuple(w_s1f.shape) != (9, 8, 96, 8) or not w_s1f.is_contiguous():
+        raise ValueError("concat_stem_fused: weight must come from pack_weight(w, S1F) of a Conv3d(64, 32, 3)")
+    if gate_blocked is not None and tuple(gate_blocked.shape) != (B, 4, H, W, 8):
+        raise ValueError("concat_stem_fused: gate must be fp32 (B,4,H,W,8) from gate_sigmoid_blocked")
+    if out_mode == F32:
+        out = torch.empty((B, 32, K, H, W), device=dev, dtype=torch.float32)
+    elif out_mode == S2D:
+        out = torch.empty((B, 8, 4, K // 2, H // 2, W // 2, 8), device=dev, dtype=torch.bfloat16)
+    else:
+        out = torch.empty((B, 4, K, H, W, 8), device=dev, dtype=torch.bfloat16)
+    _call("ss_concat_stem_fused", dev, _ptr(cf_l_b), _ptr(cf_r_b), _ptr(disp_topk), _ptr(att_topk), _ptr(w_s1f), _ptr(scale), _ptr(shift),
+          _ptr(gate_blocked), _ptr(out), int(out_mode), B, K, H, W, int(dmin), int(relu))
+    return out

@@ -37,3 +37,23 @@ def test_bf16_mode_statistical_parity(signed, maxdisp):
     assert rel_cost <= 0.05
     assert e_att.median().item() <= 0.02 and e.median().item() <= 0.05
     assert e.quantile(0.9).item() <= 0.5
+
+
+@pytest.mark.parametrize("signed,maxdisp", [(True, 64), (False, 128)])
+def test_fused_concat_stem_route_matches_the_materialised_route(signed, maxdisp):
+    """keep=False takes the kernel that generates the sparse concat volume inside concat_stem; keep=True materialises it.  The
+    routes differ only by one bf16 rounding of concat_feature's output: same top-24 selection, aggregated cost within 2 % of its
+    range; the final top-2 regression is as ill-conditioned between the two routes as it is against the oracle."""
+    p = make_params(seed=1, peaked=20.0)
+    inp = {k: v.to(DEV) for k, v in make_inputs(3, 2, 128, 256).items() if k not in ("cf_l", "cf_r")}
+    m = DisparityHotPath(maxdisp, False, signed, precision="bf16")
+    m.load_state_dict(p, strict=True)
+    m = m.to(DEV)
+    args = [inp.get(k) for k in ORDER]
+    a, b = m(*args, keep=False), m(*args, keep=True)
+    torch.cuda.synchronize()
+    assert torch.equal(a["disp_topk"], b["disp_topk"]) and torch.equal(a["pred_att_up"], b["pred_att_up"])
+    rel = ((a["cost"] - b["cost"]).abs().max() / b["cost"].abs().max()).item()
+    d = (a["pred_up"] - b["pred_up"]).abs().flatten()
+    print(f"\n[fused vs materialised volume] cost rel err {rel:.3e}; pred_up median {d.median():.5f} p90 {d.quantile(0.9):.4f}")
+    assert rel <= 2e-2 and d.median().item() <= 0.03 and d.quantile(0.9).item() <= 0.5

@@ -220,3 +220,35 @@ def test_conv_k3_s1_depth_folded(Cin, Cout, B, D, H, W):
         torch.cuda.synchronize()
         check(tc.from_blocked_bf16(out).cpu(), ref, True)
         check(plain.cpu(), y, False)
+
+
+@pytest.mark.parametrize("B,H,W,dmin", [(1, 16, 8, -16), (2, 40, 24, -16), (1, 64, 64, 0), (1, 128, 128, -16)])
+def test_concat_stem_with_the_volume_generated_in_kernel(B, H, W, dmin):
+    """ss_concat_stem_fused == sparse_concat_volume_blocked + kind-5 conv (volume never written to HBM).  The fused kernel reads
+    cf as bf16 (one more rounding than the fp32 cf of the two-kernel route) -> compared at the bf16 tolerance of this file."""
+    g = torch.Generator().manual_seed(H + W)
+    K = 24
+    cfl, cfr = torch.randn(B, 32, H, W, generator=g), torch.randn(B, 32, H, W, generator=g)
+    ind = torch.stack([torch.randperm(32, generator=g)[:K].sort()[0] for _ in range(B * H * W)]).view(B, H, W, K).permute(0, 3, 1, 2)
+    disp = (ind + dmin).float().contiguous()
+    att = torch.rand(B, K, H, W, generator=g)
+    w = torch.randn(32, 64, 3, 3, 3, generator=g) / (27 * 64) ** 0.5
+    scale, shift = torch.rand(32, generator=g) + 0.5, 0.3 * torch.randn(32, generator=g)
+    gate = torch.randn(B, 32, H, W, generator=g)
+    # reference: volume from bf16-rounded cf (what the fused kernel multiplies), integer shift, then an fp32 conv
+    xs = torch.arange(W).view(1, 1, 1, W) - disp.long()                                   # (B,K,H,W) source column
+    okx = (xs >= 0) & (xs < W)
+    right = torch.gather(bf(cfr).unsqueeze(2).expand(B, 32, K, H, W), 4, xs.clamp(0, W - 1).unsqueeze(1).expand(B, 32, K, H, W))
+    vol = torch.cat((bf(cfl).unsqueeze(2).expand(B, 32, K, H, W), right * okx.unsqueeze(1)), 1) * att.unsqueeze(1)
+    y = F.conv3d(bf(vol), bf(w), None, padding=1)
+    ref = F.relu(y * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)) * torch.sigmoid(gate).unsqueeze(2)
+    wt = tc.pack_weight(w, tc.S1F).to(DEV)
+    gb = tc.gate_sigmoid_blocked(gate.to(DEV))
+    for _ in range(2):
+        out = tc.concat_stem_fused(tc.to_blocked2d(cfl.to(DEV)), tc.to_blocked2d(cfr.to(DEV)), disp.to(DEV), att.to(DEV), wt, dmin,
+                                   scale.to(DEV), shift.to(DEV), gb, relu=True)
+        plain = tc.concat_stem_fused(tc.to_blocked2d(cfl.to(DEV)), tc.to_blocked2d(cfr.to(DEV)), disp.to(DEV), att.to(DEV), wt, dmin,
+                                     relu=False, out_mode=tc.F32)
+        torch.cuda.synchronize()
+        check(tc.from_blocked_bf16(out).cpu(), ref, True)
+        check(plain.cpu(), y, False)
