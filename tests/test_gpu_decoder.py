@@ -129,3 +129,30 @@ def test_patch_model_rebinds_forward():
     model.train()
     with pytest.raises(NotImplementedError):
         model(left, right)
+
+
+def test_stereo_head_full_size_properties_and_graph_replay():
+    """BASELINE config #1 shape (1,1024,1024) through decoder + path: shapes, finiteness, label/disparity ranges that need no
+    oracle run, and a CUDA-graph replay of the whole thing equal to the eager result bit for bit."""
+    from semstereo_b200.graph import GraphedCall
+    p = params()
+    head = StereoHead(64)
+    head.load_state_dict(p, strict=True)
+    head = head.to(DEV)
+    fl, fr = make_backbone_features(5, 1, 1024, 1024)
+    st = {f"l{i}": t.to(DEV) for i, t in enumerate(fl)}
+    st.update({f"r{i}": t.to(DEV) for i, t in enumerate(fr)})
+    call = lambda s: head([s[f"l{i}"] for i in range(5)], [s[f"r{i}"] for i in range(5)])       # noqa: E731
+    out = call(st)
+    torch.cuda.synchronize()
+    assert tuple(out["pred_up"].shape) == (1, 1024, 1024) and tuple(out["pred_label"].shape) == (1, 6, 1024, 1024)
+    for k in ("pred_up", "pred_att_up", "pred_label", "disp_topk", "att_topk"):
+        assert bool(torch.isfinite(out[k]).all()), k
+    assert float(out["disp_topk"].min()) >= -16 and float(out["disp_topk"].max()) <= 15
+    assert bool((out["disp_topk"][:, 1:] > out["disp_topk"][:, :-1]).all()), "kept bins must be strictly ascending"
+    assert float(out["att_topk"].min()) >= 0 and float(out["att_topk"].sum(2 if out["att_topk"].dim() == 5 else 1).max()) <= 1 + 1e-5
+    want = {k: out[k].clone() for k in ("pred_up", "pred_label")}
+    g = GraphedCall(call, st)
+    got = g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(got["pred_up"], want["pred_up"]) and torch.equal(got["pred_label"], want["pred_label"])
