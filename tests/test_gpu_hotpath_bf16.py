@@ -57,3 +57,21 @@ def test_fused_concat_stem_route_matches_the_materialised_route(signed, maxdisp)
     d = (a["pred_up"] - b["pred_up"]).abs().flatten()
     print(f"\n[fused vs materialised volume] cost rel err {rel:.3e}; pred_up median {d.median():.5f} p90 {d.quantile(0.9):.4f}")
     assert rel <= 2e-2 and d.median().item() <= 0.03 and d.quantile(0.9).item() <= 0.5
+
+
+@pytest.mark.parametrize("B,H,W,signed,maxdisp", [(3, 128, 384, True, 64), (1, 384, 128, False, 128), (5, 128, 128, True, 64)])
+def test_bf16_mode_odd_batches_and_aspect_ratios(B, H, W, signed, maxdisp):
+    """Odd batch sizes / non-square images through the tensor-core route (tile and wave tails of every persistent kernel):
+    each sample of a batch must equal the same sample run alone, bit for bit (no cross-sample coupling, no tail effects)."""
+    p = make_params(seed=1, peaked=20.0)
+    inp = {k: v.to(DEV) for k, v in make_inputs(17, B, H, W).items() if k not in ("cf_l", "cf_r")}
+    m = DisparityHotPath(maxdisp, False, signed, precision="bf16")
+    m.load_state_dict(p, strict=True)
+    m = m.to(DEV)
+    full = m(*[inp.get(k) for k in ORDER])
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(full["pred_up"]).all())
+    for b in (0, B - 1):
+        one = m(*[None if inp.get(k) is None else inp[k][b:b + 1].contiguous() for k in ORDER])
+        for k in ("pred_up", "pred_att_up", "disp_topk"):
+            assert torch.equal(one[k], full[k][b:b + 1]), (k, b)
