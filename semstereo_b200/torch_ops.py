@@ -1,0 +1,71 @@
+"""torch.library registration of the cost-volume / regression operators ("registers each op with
+torch.library"): `torch.ops.semstereo_b200.<op>` with shape-only fake implementations, so the operators can sit inside
+`torch.export` / `torch.compile`d callers of the reference model without graph breaks.  The real implementations are the C-ABI
+kernels (CUDA only — a CPU tensor raises, there is no fallback).  Importing this module performs the registration."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+NS = "semstereo_b200"
+
+
+@torch.library.custom_op(f"{NS}::gwc_volume", mutates_args=())
+def gwc_volume(left: torch.Tensor, right: torch.Tensor, maxdisp: int, num_groups: int, signed: bool, norm: bool) -> torch.Tensor:
+    """build_gwc_volume / build_gwc_volume_norm (models/submodule.py:198-238, submodule_.py:188-221)."""
+    return ops.gwc_volume(left.contiguous(), right.contiguous(), maxdisp, num_groups, signed, norm)
+
+
+@gwc_volume.register_fake
+def _(left, right, maxdisp, num_groups, signed, norm):
+    B, C, H, W = left.shape
+    return left.new_empty((B, num_groups, 2 * maxdisp if signed else maxdisp, H, W))
+
+
+@torch.library.custom_op(f"{NS}::concat_volume", mutates_args=())
+def concat_volume(left: torch.Tensor, right: torch.Tensor, maxdisp: int, signed: bool) -> torch.Tensor:
+    """build_concat_volume (models/submodule.py:173-187, submodule_.py:166-178)."""
+    return ops.concat_volume(left.contiguous(), right.contiguous(), maxdisp, signed)
+
+
+@concat_volume.register_fake
+def _(left, right, maxdisp, signed):
+    B, C, H, W = left.shape
+    return left.new_empty((B, 2 * C, 2 * maxdisp if signed else maxdisp, H, W))
+
+
+@torch.library.custom_op(f"{NS}::regression_topk", mutates_args=())
+def regression_topk(cost: torch.Tensor, disparity_samples: torch.Tensor, k: int) -> torch.Tensor:
+    """regression_topk (models/submodule.py:434-442)."""
+    return ops.regression_topk(cost.contiguous(), disparity_samples.contiguous(), k)
+
+
+@regression_topk.register_fake
+def _(cost, disparity_samples, k):
+    B, D, H, W = cost.shape
+    return cost.new_empty((B, 1, H, W))
+
+
+@torch.library.custom_op(f"{NS}::context_upsample", mutates_args=())
+def context_upsample(depth_low: torch.Tensor, up_weights: torch.Tensor) -> torch.Tensor:
+    """context_upsample (models/submodule_.py:311-323)."""
+    return ops.context_upsample(depth_low.contiguous(), up_weights.contiguous())
+
+
+@context_upsample.register_fake
+def _(depth_low, up_weights):
+    B, _, h, w = depth_low.shape
+    return depth_low.new_empty((B, 4 * h, 4 * w))
+
+
+@torch.library.custom_op(f"{NS}::disparity_regression", mutates_args=())
+def disparity_regression(prob: torch.Tensor, maxdisp: int, signed: bool) -> torch.Tensor:
+    """disparity_regression (models/submodule.py:164-170, submodule_.py:159-163)."""
+    return ops.disparity_regression(prob.contiguous(), float(-maxdisp if signed else 0))
+
+
+@disparity_regression.register_fake
+def _(prob, maxdisp, signed):
+    B, D, H, W = prob.shape
+    return prob.new_empty((B, H, W))

@@ -241,3 +241,13 @@ def test_ssr_upsample2_equals_two_calls():
     oa, ob = ops.ssr_upsample2(da, db, spx, lab, packed)
     assert torch.equal(oa, ops.ssr_upsample(da, spx, lab, packed))
     assert torch.equal(ob, ops.ssr_upsample(db, spx, lab, packed))
+
+
+def test_torch_library_ops_match_the_wrappers():
+    import semstereo_b200.torch_ops  # noqa: F401
+    g = torch.Generator().manual_seed(12)
+    l, r = torch.randn(1, 64, 8, 32, generator=g).to(DEV), torch.randn(1, 64, 8, 32, generator=g).to(DEV)
+    assert torch.equal(torch.ops.semstereo_b200.gwc_volume(l, r, 4, 8, True, True), ops.gwc_volume(l, r, 4, 8, True, True))
+    assert torch.equal(torch.ops.semstereo_b200.concat_volume(l, r, 4, False), ops.concat_volume(l, r, 4, False))
+    c, d = torch.randn(1, 24, 8, 32, generator=g).to(DEV), torch.randn(1, 24, 8, 32, generator=g).to(DEV)
+    assert torch.equal(torch.ops.semstereo_b200.regression_topk(c, d, 2), ops.regression_topk(c, d, 2))

@@ -136,3 +136,21 @@ def test_plan_row_tiles():
         plan_row_tiles(1000, 2)
     with pytest.raises(ValueError):
         plan_row_tiles(256, 3)
+
+
+def test_torch_library_ops_registered_with_fake_shapes():
+    """torch.ops.semstereo_b200.* exist and their fake (meta) implementations give the reference's output shapes; on CPU tensors the
+    real implementation refuses to run (no fallback)."""
+    import semstereo_b200.torch_ops  # noqa: F401  (registers)
+    ops_ns = torch.ops.semstereo_b200
+    l = torch.empty(2, 64, 8, 16, device="meta")
+    assert tuple(ops_ns.gwc_volume(l, l, 4, 8, True, True).shape) == (2, 8, 8, 8, 16)
+    assert tuple(ops_ns.gwc_volume(l, l, 4, 8, False, False).shape) == (2, 8, 4, 8, 16)
+    assert tuple(ops_ns.concat_volume(l, l, 4, True).shape) == (2, 128, 8, 8, 16)
+    c = torch.empty(2, 24, 8, 16, device="meta")
+    assert tuple(ops_ns.regression_topk(c, c, 2).shape) == (2, 1, 8, 16)
+    assert tuple(ops_ns.disparity_regression(c, 12, True).shape) == (2, 8, 16)
+    assert tuple(ops_ns.context_upsample(torch.empty(2, 1, 8, 16, device="meta"), torch.empty(2, 9, 32, 64, device="meta")).shape) == (2, 32, 64)
+    z = torch.zeros(1, 8, 4, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops_ns.gwc_volume(z, z, 2, 2, True, False)
