@@ -217,8 +217,8 @@ def main():
     H, W, md = a.height, a.width, a.maxdisp
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     head = a.stage == "head"
-    if head and (a.att_only or a.precision != "bf16" or not signed):
-        raise SystemExit("--stage head runs the US3D model, full forward, bf16")
+    if head and (a.att_only or a.precision != "bf16"):
+        raise SystemExit("--stage head runs the full forward in bf16 (the decoder has no fp32 mode)")
     workload = (f"{'SemStereo' if signed else 'SemStereo_WHU'} "
                 f"{'decoder + disparity path = everything after the backbone (forward:249-346)' if head else 'disparity hot path (forward:273-324)'}, {H}x{W} "
                 f"{'US3D' if signed else 'WHU'}-shaped pairs, maxdisp {md}, {'signed' if signed else 'unsigned'}"
@@ -253,7 +253,7 @@ def main():
     if head:
         from semstereo_b200.decoder import StereoHead
         from semstereo_b200.params import make_backbone_features, make_decoder_params
-        model = StereoHead(md)
+        model = StereoHead(md, False, signed)
         sd = dict(make_params(seed=1, peaked=20.0))
         sd.update(make_decoder_params(seed=2))
         model.load_state_dict(sd, strict=True)

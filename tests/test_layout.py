@@ -154,3 +154,21 @@ def test_torch_library_ops_registered_with_fake_shapes():
     z = torch.zeros(1, 8, 4, 8)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops_ns.gwc_volume(z, z, 2, 2, True, False)
+
+
+def test_c_abi_argument_validation_needs_no_gpu():
+    """Bad arguments are rejected by the C entry points before any CUDA call: negative code + thread-local message."""
+    import ctypes
+    from semstereo_b200 import _lib
+    lib = _lib.load()
+    null = ctypes.c_void_p(0)
+    one = ctypes.c_void_p(16)
+    assert lib.ss_conv2d_tc(0, null, 64, null, 0, null, null, null, null, 0, 1, 64, 16, 16, 0, null) == -1
+    assert "null pointer" in _lib.last_error()
+    assert lib.ss_conv2d_tc(0, one, 48, null, 0, one, null, null, one, 0, 1, 64, 16, 16, 0, null) == -2      # Cin not a multiple of 64
+    assert "multiples of 64" in _lib.last_error()
+    assert lib.ss_conv2d_tc_ntile(0, 128, 128) == 128 and lib.ss_conv2d_tc_ntile(2, 128, 6) == 16 and lib.ss_conv2d_tc_ntile(0, 100, 8) == 0
+    assert lib.ss_conv3d_tc_ntile(5, 64, 32) == 32 and lib.ss_conv3d_tc_ntile(5, 128, 32) == 0 and lib.ss_conv3d_tc_ntile(4, 128, 64) == 64
+    assert lib.ss_concat_stem_fused(null, null, null, null, null, null, null, null, null, 0, 1, 24, 16, 16, -16, 1, null) == -1
+    assert lib.ss_ssr_upsample2(one, null, one, one, one, null, one, 1, 4, 4, 6, null) == -1
+    assert lib.ss_bilinear_up2(null, null, 1, 4, 4, null) == -1
