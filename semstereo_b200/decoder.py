@@ -217,3 +217,16 @@ class StereoHead(nn.Module):
     def as_model_outputs(self, out):
         """What SemStereo.forward returns in eval mode (SemStereo.py:340-346)."""
         return self.path.as_model_outputs(out, out["pred_label"])
+
+    def as_loss_inputs(self, out):
+        """The tuple SemStereo.forward returns in TRAINING mode (SemStereo.py:329-337) — ([pred_up*4, pred*4, pred_att_up*4,
+        pred_att*4], pred_label, pred_label_r), or the two-element list in attention_weights_only mode — from an inference pass
+        run with right_label=True, so the reference's model_loss_* / LRSC_loss (models/loss.py:19-135, BASELINE config #4) can be
+        evaluated on top.  No gradients: the path is inference-only."""
+        if "pred_label_r" not in out:
+            raise ValueError("as_loss_inputs: run the forward with right_label=True")
+        if self.path.att_weights_only:
+            disp = [out["pred_att_up"] * 4, out["pred_att"] * 4]
+        else:
+            disp = [out["pred_up"] * 4, out["pred"].squeeze(1) * 4, out["pred_att_up"] * 4, out["pred_att"] * 4]
+        return disp, out["pred_label"], out["pred_label_r"]

@@ -156,3 +156,19 @@ def test_stereo_head_full_size_properties_and_graph_replay():
     got = g.replay()
     torch.cuda.synchronize()
     assert torch.equal(got["pred_up"], want["pred_up"]) and torch.equal(got["pred_label"], want["pred_label"])
+
+
+def test_loss_inputs_tuple_for_lrsc():
+    """BASELINE config #4: WHU model (unsigned), forward outputs incl. pred_label_r in the layout the reference's training forward
+    returns (SemStereo_WHU.py:329-337), so LRSC_loss / model_loss_train can be evaluated on top."""
+    p = params()
+    head = StereoHead(128, False, signed=False)
+    head.load_state_dict(p, strict=True)
+    fl, fr = make_backbone_features(9, 2, 128, 256)
+    out = head.to(DEV)([t.to(DEV) for t in fl], [t.to(DEV) for t in fr], right_label=True)
+    disp, label, label_r = head.as_loss_inputs(out)
+    assert [tuple(t.shape) for t in disp] == [(2, 128, 256), (2, 32, 64), (2, 128, 256), (2, 32, 64)]
+    assert tuple(label.shape) == tuple(label_r.shape) == (2, 6, 128, 256)
+    assert float(disp[1].min()) >= 0 and float(disp[1].max()) <= 4 * 31          # unsigned: regression over bins 0..31, x4
+    with pytest.raises(ValueError):
+        head.as_loss_inputs(head([t.to(DEV) for t in fl], [t.to(DEV) for t in fr]))
