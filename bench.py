@@ -247,6 +247,8 @@ def main():
     import torch.distributed as tdist
     rank, local, world = sdist.init_from_env("nccl")
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = sdist.bind_to_gpu_numa(local)       # before any pinned allocation: NUMA-local staging buffers
     dev = torch.device("cuda", local)
     B = a.batch
     okey = "pred_att_up" if a.att_only else "pred_up"
@@ -397,12 +399,14 @@ def main():
                                                               if a.precision == "bf16" else "fp32 everywhere (FFMA 3-D convs)")},
            "e2e": {"value": e2e_v, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps},
            "gpu_launches": rec.count, "clocks": clocks, "roofline": roof, "kernels": kernels}
+    res["host"] = {"numa_bound_cpus": len(numa_cpus) if numa_cpus else None}
     res["launch_mode"] = {"value_region": "eager" if a.no_graph else "cuda graph replay per step (+ eager NCCL gather)",
                           "eager_instrumented_ms_per_step": ms_eager / a.steps,
                           "eager_instrumented_value": world * B * a.steps / (ms_eager * 1e-3),
                           "note": "kernels[] / roofline come from the instrumented eager pass of the same K steps; gpu_launches counts "
                                   "its launches (a graph replay launches the same kernels)"}
     if world == 1 and not a.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)           # the CPU baseline gets every host core again
         times = cpu_reference(H, W, md, a.cpu_steps, 1, signed, a.att_only, a.external_cf, a.stage)
         res["cpu_baseline"] = {"value": len(times) / sum(times), "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
                                "sample": f"{len(times)} pairs at {H}x{W} through {'oracle/decoder.py + ' if head else ''}oracle/hotpath.py (torch CPU fp32), 1 warm-up"}

@@ -148,3 +148,25 @@ class TiledHotPath:
         if self.world > 1:
             dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
         return out
+
+
+def bind_to_gpu_numa(local_rank: int):
+    """Pins this process to the CPU cores NVML reports as local to GPU `local_rank` (best effort; returns the core list or None).
+    Call it BEFORE allocating pinned host buffers: page-locked staging memory is then first-touched on the GPU's own NUMA node,
+    so the H2D copies of the ranks of one box do not all cross the same inter-socket link (e2e with 8 ranks is host-memory bound)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local_rank])
+                                              if os.environ.get("CUDA_VISIBLE_DEVICES") else local_rank)
+        ncpu = os.cpu_count() or 1
+        words = (ncpu + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [i * 64 + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1 and i * 64 + b < ncpu]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:          # no NVML / no permission / exotic topology: staging still works, just not NUMA-local
+        return None
