@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--maxdisp", type=int, default=64)
     ap.add_argument("--cpu-steps", type=int, default=2, help="pairs timed for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "mixed"],
                     help="bf16: k3 s1 3-D convs on tcgen05 tensor cores (BASELINE config #3); fp32: index-exact parity mode")
     ap.add_argument("--variant", default="us3d", choices=["us3d", "whu"],
                     help="us3d: SemStereo, signed, 1024x1024, maxdisp 64 (configs #1/#3); whu: SemStereo_WHU + submodule_.py, unsigned, "
@@ -386,17 +386,19 @@ def main():
             "traffic": ncu_traffic(dom["name"], a.precision, B),
             "peak_source": pk["src"] + (" (sustained bf16 cuBLAS)" if dom["bound"] == "tensor" else " (copy)"),
             "note": ("tcgen05 bf16 implicit GEMM, fp32 accumulation in TMEM; achieved = Table-A FLOPs of the layer x batch / CUDA-event "
-                     "time of the launch inside the timed region" if a.precision == "bf16"
+                     "time of the launch inside the timed region" if a.precision != "fp32"
                      else "fp32-accurate FFMA mode; fraction is against the bf16 tensor peak")}
     value = world * B * a.steps / (ms_total * 1e-3)
     e2e_v = world * B * a.steps / (ms_e2e * 1e-3)
     res = {"metric": "stereo pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-           "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if a.precision == "bf16" else "f32",
+           "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "fp32": "f32", "mixed": "f32 attention branch + bf16 aggregation"}[a.precision],
            "data": "synthetic", "config": {"workload": workload, "pairs_per_gpu_per_step": B, "global_pairs_per_step": world * B,
                                            "l2": "per-step inputs (1.3 GB at batch 8) exceed the 126 MB L2", "parallelism": f"dp{world}",
                                            "precision_mode": ("bf16 operands / fp32 accumulation on the tensor cores for every 3-D conv, the window attention, concat_feature"
                                                               " and (stage head) the 2-D decoder; fp32 elsewhere"
-                                                              if a.precision == "bf16" else "fp32 everywhere (FFMA 3-D convs)")},
+                                                              if a.precision == "bf16" else
+                                                              ("fp32 everywhere (FFMA 3-D convs)" if a.precision == "fp32" else
+                                                               "attention branch (hourglass_att, classif_att_) fp32, aggregation branch bf16 tensor cores"))},
            "e2e": {"value": e2e_v, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps},
            "gpu_launches": rec.count, "clocks": clocks, "roofline": roof, "kernels": kernels}
     res["host"] = {"numa_bound_cpus": len(numa_cpus) if numa_cpus else None}

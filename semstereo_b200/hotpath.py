@@ -107,11 +107,13 @@ def pack_ssr(ssr: nn.Module) -> torch.Tensor:
 class DisparityHotPath(nn.Module):
     def __init__(self, maxdisp: int, att_weights_only: bool = False, signed: bool = True, num_classes: int = 6,
                  precision: str = "fp32"):
-        """precision: "fp32" = every 3-D conv on the fp32 pipe (index-exact parity mode); "bf16" = the k3 s1 convolutions
-        (78 % of the FLOPs) run on the tcgen05 tensor cores with bf16 operands and fp32 accumulation."""
+        """precision: "fp32" = everything on the fp32 pipe (index-exact parity mode); "bf16" = every conv and the window attention
+        on the tensor cores with bf16 operands and fp32 accumulation; "mixed" = the 1/8-resolution attention branch (9 % of the
+        FLOPs, but it alone decides the top-k sample selection) in fp32 and the aggregation branch in bf16: the
+        disparity samples and pred_att are those of the fp32 mode, bit for bit, at about a third of the bf16 mode's speed."""
         super().__init__()
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if precision not in ("fp32", "bf16", "mixed"):
+            raise ValueError("precision must be 'fp32', 'bf16' or 'mixed'")
         self.precision = precision
         if maxdisp % 8:
             raise ValueError("maxdisp must be a multiple of 8 (the 1/8-res volume is upsampled exactly x2)")
@@ -158,6 +160,12 @@ class DisparityHotPath(nn.Module):
     def refresh(self):
         self._cache = None
 
+    def _is_bf16(self, name: str) -> bool:
+        """Does the module `name` belong to a branch that runs on the tensor cores in this precision mode?"""
+        if self.precision == "mixed":
+            return not name.startswith(("hourglass_att", "classif_att_", "corr_feature_att_8"))
+        return self.precision == "bf16"
+
     def _apply(self, fn, *a, **k):
         self._cache = None
         return super()._apply(fn, *a, **k)
@@ -170,11 +178,9 @@ class DisparityHotPath(nn.Module):
             raise NotImplementedError("DisparityHotPath is inference-only (eval-mode BatchNorm is folded)")
         c = {}
 
-        bf16 = self.precision == "bf16"
-
         def conv(name, convmod, bn, transposed=False):
             w = convmod.weight.detach().float()
-            if bf16:      # tensor-core packing: kind from the layer geometry
+            if self._is_bf16(name):      # tensor-core packing: kind from the layer geometry
                 k, st = convmod.kernel_size[0], convmod.stride[0]
                 kind = tc.T2 if transposed else (tc.K1 if k == 1 else (tc.S2 if st == 2 else tc.S1))
                 if kind == tc.S1 and tc.ntile(tc.S1F, w.shape[1], w.shape[0]) == w.shape[0]:
@@ -194,6 +200,7 @@ class DisparityHotPath(nn.Module):
             conv(f"{hg}.conv6", m.conv6[0], m.conv6[1], True)
             conv(f"{hg}.redir1", m.redir1[0], m.redir1[1])
             conv(f"{hg}.redir2", m.redir2[0], m.redir2[1])
+            bf16 = self._is_bf16(hg)
             if bf16:
                 for dc, rd in (("conv5", "redir2"), ("conv6", "redir1")):
                     deconv, dbn = getattr(m, dc)[0], getattr(m, dc)[1]
@@ -216,7 +223,7 @@ class DisparityHotPath(nn.Module):
         for cl in ("classif_att_", "classif"):
             m = getattr(self, cl)
             conv(cl + ".0", m[0][0], m[0][1])
-            if bf16:
+            if self._is_bf16(cl):
                 c[cl + ".2.tc"] = tc.pack_head_weight(m[2].weight.detach().float())          # taps-as-N head kernel
             else:
                 c[cl + ".2.w"] = m[2].weight.detach().float().contiguous()
@@ -228,12 +235,12 @@ class DisparityHotPath(nn.Module):
             c[ca + ".w1"] = m[1].weight.detach().float().reshape(m[1].out_channels, -1).contiguous()
             c[ca + ".b1"] = m[1].bias.detach().float().contiguous()
             w0, w1 = m[0].conv.weight.detach().float(), m[1].weight.detach().float()
-            if bf16:
+            if self._is_bf16(ca):
                 c[ca + ".tc0"] = tc.pack_weight2d(w0, tc.CONV1)
                 c[ca + ".tc1"] = tc.pack_weight2d(w1, tc.CONV1)
         cf0, cf1 = self.concat_feature[0], self.concat_feature[1]
         c["cf0.scale"], c["cf0.shift"] = bn_affine(cf0.bn)
-        if bf16:
+        if self._is_bf16("concat_feature"):
             c["cf0.tc"] = tc.pack_weight(cf0.conv.weight.detach().float(), tc.C2D)
             c["cf1.tc"] = tc.pack_weight(cf1.weight.detach().float(), tc.C2D)
         else:      # fp32 mode: the 2-D 3x3 conv as the centre depth plane of a 3x3x3 kernel on a depth-1 volume
@@ -252,7 +259,7 @@ class DisparityHotPath(nn.Module):
         the bf16 blocked (B,4,1,H/4,W/4,8) tensor the fused concat_stem kernel stages."""
         with ops.label("concat_feature"):
             x = f4.unsqueeze(2)
-            if self.precision == "bf16":
+            if self._is_bf16("concat_feature"):
                 xb = f4_blocked if f4_blocked is not None else tc.to_blocked_bf16(x)
                 y = tc.conv3d_tc(tc.C2D, xb, c["cf0.tc"], 64, c["cf0.scale"], c["cf0.shift"], relu=True)
                 if blocked:
@@ -264,7 +271,7 @@ class DisparityHotPath(nn.Module):
     def _gate_logits(self, c, name, im, im_blocked=None):
         """channelAtt.im_att (SemStereo.py:93-95): 1x1 conv + BN + ReLU -> 1x1 conv + bias.  bf16 mode: both 1x1 convs run on
         the tensor cores (csrc/conv2d_tc.cu, mode CONV1) from a blocked bf16 copy of the image features."""
-        if self.precision == "bf16":
+        if self._is_bf16(name):
             with ops.label(name):
                 B, C, H, W = im.shape
                 xb = im_blocked.view(B, C // 8, H, W, 8) if im_blocked is not None else tc.to_blocked2d(im)
@@ -343,7 +350,7 @@ class DisparityHotPath(nn.Module):
         # --- attention branch @1/8 (SemStereo.py:273-278) ---
         corr = ops.gwc_volume(f8_l, f8_r, m8, 32, signed=self.signed, norm=True)
         gate8 = self._gate_logits(c, "corr_feature_att_8", f8_l)
-        if self.precision == "bf16":
+        if self._is_bf16("hourglass_att"):
             vol = tc.patch_gate_blocked(corr, c["patch.w"], gate8)
             cost_att = self._classifier_tc(c, "classif_att_", self._hourglass_tc(c, "hourglass_att", vol))
         else:
@@ -362,13 +369,14 @@ class DisparityHotPath(nn.Module):
             out["pred_att_up"] = ops.ssr_upsample(pred_att.unsqueeze(1), spx_pred, pred_label, c["ssr"])
             return out
         # --- sparse concat volume + aggregation (SemStereo.py:314-324) ---
+        main_bf16 = self._is_bf16("hourglass")
         f4l_b = None                            # bf16 blocked copy of f4_l: feeds concat_feature and the gate convs
-        if self.precision == "bf16":
+        if main_bf16:
             f4l_b = (f4_l_blocked.view(f4_l.shape[0], 16, 1, *f4_l.shape[2:], 8) if f4_l_blocked is not None
                      else tc.to_blocked_bf16(f4_l.unsqueeze(2)))
         # bf16 mode without kept intermediates: the sparse concat volume is generated inside the concat_stem kernel (never in HBM)
         nbins = (2 if self.signed else 1) * m4
-        fused = self.precision == "bf16" and not keep and nbins == 32 and f4_l.shape[-1] % 4 == 0
+        fused = main_bf16 and not keep and nbins == 32
         if cf_l is None:
             cf_l = self._concat_feature(c, f4_l, f4l_b, blocked=fused)
         elif fused:
@@ -385,7 +393,7 @@ class DisparityHotPath(nn.Module):
                 v = tc.concat_stem_fused(cf_l, cf_r, disp_topk, att_topk, c["concat_stem.tc"], int(dmin), c["concat_stem.scale"],
                                          c["concat_stem.shift"], gb, relu=True, out_mode=tc.S2D)
             cost = self._classifier_tc(c, "classif", self._hourglass_tc(c, "hourglass", v))
-        elif self.precision == "bf16":
+        elif main_bf16:
             volume = tc.sparse_concat_volume_blocked(cf_l, cf_r, disp_topk, att_topk)      # (B,8,24,H/4,W/4,8) bf16
             v = self._tc(c, "concat_stem", tc.S1, volume, 32, gate=tc.gate_sigmoid_blocked(gate4), out_mode=tc.S2D)
             cost = self._classifier_tc(c, "classif", self._hourglass_tc(c, "hourglass", v))
