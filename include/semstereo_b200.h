@@ -198,4 +198,21 @@ SS_API int ss_propagation(const float* in, float* out, int B, int D, int H, int 
 SS_API int ss_spatial_transformer_grid(const float* x, const float* y, const float* disp_samples, float* y_warped,
                                        float* x_rep_or_null, int B, int C, int K, int H, int W, void* stream);
 
+/* ---- backward (vector-Jacobian products) of the volume / regression operators: BASELINE config #5, first step ------------
+ * Gather-form, deterministic, fp32.  Shapes as in the forward entry points; every grad_* output is fully overwritten. */
+/* build_gwc_volume(_norm): grad_volume (B,G,D,H,W) -> grad_left, grad_right (B,C,H,W).  flags as ss_gwc_volume. */
+SS_API int ss_gwc_volume_backward(const float* left, const float* right, const float* grad_volume, float* grad_left, float* grad_right,
+                                  int B, int C, int H, int W, int maxdisp, int num_groups, int flags, void* stream);
+/* build_concat_volume: grad_volume (B,2C,D,H,W) -> grad_left, grad_right (B,C,H,W). */
+SS_API int ss_concat_volume_backward(const float* grad_volume, float* grad_left, float* grad_right, int B, int C, int H, int W,
+                                     int maxdisp, int flags, void* stream);
+/* disparity_regression: grad_out (B,H,W) -> grad_prob (B,D,H,W). */
+SS_API int ss_disparity_regression_backward(const float* grad_out, float* grad_prob, int B, int D, int H, int W, float dmin, void* stream);
+/* regression_topk: grad_pred (B,1,H,W) -> grad_cost, grad_samples (B,D,H,W) (zero outside the selected K; the sort carries no gradient). */
+SS_API int ss_regression_topk_backward(const float* cost, const float* disp_samples, const float* grad_pred, float* grad_cost,
+                                       float* grad_samples, int B, int D, int K, int H, int W, void* stream);
+/* context_upsample: grad_out (B,4h,4w) -> grad_depth (B,1,h,w), grad_weights (B,9,4h,4w). */
+SS_API int ss_context_upsample_backward(const float* depth_low, const float* up_weights, const float* grad_out, float* grad_depth,
+                                        float* grad_weights, int B, int h, int w, void* stream);
+
 #endif /* SEMSTEREO_B200_H */

@@ -350,3 +350,56 @@ def spatial_transformer_grid(x, y, disp_samples, want_x_rep=True):
     _call("ss_spatial_transformer_grid", dev, _ptr(x), _ptr(y), _ptr(disp_samples), _ptr(yw), _ptr(xr), B, C, K, H, W)
     return yw, xr
 
+
+
+# ---- backward (VJP) of the volume / regression operators (csrc/backward.cu) ----------------------------------------
+def gwc_volume_backward(left, right, grad_volume, maxdisp, num_groups, signed=True, norm=False):
+    dev = _require_cuda(left, right, grad_volume)
+    B, C, H, W = left.shape
+    D = 2 * maxdisp if signed else maxdisp
+    if right.shape != left.shape or tuple(grad_volume.shape) != (B, num_groups, D, H, W):
+        raise ValueError("gwc_volume_backward: left/right (B,C,H,W) and grad_volume (B,G,D,H,W) expected")
+    gl, gr = torch.empty_like(left), torch.empty_like(right)
+    flags = (SIGNED if signed else 0) | (NORM if norm else 0)
+    _call("ss_gwc_volume_backward", dev, _ptr(left), _ptr(right), _ptr(grad_volume), _ptr(gl), _ptr(gr), B, C, H, W, int(maxdisp),
+          int(num_groups), flags)
+    return gl, gr
+
+
+def concat_volume_backward(grad_volume, maxdisp, signed=True):
+    dev = _require_cuda(grad_volume)
+    B, C2, D, H, W = grad_volume.shape
+    if C2 % 2 or D != (2 * maxdisp if signed else maxdisp):
+        raise ValueError("concat_volume_backward: grad_volume must be (B,2C,D,H,W) with D matching maxdisp")
+    gl = torch.empty((B, C2 // 2, H, W), device=dev, dtype=torch.float32)
+    gr = torch.empty_like(gl)
+    _call("ss_concat_volume_backward", dev, _ptr(grad_volume), _ptr(gl), _ptr(gr), B, C2 // 2, H, W, int(maxdisp), SIGNED if signed else 0)
+    return gl, gr
+
+
+def disparity_regression_backward(grad_out, D, dmin):
+    dev = _require_cuda(grad_out)
+    B, H, W = grad_out.shape
+    gp = torch.empty((B, D, H, W), device=dev, dtype=torch.float32)
+    _call("ss_disparity_regression_backward", dev, _ptr(grad_out), _ptr(gp), B, int(D), H, W, float(dmin))
+    return gp
+
+
+def regression_topk_backward(cost, disp_samples, grad_pred, k):
+    dev = _require_cuda(cost, disp_samples, grad_pred)
+    B, D, H, W = cost.shape
+    if disp_samples.shape != cost.shape or grad_pred.numel() != B * H * W:
+        raise ValueError("regression_topk_backward: cost/samples (B,D,H,W), grad_pred (B,1,H,W) expected")
+    gc, gs = torch.empty_like(cost), torch.empty_like(cost)
+    _call("ss_regression_topk_backward", dev, _ptr(cost), _ptr(disp_samples), _ptr(grad_pred), _ptr(gc), _ptr(gs), B, D, int(k), H, W)
+    return gc, gs
+
+
+def context_upsample_backward(depth_low, up_weights, grad_out):
+    dev = _require_cuda(depth_low, up_weights, grad_out)
+    B, one, h, w = depth_low.shape
+    if one != 1 or tuple(up_weights.shape) != (B, 9, 4 * h, 4 * w) or tuple(grad_out.shape) != (B, 4 * h, 4 * w):
+        raise ValueError("context_upsample_backward: depth_low (B,1,h,w), up_weights (B,9,4h,4w), grad_out (B,4h,4w)")
+    gd, gw = torch.empty_like(depth_low), torch.empty_like(up_weights)
+    _call("ss_context_upsample_backward", dev, _ptr(depth_low), _ptr(up_weights), _ptr(grad_out), _ptr(gd), _ptr(gw), B, h, w)
+    return gd, gw

@@ -69,3 +69,70 @@ def disparity_regression(prob: torch.Tensor, maxdisp: int, signed: bool) -> torc
 def _(prob, maxdisp, signed):
     B, D, H, W = prob.shape
     return prob.new_empty((B, H, W))
+
+
+# ---- autograd: vector-Jacobian products from csrc/backward.cu (BASELINE config #5, first step) -------------------------
+def _gwc_setup(ctx, inputs, output):
+    left, right, maxdisp, num_groups, signed, norm = inputs
+    ctx.save_for_backward(left, right)
+    ctx.args = (maxdisp, num_groups, signed, norm)
+
+
+def _gwc_backward(ctx, grad):
+    left, right = ctx.saved_tensors
+    gl, gr = ops.gwc_volume_backward(left.contiguous(), right.contiguous(), grad.contiguous(), *ctx.args)
+    return gl, gr, None, None, None, None
+
+
+torch.library.register_autograd(f"{NS}::gwc_volume", _gwc_backward, setup_context=_gwc_setup)
+
+
+def _concat_setup(ctx, inputs, output):
+    ctx.args = (inputs[2], inputs[3])
+
+
+def _concat_backward(ctx, grad):
+    gl, gr = ops.concat_volume_backward(grad.contiguous(), *ctx.args)
+    return gl, gr, None, None
+
+
+torch.library.register_autograd(f"{NS}::concat_volume", _concat_backward, setup_context=_concat_setup)
+
+
+def _topk_setup(ctx, inputs, output):
+    cost, samples, k = inputs
+    ctx.save_for_backward(cost, samples)
+    ctx.k = k
+
+
+def _topk_backward(ctx, grad):
+    cost, samples = ctx.saved_tensors
+    gc, gs = ops.regression_topk_backward(cost.contiguous(), samples.contiguous(), grad.contiguous(), ctx.k)
+    return gc, gs, None
+
+
+torch.library.register_autograd(f"{NS}::regression_topk", _topk_backward, setup_context=_topk_setup)
+
+
+def _ctx_up_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _ctx_up_backward(ctx, grad):
+    depth_low, up_weights = ctx.saved_tensors
+    return ops.context_upsample_backward(depth_low.contiguous(), up_weights.contiguous(), grad.contiguous())
+
+
+torch.library.register_autograd(f"{NS}::context_upsample", _ctx_up_backward, setup_context=_ctx_up_setup)
+
+
+def _dreg_setup(ctx, inputs, output):
+    prob, maxdisp, signed = inputs
+    ctx.D, ctx.dmin = prob.shape[1], float(-maxdisp if signed else 0)
+
+
+def _dreg_backward(ctx, grad):
+    return ops.disparity_regression_backward(grad.contiguous(), ctx.D, ctx.dmin), None, None
+
+
+torch.library.register_autograd(f"{NS}::disparity_regression", _dreg_backward, setup_context=_dreg_setup)

@@ -1,0 +1,76 @@
+"""Backward (VJP) kernels of the volume / regression operators vs torch autograd through the CPU oracle (oracle/ops.py is plain
+differentiable torch): the first step of BASELINE config #5.  fp32, tolerance relative to the gradient's scale."""
+import pytest
+import torch
+
+from oracle import ops as oo
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+if torch.cuda.is_available():
+    import semstereo_b200.torch_ops  # noqa: F401  (registers torch.ops.semstereo_b200.* with autograd)
+    T = torch.ops.semstereo_b200
+
+
+def rnd(*shape, seed=0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def close(got, ref, tol=2e-5):
+    assert got.shape == ref.shape
+    err = (got.cpu() - ref).abs().max().item()
+    assert err <= tol * max(1.0, ref.abs().max().item()), (err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("B,C,H,W,M,G", [(1, 16, 3, 24, 4, 4), (2, 32, 2, 37, 6, 8), (1, 256, 2, 128, 8, 32), (1, 24, 3, 9, 12, 3)])
+@pytest.mark.parametrize("signed", [True, False])
+@pytest.mark.parametrize("norm", [False, True])
+def test_gwc_volume_backward(B, C, H, W, M, G, signed, norm):
+    l, r = rnd(B, C, H, W, seed=1).requires_grad_(), rnd(B, C, H, W, seed=2).requires_grad_()
+    gv = rnd(B, G, 2 * M if signed else M, H, W, seed=3)
+    oo.gwc_volume(l, r, M, G, signed, norm).backward(gv)
+    lc, rc = l.detach().to(DEV).requires_grad_(), r.detach().to(DEV).requires_grad_()
+    T.gwc_volume(lc, rc, M, G, signed, norm).backward(gv.to(DEV))
+    close(lc.grad, l.grad)
+    close(rc.grad, r.grad)
+
+
+@pytest.mark.parametrize("signed", [True, False])
+def test_concat_volume_backward(signed):
+    B, C, H, W, M = 2, 8, 3, 21, 5
+    l, r = rnd(B, C, H, W, seed=1).requires_grad_(), rnd(B, C, H, W, seed=2).requires_grad_()
+    gv = rnd(B, 2 * C, 2 * M if signed else M, H, W, seed=3)
+    oo.concat_volume(l, r, M, signed).backward(gv)
+    lc, rc = l.detach().to(DEV).requires_grad_(), r.detach().to(DEV).requires_grad_()
+    T.concat_volume(lc, rc, M, signed).backward(gv.to(DEV))
+    close(lc.grad, l.grad)
+    close(rc.grad, r.grad)
+
+
+@pytest.mark.parametrize("D,k", [(24, 2), (24, 5), (48, 3)])
+def test_regression_topk_backward(D, k):
+    c, s = rnd(2, D, 5, 13, seed=4).requires_grad_(), (4 * rnd(2, D, 5, 13, seed=5)).requires_grad_()
+    g = rnd(2, 1, 5, 13, seed=6)
+    oo.regression_topk(c, s, k).backward(g)
+    cc, sc = c.detach().to(DEV).requires_grad_(), s.detach().to(DEV).requires_grad_()
+    T.regression_topk(cc, sc, k).backward(g.to(DEV))
+    close(cc.grad, c.grad)
+    close(sc.grad, s.grad)
+
+
+def test_context_upsample_and_disparity_regression_backward():
+    d, w = rnd(2, 1, 6, 9, seed=7).requires_grad_(), rnd(2, 9, 24, 36, seed=8).requires_grad_()
+    g = rnd(2, 24, 36, seed=9)
+    oo.context_upsample(d, w).backward(g)
+    dc, wc = d.detach().to(DEV).requires_grad_(), w.detach().to(DEV).requires_grad_()
+    T.context_upsample(dc, wc).backward(g.to(DEV))
+    close(dc.grad, d.grad)
+    close(wc.grad, w.grad)
+    for signed in (True, False):
+        p = torch.softmax(rnd(2, 16 if signed else 8, 4, 7, seed=10), 1).requires_grad_()
+        go = rnd(2, 4, 7, seed=11)
+        oo.disparity_regression(p, 8, signed).backward(go)
+        pc = p.detach().to(DEV).requires_grad_()
+        T.disparity_regression(pc, 8, signed).backward(go.to(DEV))
+        close(pc.grad, p.grad)
