@@ -215,4 +215,15 @@ SS_API int ss_regression_topk_backward(const float* cost, const float* disp_samp
 SS_API int ss_context_upsample_backward(const float* depth_low, const float* up_weights, const float* grad_out, float* grad_depth,
                                         float* grad_weights, int B, int h, int w, void* stream);
 
+/* Propagation / Propagation_prob: grad_out (B,5,[D,]H,W) -> grad_in (B,1,[D,]H,W) (D = 1 for the 2-D module). */
+SS_API int ss_propagation_backward(const float* grad_out, float* grad_in, int B, int D, int H, int W, void* stream);
+/* disparity_variance: grad_out (B,1,H,W) -> grad_prob (B,D,H,W), grad_disparity (B,1,H,W). */
+SS_API int ss_disparity_variance_backward(const float* prob, const float* disparity, const float* grad_out, float* grad_prob,
+                                          float* grad_disparity, int B, int D, int H, int W, float dmin, void* stream);
+/* SpatialTransformer_grid: grad_y_warped, grad_x_rep (B,C,K,H,W) -> grad_x, grad_y (B,C,H,W), grad_disp (B,K,H,W).
+ * grad_y is accumulated with atomics and must be ZERO on entry; grad_x_rep / grad_x may both be NULL. */
+SS_API int ss_spatial_transformer_grid_backward(const float* y, const float* disp_samples, const float* grad_y_warped,
+                                                const float* grad_x_rep_or_null, float* grad_x_or_null, float* grad_y, float* grad_disp,
+                                                int B, int C, int K, int H, int W, void* stream);
+
 #endif /* SEMSTEREO_B200_H */

@@ -42,6 +42,9 @@ SIGNATURES = {
     "ss_disparity_regression_backward": [_P, _P, _I, _I, _I, _I, _F, _P],
     "ss_regression_topk_backward": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "ss_context_upsample_backward": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "ss_propagation_backward": [_P, _P, _I, _I, _I, _I, _P],
+    "ss_disparity_variance_backward": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "ss_spatial_transformer_grid_backward": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "ss_conv2d_tc_ntile": [_I, _I, _I],
     "ss_conv2d_tc": [_I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ss_bilinear_up2": [_P, _P, _I, _I, _I, _P],

@@ -218,6 +218,92 @@ __global__ void __launch_bounds__(128) context_upsample_backward_d_kernel(const 
   gdepth[((size_t)b * h + y) * w + x] = acc;
 }
 
+// Propagation / Propagation_prob (submodule.py:290-307, 361-377): out_s[y,x] = in[clamp(y+dy_s), clamp(x+dx_s)].
+// Gather form: pixel (y',x') collects g_s[y,x] from every (y,x) of its 3x3 neighbourhood whose clamped tap lands on it.
+__global__ void __launch_bounds__(256) propagation_backward_kernel(const float* __restrict__ gout, float* __restrict__ gin, int D, int H,
+                                                                   int W) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= W) return;
+  const int y = blockIdx.y % H, d = blockIdx.y / H, b = blockIdx.z;
+  const size_t HW = (size_t)H * W, S = (size_t)D * HW;
+  float acc = 0.0f;
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const float* g = gout + ((size_t)b * 5 + s) * S + (size_t)d * HW;
+#pragma unroll
+    for (int oy = -1; oy <= 1; ++oy)
+#pragma unroll
+      for (int ox = -1; ox <= 1; ++ox) {
+        const int yy = y + oy, xx = x + ox;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        if (min(max(yy + kPropDy[s], 0), H - 1) == y && min(max(xx + kPropDx[s], 0), W - 1) == x) acc += __ldg(g + (size_t)yy * W + xx);
+      }
+  }
+  gin[(size_t)b * S + (size_t)d * HW + (size_t)y * W + x] = acc;
+}
+
+// disparity_variance (submodule.py:257-263): var = sum_k p_k (d_k - mu)^2.
+__global__ void __launch_bounds__(256) disparity_variance_backward_kernel(const float* __restrict__ p, const float* __restrict__ mu,
+                                                                          const float* __restrict__ gout, float* __restrict__ gp,
+                                                                          float* __restrict__ gmu, int D, size_t HW, float dmin) {
+  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (pix >= HW) return;
+  const float m = __ldg(mu + (size_t)b * HW + pix), g = __ldg(gout + (size_t)b * HW + pix);
+  float acc = 0.0f;
+  for (int k = 0; k < D; ++k) {
+    const float e = dmin + (float)k - m;
+    gp[((size_t)b * D + k) * HW + pix] = g * e * e;
+    acc = fmaf(__ldg(p + ((size_t)b * D + k) * HW + pix), e, acc);
+  }
+  gmu[(size_t)b * HW + pix] = -2.0f * g * acc;
+}
+
+// SpatialTransformer_grid (submodule.py:265-288).  One thread per (b, k, y, x):
+//   grad_disp = -sum_c g_yw[c] * d(bilinear)/d(ix)   (ix = x - d up to the fp32 round trip: d ix / d d = -1)
+//   grad_src  : the four corners receive g_yw[c] * weight   (scatter: atomicAdd, like torch's grid_sampler backward)
+// grad_x (the repeated left features) is the sum of g_xrep over k and is done by the caller-facing wrapper kernel below.
+__global__ void __launch_bounds__(128) stn_backward_kernel(const float* __restrict__ src, const float* __restrict__ disp,
+                                                           const float* __restrict__ gyw, float* __restrict__ gsrc,
+                                                           float* __restrict__ gdisp, int C, int K, int H, int W) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= W) return;
+  const int y = blockIdx.y % H, k = blockIdx.y / H, b = blockIdx.z;
+  const size_t HW = (size_t)H * W;
+  const float d = __ldg(disp + ((size_t)b * K + k) * HW + (size_t)y * W + x);
+  const float ix = warp_coord((float)x - d, (float)(W - 1)), iy = warp_coord((float)y, (float)(H - 1));
+  const Bilin q = make_bilin(ix, iy, H, W);
+  const float fy0 = floorf(iy), wy0 = fy0 + 1.0f - iy, wy1 = iy - fy0;      // the y factors of the four weights
+  float gd = 0.0f;
+  for (int c = 0; c < C; ++c) {
+    const float g = __ldg(gyw + (((size_t)b * C + c) * K + k) * HW + (size_t)y * W + x);
+    const float* plane = src + ((size_t)b * C + c) * HW;
+    float* gplane = gsrc + ((size_t)b * C + c) * HW;
+    const float a00 = __ldg(plane + q.o00), a01 = __ldg(plane + q.o01), a10 = __ldg(plane + q.o10), a11 = __ldg(plane + q.o11);
+    if (q.w00 != 0.0f) atomicAdd(gplane + q.o00, g * q.w00);
+    if (q.w01 != 0.0f) atomicAdd(gplane + q.o01, g * q.w01);
+    if (q.w10 != 0.0f) atomicAdd(gplane + q.o10, g * q.w10);
+    if (q.w11 != 0.0f) atomicAdd(gplane + q.o11, g * q.w11);
+    // d out / d ix = (ne - nw) * wy0 + (se - sw) * wy1 with out-of-range corners contributing 0
+    const float fx0 = floorf(ix), fx1 = fx0 + 1.0f;
+    const bool x0ok = fx0 >= 0.0f && fx0 <= (float)(W - 1), x1ok = fx1 >= 0.0f && fx1 <= (float)(W - 1);
+    const bool y0ok = fy0 >= 0.0f && fy0 <= (float)(H - 1), y1ok = fy0 + 1.0f >= 0.0f && fy0 + 1.0f <= (float)(H - 1);
+    const float nw = (x0ok && y0ok) ? a00 : 0.0f, ne = (x1ok && y0ok) ? a01 : 0.0f;
+    const float sw = (x0ok && y1ok) ? a10 : 0.0f, se = (x1ok && y1ok) ? a11 : 0.0f;
+    gd = fmaf(g, (ne - nw) * wy0 + (se - sw) * wy1, gd);
+  }
+  gdisp[((size_t)b * K + k) * HW + (size_t)y * W + x] = -gd;
+}
+
+__global__ void __launch_bounds__(256) sum_over_k_kernel(const float* __restrict__ gxr, float* __restrict__ gx, int K, size_t HW) {
+  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t bc = blockIdx.y;
+  if (pix >= HW) return;
+  float acc = 0.0f;
+  for (int k = 0; k < K; ++k) acc += __ldg(gxr + (bc * K + k) * HW + pix);
+  gx[bc * HW + pix] = acc;
+}
+
 }  // namespace
 
 extern "C" int ss_gwc_volume_backward(const float* left, const float* right, const float* grad_volume, float* grad_left, float* grad_right,
@@ -284,5 +370,43 @@ extern "C" int ss_context_upsample_backward(const float* depth_low, const float*
   SS_CHECK_LAUNCH("ss_context_upsample_backward(weights)");
   context_upsample_backward_d_kernel<<<dim3(ceil_div(w, 128), h, B), 128, 0, (cudaStream_t)stream>>>(up_weights, grad_out, grad_depth, h, w);
   SS_CHECK_LAUNCH("ss_context_upsample_backward(depth)");
+  return SS_OK;
+}
+
+extern "C" int ss_propagation_backward(const float* grad_out, float* grad_in, int B, int D, int H, int W, void* stream) {
+  SS_REQUIRE(grad_out && grad_in && B > 0 && D > 0 && H > 0 && W > 0, "ss_propagation_backward: bad argument");
+  SS_UNSUPPORTED((long long)D * H > 65535 || B > 65535, "ss_propagation_backward: grid dimension exceeds 65535");
+  propagation_backward_kernel<<<dim3(ceil_div(W, 256), D * H, B), 256, 0, (cudaStream_t)stream>>>(grad_out, grad_in, D, H, W);
+  SS_CHECK_LAUNCH("ss_propagation_backward");
+  return SS_OK;
+}
+
+extern "C" int ss_disparity_variance_backward(const float* prob, const float* disparity, const float* grad_out, float* grad_prob,
+                                              float* grad_disparity, int B, int D, int H, int W, float dmin, void* stream) {
+  SS_REQUIRE(prob && disparity && grad_out && grad_prob && grad_disparity && B > 0 && D > 0 && H > 0 && W > 0,
+             "ss_disparity_variance_backward: bad argument");
+  SS_UNSUPPORTED(B > 65535, "ss_disparity_variance_backward: grid dimension exceeds 65535");
+  const size_t HW = (size_t)H * W;
+  disparity_variance_backward_kernel<<<dim3((unsigned)ceil_div64(HW, 256), B), 256, 0, (cudaStream_t)stream>>>(
+      prob, disparity, grad_out, grad_prob, grad_disparity, D, HW, dmin);
+  SS_CHECK_LAUNCH("ss_disparity_variance_backward");
+  return SS_OK;
+}
+
+// grad_y (B,C,H,W) is ACCUMULATED with atomics: it must be zero-filled by the caller.  grad_x_rep / grad_x may both be NULL.
+extern "C" int ss_spatial_transformer_grid_backward(const float* y, const float* disp_samples, const float* grad_y_warped,
+                                                    const float* grad_x_rep_or_null, float* grad_x_or_null, float* grad_y, float* grad_disp,
+                                                    int B, int C, int K, int H, int W, void* stream) {
+  SS_REQUIRE(y && disp_samples && grad_y_warped && grad_y && grad_disp, "ss_spatial_transformer_grid_backward: null pointer");
+  SS_REQUIRE((grad_x_rep_or_null != nullptr) == (grad_x_or_null != nullptr), "ss_spatial_transformer_grid_backward: grad_x_rep and grad_x go together");
+  SS_REQUIRE(B > 0 && C > 0 && K > 0 && H > 1 && W > 1, "ss_spatial_transformer_grid_backward: bad dimension");
+  SS_UNSUPPORTED((long long)K * H > 65535 || (long long)B * C > 65535 || B > 65535, "ss_spatial_transformer_grid_backward: grid dimension exceeds 65535");
+  stn_backward_kernel<<<dim3(ceil_div(W, 128), K * H, B), 128, 0, (cudaStream_t)stream>>>(y, disp_samples, grad_y_warped, grad_y, grad_disp, C, K, H, W);
+  SS_CHECK_LAUNCH("ss_spatial_transformer_grid_backward");
+  if (grad_x_or_null) {
+    const size_t HW = (size_t)H * W;
+    sum_over_k_kernel<<<dim3((unsigned)ceil_div64(HW, 256), B * C), 256, 0, (cudaStream_t)stream>>>(grad_x_rep_or_null, grad_x_or_null, K, HW);
+    SS_CHECK_LAUNCH("ss_spatial_transformer_grid_backward(x)");
+  }
   return SS_OK;
 }

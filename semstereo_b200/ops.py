@@ -403,3 +403,40 @@ def context_upsample_backward(depth_low, up_weights, grad_out):
     gd, gw = torch.empty_like(depth_low), torch.empty_like(up_weights)
     _call("ss_context_upsample_backward", dev, _ptr(depth_low), _ptr(up_weights), _ptr(grad_out), _ptr(gd), _ptr(gw), B, h, w)
     return gd, gw
+
+
+def propagation_backward(grad_out):
+    dev = _require_cuda(grad_out)
+    if grad_out.shape[1] != 5:
+        raise ValueError("propagation_backward expects (B,5,[D,]H,W)")
+    if grad_out.dim() == 4:
+        B, _, H, W = grad_out.shape
+        D, gin = 1, torch.empty((B, 1, H, W), device=dev, dtype=torch.float32)
+    else:
+        B, _, D, H, W = grad_out.shape
+        gin = torch.empty((B, 1, D, H, W), device=dev, dtype=torch.float32)
+    _call("ss_propagation_backward", dev, _ptr(grad_out), _ptr(gin), B, D, H, W)
+    return gin
+
+
+def disparity_variance_backward(prob, disparity, grad_out, dmin):
+    dev = _require_cuda(prob, disparity, grad_out)
+    B, D, H, W = prob.shape
+    gp, gm = torch.empty_like(prob), torch.empty((B, 1, H, W), device=dev, dtype=torch.float32)
+    _call("ss_disparity_variance_backward", dev, _ptr(prob), _ptr(disparity), _ptr(grad_out), _ptr(gp), _ptr(gm), B, D, H, W, float(dmin))
+    return gp, gm
+
+
+def spatial_transformer_grid_backward(y, disp_samples, grad_y_warped, grad_x_rep=None):
+    """Returns (grad_x or None, grad_y, grad_disp)."""
+    dev = _require_cuda(y, disp_samples, grad_y_warped, grad_x_rep)
+    B, C, H, W = y.shape
+    K = disp_samples.shape[1]
+    if tuple(grad_y_warped.shape) != (B, C, K, H, W):
+        raise ValueError("spatial_transformer_grid_backward: grad_y_warped must be (B,C,K,H,W)")
+    gy = torch.zeros_like(y)
+    gd = torch.empty_like(disp_samples)
+    gx = torch.empty_like(y) if grad_x_rep is not None else None
+    _call("ss_spatial_transformer_grid_backward", dev, _ptr(y), _ptr(disp_samples), _ptr(grad_y_warped), _ptr(grad_x_rep), _ptr(gx),
+          _ptr(gy), _ptr(gd), B, C, K, H, W)
+    return gx, gy, gd

@@ -136,3 +136,73 @@ def _dreg_backward(ctx, grad):
 
 
 torch.library.register_autograd(f"{NS}::disparity_regression", _dreg_backward, setup_context=_dreg_setup)
+
+
+# ---- the remaining free functions / stateless modules of the surface, with autograd ----------------------------------------
+@torch.library.custom_op(f"{NS}::propagation", mutates_args=())
+def propagation(x: torch.Tensor) -> torch.Tensor:
+    """Propagation / Propagation_prob (models/submodule.py:290-307, 361-377): (B,1,[D,]H,W) -> (B,5,[D,]H,W)."""
+    return ops.propagation(x.contiguous())
+
+
+@propagation.register_fake
+def _(x):
+    return x.new_empty((x.shape[0], 5) + tuple(x.shape[2:]))
+
+
+torch.library.register_autograd(f"{NS}::propagation", lambda ctx, g: ops.propagation_backward(g.contiguous()))
+
+
+@torch.library.custom_op(f"{NS}::disparity_variance", mutates_args=())
+def disparity_variance(prob: torch.Tensor, maxdisp: int, disparity: torch.Tensor, signed: bool) -> torch.Tensor:
+    """disparity_variance (models/submodule.py:257-263)."""
+    return ops.disparity_variance(prob.contiguous(), disparity.contiguous(), float(-maxdisp if signed else 0))
+
+
+@disparity_variance.register_fake
+def _(prob, maxdisp, disparity, signed):
+    B, D, H, W = prob.shape
+    return prob.new_empty((B, 1, H, W))
+
+
+def _dvar_setup(ctx, inputs, output):
+    prob, maxdisp, disparity, signed = inputs
+    ctx.save_for_backward(prob, disparity)
+    ctx.dmin = float(-maxdisp if signed else 0)
+
+
+def _dvar_backward(ctx, grad):
+    prob, disparity = ctx.saved_tensors
+    gp, gm = ops.disparity_variance_backward(prob.contiguous(), disparity.contiguous(), grad.contiguous(), ctx.dmin)
+    return gp, None, gm.view_as(disparity), None
+
+
+torch.library.register_autograd(f"{NS}::disparity_variance", _dvar_backward, setup_context=_dvar_setup)
+
+
+@torch.library.custom_op(f"{NS}::spatial_transformer_grid", mutates_args=())
+def spatial_transformer_grid(x: torch.Tensor, y: torch.Tensor, disp_range_samples: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """SpatialTransformer_grid (models/submodule.py:265-288): returns (y_warped, x_repeated), both (B,C,K,H,W)."""
+    yw, xr = ops.spatial_transformer_grid(x.contiguous(), y.contiguous(), disp_range_samples.contiguous())
+    return yw, xr
+
+
+@spatial_transformer_grid.register_fake
+def _(x, y, disp_range_samples):
+    B, C, H, W = y.shape
+    K = disp_range_samples.shape[1]
+    return y.new_empty((B, C, K, H, W)), y.new_empty((B, C, K, H, W))
+
+
+def _stn_setup(ctx, inputs, output):
+    x, y, disp = inputs
+    ctx.save_for_backward(y, disp)
+
+
+def _stn_backward(ctx, g_yw, g_xr):
+    y, disp = ctx.saved_tensors
+    gx, gy, gd = ops.spatial_transformer_grid_backward(y.contiguous(), disp.contiguous(), g_yw.contiguous(), g_xr.contiguous())
+    return gx, gy, gd
+
+
+torch.library.register_autograd(f"{NS}::spatial_transformer_grid", _stn_backward, setup_context=_stn_setup)

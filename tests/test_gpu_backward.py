@@ -74,3 +74,43 @@ def test_context_upsample_and_disparity_regression_backward():
         pc = p.detach().to(DEV).requires_grad_()
         T.disparity_regression(pc, 8, signed).backward(go.to(DEV))
         close(pc.grad, p.grad)
+
+
+def test_propagation_and_variance_backward():
+    for shape in ((2, 1, 6, 9), (1, 1, 4, 5, 7)):
+        x = rnd(*shape, seed=12).requires_grad_()
+        g = rnd(shape[0], 5, *shape[2:], seed=13)
+        (oo.propagation(x) if len(shape) == 4 else oo.propagation_prob(x)).backward(g)
+        xc = x.detach().to(DEV).requires_grad_()
+        T.propagation(xc).backward(g.to(DEV))
+        close(xc.grad, x.grad)
+    for signed in (True, False):
+        D = 16 if signed else 8
+        p = torch.softmax(rnd(2, D, 4, 7, seed=14), 1).requires_grad_()
+        mu = (3 * rnd(2, 1, 4, 7, seed=15)).requires_grad_()
+        go = rnd(2, 1, 4, 7, seed=16)
+        oo.disparity_variance(p, 8, mu, signed).backward(go)
+        pc, mc = p.detach().to(DEV).requires_grad_(), mu.detach().to(DEV).requires_grad_()
+        T.disparity_variance(pc, 8, mc, signed).backward(go.to(DEV))
+        close(pc.grad, p.grad)
+        close(mc.grad, mu.grad)
+
+
+@pytest.mark.parametrize("integer_disp", [False, True])
+def test_spatial_transformer_grid_backward(integer_disp):
+    B, C, K, H, W = 2, 6, 5, 7, 19
+    x, y = rnd(B, C, H, W, seed=17).requires_grad_(), rnd(B, C, H, W, seed=18).requires_grad_()
+    d = 4 * rnd(B, K, H, W, seed=19)
+    if integer_disp:
+        d = d.round()
+    d = (d + 0.25 * (not integer_disp)).requires_grad_()      # keep real-valued samples away from integers (kink of the bilinear)
+    g1, g2 = rnd(B, C, K, H, W, seed=20), rnd(B, C, K, H, W, seed=21)
+    yw, xr = oo.spatial_transformer_grid(x, y, d)
+    (yw * g1 + xr * g2).sum().backward()
+    xc, yc, dc = (t.detach().to(DEV).requires_grad_() for t in (x, y, d))
+    yw2, xr2 = T.spatial_transformer_grid(xc, yc, dc)
+    (yw2 * g1.to(DEV) + xr2 * g2.to(DEV)).sum().backward()
+    close(xc.grad, x.grad)
+    close(yc.grad, y.grad, 5e-5)                              # atomics: summation order differs
+    if not integer_disp:                                      # at integer positions the derivative w.r.t. the sample is one-sided
+        close(dc.grad, d.grad, 5e-5)
