@@ -17,6 +17,17 @@ def _c(t):
     return t.contiguous().float()
 
 
+def _grad(*ts):
+    """True when the call must be recorded by autograd: the differentiable route goes through the torch.library ops of
+    torch_ops.py (backward kernels in csrc/backward.cu); inference calls skip the dispatcher."""
+    return torch.is_grad_enabled() and any(t.requires_grad for t in ts)
+
+
+def _T():
+    from . import torch_ops  # noqa: F401  (registers torch.ops.semstereo_b200.* on first use)
+    return torch.ops.semstereo_b200
+
+
 def make_surface(signed: bool) -> dict:
     ns: dict = {}
 
@@ -24,30 +35,35 @@ def make_surface(signed: bool) -> dict:
         return float(-maxdisp) if signed else 0.0
 
     # ---- volume builders (submodule.py:173-255 / submodule_.py:166-237) -------------------------------
+    def _gwc(a, b, maxdisp, groups, sg, norm):
+        a, b = _c(a), _c(b)
+        return _T().gwc_volume(a, b, maxdisp, groups, sg, norm) if _grad(a, b) else ops.gwc_volume(a, b, maxdisp, groups, sg, norm)
+
     def build_concat_volume(refimg_fea, targetimg_fea, maxdisp):
-        return ops.concat_volume(_c(refimg_fea), _c(targetimg_fea), maxdisp, signed)
+        a, b = _c(refimg_fea), _c(targetimg_fea)
+        return _T().concat_volume(a, b, maxdisp, signed) if _grad(a, b) else ops.concat_volume(a, b, maxdisp, signed)
 
     def groupwise_correlation(fea1, fea2, num_groups):
         B, C, H, W = fea1.shape
         assert C % num_groups == 0
-        return ops.gwc_volume(_c(fea1), _c(fea2), 1, num_groups, signed=False, norm=False).squeeze(2)
+        return _gwc(fea1, fea2, 1, num_groups, False, False).squeeze(2)
 
     def groupwise_correlation_norm(fea1, fea2, num_groups):
         B, C, H, W = fea1.shape
         assert C % num_groups == 0
-        return ops.gwc_volume(_c(fea1), _c(fea2), 1, num_groups, signed=False, norm=True).squeeze(2)
+        return _gwc(fea1, fea2, 1, num_groups, False, True).squeeze(2)
 
     def norm_correlation(fea1, fea2):
-        return ops.gwc_volume(_c(fea1), _c(fea2), 1, 1, signed=False, norm=True).squeeze(2)
+        return _gwc(fea1, fea2, 1, 1, False, True).squeeze(2)
 
     def build_gwc_volume(refimg_fea, targetimg_fea, maxdisp, num_groups):
-        return ops.gwc_volume(_c(refimg_fea), _c(targetimg_fea), maxdisp, num_groups, signed, False)
+        return _gwc(refimg_fea, targetimg_fea, maxdisp, num_groups, signed, False)
 
     def build_gwc_volume_norm(refimg_fea, targetimg_fea, maxdisp, num_groups):
-        return ops.gwc_volume(_c(refimg_fea), _c(targetimg_fea), maxdisp, num_groups, signed, True)
+        return _gwc(refimg_fea, targetimg_fea, maxdisp, num_groups, signed, True)
 
     def build_norm_correlation_volume(refimg_fea, targetimg_fea, maxdisp):
-        return ops.gwc_volume(_c(refimg_fea), _c(targetimg_fea), maxdisp, 1, signed, True)
+        return _gwc(refimg_fea, targetimg_fea, maxdisp, 1, signed, True)
 
     # ---- regression (submodule.py:164-170, 257-263, 434-442) ------------------------------------------
     def disparity_regression(x, maxdisp):
@@ -55,33 +71,48 @@ def make_surface(signed: bool) -> dict:
         nb = 2 * maxdisp if signed else maxdisp
         if x.shape[1] != nb:
             raise RuntimeError(f"The size of tensor a ({x.shape[1]}) must match the size of tensor b ({nb}) at non-singleton dimension 1")
-        return ops.disparity_regression(_c(x), dmin(maxdisp))
+        x = _c(x)
+        return _T().disparity_regression(x, maxdisp, signed) if _grad(x) else ops.disparity_regression(x, dmin(maxdisp))
 
     def disparity_variance(x, maxdisp, disparity):
         assert len(x.shape) == 4
         nb = 2 * maxdisp if signed else maxdisp
         if x.shape[1] != nb:
             raise RuntimeError(f"The size of tensor a ({x.shape[1]}) must match the size of tensor b ({nb}) at non-singleton dimension 1")
-        return ops.disparity_variance(_c(x), _c(disparity), dmin(maxdisp))
+        x, disparity = _c(x), _c(disparity)
+        if _grad(x, disparity):
+            return _T().disparity_variance(x, maxdisp, disparity, signed)
+        return ops.disparity_variance(x, disparity, dmin(maxdisp))
 
     def regression_topk(cost, disparity_samples, k):
-        return ops.regression_topk(_c(cost), _c(disparity_samples), k)
+        cost, disparity_samples = _c(cost), _c(disparity_samples)
+        if _grad(cost, disparity_samples):
+            return _T().regression_topk(cost, disparity_samples, k)
+        return ops.regression_topk(cost, disparity_samples, k)
 
     # ---- warps / propagation (submodule.py:265-307, 361-377) ------------------------------------------
     def SpatialTransformer_grid(x, y, disp_range_samples):
-        return ops.spatial_transformer_grid(_c(x), _c(y), _c(disp_range_samples), want_x_rep=True)
+        x, y, disp_range_samples = _c(x), _c(y), _c(disp_range_samples)
+        if _grad(x, y, disp_range_samples):
+            return _T().spatial_transformer_grid(x, y, disp_range_samples)
+        return ops.spatial_transformer_grid(x, y, disp_range_samples, want_x_rep=True)
 
     class Propagation(nn.Module):
         def forward(self, disparity_samples):
-            return ops.propagation(_c(disparity_samples))
+            x = _c(disparity_samples)
+            return _T().propagation(x) if _grad(x) else ops.propagation(x)
 
     class Propagation_prob(nn.Module):
         def forward(self, prob_volume):
-            return ops.propagation(_c(prob_volume))
+            x = _c(prob_volume)
+            return _T().propagation(x) if _grad(x) else ops.propagation(x)
 
     # ---- upsamplers (submodule.py:412-431, submodule_.py:311-323) --------------------------------------
     def context_upsample(depth_low, up_weights):
-        return ops.context_upsample(_c(depth_low), _c(up_weights))
+        depth_low, up_weights = _c(depth_low), _c(up_weights)
+        if _grad(depth_low, up_weights):
+            return _T().context_upsample(depth_low, up_weights)
+        return ops.context_upsample(depth_low, up_weights)
 
     class SSR_upsample(hotpath._SSRParams):
         def __init__(self, num_classes):

@@ -114,3 +114,29 @@ def test_spatial_transformer_grid_backward(integer_disp):
     close(yc.grad, y.grad, 5e-5)                              # atomics: summation order differs
     if not integer_disp:                                      # at integer positions the derivative w.r.t. the sample is one-sided
         close(dc.grad, d.grad, 5e-5)
+
+
+def test_surface_functions_are_differentiable():
+    """The reference-named surface (semstereo_b200.submodule) records autograd when an input requires grad: a toy loss through
+    build_gwc_volume_norm -> softmax -> disparity_regression + SpatialTransformer_grid back-propagates to the features exactly
+    like the oracle composition does."""
+    import semstereo_b200.submodule as sm
+    l, r = rnd(1, 32, 4, 24, seed=30), rnd(1, 32, 4, 24, seed=31)
+
+    def loss(gwc, reg, stn, a, b):
+        vol = gwc(a, b, 4, 8)                                  # (1,8,8,4,24)
+        p = torch.softmax(vol.mean(1), 1)                      # (1,8,4,24)
+        mu = reg(p, 4)                                         # (1,4,24)
+        yw, xr = stn(a, b, torch.stack((mu, mu + 1.5), 1))     # (1,32,2,4,24)
+        return (yw * xr).mean() + mu.square().mean()
+
+    a, b = l.clone().requires_grad_(), r.clone().requires_grad_()
+    loss(lambda x, y, m, g: oo.gwc_volume(x, y, m, g, True, True), lambda p, m: oo.disparity_regression(p, m, True),
+         oo.spatial_transformer_grid, a, b).backward()
+    ac, bc = l.to(DEV).requires_grad_(), r.to(DEV).requires_grad_()
+    out = loss(sm.build_gwc_volume_norm, sm.disparity_regression, sm.SpatialTransformer_grid, ac, bc)
+    out.backward()
+    close(ac.grad, a.grad, 1e-4)
+    close(bc.grad, b.grad, 1e-4)
+    with torch.no_grad():                                      # inference calls bypass the dispatcher and still agree
+        assert torch.equal(sm.build_gwc_volume_norm(ac, bc, 4, 8), sm.build_gwc_volume_norm(ac.detach(), bc.detach(), 4, 8))
