@@ -306,9 +306,20 @@ def main():
     #      (semstereo_b200.graph.GraphedCall: the same kernels, bit-identical results) + the eager NCCL gather.  --no-graph
     #      times the eager launches instead. ----
     ms_total = ms_eager
+    graph_used, graph_err = False, ""
     if not a.no_graph:
         from semstereo_b200.graph import GraphedCall
-        gc = GraphedCall(call, devin)
+        gc = None
+        try:
+            gc = GraphedCall(call, devin)
+        except Exception as e:             # measurement falls back to the eager launches (all ranks together); the product is untouched
+            graph_err = f"{type(e).__name__}: {e}"[:200]
+            torch.cuda.synchronize()
+        ok = torch.tensor([0 if gc is None else 1], device=dev)
+        if world > 1:
+            tdist.all_reduce(ok, op=tdist.ReduceOp.MIN)
+        graph_used = bool(ok.item())
+    if graph_used:
 
         def gstep():
             o = gc.replay()
@@ -402,7 +413,8 @@ def main():
            "e2e": {"value": e2e_v, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps},
            "gpu_launches": rec.count, "clocks": clocks, "roofline": roof, "kernels": kernels}
     res["host"] = {"numa_bound_cpus": len(numa_cpus) if numa_cpus else None}
-    res["launch_mode"] = {"value_region": "eager" if a.no_graph else "cuda graph replay per step (+ eager NCCL gather)",
+    res["launch_mode"] = {"value_region": "cuda graph replay per step (+ eager NCCL gather)" if graph_used else
+                          ("eager" + (f" (graph capture failed: {graph_err})" if graph_err else "")),
                           "eager_instrumented_ms_per_step": ms_eager / a.steps,
                           "eager_instrumented_value": world * B * a.steps / (ms_eager * 1e-3),
                           "note": "kernels[] / roofline come from the instrumented eager pass of the same K steps; gpu_launches counts "
