@@ -110,7 +110,7 @@ def plan_row_tiles(H: int, n_tiles: int, halo: int = EXACT_HALO):
 
 
 class TiledHotPath:
-    """Runs `path` on row bands of one large image batch and stitches the kept rows.  With a process group the bands are dealt
+    """Runs `path` on row (or column) bands of one large image batch and stitches the kept rows.  With a process group the bands are dealt
     round-robin to the ranks and the stitched disparity is summed across ranks (every row is written by exactly one rank, the
     others contribute zeros, so the sum is exact).  With halo >= EXACT_HALO no kept row can see a cut; what remains is the fp32
     rounding of the reference's own grid normalisation (SpatialTransformer_grid divides by (H-1)/2 and multiplies back,
@@ -118,33 +118,43 @@ class TiledHotPath:
     (measured, tests/test_gpu_hotpath.py).  A smaller halo trades seam accuracy for less recomputation.  The reference has no
     tiling at all (main_us3d.py feeds whole crops)."""
 
-    def __init__(self, path, n_tiles: int, halo: int = EXACT_HALO, group=None):
-        self.path, self.n_tiles, self.halo, self.group = path, n_tiles, halo, group
+    def __init__(self, path, n_tiles: int, halo: int | None = None, group=None, axis: str = "h"):
+        """axis "h": row bands (halo = receptive field only).  axis "w": column bands; the halo must additionally cover the
+        disparity range on the side(s) the right image is read from (signed models: both), so the default is the receptive field
+        plus maxdisp rounded up to the 128-px grid (the same halo is used on both sides)."""
+        if axis not in ("h", "w"):
+            raise ValueError("TiledHotPath: axis must be 'h' or 'w'")
+        if halo is None:
+            halo = EXACT_HALO if axis == "h" else -(-(EXACT_HALO + int(path.maxdisp)) // TILE_UNIT) * TILE_UNIT
+        self.path, self.n_tiles, self.halo, self.group, self.axis = path, n_tiles, halo, group, axis
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
 
     def __call__(self, inputs: dict):
         order = ("f8_l", "f8_r", "f4_l", "f4_r", "cf_l", "cf_r", "spx_pred", "pred_label")
-        H = inputs["spx_pred"].shape[-2]
+        dim = -2 if self.axis == "h" else -1
+        L = inputs["spx_pred"].shape[dim]
         key = "pred_att_up" if self.path.att_weights_only else "pred_up"
         out = None
-        for t, (e0, e1, k0, k1) in enumerate(plan_row_tiles(H, self.n_tiles, self.halo)):
+        for t, (e0, e1, k0, k1) in enumerate(plan_row_tiles(L, self.n_tiles, self.halo)):
             if t % self.world != self.rank:
                 continue
             args = []
             for k in order:
                 x = inputs.get(k)
                 if x is not None:
-                    s = H // x.shape[-2]                 # 8, 4 or 1
-                    x = x[..., e0 // s: e1 // s, :].contiguous()
+                    s = L // x.shape[dim]                # 8, 4 or 1
+                    x = x.narrow(dim, e0 // s, (e1 - e0) // s).contiguous()
                 args.append(x)
             o = self.path(*args)[key]
             if out is None:
-                out = o.new_zeros((o.shape[0], H, o.shape[-1]))
-            out[:, k0:k1] = o[:, k0 - e0: k1 - e0]
+                full = list(o.shape)
+                full[dim] = L
+                out = o.new_zeros(full)
+            out.narrow(dim, k0, k1 - k0).copy_(o.narrow(dim, k0 - e0, k1 - k0))
         if out is None:                                    # more ranks than tiles
             ref = inputs["spx_pred"]
-            out = ref.new_zeros((ref.shape[0], H, ref.shape[-1]))
+            out = ref.new_zeros((ref.shape[0], ref.shape[-2], ref.shape[-1]))
         if self.world > 1:
             dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
         return out

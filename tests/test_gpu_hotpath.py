@@ -207,3 +207,18 @@ def test_other_disparity_ranges(signed, maxdisp):
     agree = (outb["disp_topk"] == out["disp_topk"]).all(dim=1).float().mean().item()
     assert agree >= 0.6           # 24 of 64 bins: more near-ties at the selection boundary than with 32 bins (measured 0.83 / 0.73)
     assert (outb["pred_att_up"] - out["pred_att_up"]).abs().median().item() <= 0.1      # disparity range is twice the 32-bin case
+
+
+def test_column_tiles_with_disparity_halo_match_the_untiled_run():
+    """A 2048-column image as two column bands with the default halo (receptive field + maxdisp, on the 128-px grid = 512): the
+    kept columns see neither the cut nor a missing disparity neighbour -> equal to the untiled run up to fp32 rounding of the
+    grid normalisation (which depends on the tile WIDTH here) and the isolated top-k flips it can trigger."""
+    from semstereo_b200.dist import TiledHotPath
+    m = build(64, True, False, 20.0)
+    inp = {k: v.to(DEV) for k, v in make_inputs(33, 1, 128, 2048).items()}
+    full = m(*[inp[k] for k in ORDER])["pred_up"]
+    t = TiledHotPath(m, n_tiles=2, axis="w")
+    assert t.halo == 512
+    d = (t(inp) - full).abs()
+    print(f"\n[column tiles, halo {t.halo}] max |diff| {float(d.max()):.2e}, pixels > 1e-3: {float((d > 1e-3).float().mean()):.2e}")
+    assert float((d > 1e-3).float().mean()) <= 1e-3 and float(d.median()) <= 1e-5

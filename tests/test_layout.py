@@ -99,6 +99,10 @@ full2 = RowPath()(*[inp2[k] for k in names])["pred_up"]
 for n_tiles, halo in ((3, 128), (2, 0), (5, 256)):
     got2 = sd.TiledHotPath(RowPath(), n_tiles=n_tiles, halo=halo)(inp2)
     assert torch.equal(got2, full2), (rank, n_tiles, halo)
+inp3 = {k: v.transpose(-1, -2).contiguous() for k, v in inp2.items()}          # the same test along W (column bands)
+full3 = RowPath()(*[inp3[k] for k in names])["pred_up"]
+got3 = sd.TiledHotPath(RowPath(), n_tiles=3, halo=128, axis="w")(inp3)
+assert torch.equal(got3, full3), rank
 dist.barrier(); dist.destroy_process_group()
 print("ok", rank)
 '''
