@@ -172,3 +172,22 @@ def test_loss_inputs_tuple_for_lrsc():
     assert float(disp[1].min()) >= 0 and float(disp[1].max()) <= 4 * 31          # unsigned: regression over bins 0..31, x4
     with pytest.raises(ValueError):
         head.as_loss_inputs(head([t.to(DEV) for t in fl], [t.to(DEV) for t in fr]))
+
+
+def test_stereo_head_full_size_against_oracle():
+    """Decoder + path at the headline size (1, 1024, 1024): the oracle (decoder + path, ~3 s on the host cores) is compared directly."""
+    p = params()
+    fl, fr = make_backbone_features(5, 1, 1024, 1024)
+    d = od.forward(p, fl, fr, right_label=False)
+    ref = oh.forward(p, {k: d[k] for k in ("f8_l", "f8_r", "f4_l", "f4_r", "spx_pred", "pred_label")}, 64, signed=True, keep=True)
+    head = StereoHead(64)
+    head.load_state_dict(p, strict=True)
+    out = head.to(DEV)([t.to(DEV) for t in fl], [t.to(DEV) for t in fr], keep=True)
+    torch.cuda.synchronize()
+    for k in ("pred_label", "spx_pred", "f4_l", "f8_r"):
+        rmax, rmean = rel(out[k].cpu(), d[k])
+        assert rmax <= 4e-2 and rmean <= 1.5e-2, (k, rmax, rmean)
+    agree = (out["ind_k"].cpu() == ref["ind_k"]).all(dim=2).float().mean().item()
+    e = (out["pred_up"].cpu() - ref["pred_up"]).abs().flatten()
+    print(f"\n[stereo head 1024x1024] top-24 agreement {agree:.4f}; pred_up median {e.median():.4f} p90 {e.quantile(0.9):.4f} (1/4-res px)")
+    assert agree >= 0.85 and e.median().item() <= 0.06 and e.quantile(0.9).item() <= 0.8
