@@ -224,27 +224,28 @@ def test_column_tiles_with_disparity_halo_match_the_untiled_run():
     assert float((d > 1e-3).float().mean()) <= 1e-3 and float(d.median()) <= 1e-5
 
 
-def test_full_size_against_oracle():
-    """BASELINE config #1 at its real size (1, 1024, 1024, maxdisp 64): the oracle needs ~2 s on the box's host cores, so the headline
-    shape is checked directly, not only through properties.  fp32 mode: top-24 indices identical on >= 99.9 % of the pixels,
+@pytest.mark.parametrize("signed,maxdisp,H,W", [(True, 64, 1024, 1024), (False, 128, 384, 768)])
+def test_full_size_against_oracle(signed, maxdisp, H, W):
+    """BASELINE config #1 at its real size (1, 1024, 1024, maxdisp 64) and the WHU shape of config #4 (384 x 768, maxdisp 128,
+    unsigned): the oracle needs ~2 s on the box's host cores, so the headline shapes are checked directly, not only through properties.  fp32 mode: top-24 indices identical on >= 99.9 % of the pixels,
     attention-branch disparity within 1e-3 px where they are; bf16 mode: the statistical bounds of DESIGN.md section 2."""
     p = make_params(seed=1, peaked=20.0)
-    inp = make_inputs(5, 1, 1024, 1024)
-    ref = oh.forward(p, inp, 64, signed=True, keep=True)
-    m = DisparityHotPath(64, False, True)
+    inp = make_inputs(5, 1, H, W)
+    ref = oh.forward(p, inp, maxdisp, signed=signed, keep=True)
+    m = DisparityHotPath(maxdisp, False, signed)
     m.load_state_dict(p, strict=True)
     out = run(m.to(DEV), inp)
-    same = (out["ind_k"] == ref["ind_k"]).all(dim=2)                       # (1,1,256,256)
+    same = (out["ind_k"] == ref["ind_k"]).all(dim=2)                       # (1,1,H/4,W/4)
     assert same.float().mean().item() >= 0.999
     up = torch.nn.functional.interpolate(same.float(), scale_factor=4, mode="nearest")[0, 0] == 1
     good = torch.nn.functional.max_pool2d((~up).float()[None, None], 9, 1, 4)[0, 0] == 0     # away from pixels whose samples differ
     assert maxerr(out["pred_att_up"][0][good], ref["pred_att_up"][0][good]) <= 1e-3
     assert maxerr(out["cost_att"], ref["cost_att"]) <= 2e-2
-    mb = DisparityHotPath(64, False, True, precision="bf16")
+    mb = DisparityHotPath(maxdisp, False, signed, precision="bf16")
     mb.load_state_dict(p, strict=True)
     outb = run(mb.to(DEV), inp, keep=False)
     agree = (outb["disp_topk"] == ref["disp_topk"]).all(dim=1).float().mean().item()
     e = (outb["pred_up"] - ref["pred_up"]).abs().flatten()
-    print(f"\n[1024x1024] fp32 index agreement {same.float().mean().item():.6f}; bf16 top-24 agreement {agree:.4f}, "
+    print(f"\n[{H}x{W}] fp32 index agreement {same.float().mean().item():.6f}; bf16 top-24 agreement {agree:.4f}, "
           f"pred_up median {e.median():.4f} p90 {e.quantile(0.9):.4f} (1/4-res px)")
     assert agree >= 0.90 and e.median().item() <= 0.05 and e.quantile(0.9).item() <= 0.5
