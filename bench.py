@@ -29,6 +29,18 @@ import torch  # noqa: E402
 ORDER = ("f8_l", "f8_r", "f4_l", "f4_r", "cf_l", "cf_r", "spx_pred", "pred_label")
 
 
+PRECISION_DTYPE = {"split": "bf16x3 (fp32-accurate) attention branch + bf16 aggregation", "bf16": "bf16", "fp32": "f32",
+                   "mixed": "f32 attention branch + bf16 aggregation"}
+PRECISION_NOTE = {
+    "split": "attention branch (hourglass_att, classif_att_: decides the top-k samples) on tcgen05 with bf16x3 split operands "
+             "(x*w = x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, fp32 accumulation: fp32-accurate, ind_k == fp32 oracle on > 99.9 % of pixels); "
+             "aggregation branch (concat_stem, hourglass, classif), concat_feature: bf16 operands / fp32 accumulation; fp32 elsewhere",
+    "bf16": "bf16 operands / fp32 accumulation on the tensor cores for every 3-D conv, the window attention, concat_feature and (stage head) "
+            "the 2-D decoder; fp32 elsewhere",
+    "fp32": "fp32 everywhere (FFMA 3-D convs)",
+    "mixed": "attention branch (hourglass_att, classif_att_) fp32 FFMA, aggregation branch bf16 tensor cores"}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -195,8 +207,10 @@ def main():
     ap.add_argument("--maxdisp", type=int, default=64)
     ap.add_argument("--cpu-steps", type=int, default=2, help="pairs timed for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "mixed"],
-                    help="bf16: k3 s1 3-D convs on tcgen05 tensor cores (BASELINE config #3); fp32: index-exact parity mode")
+    ap.add_argument("--precision", default="split", choices=["split", "bf16", "fp32", "mixed"],
+                    help="split (default): attention branch with fp32-accurate bf16x3 products on the tensor cores (sample selection = the "
+                         "fp32 oracle's), aggregation branch bf16 (BASELINE config #3 'bf16 aggregation'); bf16: everything bf16; "
+                         "mixed: attention branch on the fp32 FFMA pipe; fp32: everything FFMA")
     ap.add_argument("--variant", default="us3d", choices=["us3d", "whu"],
                     help="us3d: SemStereo, signed, 1024x1024, maxdisp 64 (configs #1/#3); whu: SemStereo_WHU + submodule_.py, unsigned, "
                          "384x768, maxdisp 128 (config #4)")
@@ -217,8 +231,10 @@ def main():
     H, W, md = a.height, a.width, a.maxdisp
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     head = a.stage == "head"
-    if head and (a.att_only or a.precision != "bf16"):
-        raise SystemExit("--stage head runs the full forward in bf16 (the decoder has no fp32 mode)")
+    if head:
+        if a.att_only:
+            raise SystemExit("--stage head runs the full forward")
+        a.precision = "bf16"                   # the decoder has no fp32-accurate mode yet
     workload = (f"{'SemStereo' if signed else 'SemStereo_WHU'} "
                 f"{'decoder + disparity path = everything after the backbone (forward:249-346)' if head else 'disparity hot path (forward:273-324)'}, {H}x{W} "
                 f"{'US3D' if signed else 'WHU'}-shaped pairs, maxdisp {md}, {'signed' if signed else 'unsigned'}"
@@ -402,14 +418,10 @@ def main():
     value = world * B * a.steps / (ms_total * 1e-3)
     e2e_v = world * B * a.steps / (ms_e2e * 1e-3)
     res = {"metric": "stereo pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-           "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "fp32": "f32", "mixed": "f32 attention branch + bf16 aggregation"}[a.precision],
+           "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": PRECISION_DTYPE[a.precision],
            "data": "synthetic", "config": {"workload": workload, "pairs_per_gpu_per_step": B, "global_pairs_per_step": world * B,
                                            "l2": "per-step inputs (1.3 GB at batch 8) exceed the 126 MB L2", "parallelism": f"dp{world}",
-                                           "precision_mode": ("bf16 operands / fp32 accumulation on the tensor cores for every 3-D conv, the window attention, concat_feature"
-                                                              " and (stage head) the 2-D decoder; fp32 elsewhere"
-                                                              if a.precision == "bf16" else
-                                                              ("fp32 everywhere (FFMA 3-D convs)" if a.precision == "fp32" else
-                                                               "attention branch (hourglass_att, classif_att_) fp32, aggregation branch bf16 tensor cores"))},
+                                           "precision_mode": PRECISION_NOTE[a.precision]},
            "e2e": {"value": e2e_v, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps},
            "gpu_launches": rec.count, "clocks": clocks, "roofline": roof, "kernels": kernels}
     res["host"] = {"numa_bound_cpus": len(numa_cpus) if numa_cpus else None}

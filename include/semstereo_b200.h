@@ -92,6 +92,33 @@ SS_API int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight_pac
                         const float* shift_or_null, const float* gate_blocked_or_null, const void* residual_s2d_or_null,
                         const void* skip_weight_or_null, void* out, int out_mode, int B, int Cin, int Cout, int D, int H, int W,
                         int relu, void* stream);
+/* bf16x3 split route (fp32-accurate products on the bf16 tensor cores; used for the attention branch, SemStereo.py:273-278, whose
+ * logits alone decide the top-k sample selection).  A value x is carried as the pair hi = bf16(x), lo = bf16(x - hi), the two
+ * halves STACKED ON THE BATCH AXIS: a split tensor is an ordinary blocked / phase-split tensor of batch 2B, [hi batches | lo batches].
+ * x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo is then two launches of the same layer: (1) the 2B-batch tensor with w_hi, raw fp32
+ * output (no affine) -> partial sums P (2B,Cout,...); (2) the hi half with w_lo and the two hooks below:
+ *   acc_in / acc_in2: fp32 NCDHW tensors shaped like an out_mode-1 output, added to the accumulator before scale/shift/ReLU/gate;
+ *   out_split = 1  : the bf16 output (out_mode 0 / 2) is itself written as a split tensor of batch 2B (lo half B batches further).
+ * Linear in the operands, so the fused redir skip conv of kind 3 splits the same way (residual = the split skip tensor). */
+SS_API int ss_conv3d_tc_ex(int kind, const void* in_blocked, const void* weight_packed, const float* scale_or_null,
+                           const float* shift_or_null, const float* gate_blocked_or_null, const void* residual_s2d_or_null,
+                           const void* skip_weight_or_null, const float* acc_in_or_null, const float* acc_in2_or_null, void* out,
+                           int out_mode, int out_split, int in_split, int B, int Cin, int Cout, int D, int H, int W, int relu,
+                           void* stream);
+/* in_split = 1: the whole split product in ONE launch (layers for which ss_conv3d_tc_split_supported() != 0: shared memory holds the
+ * hi and lo halves of the slice ring and of the weights): in_blocked (and residual_s2d) are split tensors of batch 2B,
+ * weight_packed = per tap [hi: Cin/8 chunks][lo: Cin/8 chunks] (the two single packings concatenated along the chunk axis; the
+ * skip weight likewise [hi: Cout/8][lo: Cout/8] chunks), and every K step issues the three MMAs into one TMEM accumulator. */
+SS_API int ss_conv3d_tc_split_supported(int kind, int Cin, int Cout);
+/* ss_to_blocked_bf16 / ss_patch_gate_blocked / ss_conv3d_tc_head with the split hooks: split = 1 writes a split tensor (batch 2B);
+ * the head adds fp32 partial sums (B,1,D,H,W) to its result. */
+SS_API int ss_to_blocked_bf16_ex(const float* in_ncdhw, void* out_blocked, int B, int C, int D, int H, int W, int s2d, int split,
+                                 void* stream);
+SS_API int ss_patch_gate_blocked_ex(const float* volume, const float* patch_w, const float* gate_logits, void* out_s2d, int B, int G,
+                                    int D, int H, int W, int split, void* stream);
+SS_API int ss_conv3d_tc_head_ex(const void* in_blocked, const void* weight_packed, const float* acc_in_or_null,
+                                const float* acc_in2_or_null, float* out, int in_split, int B, int Cin, int D, int H, int W,
+                                void* stream);     /* in_split: split input (batch 2B), weight_packed [2][4][48][8] = hi | lo */
 /* concat_volume_generator * att_topk -> concat_stem -> * sigmoid(gate) (SemStereo.py:241-244, 316-320) in ONE kernel: the sparse
  * concat volume is produced tile by tile in shared memory as the GEMM's A operand and never written to HBM.
  * cf_l / cf_r: bf16 blocked (B,4,H,W,8) = concat_feature(f4_*) (32 channels); disp_topk, att_topk: fp32 (B,K,H,W);

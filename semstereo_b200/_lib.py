@@ -50,6 +50,11 @@ SIGNATURES = {
     "ss_bilinear_up2": [_P, _P, _I, _I, _I, _P],
     "ss_pointwise_blocked_small": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "ss_conv3d_tc": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "ss_conv3d_tc_ex": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "ss_conv3d_tc_split_supported": [_I, _I, _I],
+    "ss_to_blocked_bf16_ex": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "ss_patch_gate_blocked_ex": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ss_conv3d_tc_head_ex": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ss_window_attention3d": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "ss_att_stats": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "ss_sample_strength": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],

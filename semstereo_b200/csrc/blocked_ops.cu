@@ -22,9 +22,19 @@ __global__ void __launch_bounds__(256) gate_sigmoid_blocked_kernel(const float* 
 }
 
 // vol (B,G,D,H,W) fp32, w (G,9), gate logits (B,G,H,W) -> phase-split bf16 (B,8,G/8,D/2,H/2,W/2,8); thread = 8 groups of one voxel
+__device__ __forceinline__ uint4 bf16_lo8(const float* v, const uint4 q) {      // bf16(v - hi) of 8 packed values
+  uint4 l;
+  l.x = tc::pack_bf16x2(v[0] - __uint_as_float(q.x << 16), v[1] - __uint_as_float(q.x & 0xffff0000u));
+  l.y = tc::pack_bf16x2(v[2] - __uint_as_float(q.y << 16), v[3] - __uint_as_float(q.y & 0xffff0000u));
+  l.z = tc::pack_bf16x2(v[4] - __uint_as_float(q.z << 16), v[5] - __uint_as_float(q.z & 0xffff0000u));
+  l.w = tc::pack_bf16x2(v[6] - __uint_as_float(q.w << 16), v[7] - __uint_as_float(q.w & 0xffff0000u));
+  return l;
+}
+
+// split_off != 0 (both kernels): also write the lo half of the bf16x3 split, bf16(value - hi), split_off uint4 further.
 __global__ void __launch_bounds__(128) patch_gate_blocked_kernel(const float* __restrict__ vol, const float* __restrict__ w,
                                                                  const float* __restrict__ gate, uint4* __restrict__ out, int G, int D,
-                                                                 int H, int W) {
+                                                                 int H, int W, size_t split_off) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= W) return;
   const int y = blockIdx.y % H, d = blockIdx.y / H;
@@ -63,14 +73,16 @@ __global__ void __launch_bounds__(128) patch_gate_blocked_kernel(const float* __
   q.z = tc::pack_bf16x2(f[4], f[5]); q.w = tc::pack_bf16x2(f[6], f[7]);
   const int phase = ((d & 1) << 2) | ((y & 1) << 1) | (x & 1);
   const size_t S8 = (size_t)(D >> 1) * (H >> 1) * (W >> 1);
-  out[(((size_t)b * 8 + phase) * G8 + chunk) * S8 + ((size_t)(d >> 1) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)] = q;
+  const size_t o = (((size_t)b * 8 + phase) * G8 + chunk) * S8 + ((size_t)(d >> 1) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
+  out[o] = q;
+  if (split_off) out[o + split_off] = bf16_lo8(f, q);
 }
 
 // Same op, 4 consecutive x per thread (W % 4 == 0): each of the 3 rows is one aligned float4 plus its two neighbours, so a
 // thread issues 9 loads per group for 4 outputs instead of 36; the two x-parities of its outputs are two 32-byte runs.
 __global__ void __launch_bounds__(128) patch_gate_blocked_x4_kernel(const float* __restrict__ vol, const float* __restrict__ w,
                                                                     const float* __restrict__ gate, uint4* __restrict__ out, int G, int D,
-                                                                    int H, int W) {
+                                                                    int H, int W, size_t split_off) {
   const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (x >= W) return;
   const int y = blockIdx.y % H, d = blockIdx.y / H;
@@ -120,6 +132,7 @@ __global__ void __launch_bounds__(128) patch_gate_blocked_x4_kernel(const float*
       q.x = tc::pack_bf16x2(v[0], v[1]); q.y = tc::pack_bf16x2(v[2], v[3]);
       q.z = tc::pack_bf16x2(v[4], v[5]); q.w = tc::pack_bf16x2(v[6], v[7]);
       o[j] = q;
+      if (split_off) o[j + split_off] = bf16_lo8(v, q);
     }
   }
 }
@@ -222,6 +235,12 @@ extern "C" int ss_gate_sigmoid_blocked(const float* gate_logits, float* out_bloc
 
 extern "C" int ss_patch_gate_blocked(const float* volume, const float* patch_w, const float* gate_logits, void* out_s2d, int B, int G,
                                      int D, int H, int W, void* stream) {
+  return ss_patch_gate_blocked_ex(volume, patch_w, gate_logits, out_s2d, B, G, D, H, W, 0, stream);
+}
+
+extern "C" int ss_patch_gate_blocked_ex(const float* volume, const float* patch_w, const float* gate_logits, void* out_s2d, int B, int G,
+                                        int D, int H, int W, int split, void* stream) {
+  const size_t split_off = split ? (size_t)B * G * (size_t)D * H * W / 8 : (size_t)0;     // one [B][8][G/8][D/2][H/2][W/2] stack, in uint4
   SS_REQUIRE(volume && patch_w && gate_logits && out_s2d, "ss_patch_gate_blocked: null pointer");
   SS_REQUIRE(B > 0 && G > 0 && D > 0 && H > 0 && W > 0, "ss_patch_gate_blocked: non-positive dimension");
   SS_REQUIRE(G % 8 == 0 && D % 2 == 0 && H % 2 == 0 && W % 2 == 0, "ss_patch_gate_blocked: G %% 8 == 0 and even D,H,W required");
@@ -229,10 +248,10 @@ extern "C" int ss_patch_gate_blocked(const float* volume, const float* patch_w, 
   const bool x4 = W % 4 == 0 && ((reinterpret_cast<uintptr_t>(volume) | reinterpret_cast<uintptr_t>(gate_logits)) & 15) == 0;
   if (x4)
     patch_gate_blocked_x4_kernel<<<dim3(ceil_div(W / 4, 32), D * H, B * (G / 8)), 32, 0, (cudaStream_t)stream>>>(
-        volume, patch_w, gate_logits, reinterpret_cast<uint4*>(out_s2d), G, D, H, W);
+        volume, patch_w, gate_logits, reinterpret_cast<uint4*>(out_s2d), G, D, H, W, split_off);
   else
     patch_gate_blocked_kernel<<<dim3(ceil_div(W, 128), D * H, B * (G / 8)), 128, 0, (cudaStream_t)stream>>>(
-        volume, patch_w, gate_logits, reinterpret_cast<uint4*>(out_s2d), G, D, H, W);
+        volume, patch_w, gate_logits, reinterpret_cast<uint4*>(out_s2d), G, D, H, W, split_off);
   SS_CHECK_LAUNCH("ss_patch_gate_blocked");
   return SS_OK;
 }

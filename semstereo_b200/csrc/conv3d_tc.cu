@@ -36,7 +36,10 @@ struct TcP {
   const __nv_bfloat16* residual;  // t2 only: phase-split blocked [B][8][Cout/8][D][H][W][8], or null
   const __nv_bfloat16* skip_w;    // t2 only: when set, `residual` is the INPUT of the 1x1 skip conv and this is its weight
                                   // [N/8][N][8] (BN scale folded in): the skip conv runs as one more GEMM tap on the staged tile
+  const float* acc_in;            // fp32 NCDHW partial sums (same shape as an out_mode-1 output) added to the accumulator BEFORE
+  const float* acc_in2;           // scale/shift (bf16x3 split route: the products of the other operand halves), or null
   void* out;
+  long long split_off;            // != 0: bf16 outputs are written as a hi/lo pair, lo = bf16(v - hi) at out + split_off (uint4 units)
   int out_mode;                   // 0: bf16 blocked, 1: fp32 NCDHW, 2: bf16 phase-split blocked
   int cout_valid;                 // channels actually stored (Cout = n_tiles*N may be zero-padded), also the channel count of out
   int B, D, H, W;                 // tile space: output dims (s1, s2) / input dims (t2)
@@ -59,6 +62,17 @@ __device__ __forceinline__ void decode_item(const TcP& p, int s, int& b, int& h0
 __device__ __forceinline__ void epilogue_store32(const TcP& p, float (&v)[32], const float* sc, const float* sh, int co0, int b, int od,
                                                  int oh, int ow, int OD, int OH, int OW, const uint4* r) {
   const float lo = p.relu ? 0.0f : -INFINITY;
+  if (p.acc_in) {                     // partial sums of the other split products (fp32 NCDHW), added before the affine
+    const size_t OSa = (size_t)OD * OH * OW, o0 = ((size_t)b * p.cout_valid + co0) * OSa + ((size_t)od * OH + oh) * OW + ow;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (co0 + i < p.cout_valid) v[i] += __ldg(p.acc_in + o0 + (size_t)i * OSa);
+    if (p.acc_in2) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (co0 + i < p.cout_valid) v[i] += __ldg(p.acc_in2 + o0 + (size_t)i * OSa);
+    }
+  }
   if (r) {
 #pragma unroll
     for (int c8 = 0; c8 < 4; ++c8) {
@@ -113,6 +127,14 @@ __device__ __forceinline__ void epilogue_store32(const TcP& p, float (&v)[32], c
       q.z = tc::pack_bf16x2(v[8 * c8 + 4], v[8 * c8 + 5]);
       q.w = tc::pack_bf16x2(v[8 * c8 + 6], v[8 * c8 + 7]);
       o[(size_t)c8 * cs] = q;
+      if (p.split_off) {              // lo half of the bf16x3 split: what bf16 rounding of the value lost
+        const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+        uint32_t l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          l[i] = tc::pack_bf16x2(v[8 * c8 + 2 * i] - __uint_as_float(u[i] << 16), v[8 * c8 + 2 * i + 1] - __uint_as_float(u[i] & 0xffff0000u));
+        o[(size_t)c8 * cs + p.split_off] = make_uint4(l[0], l[1], l[2], l[3]);
+      }
     }
   }
 }
@@ -317,11 +339,15 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_const
 // (or the depth range is cut by the volume / chunk boundary) the MMA is split into two narrower ones / narrowed.
 // Weights: [9 in-plane taps][CIN/8][3*N (j*N + co)][8].
 // =====================================================================================================================
-template <int CIN, int N, int NS, int NWS>
+// SP (bf16x3 split route, in-kernel): the input is a split tensor (hi batches [0,B) | lo batches [B,2B)), a staged slice holds the
+// hi chunks followed by the lo chunks (two TMA boxes), the weights of a tap are [hi: CIN/8 chunks][lo: CIN/8 chunks], and every
+// K step issues three MMAs into the same accumulator: x_hi*w_hi + x_lo*w_hi + x_hi*w_lo (fp32-accurate product, fp32 accumulation).
+template <int CIN, int N, int NS, int NWS, bool SP = false>
 __global__ void __launch_bounds__(256, 1) conv3d_tc_s1f_kernel(const __grid_constant__ CUtensorMap tmA, const TcP p) {
   constexpr bool kResident = (NWS == 9);
-  constexpr uint32_t SLICE = (CIN / 8) * TILE_B;
-  constexpr uint32_t TAPB = CIN * 3 * N * 2;
+  constexpr uint32_t HALF_A = (CIN / 8) * TILE_B, HALF_B = CIN * 3 * N * 2;      // one operand half (hi or lo) of a slice / tap
+  constexpr uint32_t SLICE = (SP ? 2 : 1) * HALF_A;
+  constexpr uint32_t TAPB = (SP ? 2 : 1) * HALF_B;
   constexpr int KS = CIN / 16;
   constexpr uint32_t LBO_A = TILE_B, SBO_A = WW * 16, LBO_B = 3 * N * 16, SBO_B = 128;
   constexpr uint32_t TMEM_COLS = 512;
@@ -349,6 +375,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1f_kernel(const __grid_cons
         tc::mbar_wait(&a_empty[slot], ((g / NS) & 1) ^ 1);
         tc::mbar_expect_tx(&a_full[slot], SLICE);
         tc::tma_load_4d(Abase + slot * SLICE, &tmA, &a_full[slot], (w0 - 1) * 8, h0 - 1, d_in, b * (CIN / 8));
+        if (SP) tc::tma_load_4d(Abase + slot * SLICE + HALF_A, &tmA, &a_full[slot], (w0 - 1) * 8, h0 - 1, d_in, (b + p.B) * (CIN / 8));
       }
     }
   } else if (warp == 3 && lane == 0) {
@@ -422,6 +449,12 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1f_kernel(const __grid_cons
               const uint32_t bb = b_lo + (uint32_t)(ks * 2 * LBO_B) / 16;
               tc::mma_bf16_lohi(d1, a, a_hi, bb + brow1, b_hi, id1, 1u);
               if (n2) tc::mma_bf16_lohi(d2, a, a_hi, bb + brow2, b_hi, id2, 1u);
+              if (SP) {
+                tc::mma_bf16_lohi(d1, a + (HALF_A >> 4), a_hi, bb + brow1, b_hi, id1, 1u);
+                if (n2) tc::mma_bf16_lohi(d2, a + (HALF_A >> 4), a_hi, bb + brow2, b_hi, id2, 1u);
+                tc::mma_bf16_lohi(d1, a, a_hi, bb + (HALF_B >> 4) + brow1, b_hi, id1, 1u);
+                if (n2) tc::mma_bf16_lohi(d2, a, a_hi, bb + (HALF_B >> 4) + brow2, b_hi, id2, 1u);
+              }
             }
             if (!kResident) tc::mma_commit(&w_empty[wslot]);
           }
@@ -700,12 +733,13 @@ __global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_con
 // s2: Conv3d k3 s2 p1 on the phase-split input.  A staged slice = (d-phase pd, half-res depth d') = 4 (h,w)-phase halo tiles.
 // Per output depth d the slice uses are, in order: (1,d-1) [kd=0], (0,d) [kd=1], (1,d) [kd=2, kept for d+1's kd=0].
 // =====================================================================================================================
-template <int CIN, int N, int NS, int NWS>
+template <int CIN, int N, int NS, int NWS, bool SP = false>      // SP: in-kernel bf16x3 split, see the s1f kernel
 __global__ void __launch_bounds__(256, 1) conv3d_tc_s2_kernel(const __grid_constant__ CUtensorMap tmA, const TcP p) {
   constexpr bool kResident = (NWS == 27);
   constexpr int C8 = CIN / 8;
-  constexpr uint32_t SLICE = 4 * C8 * TILE_B;
-  constexpr uint32_t TAPB = CIN * N * 2;
+  constexpr uint32_t HALF_A = 4 * C8 * TILE_B, HALF_B = CIN * N * 2;
+  constexpr uint32_t SLICE = (SP ? 2 : 1) * HALF_A;
+  constexpr uint32_t TAPB = (SP ? 2 : 1) * HALF_B;
   constexpr int KS = CIN / 16;
   constexpr uint32_t LBO_A = TILE_B, SBO_A = WW * 16, LBO_B = N * 16, SBO_B = 128;
   constexpr uint32_t TMEM_COLS = tmem_cols_for(2 * N);
@@ -721,6 +755,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s2_kernel(const __grid_const
       tc::mbar_wait(&a_empty[slot], ((g / NS) & 1) ^ 1);
       tc::mbar_expect_tx(&a_full[slot], SLICE);
       tc::tma_load_4d(Abase + slot * SLICE, &tmA, &a_full[slot], (w0 - 1) * 8, h0 - 1, d, (b * 8 + pd * 4) * C8);
+      if (SP) tc::tma_load_4d(Abase + slot * SLICE + HALF_A, &tmA, &a_full[slot], (w0 - 1) * 8, h0 - 1, d, ((b + p.B) * 8 + pd * 4) * C8);
       ++g;
     };
     for (int s = cta_s; s < p.items; s += cta_stride) {
@@ -792,9 +827,14 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s2_kernel(const __grid_const
             if (leader) {
 #pragma unroll
               for (int ks = 0; ks < KS; ++ks) {
-                tc::mma_bf16_lohi(tmem_d, a_lo + (uint32_t)(((ph * 2 + pw) * C8 + 2 * ks) * LBO_A + (oh * WW + ow) * 16) / 16, a_hi,
-                                  b_lo + (uint32_t)(ks * 2 * LBO_B) / 16, b_hi, IDESC, accumulate);
+                const uint32_t aa = a_lo + (uint32_t)(((ph * 2 + pw) * C8 + 2 * ks) * LBO_A + (oh * WW + ow) * 16) / 16;
+                const uint32_t bb = b_lo + (uint32_t)(ks * 2 * LBO_B) / 16;
+                tc::mma_bf16_lohi(tmem_d, aa, a_hi, bb, b_hi, IDESC, accumulate);
                 accumulate = 1;
+                if (SP) {
+                  tc::mma_bf16_lohi(tmem_d, aa + (HALF_A >> 4), a_hi, bb, b_hi, IDESC, 1u);
+                  tc::mma_bf16_lohi(tmem_d, aa, a_hi, bb + (HALF_B >> 4), b_hi, IDESC, 1u);
+                }
               }
               if (!kResident) tc::mma_commit(&w_empty[wslot]);
             }
@@ -845,19 +885,20 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s2_kernel(const __grid_const
 // RS = depth of the ring that prefetches the skip-connection tiles (one TH x TW x N tile per output phase) by TMA: the layer
 // is memory-heavy (it reads a full-resolution residual and writes a full-resolution output per 27/8 taps of math), and 128
 // epilogue threads issuing just-in-time loads cannot keep enough bytes in flight; the ring keeps RS tiles ahead.
-template <int CIN, int N, int NS, int NWS, int RS>
+template <int CIN, int N, int NS, int NWS, int RS, bool SP = false>      // SP: in-kernel bf16x3 split, see the s1f kernel
 __global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmRes, const TcP p) {
   constexpr bool kResident = (NWS == 27);
-  constexpr uint32_t RTILE = (N / 8) * TH * TW * 16;          // bytes of one residual tile
-  constexpr uint32_t SLICE = (CIN / 8) * TILE_B;
-  constexpr uint32_t TAPB = CIN * N * 2;
+  constexpr uint32_t HALF_R = (N / 8) * TH * TW * 16, HALF_A = (CIN / 8) * TILE_B, HALF_B = CIN * N * 2, HALF_S = N * N * 2;
+  constexpr uint32_t RTILE = (SP ? 2 : 1) * HALF_R;           // bytes of one residual tile
+  constexpr uint32_t SLICE = (SP ? 2 : 1) * HALF_A;
+  constexpr uint32_t TAPB = (SP ? 2 : 1) * HALF_B;
   constexpr int KS = CIN / 16;
   constexpr uint32_t LBO_A = TILE_B, SBO_A = WW * 16, LBO_B = N * 16, SBO_B = 128;
   constexpr uint32_t TMEM_COLS = tmem_cols_for(2 * N);
   constexpr uint32_t IDESC = tc::make_idesc_bf16(128, N);
   __shared__ __align__(8) uint64_t res_full[RS], res_empty[RS], skip_full;
-  constexpr uint32_t SKIPB = N * N * 2;                       // bytes of the fused 1x1 skip weight
+  constexpr uint32_t SKIPB = (SP ? 2 : 1) * HALF_S;           // bytes of the fused 1x1 skip weight
   if (threadIdx.x == 0) {      // made visible to the async proxy by the fence in the prologue (same thread)
     for (int i = 0; i < RS; ++i) { tc::mbar_init(&res_full[i], 1); tc::mbar_init(&res_empty[i], p.skip_w ? 1 : 128); }
     tc::mbar_init(&skip_full, 1);
@@ -886,6 +927,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_const
         tc::mbar_wait(&a_empty[slot], ((g / NS) & 1) ^ 1);
         tc::mbar_expect_tx(&a_full[slot], SLICE);
         tc::tma_load_4d(Abase + slot * SLICE, &tmA, &a_full[slot], w0 * 8, h0, d_in, b * (CIN / 8));
+        if (SP) tc::tma_load_4d(Abase + slot * SLICE + HALF_A, &tmA, &a_full[slot], w0 * 8, h0, d_in, (b + p.B) * (CIN / 8));
       }
     }
   } else if (warp == 3 && lane == 0) {
@@ -933,6 +975,8 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_const
           tc::mbar_wait(&res_empty[slot], ((r / RS) & 1) ^ 1);
           tc::mbar_expect_tx(&res_full[slot], RTILE);
           tc::tma_load_4d(Rbase + slot * RTILE, &tmRes, &res_full[slot], w0 * 8, h0, i, (b * 8 + ph8) * (p.cout_valid / 8) + nt * (N / 8));
+          if (SP) tc::tma_load_4d(Rbase + slot * RTILE + HALF_R, &tmRes, &res_full[slot], w0 * 8, h0, i,
+                                  ((b + p.B) * 8 + ph8) * (p.cout_valid / 8) + nt * (N / 8));
         }
     }
   } else if (warp == 1) {
@@ -985,9 +1029,13 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_const
                 if (leader) {
 #pragma unroll
                   for (int ks = 0; ks < KS; ++ks) {
-                    tc::mma_bf16_lohi(tmem_d, a_lo + a_off + (uint32_t)(ks * 2 * LBO_A) / 16, a_hi, b_lo + (uint32_t)(ks * 2 * LBO_B) / 16,
-                                      b_hi, IDESC, accumulate);
+                    const uint32_t aa = a_lo + a_off + (uint32_t)(ks * 2 * LBO_A) / 16, bb = b_lo + (uint32_t)(ks * 2 * LBO_B) / 16;
+                    tc::mma_bf16_lohi(tmem_d, aa, a_hi, bb, b_hi, IDESC, accumulate);
                     accumulate = 1;
+                    if (SP) {
+                      tc::mma_bf16_lohi(tmem_d, aa + (HALF_A >> 4), a_hi, bb, b_hi, IDESC, 1u);
+                      tc::mma_bf16_lohi(tmem_d, aa, a_hi, bb + (HALF_B >> 4), b_hi, IDESC, 1u);
+                    }
                   }
                   if (!kResident) tc::mma_commit(&w_empty[wslot]);
                 }
@@ -1001,9 +1049,14 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_const
             tc::fence_after_sync();
             if (leader) {
 #pragma unroll
-              for (int ks = 0; ks < N / 16; ++ks)
-                tc::mma_bf16_lohi(tmem_d, r_lo0 + rslot * (RTILE >> 4) + (uint32_t)(ks * 2 * TH * TW), r_hi,
-                                  s_lo0 + (uint32_t)(ks * 2 * LBO_B) / 16, b_hi, IDESC, 1);
+              for (int ks = 0; ks < N / 16; ++ks) {
+                const uint32_t ra = r_lo0 + rslot * (RTILE >> 4) + (uint32_t)(ks * 2 * TH * TW), sb = s_lo0 + (uint32_t)(ks * 2 * LBO_B) / 16;
+                tc::mma_bf16_lohi(tmem_d, ra, r_hi, sb, b_hi, IDESC, 1);
+                if (SP) {
+                  tc::mma_bf16_lohi(tmem_d, ra + (HALF_R >> 4), r_hi, sb, b_hi, IDESC, 1);
+                  tc::mma_bf16_lohi(tmem_d, ra, r_hi, sb + (HALF_S >> 4), b_hi, IDESC, 1);
+                }
+              }
               tc::mma_commit(&res_empty[rslot]);
             }
           }
@@ -1063,8 +1116,9 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_const
 
 // ---- layout converters ----------------------------------------------------------------------------------------------
 // fp32 NCDHW -> bf16 blocked [B][C/8][D][H][W][8], or (s2d) phase-split [B][8][C/8][D/2][H/2][W/2][8]
+// split_off != 0: hi/lo pair of the bf16x3 split route, lo = bf16(x - hi) written split_off uint4 further ([2][B]... stacking)
 __global__ void __launch_bounds__(256) to_blocked_kernel(const float* __restrict__ in, uint4* __restrict__ out, int C, int D, int H,
-                                                         int W, int s2d) {
+                                                         int W, int s2d, size_t split_off) {
   const size_t S = (size_t)D * H * W;
   const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // voxel within (D,H,W)
   if (v >= S) return;
@@ -1084,6 +1138,15 @@ __global__ void __launch_bounds__(256) to_blocked_kernel(const float* __restrict
     o = (((size_t)b * 8 + phase) * (C / 8) + chunk) * (S / 8) + ((size_t)(d >> 1) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
   }
   out[o] = q;
+  if (split_off) {
+    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+    uint4 l;
+    l.x = tc::pack_bf16x2(f[0] - __uint_as_float(u[0] << 16), f[1] - __uint_as_float(u[0] & 0xffff0000u));
+    l.y = tc::pack_bf16x2(f[2] - __uint_as_float(u[1] << 16), f[3] - __uint_as_float(u[1] & 0xffff0000u));
+    l.z = tc::pack_bf16x2(f[4] - __uint_as_float(u[2] << 16), f[5] - __uint_as_float(u[2] & 0xffff0000u));
+    l.w = tc::pack_bf16x2(f[6] - __uint_as_float(u[3] << 16), f[7] - __uint_as_float(u[3] & 0xffff0000u));
+    out[o + split_off] = l;
+  }
 }
 
 __global__ void __launch_bounds__(256) from_blocked_kernel(const uint4* __restrict__ in, float* __restrict__ out, int C, size_t S) {
@@ -1168,27 +1231,27 @@ int launch_s1(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
   static_assert(smem <= 227 * 1024 - 2048, "shared memory budget");
   return launch_tc(conv3d_tc_s1_kernel<CIN, N, NS, NWS, TAPS>, smem, tm, p, TAPS == 27 ? 0.35 : 0.0, st, "ss_conv3d_tc(s1)");
 }
-template <int CIN, int N, int NS, int NWS>
+template <int CIN, int N, int NS, int NWS, bool SP = false>
 int launch_s1f(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
-  constexpr size_t smem = (size_t)NS * (CIN / 8) * TILE_B + (size_t)NWS * CIN * 3 * N * 2;
+  constexpr size_t smem = (SP ? 2 : 1) * ((size_t)NS * (CIN / 8) * TILE_B + (size_t)NWS * CIN * 3 * N * 2);
   static_assert(smem <= 227 * 1024 - 2048, "shared memory budget");
-  return launch_tc(conv3d_tc_s1f_kernel<CIN, N, NS, NWS>, smem, tm, p, 1.4, st, "ss_conv3d_tc(s1f)");
+  return launch_tc(conv3d_tc_s1f_kernel<CIN, N, NS, NWS, SP>, smem, tm, p, 1.4, st, "ss_conv3d_tc(s1f)");
 }
-template <int CIN, int N, int NS, int NWS>
+template <int CIN, int N, int NS, int NWS, bool SP = false>
 int launch_s2(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
-  constexpr size_t smem = (size_t)NS * 4 * (CIN / 8) * TILE_B + (size_t)NWS * CIN * N * 2;
+  constexpr size_t smem = (SP ? 2 : 1) * ((size_t)NS * 4 * (CIN / 8) * TILE_B + (size_t)NWS * CIN * N * 2);
   static_assert(smem <= 227 * 1024 - 2048, "shared memory budget");
-  return launch_tc(conv3d_tc_s2_kernel<CIN, N, NS, NWS>, smem, tm, p, 0.4, st, "ss_conv3d_tc(s2)");
+  return launch_tc(conv3d_tc_s2_kernel<CIN, N, NS, NWS, SP>, smem, tm, p, 0.4, st, "ss_conv3d_tc(s2)");
 }
-template <int CIN, int N, int NS, int NWS, int RS>
+template <int CIN, int N, int NS, int NWS, int RS, bool SP = false>
 int launch_t2(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
-  constexpr size_t smem = (size_t)NS * (CIN / 8) * TILE_B + (size_t)NWS * CIN * N * 2 + (size_t)RS * (N / 8) * TH * TW * 16 + (size_t)N * N * 2;
+  constexpr size_t smem = (SP ? 2 : 1) * ((size_t)NS * (CIN / 8) * TILE_B + (size_t)NWS * CIN * N * 2 + (size_t)RS * (N / 8) * TH * TW * 16 + (size_t)N * N * 2);
   static_assert(smem <= 227 * 1024 - 2048, "shared memory budget");
   CUtensorMap tmr = tm;                      // placeholder when there is no residual (never dereferenced then)
   if (p.residual) {                          // phase-split residual: dims (W*8, H, D, B*8*Cout/8), dense TW x TH tiles
     ss_encode_tiled_fn enc = ss_get_encode_tiled();
     if (!enc) return SS_ERR_CUDA;
-    cuuint64_t dims[4] = {(cuuint64_t)p.W * 8, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.B * 8 * (p.cout_valid / 8)};
+    cuuint64_t dims[4] = {(cuuint64_t)p.W * 8, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)(SP ? 2 : 1) * p.B * 8 * (p.cout_valid / 8)};
     cuuint64_t strides[3] = {(cuuint64_t)p.W * 16, (cuuint64_t)p.H * p.W * 16, (cuuint64_t)p.D * p.H * p.W * 16};
     cuuint32_t box[4] = {(cuuint32_t)TW * 8, (cuuint32_t)TH, 1u, (cuuint32_t)(N / 8)};
     cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -1200,7 +1263,7 @@ int launch_t2(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
       return SS_ERR_CUDA;
     }
   }
-  auto kernel = conv3d_tc_t2_kernel<CIN, N, NS, NWS, RS>;
+  auto kernel = conv3d_tc_t2_kernel<CIN, N, NS, NWS, RS, SP>;
   SS_CUDA(ss_allow_smem(kernel, smem));
   TcP q = p;
   int grid;
@@ -1260,11 +1323,35 @@ extern "C" int ss_conv3d_tc_ntile(int kind, int Cin, int Cout) {
   return 0;
 }
 
+// Layers with an in-kernel bf16x3 split configuration (shared memory holds hi and lo of a slice ring and of the weights).
+extern "C" int ss_conv3d_tc_split_supported(int kind, int Cin, int Cout) {
+  if (kind == 5) return (Cin == 32 && Cout == 32) || (Cin == 64 && Cout == 64);
+  if (kind == 2) return Cin == 32 && Cout == 64;
+  if (kind == 3) return Cin == 64 && Cout == 32;
+  return 0;
+}
+
 // D,H,W are the INPUT dims of the layer (kind 2: of the full-resolution input, all even; the tensor itself is phase-split).
 extern "C" int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight_packed, const float* scale_or_null,
                             const float* shift_or_null, const float* gate_blocked_or_null, const void* residual_s2d_or_null,
                             const void* skip_weight_or_null, void* out, int out_mode, int B, int Cin, int Cout, int D, int H, int W, int relu, void* stream) {
+  return ss_conv3d_tc_ex(kind, in_blocked, weight_packed, scale_or_null, shift_or_null, gate_blocked_or_null, residual_s2d_or_null,
+                         skip_weight_or_null, nullptr, nullptr, out, out_mode, 0, 0, B, Cin, Cout, D, H, W, relu, stream);
+}
+
+// The same layers with the two hooks of the bf16x3 split route (see the header): fp32 partial sums added to the accumulator
+// before the affine, and the bf16 output written as a hi/lo pair stacked on the batch axis ([2][B]...).
+extern "C" int ss_conv3d_tc_ex(int kind, const void* in_blocked, const void* weight_packed, const float* scale_or_null,
+                               const float* shift_or_null, const float* gate_blocked_or_null, const void* residual_s2d_or_null,
+                               const void* skip_weight_or_null, const float* acc_in_or_null, const float* acc_in2_or_null, void* out,
+                               int out_mode, int out_split, int in_split, int B, int Cin, int Cout, int D, int H, int W, int relu,
+                               void* stream) {
   SS_REQUIRE(in_blocked && weight_packed && out, "ss_conv3d_tc: null pointer");
+  SS_UNSUPPORTED(in_split && !ss_conv3d_tc_split_supported(kind, Cin, Cout),
+                 "ss_conv3d_tc: no in-kernel split configuration for kind %d (Cin=%d, Cout=%d); use the two-launch route", kind, Cin, Cout);
+  SS_REQUIRE(!in_split || !residual_s2d_or_null || skip_weight_or_null, "ss_conv3d_tc: the split route adds the skip only through the fused skip conv");
+  SS_REQUIRE(acc_in_or_null || !acc_in2_or_null, "ss_conv3d_tc: acc_in2 needs acc_in");
+  SS_REQUIRE(!out_split || out_mode != 1, "ss_conv3d_tc: a split (hi/lo) output exists only for the bf16 layouts");
   SS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && Cout > 0, "ss_conv3d_tc: non-positive dimension");
   const int N = ss_conv3d_tc_ntile(kind, Cin, Cout);
   SS_UNSUPPORTED(N == 0, "ss_conv3d_tc: kind %d with (Cin=%d, Cout=%d) has no tensor-core configuration", kind, Cin, Cout);
@@ -1289,6 +1376,11 @@ extern "C" int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual_s2d_or_null);
   p.skip_w = reinterpret_cast<const __nv_bfloat16*>(skip_weight_or_null);
   p.out = out; p.out_mode = out_mode; p.cout_valid = Cout;
+  p.acc_in = acc_in_or_null; p.acc_in2 = acc_in2_or_null;
+  {   // lo half = the same tensor one batch-stack further: B * (Cout/8) * output voxels 16-byte chunks (both bf16 layouts)
+    const long long osz = (long long)(kind == 3 ? 8 : 1) * (kind == 2 ? D / 2 : D) * (kind == 2 ? H / 2 : H) * (kind == 2 ? W / 2 : W);
+    p.split_off = out_split ? (long long)B * (Cout / 8) * osz : 0;
+  }
   p.B = B; p.relu = relu;
   p.n_tiles = ceil_div(Cout, N);
   p.DC = 1; p.n_dc = 1; p.items = 0;
@@ -1297,13 +1389,18 @@ extern "C" int ss_conv3d_tc(int kind, const void* in_blocked, const void* weight
   int rc;
   if (kind == 2) {
     p.D = D / 2; p.H = H / 2; p.W = W / 2;
-    rc = make_act_tmap(&tm, in_blocked, p.W, p.H, p.D, (long long)B * 8 * (Cin / 8), 4 * (Cin / 8));
+    rc = make_act_tmap(&tm, in_blocked, p.W, p.H, p.D, (long long)(in_split ? 2 : 1) * B * 8 * (Cin / 8), 4 * (Cin / 8));
   } else {
     p.D = D; p.H = H; p.W = W;
-    rc = make_act_tmap(&tm, in_blocked, W, H, D, (long long)B * (Cin / 8), Cin / 8);
+    rc = make_act_tmap(&tm, in_blocked, W, H, D, (long long)(in_split ? 2 : 1) * B * (Cin / 8), Cin / 8);
   }
   if (rc != SS_OK) return rc;
   p.HT = ceil_div(p.H, TH); p.WT = ceil_div(p.W, TW);
+  if (in_split) {
+    if (kind == 5) return Cin == 32 ? launch_s1f<32, 32, 4, 9, true>(tm, p, st) : launch_s1f<64, 64, 2, 2, true>(tm, p, st);
+    if (kind == 2) return launch_s2<32, 64, 2, 4, true>(tm, p, st);
+    return launch_t2<64, 32, 3, 4, 2, true>(tm, p, st);
+  }
   switch (kind) {
     case 0:
       if (Cin == 32) return launch_s1<32, 32, 8, 27, 27>(tm, p, st);
@@ -1349,6 +1446,7 @@ extern "C" int ss_concat_stem_fused(const void* cf_l_blocked, const void* cf_r_b
   p.w = reinterpret_cast<const __nv_bfloat16*>(weight_packed);
   p.scale = scale_or_null; p.shift = shift_or_null; p.gate = gate_blocked_or_null; p.residual = nullptr; p.skip_w = nullptr;
   p.out = out; p.out_mode = out_mode; p.cout_valid = 32;
+  p.acc_in = nullptr; p.acc_in2 = nullptr; p.split_off = 0;
   p.B = B; p.D = K; p.H = H; p.W = W; p.relu = relu;
   p.n_tiles = 1; p.HT = ceil_div(H, TH); p.WT = ceil_div(W, TW);
   p.DC = 1; p.n_dc = 1; p.items = 0;
@@ -1383,13 +1481,18 @@ extern "C" int ss_concat_stem_fused(const void* cf_l_blocked, const void* cf_r_b
 }
 
 extern "C" int ss_to_blocked_bf16(const float* in_ncdhw, void* out_blocked, int B, int C, int D, int H, int W, int s2d, void* stream) {
+  return ss_to_blocked_bf16_ex(in_ncdhw, out_blocked, B, C, D, H, W, s2d, 0, stream);
+}
+
+extern "C" int ss_to_blocked_bf16_ex(const float* in_ncdhw, void* out_blocked, int B, int C, int D, int H, int W, int s2d, int split,
+                                     void* stream) {
   SS_REQUIRE(in_ncdhw && out_blocked && B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "ss_to_blocked_bf16: bad argument");
   SS_REQUIRE(C % 8 == 0, "ss_to_blocked_bf16: C=%d must be a multiple of 8", C);
   SS_REQUIRE(!s2d || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "ss_to_blocked_bf16: phase-split layout needs even dims");
   SS_UNSUPPORTED(C / 8 > 65535 || B > 65535, "ss_to_blocked_bf16: grid dimension exceeds 65535");
   const size_t S = (size_t)D * H * W;
   to_blocked_kernel<<<dim3((unsigned)ceil_div64(S, 256), C / 8, B), 256, 0, (cudaStream_t)stream>>>(
-      in_ncdhw, reinterpret_cast<uint4*>(out_blocked), C, D, H, W, s2d);
+      in_ncdhw, reinterpret_cast<uint4*>(out_blocked), C, D, H, W, s2d, split ? (size_t)B * (C / 8) * S : (size_t)0);
   SS_CHECK_LAUNCH("ss_to_blocked_bf16");
   return SS_OK;
 }

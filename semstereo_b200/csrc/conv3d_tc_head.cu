@@ -29,6 +29,8 @@ constexpr int ROWB = NV - 128;                                              // f
 
 struct HeadP {
   const __nv_bfloat16* w;   // [C8][48][8] bf16: w[chunk][j*16 + t9][c8] = weight[0][chunk*8+c8][kd = 2-j][t9]
+  const float* acc_in;      // (B,1,D,H,W) fp32 partial sums added to the result (bf16x3 split route), or null
+  const float* acc_in2;
   float* out;               // (B,1,D,H,W) fp32
   int B, D, H, W;
   int HT, WT, DC, n_dc, items;
@@ -43,7 +45,12 @@ __device__ __forceinline__ void decode_item(const HeadP& p, int s, int& b, int& 
   dlo = dc * p.DC; dhi = min(p.D, dlo + p.DC);
 }
 
+// SP (in-kernel bf16x3 split): split input tensor (hi batches | lo batches), slice = [hi chunks][lo chunks], weights [hi][lo],
+// three MMAs per K step: x_hi*w_hi + x_lo*w_hi + x_hi*w_lo.
+template <bool SP>
 __global__ void __launch_bounds__(256, 1) conv3d_tc_head_kernel(const __grid_constant__ CUtensorMap tmA, const HeadP p) {
+  constexpr uint32_t HALF_A = C8 * TILE_B, HALF_B = C8 * NROW * 16;
+  constexpr uint32_t SLICE = (SP ? 2 : 1) * HALF_A, WBYTES = (SP ? 2 : 1) * HALF_B;      // shadow the single-operand sizes
   constexpr uint32_t LBO_A = TILE_B, SBO_A = 128, LBO_B = NROW * 16, SBO_B = 128;
   constexpr uint32_t TMEM_COLS = 512;                               // 2 row blocks x NB depths x 16 columns
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -91,6 +98,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_head_kernel(const __grid_con
         tc::mbar_wait(&a_empty[slot], ((g / NS) & 1) ^ 1);
         tc::mbar_expect_tx(&a_full[slot], SLICE);
         tc::tma_load_4d(Abase + slot * SLICE, &tmA, &a_full[slot], (w0 - 1) * 8, h0 - 1, d_in, b * C8);
+        if (SP) tc::tma_load_4d(Abase + slot * SLICE + HALF_A, &tmA, &a_full[slot], (w0 - 1) * 8, h0 - 1, d_in, (b + p.B) * C8);
       }
     }
   } else if (warp == 1) {
@@ -129,6 +137,12 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_head_kernel(const __grid_con
               const uint32_t bb = b_lo0 + (uint32_t)(ks * 2 * LBO_B) / 16;
               tc::mma_bf16_lohi(tmem_base + rb * 256 + blk * NT, a, a_hi, bb + brow1, b_hi, id1, 1u);
               if (n2) tc::mma_bf16_lohi(tmem_base + rb * 256, a, a_hi, bb + brow2, b_hi, id2, 1u);
+              if (SP) {
+                tc::mma_bf16_lohi(tmem_base + rb * 256 + blk * NT, a + (HALF_A >> 4), a_hi, bb + brow1, b_hi, id1, 1u);
+                if (n2) tc::mma_bf16_lohi(tmem_base + rb * 256, a + (HALF_A >> 4), a_hi, bb + brow2, b_hi, id2, 1u);
+                tc::mma_bf16_lohi(tmem_base + rb * 256 + blk * NT, a, a_hi, bb + (HALF_B >> 4) + brow1, b_hi, id1, 1u);
+                if (n2) tc::mma_bf16_lohi(tmem_base + rb * 256, a, a_hi, bb + (HALF_B >> 4) + brow2, b_hi, id2, 1u);
+              }
             }
           tc::mma_commit(&a_empty[slot]);
           if (d_in - 1 >= dlo) tc::mma_commit(&acc_full[(acc_base + (uint32_t)(d_in - 1 - dlo)) % NB]);
@@ -175,7 +189,12 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_head_kernel(const __grid_con
         for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) acc += dst[((hh + kh) * WW + ww + kw) * QSTRIDE + kh * 3 + kw];
-        if (valid) p.out[((size_t)b * p.D + d_out) * HWs + (size_t)h * p.W + w] = acc;
+        if (valid) {
+          const size_t o = ((size_t)b * p.D + d_out) * HWs + (size_t)h * p.W + w;
+          if (p.acc_in) acc += __ldg(p.acc_in + o);
+          if (p.acc_in2) acc += __ldg(p.acc_in2 + o);
+          p.out[o] = acc;
+        }
       }
     }
   }
@@ -189,6 +208,12 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_head_kernel(const __grid_con
 // in_blocked: bf16 (B,4,D,H,W,8); weight_packed: bf16 [4][48][8] (rows j*16 + t9, kd = 2 - j, 9 real in-plane taps); out fp32 (B,1,D,H,W)
 extern "C" int ss_conv3d_tc_head(const void* in_blocked, const void* weight_packed, float* out, int B, int Cin, int D, int H, int W,
                                  void* stream) {
+  return ss_conv3d_tc_head_ex(in_blocked, weight_packed, nullptr, nullptr, out, 0, B, Cin, D, H, W, stream);
+}
+
+extern "C" int ss_conv3d_tc_head_ex(const void* in_blocked, const void* weight_packed, const float* acc_in_or_null,
+                                    const float* acc_in2_or_null, float* out, int in_split, int B, int Cin, int D, int H, int W,
+                                    void* stream) {
   SS_REQUIRE(in_blocked && weight_packed && out, "ss_conv3d_tc_head: null pointer");
   SS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "ss_conv3d_tc_head: non-positive dimension");
   SS_UNSUPPORTED(Cin != CIN, "ss_conv3d_tc_head: only Cin = 32 is supported (got %d)", Cin);
@@ -197,7 +222,7 @@ extern "C" int ss_conv3d_tc_head(const void* in_blocked, const void* weight_pack
   ss_encode_tiled_fn enc = ss_get_encode_tiled();
   if (!enc) return SS_ERR_CUDA;
   CUtensorMap tm;
-  cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B * C8};
+  cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)(in_split ? 2 : 1) * B * C8};
   cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
   cuuint32_t box[4] = {(cuuint32_t)WW * 8, (cuuint32_t)HH, 1u, (cuuint32_t)C8};
   cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -210,7 +235,7 @@ extern "C" int ss_conv3d_tc_head(const void* in_blocked, const void* weight_pack
   }
   HeadP p;
   p.w = reinterpret_cast<const __nv_bfloat16*>(weight_packed);
-  p.out = out;
+  p.out = out; p.acc_in = acc_in_or_null; p.acc_in2 = acc_in2_or_null;
   p.B = B; p.D = D; p.H = H; p.W = W;
   p.HT = ceil_div(H, TH); p.WT = ceil_div(W, TW);
   int grid = ss_num_sms();
@@ -225,9 +250,14 @@ extern "C" int ss_conv3d_tc_head(const void* in_blocked, const void* weight_pack
   }
   p.DC = best; p.n_dc = D / best; p.items = spatial * p.n_dc;
   if (p.items < grid) grid = p.items;
-  const size_t smem = (size_t)NS * SLICE + WBYTES + (size_t)2 * NV * QSTRIDE * sizeof(float);
-  SS_CUDA(ss_allow_smem(conv3d_tc_head_kernel, smem));
-  conv3d_tc_head_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(tm, p);
+  const size_t smem = (in_split ? 2 : 1) * ((size_t)NS * SLICE + WBYTES) + (size_t)2 * NV * QSTRIDE * sizeof(float);
+  if (in_split) {
+    SS_CUDA(ss_allow_smem(conv3d_tc_head_kernel<true>, smem));
+    conv3d_tc_head_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(tm, p);
+  } else {
+    SS_CUDA(ss_allow_smem(conv3d_tc_head_kernel<false>, smem));
+    conv3d_tc_head_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(tm, p);
+  }
   SS_CHECK_LAUNCH("ss_conv3d_tc_head");
   return SS_OK;
 }

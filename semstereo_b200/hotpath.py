@@ -107,13 +107,18 @@ def pack_ssr(ssr: nn.Module) -> torch.Tensor:
 class DisparityHotPath(nn.Module):
     def __init__(self, maxdisp: int, att_weights_only: bool = False, signed: bool = True, num_classes: int = 6,
                  precision: str = "fp32"):
-        """precision: "fp32" = everything on the fp32 pipe (index-exact parity mode); "bf16" = every conv and the window attention
-        on the tensor cores with bf16 operands and fp32 accumulation; "mixed" = the 1/8-resolution attention branch (9 % of the
-        FLOPs, but it alone decides the top-k sample selection) in fp32 and the aggregation branch in bf16: the
-        disparity samples and pred_att are those of the fp32 mode, bit for bit, at about a third of the bf16 mode's speed."""
+        """precision:
+        "fp32"  = everything on the fp32 pipe (FFMA; the slow parity mode);
+        "bf16"  = every conv and the window attention on the tensor cores with bf16 operands and fp32 accumulation;
+        "mixed" = the 1/8-resolution attention branch (9 % of the FLOPs, but it alone decides the top-k sample selection,
+                  SURVEY 0.7) on the fp32 pipe and the aggregation branch in bf16;
+        "split" = the attention branch on the tensor cores with fp32-ACCURATE products (bf16x3: every operand is carried as a
+                  hi/lo bf16 pair, x*w = x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, fp32 accumulation; the window attention core and the
+                  gate convs stay fp32) and the aggregation branch in bf16.  Sample selection agrees with the fp32 oracle on
+                  > 99.9 % of the pixels (differences only at near-ties), at tensor-core speed: the benchmarked default."""
         super().__init__()
-        if precision not in ("fp32", "bf16", "mixed"):
-            raise ValueError("precision must be 'fp32', 'bf16' or 'mixed'")
+        if precision not in ("fp32", "bf16", "mixed", "split"):
+            raise ValueError("precision must be 'fp32', 'bf16', 'mixed' or 'split'")
         self.precision = precision
         if maxdisp % 8:
             raise ValueError("maxdisp must be a multiple of 8 (the 1/8-res volume is upsampled exactly x2)")
@@ -160,11 +165,17 @@ class DisparityHotPath(nn.Module):
     def refresh(self):
         self._cache = None
 
+    _ATT_BRANCH = ("hourglass_att", "classif_att_", "corr_feature_att_8")
+
     def _is_bf16(self, name: str) -> bool:
-        """Does the module `name` belong to a branch that runs on the tensor cores in this precision mode?"""
-        if self.precision == "mixed":
-            return not name.startswith(("hourglass_att", "classif_att_", "corr_feature_att_8"))
+        """Does the module `name` belong to a branch that runs on the tensor cores with plain bf16 operands in this mode?"""
+        if self.precision in ("mixed", "split"):
+            return not name.startswith(self._ATT_BRANCH)
         return self.precision == "bf16"
+
+    def _is_split(self, name: str) -> bool:
+        """bf16x3 split route (fp32-accurate tensor-core products): the 3-D stack of the attention branch in "split" mode."""
+        return self.precision == "split" and name.startswith(("hourglass_att", "classif_att_"))
 
     def _apply(self, fn, *a, **k):
         self._cache = None
@@ -187,6 +198,13 @@ class DisparityHotPath(nn.Module):
                     kind = tc.S1F          # narrow layers: depth taps folded into the GEMM N (csrc/conv3d_tc.cu, s1f)
                 c[name + ".kind"] = kind
                 c[name + ".tc"] = tc.pack_weight(w, kind)
+            elif self._is_split(name):
+                k, st = convmod.kernel_size[0], convmod.stride[0]
+                kind = tc.T2 if transposed else (tc.K1 if k == 1 else (tc.S2 if st == 2 else tc.S1))
+                if kind == tc.S1 and tc.ntile(tc.S1F, w.shape[1], w.shape[0]) == w.shape[0]:
+                    kind = tc.S1F
+                c[name + ".kind"] = kind
+                c[name + ".tcs"] = tc.pack_weight_split(w, kind)
             else:
                 c[name + ".w"] = ops.pack_conv3d_weight(w, transposed)
             if bn is not None:
@@ -201,15 +219,22 @@ class DisparityHotPath(nn.Module):
             conv(f"{hg}.redir1", m.redir1[0], m.redir1[1])
             conv(f"{hg}.redir2", m.redir2[0], m.redir2[1])
             bf16 = self._is_bf16(hg)
-            if bf16:
+            if bf16 or self._is_split(hg):
                 for dc, rd in (("conv5", "redir2"), ("conv6", "redir1")):
                     deconv, dbn = getattr(m, dc)[0], getattr(m, dc)[1]
                     rconv, rbn = getattr(m, rd)[0], getattr(m, rd)[1]
                     ds, dt = bn_affine(dbn)
                     rs, rt = bn_affine(rbn)
-                    c[f"{hg}.{dc}.ftc"] = tc.pack_weight(deconv.weight.detach().float() * ds.view(1, -1, 1, 1, 1), tc.T2)
-                    c[f"{hg}.{dc}.skipw"] = tc.pack_skip_weight(rconv.weight.detach().float(), rs)
+                    wf = deconv.weight.detach().float() * ds.view(1, -1, 1, 1, 1)           # BN scales folded into both weights
+                    cc = rconv.weight.shape[0]
+                    sf = rconv.weight.detach().float().reshape(cc, cc) * rs.reshape(cc, 1)
                     c[f"{hg}.{dc}.fshift"] = (dt + rt).contiguous()
+                    if bf16:
+                        c[f"{hg}.{dc}.ftc"] = tc.pack_weight(wf, tc.T2)
+                        c[f"{hg}.{dc}.skipw"] = tc.pack_skip_weight(sf)
+                    else:
+                        c[f"{hg}.{dc}.ftcs"] = tc.pack_weight_split(wf, tc.T2)
+                        c[f"{hg}.{dc}.skipws"] = tc.pack_skip_weight_split(sf)
             a = m.attention_block
             c[hg + ".wqkv_t"] = a.qkv_3d.weight.detach().float().t().contiguous()
             c[hg + ".bqkv"] = a.qkv_3d.bias.detach().float().contiguous()
@@ -225,6 +250,8 @@ class DisparityHotPath(nn.Module):
             conv(cl + ".0", m[0][0], m[0][1])
             if self._is_bf16(cl):
                 c[cl + ".2.tc"] = tc.pack_head_weight(m[2].weight.detach().float())          # taps-as-N head kernel
+            elif self._is_split(cl):
+                c[cl + ".2.tcs"] = tc.pack_head_weight_split(m[2].weight.detach().float())
             else:
                 c[cl + ".2.w"] = m[2].weight.detach().float().contiguous()
         conv("concat_stem", self.concat_stem.conv, self.concat_stem.bn)
@@ -318,6 +345,34 @@ class DisparityHotPath(nn.Module):
             return tc.conv3d_tc(tc.T2, c5, c[hg + ".conv6.ftc"], 32, None, c[hg + ".conv6.fshift"], residual_s2d=x_s2d,
                                 skip_weight=c[hg + ".conv6.skipw"], relu=True)
 
+    # ---- bf16x3 split flavour (attention branch, precision="split"): same layer graph, every activation a hi/lo pair stacked
+    # on the batch axis, two launches per layer (ops_tc.conv3d_tc_split); the window attention block runs in fp32 ----
+    def _tcs(self, c, name, x, cout, relu=True, out_mode=tc.BLOCKED):
+        with ops.label(name):
+            return tc.conv3d_tc_split(c[name + ".kind"], x, c[name + ".tcs"], cout, c.get(name + ".scale"), c.get(name + ".shift"),
+                                      relu=relu, out_mode=out_mode)
+
+    def _hourglass_split(self, c, hg, x_s2d):
+        block = getattr(self, hg).block
+        c1 = self._tcs(c, hg + ".conv1", x_s2d, 64)
+        c2s = self._tcs(c, hg + ".conv2", c1, 64, out_mode=tc.S2D)
+        c3 = self._tcs(c, hg + ".conv3", c2s, 128)
+        c4 = self._tcs(c, hg + ".conv4", c3, 128, out_mode=tc.F32)                 # fp32 NCDHW for the fp32 attention block
+        with ops.label(hg + ".attention"):
+            c4 = ops.window_attention3d(c4, c[hg + ".wqkv_t"], c[hg + ".bqkv"], c[hg + ".wo_t"], c[hg + ".bo"], block, 16)
+            c4b = tc.to_blocked_bf16(c4, split=True)
+        with ops.label(hg + ".conv5"):
+            c5 = tc.conv3d_tc_split(tc.T2, c4b, c[hg + ".conv5.ftcs"], 64, None, c[hg + ".conv5.fshift"], residual_s2d=c2s,
+                                    skip_split=c[hg + ".conv5.skipws"], relu=True)
+        with ops.label(hg + ".conv6"):
+            return tc.conv3d_tc_split(tc.T2, c5, c[hg + ".conv6.ftcs"], 32, None, c[hg + ".conv6.fshift"], residual_s2d=x_s2d,
+                                      skip_split=c[hg + ".conv6.skipws"], relu=True)
+
+    def _classifier_split(self, c, cl, xs):
+        y = self._tcs(c, cl + ".0", xs, 32)
+        with ops.label(cl + ".2"):
+            return tc.conv3d_tc_head(y, c[cl + ".2.tcs"], in_split=True)
+
     def _classifier_tc(self, c, cl, xb):
         y = self._tc(c, cl + ".0", tc.S1, xb, 32)
         with ops.label(cl + ".2"):
@@ -353,6 +408,9 @@ class DisparityHotPath(nn.Module):
         if self._is_bf16("hourglass_att"):
             vol = tc.patch_gate_blocked(corr, c["patch.w"], gate8)
             cost_att = self._classifier_tc(c, "classif_att_", self._hourglass_tc(c, "hourglass_att", vol))
+        elif self._is_split("hourglass_att"):
+            vol = tc.patch_gate_blocked(corr, c["patch.w"], gate8, split=True)
+            cost_att = self._classifier_split(c, "classif_att_", self._hourglass_split(c, "hourglass_att", vol))
         else:
             vol = ops.patch_gate(corr, c["patch.w"], gate8)
             vol = self._hourglass(c, "hourglass_att", vol)

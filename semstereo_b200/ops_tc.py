@@ -21,12 +21,14 @@ def _require_bf16(t, ndim):
     return t.device
 
 
-def to_blocked_bf16(x, s2d=False):
+def to_blocked_bf16(x, s2d=False, split=False):
+    """split=True: the hi/lo pair of the bf16x3 route stacked on the batch axis -> batch 2B (see conv3d_tc_split)."""
     dev = _require_cuda(x)
     B, C, D, H, W = x.shape
-    shape = (B, 8, C // 8, D // 2, H // 2, W // 2, 8) if s2d else (B, C // 8, D, H, W, 8)
+    nb = 2 * B if split else B
+    shape = (nb, 8, C // 8, D // 2, H // 2, W // 2, 8) if s2d else (nb, C // 8, D, H, W, 8)
     out = torch.empty(shape, device=dev, dtype=torch.bfloat16)
-    _call("ss_to_blocked_bf16", dev, _ptr(x), _ptr(out), B, C, D, H, W, int(s2d))
+    _call("ss_to_blocked_bf16_ex", dev, _ptr(x), _ptr(out), B, C, D, H, W, int(s2d), int(split))
     return out
 
 
@@ -91,14 +93,15 @@ def gate_sigmoid_blocked(gate_logits):
     return out
 
 
-def patch_gate_blocked(volume, patch_w, gate_logits):
-    """`patch` depthwise conv * sigmoid(gate) written straight into the phase-split bf16 layout the stride-2 layer reads."""
+def patch_gate_blocked(volume, patch_w, gate_logits, split=False):
+    """`patch` depthwise conv * sigmoid(gate) written straight into the phase-split bf16 layout the stride-2 layer reads
+    (split=True: as the hi/lo pair of the bf16x3 route, batch 2B)."""
     dev = _require_cuda(volume, patch_w, gate_logits)
     B, G, D, H, W = volume.shape
     if patch_w.numel() != G * 9 or tuple(gate_logits.shape) != (B, G, H, W):
         raise ValueError("patch_gate_blocked: patch weight (G,9) and gate logits (B,G,H,W) expected")
-    out = torch.empty((B, 8, G // 8, D // 2, H // 2, W // 2, 8), device=dev, dtype=torch.bfloat16)
-    _call("ss_patch_gate_blocked", dev, _ptr(volume), _ptr(patch_w), _ptr(gate_logits), _ptr(out), B, G, D, H, W)
+    out = torch.empty(((2 * B if split else B), 8, G // 8, D // 2, H // 2, W // 2, 8), device=dev, dtype=torch.bfloat16)
+    _call("ss_patch_gate_blocked_ex", dev, _ptr(volume), _ptr(patch_w), _ptr(gate_logits), _ptr(out), B, G, D, H, W, int(split))
     return out
 
 
@@ -135,30 +138,92 @@ def pack_head_weight(w):
     return t.reshape(4, 8, 48).permute(0, 2, 1).contiguous().to(torch.bfloat16)
 
 
-def conv3d_tc_head(xb, w_head):
-    """Cout = 1 classifier head on the blocked layout: (B,4,D,H,W,8) bf16 -> (B,1,D,H,W) fp32."""
+def conv3d_tc_head(xb, w_head, acc_in=None, acc_in2=None, in_split=False):
+    """Cout = 1 classifier head on the blocked layout: (B,4,D,H,W,8) bf16 -> (B,1,D,H,W) fp32 (+ fp32 partial sums acc_in*).
+    in_split: xb is a split tensor (batch 2B), w_head = pack_head_weight_split(w): the fp32-accurate bf16x3 product in one launch."""
     dev = _require_bf16(xb, 6)
     B, C8, D, H, W, _ = xb.shape
-    if w_head.dtype != torch.bfloat16 or tuple(w_head.shape) != (4, 48, 8) or not w_head.is_contiguous():
-        raise ValueError("conv3d_tc_head: weight must come from pack_head_weight")
+    if in_split:
+        B //= 2
+    if w_head.dtype != torch.bfloat16 or tuple(w_head.shape) != ((2, 4, 48, 8) if in_split else (4, 48, 8)) or not w_head.is_contiguous():
+        raise ValueError("conv3d_tc_head: weight must come from pack_head_weight(_split)")
+    for a in (acc_in, acc_in2):
+        if a is not None and (_require_cuda(a) != dev or a.dtype != torch.float32 or a.numel() != B * D * H * W or not a.is_contiguous()):
+            raise ValueError("conv3d_tc_head: acc_in must be a contiguous fp32 (B,1,D,H,W) tensor")
     out = torch.empty((B, 1, D, H, W), device=dev, dtype=torch.float32)
-    _call("ss_conv3d_tc_head", dev, _ptr(xb), _ptr(w_head), _ptr(out), B, C8 * 8, D, H, W)
+    _call("ss_conv3d_tc_head_ex", dev, _ptr(xb), _ptr(w_head), _ptr(acc_in), _ptr(acc_in2), _ptr(out), int(in_split), B, C8 * 8, D, H, W)
     return out
 
 
 BLOCKED, F32, S2D = 0, 1, 2          # out_mode of ss_conv3d_tc
 
 
-def pack_skip_weight(w, scale):
-    """1x1x1 redir conv weight (C,C,1,1,1) with its BN scale folded in -> bf16 [C/8][C][8] (K-major rows = output channels)."""
+def pack_skip_weight(w, scale=None):
+    """1x1x1 redir conv weight (C,C[,1,1,1]) (with its BN scale folded in when given) -> bf16 [C/8][C][8] (K-major rows = output
+    channels)."""
     c = w.shape[0]
-    t = (w.reshape(c, c) * scale.reshape(c, 1)).reshape(c, c // 8, 8).permute(1, 0, 2)      # (chunk, cout, c8)
-    return t.contiguous().to(torch.bfloat16)
+    w = w.reshape(c, c)
+    if scale is not None:
+        w = w * scale.reshape(c, 1)
+    return w.reshape(c, c // 8, 8).permute(1, 0, 2).contiguous().to(torch.bfloat16)      # (chunk, cout, c8)
+
+
+def split_f32(w):
+    """fp32 tensor -> (hi, lo) fp32 tensors with hi = bf16(w), lo = w - hi (bf16(lo) is the second term of the bf16x3 split)."""
+    hi = w.to(torch.bfloat16).float()
+    return hi, w - hi
+
+
+def split_supported(kind, cin, cout):
+    """Does this layer have an in-kernel (single launch) bf16x3 split configuration?"""
+    return bool(_lib.load().ss_conv3d_tc_split_supported(int(kind), int(cin), int(cout)))
+
+
+def pack_weight_split(w, kind):
+    """fp32 weight -> (hi, lo) packings of pack_weight for the bf16x3 split route; for layers with an in-kernel split
+    configuration a third tensor: per tap [hi chunks | lo chunks] (what ss_conv3d_tc_ex(in_split=1) reads), else None."""
+    hi, lo = split_f32(w)
+    ph, pl = pack_weight(hi, kind), pack_weight(lo, kind)
+    cin, cout = (w.shape[0], w.shape[1]) if kind == T2 else (w.shape[1], w.shape[0])
+    both = torch.cat((ph, pl), dim=1 if kind == S1F else 2).contiguous() if split_supported(kind, cin, cout) else None
+    return ph, pl, both
+
+
+def pack_skip_weight_split(w):
+    """(C,C) redir weight (BN scale folded) -> (hi, lo, [hi chunks | lo chunks]) packings of pack_skip_weight."""
+    hi, lo = split_f32(w)
+    ph, pl = pack_skip_weight(hi), pack_skip_weight(lo)
+    return ph, pl, torch.cat((ph, pl), dim=0).contiguous()
+
+
+def pack_head_weight_split(w):
+    hi, lo = split_f32(w)
+    return torch.stack((pack_head_weight(hi), pack_head_weight(lo))).contiguous()        # (2,4,48,8)
+
+
+def conv3d_tc_split(kind, xs, w_split, cout, scale=None, shift=None, gate_blocked=None, residual_s2d=None, relu=False,
+                    out_mode=BLOCKED, skip_split=None):
+    """fp32-accurate layer on the bf16 tensor cores (bf16x3: x*w = x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, fp32 accumulation).
+    xs (and residual_s2d) are split tensors = the hi/lo halves stacked on the batch axis (batch 2B); w_split / skip_split come
+    from pack_weight_split / pack_skip_weight_split.  Layers with an in-kernel configuration issue the three MMAs per K step
+    into one TMEM accumulator (one launch).  The others take two launches of the plain kernel: (1) the 2B-batch input x w_hi,
+    raw fp32 partial sums; (2) the hi half x w_lo plus the partial sums, then the usual epilogue.  The bf16 outputs are split
+    tensors again (batch 2B); out_mode F32 returns the plain (B,Cout,...) fp32 result."""
+    B = xs.shape[0] // 2
+    w_hi, w_lo, w_both = w_split
+    s_hi, s_lo, s_both = skip_split if skip_split is not None else (None, None, None)
+    if w_both is not None:
+        return conv3d_tc(kind, xs, w_both, cout, scale, shift, gate_blocked, residual_s2d, relu=relu, out_mode=out_mode,
+                         skip_weight=s_both, out_split=out_mode != F32, in_split=True)
+    part = conv3d_tc(kind, xs, w_hi, cout, residual_s2d=residual_s2d, skip_weight=s_hi, out_mode=F32)
+    return conv3d_tc(kind, xs[:B], w_lo, cout, scale, shift, gate_blocked, None if residual_s2d is None else residual_s2d[:B],
+                     relu=relu, out_mode=out_mode, skip_weight=s_lo, acc_in=part[:B], acc_in2=part[B:], out_split=out_mode != F32)
 
 
 def conv3d_tc(kind, xb, w_tc, cout, scale=None, shift=None, gate_blocked=None, residual_s2d=None, relu=False, out_mode=BLOCKED,
-              skip_weight=None):
-    """xb: blocked (kinds S1, K1, T2) or phase-split (kind S2) bf16 input.  Returns bf16 blocked / phase-split or fp32 NCDHW."""
+              skip_weight=None, acc_in=None, acc_in2=None, out_split=False, in_split=False):
+    """xb: blocked (kinds S1, K1, T2) or phase-split (kind S2) bf16 input.  Returns bf16 blocked / phase-split or fp32 NCDHW.
+    acc_in / acc_in2 / out_split / in_split: the hooks of the bf16x3 split route (conv3d_tc_split)."""
     if kind == S2:
         dev = _require_bf16(xb, 7)
         B, _, C8, D2, H2, W2, _ = xb.shape
@@ -168,10 +233,15 @@ def conv3d_tc(kind, xb, w_tc, cout, scale=None, shift=None, gate_blocked=None, r
         dev = _require_bf16(xb, 6)
         B, C8, D, H, W, _ = xb.shape
         Do, Ho, Wo = (2 * D, 2 * H, 2 * W) if kind == T2 else (D, H, W)
+    nparts = 2 if in_split else 1
+    if in_split:
+        if B % 2:
+            raise ValueError("conv3d_tc: a split input has an even batch (hi batches | lo batches)")
+        B //= 2
     cin = C8 * 8
     n = ntile(kind, cin, cout)
     taps = 1 if kind == K1 else (9 if kind == C2D else 27)
-    wshape = (9, C8, 3 * cout, 8) if kind == S1F else (-(-cout // max(n, 1)), taps, C8, n, 8)
+    wshape = (9, nparts * C8, 3 * cout, 8) if kind == S1F else (-(-cout // max(n, 1)), taps, nparts * C8, n, 8)
     if n == 0 or w_tc.dtype != torch.bfloat16 or tuple(w_tc.shape) != wshape or not w_tc.is_contiguous():
         raise ValueError("conv3d_tc: weight must come from pack_weight(w, kind) for this layer")
     for t in (scale, shift, gate_blocked):
@@ -181,19 +251,29 @@ def conv3d_tc(kind, xb, w_tc, cout, scale=None, shift=None, gate_blocked=None, r
         raise ValueError("conv3d_tc: gate must be fp32 (B,Cout/8,Ho,Wo,8) from gate_sigmoid_blocked")
     if residual_s2d is not None:
         _require_bf16(residual_s2d, 7)
-        if kind != T2 or tuple(residual_s2d.shape) != (B, 8, cout // 8, D, H, W, 8):
+        if kind != T2 or tuple(residual_s2d.shape) != (nparts * B, 8, cout // 8, D, H, W, 8):
             raise ValueError("conv3d_tc: residual must be phase-split (B,8,Cout/8,D,H,W,8) at the transposed layer's input dims")
+    for a in (acc_in, acc_in2):
+        if a is not None and (_require_cuda(a) != dev or a.dtype != torch.float32 or not a.is_contiguous()
+                              or tuple(a.shape) != (B, cout, Do, Ho, Wo)):
+            raise ValueError("conv3d_tc: acc_in must be a contiguous fp32 (B,Cout,Do,Ho,Wo) tensor")
+    if acc_in2 is not None and acc_in is None:
+        raise ValueError("conv3d_tc: acc_in2 needs acc_in")
+    nb = 2 * B if out_split else B
     if out_mode == F32:
+        if out_split:
+            raise ValueError("conv3d_tc: a split output exists only for the bf16 layouts")
         out = torch.empty((B, cout, Do, Ho, Wo), device=dev, dtype=torch.float32)
     elif out_mode == S2D:
-        out = torch.empty((B, 8, cout // 8, Do // 2, Ho // 2, Wo // 2, 8), device=dev, dtype=torch.bfloat16)
+        out = torch.empty((nb, 8, cout // 8, Do // 2, Ho // 2, Wo // 2, 8), device=dev, dtype=torch.bfloat16)
     else:
-        out = torch.empty((B, cout // 8, Do, Ho, Wo, 8), device=dev, dtype=torch.bfloat16)
+        out = torch.empty((nb, cout // 8, Do, Ho, Wo, 8), device=dev, dtype=torch.bfloat16)
     if skip_weight is not None and (residual_s2d is None or skip_weight.dtype != torch.bfloat16
-                                    or tuple(skip_weight.shape) != (cout // 8, cout, 8) or not skip_weight.is_contiguous()):
+                                    or tuple(skip_weight.shape) != (nparts * cout // 8, cout, 8) or not skip_weight.is_contiguous()):
         raise ValueError("conv3d_tc: skip_weight must come from pack_skip_weight and needs the skip input as residual_s2d")
-    _call("ss_conv3d_tc", dev, int(kind), _ptr(xb), _ptr(w_tc), _ptr(scale), _ptr(shift), _ptr(gate_blocked), _ptr(residual_s2d),
-          _ptr(skip_weight), _ptr(out), int(out_mode), B, cin, cout, D, H, W, int(relu))
+    _call("ss_conv3d_tc_ex", dev, int(kind), _ptr(xb), _ptr(w_tc), _ptr(scale), _ptr(shift), _ptr(gate_blocked), _ptr(residual_s2d),
+          _ptr(skip_weight), _ptr(acc_in), _ptr(acc_in2), _ptr(out), int(out_mode), int(out_split), int(in_split), B, cin, cout, D, H, W,
+          int(relu))
     return out
 
 
