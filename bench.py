@@ -8,7 +8,8 @@
 A "step" is one pass of the hot path (SemStereo.forward:273-324: gwc volume -> attention hourglass -> top-k ->
 sparse concat volume -> hourglass2 -> regression_topk -> SSR upsample) over one batch of synthetic stereo-pair
 features of a 1024x1024 US3D-shaped pair (maxdisp 64), random-init weights.  Weak scaling: every rank processes
-`--batch` pairs per step; outputs are all-gathered over NCCL every step.  One JSON line is printed by rank 0.
+`--batch` pairs per step; the outputs are gathered to rank 0 over NCCL every step (side stream, overlapping the next step).
+One JSON line is printed by rank 0.
 """
 from __future__ import annotations
 
@@ -287,16 +288,37 @@ def main():
     model = model.to(dev)
     devin = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
     out_host = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
-    gathered = torch.empty((world * B, H, W), device=dev) if world > 1 else None
+    # Output gather (the only collective): to rank 0, as nn.DataParallel gathers to device 0 (main_us3d.py:100), issued on a SIDE
+    # stream from a double-buffered copy of the result, so that it overlaps the next step's kernels instead of serialising with
+    # them (round 1: an eager all-gather on the compute stream cost 6 % of a step at N = 8).
+    gathered = torch.empty((world * B, H, W), device=dev) if (world > 1 and rank == 0) else None
+    gather_stream = torch.cuda.Stream(dev) if world > 1 else None
+    gbuf = [torch.empty((B, H, W), device=dev) for _ in range(2)] if world > 1 else None
+    gdone = [torch.cuda.Event() for _ in range(2)] if world > 1 else None
+    gstep_no = [0]
+
+    def gather_async(o):
+        """Copy the step's result aside (33 MB device-to-device) and gather it to rank 0 on the side stream."""
+        i = gstep_no[0] % 2
+        gstep_no[0] += 1
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(gdone[i])                       # the gather that last read this buffer (two steps ago) has finished
+        gbuf[i].copy_(o)
+        gather_stream.wait_stream(cur)
+        with torch.cuda.stream(gather_stream):
+            tdist.gather(gbuf[i], list(gathered.split(B)) if rank == 0 else None, dst=0)
+            gdone[i].record(gather_stream)
+        return o
 
     def step(inputs):
         o = call(inputs)
         if world > 1:
-            tdist.all_gather_into_tensor(gathered, o)
+            gather_async(o)
         return o
 
     def barrier():
         if world > 1:
+            torch.cuda.synchronize()                   # incl. the side-stream gathers of this rank
             tdist.barrier()
         torch.cuda.synchronize()
 
@@ -340,7 +362,7 @@ def main():
         def gstep():
             o = gc.replay()
             if world > 1:
-                tdist.all_gather_into_tensor(gathered, o)
+                gather_async(o)
 
         for _ in range(a.warmup):
             gstep()
@@ -363,7 +385,7 @@ def main():
 
     def gather(o):
         if world > 1:
-            tdist.all_gather_into_tensor(gathered, o)
+            gather_async(o)
         return o
 
     pipe = HostPipeline(model, depth=2, post=gather, keys=tuple(host), call=call)
@@ -425,7 +447,7 @@ def main():
            "e2e": {"value": e2e_v, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps},
            "gpu_launches": rec.count, "clocks": clocks, "roofline": roof, "kernels": kernels}
     res["host"] = {"numa_bound_cpus": len(numa_cpus) if numa_cpus else None}
-    res["launch_mode"] = {"value_region": "cuda graph replay per step (+ eager NCCL gather)" if graph_used else
+    res["launch_mode"] = {"value_region": "cuda graph replay per step (+ NCCL gather to rank 0 on a side stream)" if graph_used else
                           ("eager" + (f" (graph capture failed: {graph_err})" if graph_err else "")),
                           "eager_instrumented_ms_per_step": ms_eager / a.steps,
                           "eager_instrumented_value": world * B * a.steps / (ms_eager * 1e-3),

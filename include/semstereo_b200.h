@@ -111,7 +111,10 @@ SS_API int ss_conv3d_tc_ex(int kind, const void* in_blocked, const void* weight_
  * skip weight likewise [hi: Cout/8][lo: Cout/8] chunks), and every K step issues the three MMAs into one TMEM accumulator. */
 SS_API int ss_conv3d_tc_split_supported(int kind, int Cin, int Cout);
 /* ss_to_blocked_bf16 / ss_patch_gate_blocked / ss_conv3d_tc_head with the split hooks: split = 1 writes a split tensor (batch 2B);
- * the head adds fp32 partial sums (B,1,D,H,W) to its result. */
+ * the head adds fp32 partial sums (B,1,D,H,W) to its result.  ss_to_blocked_bf16_ex split = 2: the channel-stacked K-concat form
+ * [hi | lo | hi], bf16 (B, 3C/8, D, H, W, 8): a 1x1 conv with the weight [w_hi | w_hi | w_lo] (K = 3C) over it IS the bf16x3
+ * product in one GEMM -- used with ss_conv2d_tc mode 1 for the channelAtt gate convs (SemStereo.py:93-95) and the qkv / final
+ * 1x1x1 projections of attention_block (submodule_other.py:795-803; a 3-D volume is a 2-D image of D*H rows for a 1x1 conv). */
 SS_API int ss_to_blocked_bf16_ex(const float* in_ncdhw, void* out_blocked, int B, int C, int D, int H, int W, int s2d, int split,
                                  void* stream);
 SS_API int ss_patch_gate_blocked_ex(const float* volume, const float* patch_w, const float* gate_logits, void* out_s2d, int B, int G,
@@ -172,6 +175,12 @@ SS_API int ss_sparse_concat_volume_blocked(const float* cf_l, const float* cf_r,
 SS_API int ss_window_attention3d(const float* x, const float* wqkv_t, const float* bqkv, const float* wo_t, const float* bo,
                                  float* out, int B, int C, int D, int H, int W, int bd, int bh, int bw, int num_heads,
                                  void* stream);
+
+/* bf16x3 split route: the fp32 softmax(q k^T * scale) v core alone.  qkv fp32 (B,3C,D,H,W) (channel = which*C + head*8 + j, what
+ * qkv_3d produces, submodule_other.py:813-816) -> out_tri bf16 (B, 3*C/8, D, H, W, 8) in the [hi | lo | hi] K-concat form of
+ * ss_to_blocked_bf16_ex(split = 2), ready for the final 1x1x1 conv as an fp32-accurate GEMM. */
+SS_API int ss_window_attention_core_f32(const float* qkv, void* out_tri, int B, int C, int D, int H, int W, int bd, int bh, int bw,
+                                        int num_heads, void* stream);
 
 /* Tensor-core mode: the qkv Linear and the final 1x1x1 conv run as ss_conv3d_tc kind 1 layers (Cin=128 -> 384 / 128, bias as
  * shift); this is the softmax(q k^T * scale) v core in between on the blocked layout, where head h is channel chunk h:

@@ -55,6 +55,7 @@ SIGNATURES = {
     "ss_to_blocked_bf16_ex": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ss_patch_gate_blocked_ex": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ss_conv3d_tc_head_ex": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ss_window_attention_core_f32": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "ss_window_attention3d": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "ss_att_stats": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "ss_sample_strength": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],

@@ -38,11 +38,30 @@ def _digest():
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Idempotent and safe under torchrun: the digest check, compile and link run under an inter-process file lock (every rank
+    of a fresh tree would otherwise write the same objects), and the library and its stamp are moved into place atomically, so no
+    process can dlopen a half-written .so."""
+    import fcntl
     os.makedirs(OBJ, exist_ok=True)
     stamp = os.path.join(OBJ, "digest.txt")
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+
+    def fresh():
+        return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig
+
+    if not force and fresh():
         return LIB
+    with open(os.path.join(OBJ, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and fresh():          # another process built it while we waited
+                return LIB
+            return _build_locked(dig, stamp, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(dig: str, stamp: str, verbose: bool) -> str:
     if not os.path.exists(NVCC):
         raise RuntimeError(f"nvcc not found at {NVCC}; cannot build {LIB}")
 
@@ -58,11 +77,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    tmp = f"{LIB}.{os.getpid()}.tmp"
+    cmd = [NVCC, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    open(stamp, "w").write(dig)
+    if os.path.exists(stamp):
+        os.remove(stamp)                       # never a fresh stamp next to an old library
+    os.replace(tmp, LIB)
+    with open(stamp + ".tmp", "w") as f:
+        f.write(dig)
+    os.replace(stamp + ".tmp", stamp)
     return LIB
 
 

@@ -139,7 +139,102 @@ __global__ void __launch_bounds__(256) window_attention3d_kernel(const AttnP p) 
   }
 }
 
+// The softmax(q k^T * scale) v core alone, fp32, for the bf16x3 split route: the qkv Linear and the final 1x1x1 conv run as
+// fp32-accurate tensor-core GEMMs around it (ss_conv2d_tc over the [hi | lo | hi] K-concat form), so this kernel reads the fp32
+// qkv volume (B,3C,D,H,W; channel = which*C + head*hd + j) and writes the head outputs directly in that K-concat form:
+// bf16 (B, 3*C/8, D, H, W, 8) -- a head (hd = 8 channels) is exactly one 16-byte channel chunk.
+__global__ void __launch_bounds__(256) window_attention_core_f32_kernel(const float* __restrict__ qkv, uint4* __restrict__ out, int D,
+                                                                       int H, int W, int bd, int bh, int bw, int nd, int nh, int nw, int T) {
+  extern __shared__ __align__(16) float smem[];        // [3][heads][T][hd]
+  int wid = blockIdx.x;
+  const int wx = wid % nw;  wid /= nw;
+  const int wy = wid % nh;  wid /= nh;
+  const int wz = wid % nd;
+  const int b = wid / nd;
+  const size_t cs = (size_t)D * H * W;
+  const size_t wbase = ((size_t)wz * bd * H + (size_t)wy * bh) * W + (size_t)wx * bw;
+  const int bhw = bh * bw;
+  auto tok_off = [&](int t) -> size_t {
+    const int dd = t / bhw, r = t - dd * bhw, hh = r / bw, ww = r - hh * bw;
+    return ((size_t)dd * H + hh) * W + ww;
+  };
+  const float* src = qkv + (size_t)b * 3 * kC * cs + wbase;
+  for (int i = threadIdx.x; i < 3 * kC * T; i += blockDim.x) {
+    const int c = i / T, t = i - c * T;                 // c = which*C + head*hd + j
+    smem[((size_t)(c >> 3) * T + t) * kHd + (c & 7)] = __ldg(src + (size_t)c * cs + tok_off(t));
+  }
+  __syncthreads();
+  const float scale = 0.35355339059327379f;             // hd^-0.5 with hd = 8
+  const float* Q = smem;
+  const float* Km = smem + (size_t)kHeads * T * kHd;
+  const float* V = smem + (size_t)2 * kHeads * T * kHd;
+  uint4* ob = out + (size_t)b * 3 * kHeads * cs + wbase;
+  for (int id = threadIdx.x; id < kHeads * T; id += blockDim.x) {
+    const int tq = id % T, h = id / T;
+    float q[kHd];
+    {
+      const float4* qp = reinterpret_cast<const float4*>(Q + ((size_t)h * T + tq) * kHd);
+      const float4 a = qp[0], c = qp[1];
+      q[0] = a.x * scale; q[1] = a.y * scale; q[2] = a.z * scale; q[3] = a.w * scale;
+      q[4] = c.x * scale; q[5] = c.y * scale; q[6] = c.z * scale; q[7] = c.w * scale;
+    }
+    const float4* kp = reinterpret_cast<const float4*>(Km + (size_t)h * T * kHd);
+    const float4* vp = reinterpret_cast<const float4*>(V + (size_t)h * T * kHd);
+    // online softmax: one pass over the keys
+    float m = -INFINITY, l = 0.0f, o[kHd];
+#pragma unroll
+    for (int j = 0; j < kHd; ++j) o[j] = 0.0f;
+    for (int tk = 0; tk < T; ++tk) {
+      const float4 a = kp[2 * tk], c = kp[2 * tk + 1];
+      float sc = q[0] * a.x;
+      sc = fmaf(q[1], a.y, sc); sc = fmaf(q[2], a.z, sc); sc = fmaf(q[3], a.w, sc);
+      sc = fmaf(q[4], c.x, sc); sc = fmaf(q[5], c.y, sc); sc = fmaf(q[6], c.z, sc); sc = fmaf(q[7], c.w, sc);
+      const float mn = fmaxf(m, sc);
+      const float corr = expf(m - mn), pe = expf(sc - mn);
+      m = mn;
+      l = fmaf(l, corr, pe);
+      const float4 va = vp[2 * tk], vc = vp[2 * tk + 1];
+      o[0] = fmaf(o[0], corr, pe * va.x); o[1] = fmaf(o[1], corr, pe * va.y); o[2] = fmaf(o[2], corr, pe * va.z); o[3] = fmaf(o[3], corr, pe * va.w);
+      o[4] = fmaf(o[4], corr, pe * vc.x); o[5] = fmaf(o[5], corr, pe * vc.y); o[6] = fmaf(o[6], corr, pe * vc.z); o[7] = fmaf(o[7], corr, pe * vc.w);
+    }
+    const float inv = 1.0f / l;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float x0 = o[2 * j] * inv, x1 = o[2 * j + 1] * inv;
+      __nv_bfloat162 hv = __floats2bfloat162_rn(x0, x1);
+      hi[j] = *reinterpret_cast<uint32_t*>(&hv);
+      __nv_bfloat162 lv = __floats2bfloat162_rn(x0 - __uint_as_float(hi[j] << 16), x1 - __uint_as_float(hi[j] & 0xffff0000u));
+      lo[j] = *reinterpret_cast<uint32_t*>(&lv);
+    }
+    const size_t vo = tok_off(tq);
+    const uint4 qh = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    ob[(size_t)h * cs + vo] = qh;
+    ob[(size_t)(kHeads + h) * cs + vo] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    ob[(size_t)(2 * kHeads + h) * cs + vo] = qh;
+  }
+}
+
 }  // namespace
+
+extern "C" int ss_window_attention_core_f32(const float* qkv, void* out_tri, int B, int C, int D, int H, int W, int bd, int bh, int bw,
+                                            int num_heads, void* stream) {
+  SS_REQUIRE(qkv && out_tri, "ss_window_attention_core_f32: null pointer");
+  SS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && bd > 0 && bh > 0 && bw > 0, "ss_window_attention_core_f32: non-positive dimension");
+  SS_REQUIRE((reinterpret_cast<uintptr_t>(out_tri) & 15) == 0, "ss_window_attention_core_f32: output must be 16-byte aligned");
+  SS_UNSUPPORTED(C != kC || num_heads != kHeads, "ss_window_attention_core_f32: only C=128 with 16 heads is supported (got C=%d, heads=%d)", C, num_heads);
+  SS_UNSUPPORTED(D % bd || H % bh || W % bw, "ss_window_attention_core_f32: D,H,W (%d,%d,%d) must be multiples of the window (%d,%d,%d)", D, H, W, bd, bh, bw);
+  const int T = bd * bh * bw;
+  SS_UNSUPPORTED(T > 96, "ss_window_attention_core_f32: window of %d tokens unsupported (<= 96)", T);
+  const size_t smem = (size_t)3 * kC * T * sizeof(float);
+  const long long nwin = (long long)B * (D / bd) * (H / bh) * (W / bw);
+  SS_UNSUPPORTED(nwin > 0x7fffffffLL, "ss_window_attention_core_f32: too many windows");
+  SS_CUDA(ss_allow_smem(window_attention_core_f32_kernel, smem));
+  window_attention_core_f32_kernel<<<(unsigned)nwin, 256, smem, (cudaStream_t)stream>>>(qkv, reinterpret_cast<uint4*>(out_tri), D, H, W,
+                                                                                        bd, bh, bw, D / bd, H / bh, W / bw, T);
+  SS_CHECK_LAUNCH("ss_window_attention_core_f32");
+  return SS_OK;
+}
 
 extern "C" int ss_window_attention3d(const float* x, const float* wqkv_t, const float* bqkv, const float* wo_t, const float* bo,
                                      float* out, int B, int C, int D, int H, int W, int bd, int bh, int bw, int num_heads,

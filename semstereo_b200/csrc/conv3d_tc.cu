@@ -36,11 +36,11 @@ struct TcP {
   const __nv_bfloat16* residual;  // t2 only: phase-split blocked [B][8][Cout/8][D][H][W][8], or null
   const __nv_bfloat16* skip_w;    // t2 only: when set, `residual` is the INPUT of the 1x1 skip conv and this is its weight
                                   // [N/8][N][8] (BN scale folded in): the skip conv runs as one more GEMM tap on the staged tile
-  const float* acc_in;            // fp32 NCDHW partial sums (same shape as an out_mode-1 output) added to the accumulator BEFORE
+  const float* acc_in;            // fp32 partial sums in the out_mode-3 layout [B][Cout/4][D][H][W][4], added to the accumulator BEFORE
   const float* acc_in2;           // scale/shift (bf16x3 split route: the products of the other operand halves), or null
   void* out;
   long long split_off;            // != 0: bf16 outputs are written as a hi/lo pair, lo = bf16(v - hi) at out + split_off (uint4 units)
-  int out_mode;                   // 0: bf16 blocked, 1: fp32 NCDHW, 2: bf16 phase-split blocked
+  int out_mode;                   // 0: bf16 blocked, 1: fp32 NCDHW, 2: bf16 phase-split blocked, 3: fp32 [B][Cout/4][D][H][W][4]
   int cout_valid;                 // channels actually stored (Cout = n_tiles*N may be zero-padded), also the channel count of out
   int B, D, H, W;                 // tile space: output dims (s1, s2) / input dims (t2)
   int relu;
@@ -59,18 +59,34 @@ __device__ __forceinline__ void decode_item(const TcP& p, int s, int& b, int& h0
 // Applies the fused epilogue to 32 consecutive output channels (co0 ...) of one voxel and stores them.
 // (od,oh,ow) / (OD,OH,OW): output voxel and output dims.  r: the 4 residual chunks of these channels, already loaded (the
 // loads are issued BEFORE the wait on the accumulator so their latency hides behind the MMAs), or nullptr.
+// EPI (compile time, so that the plain bf16 kernels keep their register budget): bit 0 = the bf16 output may be a hi/lo pair
+// (p.split_off), bit 1 = fp32 partial sums may come in (p.acc_in*) and the fp32 [C/4][...][4] output mode 3 exists.
+template <int EPI = 0>
 __device__ __forceinline__ void epilogue_store32(const TcP& p, float (&v)[32], const float* sc, const float* sh, int co0, int b, int od,
                                                  int oh, int ow, int OD, int OH, int OW, const uint4* r) {
   const float lo = p.relu ? 0.0f : -INFINITY;
-  if (p.acc_in) {                     // partial sums of the other split products (fp32 NCDHW), added before the affine
-    const size_t OSa = (size_t)OD * OH * OW, o0 = ((size_t)b * p.cout_valid + co0) * OSa + ((size_t)od * OH + oh) * OW + ow;
+  if constexpr ((EPI & 2) != 0) {
+    const size_t OSa = (size_t)OD * OH * OW, o0 = ((size_t)b * (p.cout_valid / 4) + co0 / 4) * OSa + ((size_t)od * OH + oh) * OW + ow;
+    if (p.out_mode == 3) {            // raw partial sums out: 8 coalesced 128-bit stores (8 lanes = 128 contiguous bytes)
+      float4* o = reinterpret_cast<float4*>(p.out) + o0;
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (co0 + i < p.cout_valid) v[i] += __ldg(p.acc_in + o0 + (size_t)i * OSa);
-    if (p.acc_in2) {
+      for (int q = 0; q < 8; ++q)
+        if (co0 + 4 * q < p.cout_valid) o[(size_t)q * OSa] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      return;
+    }
+    if (p.acc_in) {                   // partial sums of the other split products, added before the affine
+      const float4* a = reinterpret_cast<const float4*>(p.acc_in) + o0;
+      const float4* a2 = p.acc_in2 ? reinterpret_cast<const float4*>(p.acc_in2) + o0 : nullptr;
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (co0 + i < p.cout_valid) v[i] += __ldg(p.acc_in2 + o0 + (size_t)i * OSa);
+      for (int q = 0; q < 8; ++q)
+        if (co0 + 4 * q < p.cout_valid) {
+          float4 t = __ldg(a + (size_t)q * OSa);
+          if (a2) {
+            const float4 u = __ldg(a2 + (size_t)q * OSa);
+            t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+          }
+          v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+        }
     }
   }
   if (r) {
@@ -127,7 +143,7 @@ __device__ __forceinline__ void epilogue_store32(const TcP& p, float (&v)[32], c
       q.z = tc::pack_bf16x2(v[8 * c8 + 4], v[8 * c8 + 5]);
       q.w = tc::pack_bf16x2(v[8 * c8 + 6], v[8 * c8 + 7]);
       o[(size_t)c8 * cs] = q;
-      if (p.split_off) {              // lo half of the bf16x3 split: what bf16 rounding of the value lost
+      if ((EPI & 1) != 0 && p.split_off) {      // lo half of the bf16x3 split: what bf16 rounding of the value lost
         const uint32_t u[4] = {q.x, q.y, q.z, q.w};
         uint32_t l[4];
 #pragma unroll
@@ -176,7 +192,7 @@ constexpr uint32_t tmem_cols_for(int n2) { return n2 <= 32 ? 32 : n2 <= 64 ? 64 
 // =====================================================================================================================
 // s1: Conv3d k3 s1 p1 (TAPS = 27) / Conv3d k1 (TAPS = 1).  NWS == TAPS -> weights resident, else streamed tap ring.
 // =====================================================================================================================
-template <int CIN, int N, int NS, int NWS, int TAPS>
+template <int CIN, int N, int NS, int NWS, int TAPS, int EPI = 0>
 __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_constant__ CUtensorMap tmA, const TcP p) {
   constexpr bool kResident = (NWS == TAPS);
   constexpr bool k3 = (TAPS == 27);            // taps along the depth axis
@@ -319,7 +335,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_const
             tc::mbar_arrive(&acc_empty[as]);
           }
           if (!valid || nt * N + j * 32 >= p.cout_valid) continue;
-          epilogue_store32(p, v, s_scale + j * 32, s_shift + j * 32, nt * N + j * 32, b, d_out, h, w, p.D, p.H, p.W, nullptr);
+          epilogue_store32<EPI>(p, v, s_scale + j * 32, s_shift + j * 32, nt * N + j * 32, b, d_out, h, w, p.D, p.H, p.W, nullptr);
         }
       }
     }
@@ -493,7 +509,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1f_kernel(const __grid_cons
             tc::mbar_arrive(&acc_empty[blk]);
           }
           if (!valid) continue;
-          epilogue_store32(p, v, s_scale + j * 32, s_shift + j * 32, j * 32, b, d_out, h, w, p.D, p.H, p.W, nullptr);
+          epilogue_store32<SP ? 1 : 0>(p, v, s_scale + j * 32, s_shift + j * 32, j * 32, b, d_out, h, w, p.D, p.H, p.W, nullptr);
         }
       }
     }
@@ -733,7 +749,7 @@ __global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_con
 // s2: Conv3d k3 s2 p1 on the phase-split input.  A staged slice = (d-phase pd, half-res depth d') = 4 (h,w)-phase halo tiles.
 // Per output depth d the slice uses are, in order: (1,d-1) [kd=0], (0,d) [kd=1], (1,d) [kd=2, kept for d+1's kd=0].
 // =====================================================================================================================
-template <int CIN, int N, int NS, int NWS, bool SP = false>      // SP: in-kernel bf16x3 split, see the s1f kernel
+template <int CIN, int N, int NS, int NWS, bool SP = false, int EPI = 0>      // SP: in-kernel bf16x3 split, see the s1f kernel
 __global__ void __launch_bounds__(256, 1) conv3d_tc_s2_kernel(const __grid_constant__ CUtensorMap tmA, const TcP p) {
   constexpr bool kResident = (NWS == 27);
   constexpr int C8 = CIN / 8;
@@ -870,7 +886,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s2_kernel(const __grid_const
             tc::mbar_arrive(&acc_empty[as]);
           }
           if (!valid || nt * N + j * 32 >= p.cout_valid) continue;
-          epilogue_store32(p, v, s_scale + j * 32, s_shift + j * 32, nt * N + j * 32, b, d_out, h, w, p.D, p.H, p.W, nullptr);
+          epilogue_store32<(SP ? 1 : 0) | EPI>(p, v, s_scale + j * 32, s_shift + j * 32, nt * N + j * 32, b, d_out, h, w, p.D, p.H, p.W, nullptr);
         }
       }
     }
@@ -885,7 +901,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s2_kernel(const __grid_const
 // RS = depth of the ring that prefetches the skip-connection tiles (one TH x TW x N tile per output phase) by TMA: the layer
 // is memory-heavy (it reads a full-resolution residual and writes a full-resolution output per 27/8 taps of math), and 128
 // epilogue threads issuing just-in-time loads cannot keep enough bytes in flight; the ring keeps RS tiles ahead.
-template <int CIN, int N, int NS, int NWS, int RS, bool SP = false>      // SP: in-kernel bf16x3 split, see the s1f kernel
+template <int CIN, int N, int NS, int NWS, int RS, bool SP = false, int EPI = 0>      // SP: in-kernel bf16x3 split, see the s1f kernel
 __global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmRes, const TcP p) {
   constexpr bool kResident = (NWS == 27);
@@ -1105,7 +1121,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_const
             }
             const int co0 = nt * N + j * 32;
             if (!valid || co0 >= p.cout_valid) continue;
-            epilogue_store32(p, v, s_scale + j * 32, s_shift + j * 32, co0, b, 2 * i + pd, 2 * h + ph, 2 * w + pw, 2 * p.D, 2 * p.H,
+            epilogue_store32<(SP ? 1 : 0) | EPI>(p, v, s_scale + j * 32, s_shift + j * 32, co0, b, 2 * i + pd, 2 * h + ph, 2 * w + pw, 2 * p.D, 2 * p.H,
                              2 * p.W, use_res ? rpre[j] : nullptr);
           }
         }
@@ -1116,9 +1132,11 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_t2_kernel(const __grid_const
 
 // ---- layout converters ----------------------------------------------------------------------------------------------
 // fp32 NCDHW -> bf16 blocked [B][C/8][D][H][W][8], or (s2d) phase-split [B][8][C/8][D/2][H/2][W/2][8]
-// split_off != 0: hi/lo pair of the bf16x3 split route, lo = bf16(x - hi) written split_off uint4 further ([2][B]... stacking)
+// split_off != 0: hi/lo pair of the bf16x3 split route, lo = bf16(x - hi) written split_off uint4 further ([2][B]... stacking).
+// tri != 0 (not with s2d): channel-stacked K-concat form [hi | lo | hi] with 3*C/8 chunks per sample, for 1x1 convs that run the
+// three split products as ONE GEMM with K = 3*C against the weights [w_hi | w_hi | w_lo].
 __global__ void __launch_bounds__(256) to_blocked_kernel(const float* __restrict__ in, uint4* __restrict__ out, int C, int D, int H,
-                                                         int W, int s2d, size_t split_off) {
+                                                         int W, int s2d, size_t split_off, int tri) {
   const size_t S = (size_t)D * H * W;
   const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // voxel within (D,H,W)
   if (v >= S) return;
@@ -1131,7 +1149,11 @@ __global__ void __launch_bounds__(256) to_blocked_kernel(const float* __restrict
   q.x = tc::pack_bf16x2(f[0], f[1]); q.y = tc::pack_bf16x2(f[2], f[3]);
   q.z = tc::pack_bf16x2(f[4], f[5]); q.w = tc::pack_bf16x2(f[6], f[7]);
   size_t o;
-  if (!s2d) o = ((size_t)b * (C / 8) + chunk) * S + v;
+  if (tri) {
+    o = ((size_t)b * 3 * (C / 8) + chunk) * S + v;
+    out[o + 2 * (size_t)(C / 8) * S] = q;
+    split_off = (size_t)(C / 8) * S;
+  } else if (!s2d) o = ((size_t)b * (C / 8) + chunk) * S + v;
   else {
     const int x = (int)(v % W), y = (int)((v / W) % H), d = (int)(v / ((size_t)W * H));
     const int phase = ((d & 1) << 2) | ((y & 1) << 1) | (x & 1);
@@ -1225,11 +1247,11 @@ int launch_tc(K kernel, size_t smem, const CUtensorMap& tm, TcP p, double halo_c
   return SS_OK;
 }
 
-template <int CIN, int N, int NS, int NWS, int TAPS>
+template <int CIN, int N, int NS, int NWS, int TAPS, int EPI = 0>
 int launch_s1(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
   constexpr size_t smem = (size_t)NS * (CIN / 8) * TILE_B + (size_t)NWS * CIN * N * 2;
   static_assert(smem <= 227 * 1024 - 2048, "shared memory budget");
-  return launch_tc(conv3d_tc_s1_kernel<CIN, N, NS, NWS, TAPS>, smem, tm, p, TAPS == 27 ? 0.35 : 0.0, st, "ss_conv3d_tc(s1)");
+  return launch_tc(conv3d_tc_s1_kernel<CIN, N, NS, NWS, TAPS, EPI>, smem, tm, p, TAPS == 27 ? 0.35 : 0.0, st, "ss_conv3d_tc(s1)");
 }
 template <int CIN, int N, int NS, int NWS, bool SP = false>
 int launch_s1f(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
@@ -1237,13 +1259,13 @@ int launch_s1f(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
   static_assert(smem <= 227 * 1024 - 2048, "shared memory budget");
   return launch_tc(conv3d_tc_s1f_kernel<CIN, N, NS, NWS, SP>, smem, tm, p, 1.4, st, "ss_conv3d_tc(s1f)");
 }
-template <int CIN, int N, int NS, int NWS, bool SP = false>
+template <int CIN, int N, int NS, int NWS, bool SP = false, int EPI = 0>
 int launch_s2(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
   constexpr size_t smem = (SP ? 2 : 1) * ((size_t)NS * 4 * (CIN / 8) * TILE_B + (size_t)NWS * CIN * N * 2);
   static_assert(smem <= 227 * 1024 - 2048, "shared memory budget");
-  return launch_tc(conv3d_tc_s2_kernel<CIN, N, NS, NWS, SP>, smem, tm, p, 0.4, st, "ss_conv3d_tc(s2)");
+  return launch_tc(conv3d_tc_s2_kernel<CIN, N, NS, NWS, SP, EPI>, smem, tm, p, 0.4, st, "ss_conv3d_tc(s2)");
 }
-template <int CIN, int N, int NS, int NWS, int RS, bool SP = false>
+template <int CIN, int N, int NS, int NWS, int RS, bool SP = false, int EPI = 0>
 int launch_t2(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
   constexpr size_t smem = (SP ? 2 : 1) * ((size_t)NS * (CIN / 8) * TILE_B + (size_t)NWS * CIN * N * 2 + (size_t)RS * (N / 8) * TH * TW * 16 + (size_t)N * N * 2);
   static_assert(smem <= 227 * 1024 - 2048, "shared memory budget");
@@ -1263,7 +1285,7 @@ int launch_t2(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
       return SS_ERR_CUDA;
     }
   }
-  auto kernel = conv3d_tc_t2_kernel<CIN, N, NS, NWS, RS, SP>;
+  auto kernel = conv3d_tc_t2_kernel<CIN, N, NS, NWS, RS, SP, EPI>;
   SS_CUDA(ss_allow_smem(kernel, smem));
   TcP q = p;
   int grid;
@@ -1351,15 +1373,22 @@ extern "C" int ss_conv3d_tc_ex(int kind, const void* in_blocked, const void* wei
                  "ss_conv3d_tc: no in-kernel split configuration for kind %d (Cin=%d, Cout=%d); use the two-launch route", kind, Cin, Cout);
   SS_REQUIRE(!in_split || !residual_s2d_or_null || skip_weight_or_null, "ss_conv3d_tc: the split route adds the skip only through the fused skip conv");
   SS_REQUIRE(acc_in_or_null || !acc_in2_or_null, "ss_conv3d_tc: acc_in2 needs acc_in");
-  SS_REQUIRE(!out_split || out_mode != 1, "ss_conv3d_tc: a split (hi/lo) output exists only for the bf16 layouts");
+  SS_REQUIRE(!out_split || out_mode == 0 || out_mode == 2, "ss_conv3d_tc: a split (hi/lo) output exists only for the bf16 layouts");
   SS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && Cout > 0, "ss_conv3d_tc: non-positive dimension");
   const int N = ss_conv3d_tc_ntile(kind, Cin, Cout);
   SS_UNSUPPORTED(N == 0, "ss_conv3d_tc: kind %d with (Cin=%d, Cout=%d) has no tensor-core configuration", kind, Cin, Cout);
   SS_REQUIRE((reinterpret_cast<uintptr_t>(in_blocked) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(weight_packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual_s2d_or_null) & 15) == 0,
              "ss_conv3d_tc: pointers must be 16-byte aligned");
-  SS_REQUIRE(out_mode >= 0 && out_mode <= 2, "ss_conv3d_tc: out_mode must be 0, 1 or 2");
-  SS_REQUIRE(out_mode == 1 || Cout % 8 == 0, "ss_conv3d_tc: a bf16 blocked output needs Cout %% 8 == 0");
+  SS_REQUIRE(out_mode >= 0 && out_mode <= 3, "ss_conv3d_tc: out_mode must be 0, 1, 2 or 3");
+  SS_REQUIRE(out_mode == 1 || Cout % 8 == 0, "ss_conv3d_tc: a blocked output needs Cout %% 8 == 0");
+  // the fp32 partial-sum hooks (two-launch split route) are compiled only into the kernels of the layers that need them
+  const bool ex = acc_in_or_null || out_mode == 3 || (out_split && !in_split);
+  SS_UNSUPPORTED(ex && !(!in_split && ((kind == 0 && Cin == 128 && Cout == 128) || (kind == 2 && Cin == 64 && Cout == 128) ||
+                                      (kind == 3 && Cin == 128 && Cout == 64))),
+                 "ss_conv3d_tc: partial-sum hooks / out_mode 3 exist only for the 128-channel layers (kind %d, Cin=%d, Cout=%d)", kind, Cin, Cout);
+  SS_REQUIRE((reinterpret_cast<uintptr_t>(acc_in_or_null) & 15) == 0 && (reinterpret_cast<uintptr_t>(acc_in2_or_null) & 15) == 0,
+             "ss_conv3d_tc: partial sums must be 16-byte aligned");
   SS_REQUIRE(!gate_blocked_or_null || Cout % 8 == 0, "ss_conv3d_tc: the blocked gate needs Cout %% 8 == 0");
   SS_REQUIRE(out_mode != 2 || (kind != 3 && ((kind == 2 ? D / 2 : D) % 2 == 0) && ((kind == 2 ? H / 2 : H) % 2 == 0) &&
                                ((kind == 2 ? W / 2 : W) % 2 == 0)),
@@ -1405,14 +1434,14 @@ extern "C" int ss_conv3d_tc_ex(int kind, const void* in_blocked, const void* wei
     case 0:
       if (Cin == 32) return launch_s1<32, 32, 8, 27, 27>(tm, p, st);
       if (Cin == 64) return launch_s1<64, 32, 5, 27, 27>(tm, p, st);
-      return launch_s1<128, 128, 3, 2, 27>(tm, p, st);
+      return ex ? launch_s1<128, 128, 3, 2, 27, 3>(tm, p, st) : launch_s1<128, 128, 3, 2, 27>(tm, p, st);
     case 1:
       if (Cin == 32) return launch_s1<32, 32, 4, 1, 1>(tm, p, st);
       if (Cin == 64) return N == 64 ? launch_s1<64, 64, 4, 1, 1>(tm, p, st) : launch_s1<64, 32, 4, 1, 1>(tm, p, st);
       return N == 128 ? launch_s1<128, 128, 4, 1, 1>(tm, p, st) : launch_s1<128, 64, 4, 1, 1>(tm, p, st);
     case 2:
       if (Cin == 32) return launch_s2<32, 64, 2, 27>(tm, p, st);
-      return launch_s2<64, 128, 2, 2>(tm, p, st);
+      return ex ? launch_s2<64, 128, 2, 2, false, 3>(tm, p, st) : launch_s2<64, 128, 2, 2>(tm, p, st);
     case 4:
       if (Cin == 128) return launch_s1<128, 64, 3, 2, 9>(tm, p, st);
       return launch_s1<64, 32, 4, 9, 9>(tm, p, st);
@@ -1422,7 +1451,7 @@ extern "C" int ss_conv3d_tc_ex(int kind, const void* in_blocked, const void* wei
       if (Cin == 32 && Cout == 64) return launch_s1f<32, 64, 6, 9>(tm, p, st);
       return launch_s1f<64, 64, 4, 4>(tm, p, st);
     default:
-      if (Cin == 128) return launch_t2<128, 64, 3, 2, 2>(tm, p, st);
+      if (Cin == 128) return ex ? launch_t2<128, 64, 3, 2, 2, false, 3>(tm, p, st) : launch_t2<128, 64, 3, 2, 2>(tm, p, st);
       return launch_t2<64, 32, 3, 27, 4>(tm, p, st);
   }
 }
@@ -1489,10 +1518,11 @@ extern "C" int ss_to_blocked_bf16_ex(const float* in_ncdhw, void* out_blocked, i
   SS_REQUIRE(in_ncdhw && out_blocked && B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "ss_to_blocked_bf16: bad argument");
   SS_REQUIRE(C % 8 == 0, "ss_to_blocked_bf16: C=%d must be a multiple of 8", C);
   SS_REQUIRE(!s2d || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "ss_to_blocked_bf16: phase-split layout needs even dims");
+  SS_REQUIRE(split >= 0 && split <= 2 && !(split == 2 && s2d), "ss_to_blocked_bf16: split must be 0, 1 or 2 (2 not with s2d)");
   SS_UNSUPPORTED(C / 8 > 65535 || B > 65535, "ss_to_blocked_bf16: grid dimension exceeds 65535");
   const size_t S = (size_t)D * H * W;
   to_blocked_kernel<<<dim3((unsigned)ceil_div64(S, 256), C / 8, B), 256, 0, (cudaStream_t)stream>>>(
-      in_ncdhw, reinterpret_cast<uint4*>(out_blocked), C, D, H, W, s2d, split ? (size_t)B * (C / 8) * S : (size_t)0);
+      in_ncdhw, reinterpret_cast<uint4*>(out_blocked), C, D, H, W, s2d, split == 1 ? (size_t)B * (C / 8) * S : (size_t)0, split == 2);
   SS_CHECK_LAUNCH("ss_to_blocked_bf16");
   return SS_OK;
 }

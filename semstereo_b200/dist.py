@@ -46,31 +46,44 @@ def init_from_env(backend: str | None = None):
     return rank, local, world
 
 
-def gather_batch(local_out: torch.Tensor, batch: int, group=None) -> torch.Tensor:
-    """All ranks receive the full (batch, ...) tensor assembled from per-rank shards made by `shard_bounds`."""
+def gather_batch(local_out: torch.Tensor, batch: int, group=None, dst: int | None = None):
+    """Assembles the full (batch, ...) tensor from the per-rank shards made by `shard_bounds`.  dst=None: every rank receives it
+    (all-gather); dst=r: only rank r does (what nn.DataParallel's gather to device 0 does, main_us3d.py:100) and the other
+    ranks return None -- 1/N of the all-gather's traffic per link.  A rank whose shard is empty (batch < world) passes a
+    zero-length `local_out` of the right trailing shape."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return local_out
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     sizes = [shard_bounds(batch, r, world)[1] - shard_bounds(batch, r, world)[0] for r in range(world)]
-    if len(set(sizes)) == 1:
-        out = local_out.new_empty((batch,) + tuple(local_out.shape[1:]))
-        dist.all_gather_into_tensor(out, local_out.contiguous(), group=group)
-        return out
-    # ragged split: pad every shard to the largest one, gather, trim (collectives need equal sizes)
+    tail = tuple(local_out.shape[1:])
+    if local_out.shape[0] != sizes[rank]:
+        raise ValueError(f"gather_batch: rank {rank} holds {local_out.shape[0]} samples, its shard of a batch of {batch} has {sizes[rank]}")
+    even = len(set(sizes)) == 1
     smax = max(sizes)
-    padded = local_out.new_zeros((smax,) + tuple(local_out.shape[1:]))
-    padded[: sizes[rank]] = local_out
-    out = local_out.new_empty((world * smax,) + tuple(local_out.shape[1:]))
-    dist.all_gather_into_tensor(out, padded, group=group)
-    return torch.cat([out[r * smax: r * smax + sizes[r]] for r in range(world)], 0)
+    if even:
+        send = local_out.contiguous()
+    else:       # ragged split: pad every shard to the largest one, gather, trim (collectives need equal sizes)
+        send = local_out.new_zeros((smax,) + tail)
+        send[: sizes[rank]] = local_out
+    if dst is None:
+        out = local_out.new_empty((world * smax,) + tail)
+        dist.all_gather_into_tensor(out, send, group=group)
+    else:
+        out = local_out.new_empty((world * smax,) + tail) if rank == dst else None
+        dist.gather(send, list(out.split(smax)) if rank == dst else None, dst=dist.get_global_rank(group, dst) if group is not None else dst,
+                    group=group)
+        if rank != dst:
+            return None
+    return out if even else torch.cat([out[r * smax: r * smax + sizes[r]] for r in range(world)], 0)
 
 
 class ShardedHotPath:
     """Runs `path` (a DisparityHotPath on this rank's device) on this rank's slice of a global batch and gathers the
     full-resolution disparity.  `inputs` may be the global batch (it is sliced here) or already the local shard."""
 
-    def __init__(self, path, group=None):
-        self.path, self.group = path, group
+    def __init__(self, path, group=None, dst: int | None = None):
+        """dst: None = all-gather (every rank gets the result); r = gather to rank r only (DataParallel semantics)."""
+        self.path, self.group, self.dst = path, group, dst
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
 
@@ -79,9 +92,15 @@ class ShardedHotPath:
         if not presharded:
             global_batch = inputs[order[0]].shape[0]
             inputs = {k: shard(inputs[k], self.rank, self.world) for k in order if inputs.get(k) is not None}
-        out = self.path(*[inputs.get(k) for k in order])
-        key = "pred_att_up" if self.path.att_weights_only else "pred_up"
-        return gather_batch(out[key], global_batch, self.group)
+        elif global_batch is None:
+            raise ValueError("ShardedHotPath: presharded inputs need global_batch")
+        spx = inputs["spx_pred"]
+        if spx.shape[0] == 0:       # batch < world: this rank has nothing to compute but still takes part in the collective
+            local = spx.new_empty((0,) + tuple(spx.shape[-2:]))
+        else:
+            key = "pred_att_up" if self.path.att_weights_only else "pred_up"
+            local = self.path(*[inputs.get(k) for k in order])[key]
+        return gather_batch(local, global_batch, self.group, self.dst)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

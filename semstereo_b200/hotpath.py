@@ -106,7 +106,7 @@ def pack_ssr(ssr: nn.Module) -> torch.Tensor:
 
 class DisparityHotPath(nn.Module):
     def __init__(self, maxdisp: int, att_weights_only: bool = False, signed: bool = True, num_classes: int = 6,
-                 precision: str = "fp32"):
+                 precision: str = "split"):
         """precision:
         "fp32"  = everything on the fp32 pipe (FFMA; the slow parity mode);
         "bf16"  = every conv and the window attention on the tensor cores with bf16 operands and fp32 accumulation;
@@ -175,7 +175,7 @@ class DisparityHotPath(nn.Module):
 
     def _is_split(self, name: str) -> bool:
         """bf16x3 split route (fp32-accurate tensor-core products): the 3-D stack of the attention branch in "split" mode."""
-        return self.precision == "split" and name.startswith(("hourglass_att", "classif_att_"))
+        return self.precision == "split" and name.startswith(self._ATT_BRANCH)
 
     def _apply(self, fn, *a, **k):
         self._cache = None
@@ -240,6 +240,9 @@ class DisparityHotPath(nn.Module):
             c[hg + ".bqkv"] = a.qkv_3d.bias.detach().float().contiguous()
             c[hg + ".wo_t"] = a.final1x1.weight.detach().float().reshape(a.final1x1.out_channels, -1).t().contiguous()
             c[hg + ".bo"] = a.final1x1.bias.detach().float().contiguous()
+            if self._is_split(hg):          # fp32-accurate projections as K-concat GEMMs (ops_tc.pointwise_split)
+                c[hg + ".attn_qkv.tri"] = tc.pack_pointwise_split(a.qkv_3d.weight)
+                c[hg + ".attn_out.tri"] = tc.pack_pointwise_split(a.final1x1.weight)
             if bf16:
                 c[hg + ".attn_qkv.tc"] = tc.pack_weight(a.qkv_3d.weight.detach().float().reshape(384, 128, 1, 1, 1), tc.K1)
                 c[hg + ".attn_qkv.shift"] = c[hg + ".bqkv"]
@@ -265,6 +268,8 @@ class DisparityHotPath(nn.Module):
             if self._is_bf16(ca):
                 c[ca + ".tc0"] = tc.pack_weight2d(w0, tc.CONV1)
                 c[ca + ".tc1"] = tc.pack_weight2d(w1, tc.CONV1)
+            elif self._is_split(ca):
+                c[ca + ".tri0"], c[ca + ".tri1"] = tc.pack_pointwise_split(w0), tc.pack_pointwise_split(w1)
         cf0, cf1 = self.concat_feature[0], self.concat_feature[1]
         c["cf0.scale"], c["cf0.shift"] = bn_affine(cf0.bn)
         if self._is_bf16("concat_feature"):
@@ -304,6 +309,10 @@ class DisparityHotPath(nn.Module):
                 xb = im_blocked.view(B, C // 8, H, W, 8) if im_blocked is not None else tc.to_blocked2d(im)
                 y = tc.conv2d_tc(tc.CONV1, xb, c[name + ".tc0"], C // 2, c[name + ".s0"], c[name + ".t0"], relu=True)
                 return tc.conv2d_tc(tc.CONV1, y, c[name + ".tc1"], 32, None, c[name + ".b1"], out_f32=True)
+        if self._is_split(name):       # fp32-accurate on the tensor cores: each 1x1 conv is one GEMM over the [hi | lo | hi] K-concat form
+            with ops.label(name):
+                y = tc.pointwise_split(tc.to_blocked_tri(im), c[name + ".tri0"], im.shape[1] // 2, c[name + ".s0"], c[name + ".t0"], relu=True)
+                return tc.pointwise_split(tc.to_blocked_tri(y), c[name + ".tri1"], 32, None, c[name + ".b1"])
         y = ops.pointwise_conv2d(im, c[name + ".w0"], c[name + ".s0"], c[name + ".t0"], relu=True)
         return ops.pointwise_conv2d(y, c[name + ".w1"], None, c[name + ".b1"], relu=False)
 
@@ -358,9 +367,14 @@ class DisparityHotPath(nn.Module):
         c2s = self._tcs(c, hg + ".conv2", c1, 64, out_mode=tc.S2D)
         c3 = self._tcs(c, hg + ".conv3", c2s, 128)
         c4 = self._tcs(c, hg + ".conv4", c3, 128, out_mode=tc.F32)                 # fp32 NCDHW for the fp32 attention block
+        # attention_block (submodule_other.py:805-837): qkv Linear and final 1x1x1 conv as fp32-accurate K-concat GEMMs (a volume is
+        # a 2-D image of D*H rows for a 1x1 conv), the fp32 softmax core in between writes the K-concat form directly
         with ops.label(hg + ".attention"):
-            c4 = ops.window_attention3d(c4, c[hg + ".wqkv_t"], c[hg + ".bqkv"], c[hg + ".wo_t"], c[hg + ".bo"], block, 16)
-            c4b = tc.to_blocked_bf16(c4, split=True)
+            B, C, D, H, W = c4.shape
+            qkv = tc.pointwise_split(tc.to_blocked_tri(c4.view(B, C, D * H, W)), c[hg + ".attn_qkv.tri"], 3 * C, None, c[hg + ".bqkv"])
+            att = tc.window_attention_core_f32(qkv.view(B, 3 * C, D, H, W), block, 16)
+            c4 = tc.pointwise_split(att.view(B, 3 * C // 8, D * H, W, 8), c[hg + ".attn_out.tri"], C, None, c[hg + ".bo"])
+            c4b = tc.to_blocked_bf16(c4.view(B, C, D, H, W), split=True)
         with ops.label(hg + ".conv5"):
             c5 = tc.conv3d_tc_split(tc.T2, c4b, c[hg + ".conv5.ftcs"], 64, None, c[hg + ".conv5.fshift"], residual_s2d=c2s,
                                     skip_split=c[hg + ".conv5.skipws"], relu=True)

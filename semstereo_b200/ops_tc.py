@@ -32,6 +32,28 @@ def to_blocked_bf16(x, s2d=False, split=False):
     return out
 
 
+def to_blocked_tri(x):
+    """fp32 (B,C,H,W) -> bf16 (B, 3C/8, H, W, 8) = [hi | lo | hi] chunks: the K-concat operand of pointwise_split."""
+    dev = _require_cuda(x)
+    B, C, H, W = x.shape
+    out = torch.empty((B, 3 * C // 8, H, W, 8), device=dev, dtype=torch.bfloat16)
+    _call("ss_to_blocked_bf16_ex", dev, _ptr(x), _ptr(out), B, C, 1, H, W, 0, 2)
+    return out
+
+
+def pack_pointwise_split(w):
+    """1x1 conv weight (Cout,Cin[,1,1[,1]]) fp32 -> the CONV1 packing of [w_hi | w_hi | w_lo] (K = 3*Cin) for pointwise_split."""
+    w = w.detach().float().reshape(w.shape[0], -1)
+    hi, lo = split_f32(w)
+    return pack_weight2d(torch.cat((hi, hi, lo), 1).reshape(w.shape[0], -1, 1, 1), CONV1)
+
+
+def pointwise_split(x_tri, w_tri, cout, scale=None, shift=None, relu=False):
+    """fp32-accurate 1x1 convolution on the tensor cores: x_tri from to_blocked_tri (or a kernel that writes that form), w_tri
+    from pack_pointwise_split; one GEMM with K = 3*Cin = x_hi*w_hi + x_lo*w_hi + x_hi*w_lo.  Returns fp32 (B,Cout,H,W)."""
+    return conv2d_tc(CONV1, x_tri, w_tri, cout, scale, shift, relu=relu, out_f32=True)
+
+
 def from_blocked_bf16(xb):
     dev = _require_bf16(xb, 6)
     B, C8, D, H, W, _ = xb.shape
@@ -128,6 +150,20 @@ def window_attention_core(qkv_blocked, block, num_heads=16):
     return out
 
 
+def window_attention_core_f32(qkv, block, num_heads=16):
+    """fp32 softmax(q k^T * hd^-0.5) v per (window, head): qkv fp32 (B,3C,D,H,W) -> bf16 (B,3C/8,D,H,W,8) in the [hi | lo | hi]
+    K-concat form (the operand of pointwise_split for the final 1x1x1 conv)."""
+    dev = _require_cuda(qkv)
+    B, C3, D, H, W = qkv.shape
+    if C3 % 3:
+        raise ValueError("window_attention_core_f32: qkv must have 3*C channels")
+    C = C3 // 3
+    out = torch.empty((B, 3 * C // 8, D, H, W, 8), device=dev, dtype=torch.bfloat16)
+    _call("ss_window_attention_core_f32", dev, _ptr(qkv), _ptr(out), B, C, D, H, W, int(block[0]), int(block[1]), int(block[2]),
+          int(num_heads))
+    return out
+
+
 def pack_head_weight(w):
     """(1,32,3,3,3) fp32 -> bf16 [4][48][8]: rows j*16 + t9 (depth tap kd = 2 - j, 9 in-plane taps + 7 zero rows), K-major chunks
     of 8 input channels (csrc/conv3d_tc_head.cu)."""
@@ -155,7 +191,7 @@ def conv3d_tc_head(xb, w_head, acc_in=None, acc_in2=None, in_split=False):
     return out
 
 
-BLOCKED, F32, S2D = 0, 1, 2          # out_mode of ss_conv3d_tc
+BLOCKED, F32, S2D, F32B4 = 0, 1, 2, 3          # out_mode of ss_conv3d_tc (F32B4: fp32 (B,Cout/4,D,H,W,4), the partial-sum layout)
 
 
 def pack_skip_weight(w, scale=None):
@@ -215,7 +251,7 @@ def conv3d_tc_split(kind, xs, w_split, cout, scale=None, shift=None, gate_blocke
     if w_both is not None:
         return conv3d_tc(kind, xs, w_both, cout, scale, shift, gate_blocked, residual_s2d, relu=relu, out_mode=out_mode,
                          skip_weight=s_both, out_split=out_mode != F32, in_split=True)
-    part = conv3d_tc(kind, xs, w_hi, cout, residual_s2d=residual_s2d, skip_weight=s_hi, out_mode=F32)
+    part = conv3d_tc(kind, xs, w_hi, cout, residual_s2d=residual_s2d, skip_weight=s_hi, out_mode=F32B4)
     return conv3d_tc(kind, xs[:B], w_lo, cout, scale, shift, gate_blocked, None if residual_s2d is None else residual_s2d[:B],
                      relu=relu, out_mode=out_mode, skip_weight=s_lo, acc_in=part[:B], acc_in2=part[B:], out_split=out_mode != F32)
 
@@ -255,15 +291,15 @@ def conv3d_tc(kind, xb, w_tc, cout, scale=None, shift=None, gate_blocked=None, r
             raise ValueError("conv3d_tc: residual must be phase-split (B,8,Cout/8,D,H,W,8) at the transposed layer's input dims")
     for a in (acc_in, acc_in2):
         if a is not None and (_require_cuda(a) != dev or a.dtype != torch.float32 or not a.is_contiguous()
-                              or tuple(a.shape) != (B, cout, Do, Ho, Wo)):
-            raise ValueError("conv3d_tc: acc_in must be a contiguous fp32 (B,Cout,Do,Ho,Wo) tensor")
+                              or tuple(a.shape) != (B, cout // 4, Do, Ho, Wo, 4)):
+            raise ValueError("conv3d_tc: acc_in must be a contiguous fp32 (B,Cout/4,Do,Ho,Wo,4) tensor (out_mode F32B4)")
     if acc_in2 is not None and acc_in is None:
         raise ValueError("conv3d_tc: acc_in2 needs acc_in")
     nb = 2 * B if out_split else B
-    if out_mode == F32:
+    if out_mode in (F32, F32B4):
         if out_split:
             raise ValueError("conv3d_tc: a split output exists only for the bf16 layouts")
-        out = torch.empty((B, cout, Do, Ho, Wo), device=dev, dtype=torch.float32)
+        out = torch.empty((B, cout, Do, Ho, Wo) if out_mode == F32 else (B, cout // 4, Do, Ho, Wo, 4), device=dev, dtype=torch.float32)
     elif out_mode == S2D:
         out = torch.empty((nb, 8, cout // 8, Do // 2, Ho // 2, Wo // 2, 8), device=dev, dtype=torch.bfloat16)
     else:

@@ -13,8 +13,44 @@ import torch.nn as nn
 from . import hotpath, ops
 
 
+_PRECISION = "fp32"
+
+
+def set_precision(mode: str) -> None:
+    """Arithmetic of the 3-D modules of the surface (convbn_3d, BasicConv(is_3d), attention_block):
+    "fp32" (default) = fp32 FFMA kernels, the parity mode; "bf16" = tcgen05 tensor cores with bf16 operands / fp32 accumulation
+    for every layer geometry that has a tensor-core configuration (others stay fp32).  The free functions are always fp32."""
+    global _PRECISION
+    if mode not in ("fp32", "bf16"):
+        raise ValueError("surface precision must be 'fp32' or 'bf16'")
+    _PRECISION = mode
+
+
 def _c(t):
     return t.contiguous().float()
+
+
+class _Packed:
+    """Per-module cache of folded / packed weights.  Keyed by the identity and in-place version of every tensor it was built
+    from, so load_state_dict (in-place copy -> version bump), .to()/.cuda() (new storage) and optimizer steps all invalidate it."""
+
+    def __init__(self):
+        self.key, self.val = None, {}
+
+    def get(self, tensors, name, build):
+        key = tuple((t.data_ptr(), t._version, t.device) for t in tensors)
+        if key != self.key:
+            self.key, self.val = key, {}
+        if name not in self.val:
+            self.val[name] = build()
+        return self.val[name]
+
+
+def _no_grad_path(mod, *inputs):
+    """The fused inference kernels record no autograd graph: refuse instead of silently returning zero gradients."""
+    if torch.is_grad_enabled() and (any(t.requires_grad for t in inputs) or (mod.training and any(p.requires_grad for p in mod.parameters()))):
+        raise NotImplementedError(f"{type(mod).__name__} (B200 path) is inference-only: call it under torch.no_grad() / .eval() "
+                                  "(the training closure is BASELINE config #5, see DESIGN.md)")
 
 
 def _grad(*ts):
@@ -119,26 +155,52 @@ def make_surface(signed: bool) -> dict:
             super().__init__(num_classes)
             self.num_classes = num_classes
 
-        @torch.no_grad()
         def forward(self, depth_low, weights, pred_label):
             if self.training:
                 raise NotImplementedError("SSR_upsample (B200 path) folds eval-mode BatchNorm; call .eval()")
-            return ops.ssr_upsample(_c(depth_low), _c(weights), _c(pred_label), hotpath.pack_ssr(self))
+            _no_grad_path(self, depth_low, weights, pred_label)
+            if not hasattr(self, "_packed"):
+                object.__setattr__(self, "_packed", _Packed())
+            packed = self._packed.get(list(self.parameters()) + list(self.buffers()), "ssr", lambda: hotpath.pack_ssr(self))   # one D2H per weight change
+            with torch.no_grad():
+                return ops.ssr_upsample(_c(depth_low), _c(weights), _c(pred_label), packed)
 
     # ---- 3-D blocks (submodule_other.py:790-848, submodule.py:89-116) -----------------------------------
+    def _conv3d(mod, conv, bn, x, relu, transposed=False):
+        """Conv3d / ConvTranspose3d (+ folded eval BatchNorm, + ReLU) of a surface module through the kernels; packed weights are
+        cached on the module.  set_precision("bf16") takes the tcgen05 route where the geometry has a configuration."""
+        from . import ops_tc as tc
+        if not hasattr(mod, "_packed"):
+            object.__setattr__(mod, "_packed", _Packed())
+        src = [conv.weight] + ([bn.weight, bn.bias, bn.running_mean, bn.running_var] if bn is not None else [])
+        k, st = conv.kernel_size[0], conv.stride[0]
+        if transposed:
+            if not (conv.kernel_size == (3, 3, 3) and conv.stride == (2, 2, 2) and conv.padding == (1, 1, 1) and conv.output_padding == (1, 1, 1)):
+                raise NotImplementedError("3-D deconv (B200 path): only k3 s2 p1 op1")
+            cin, cout = conv.weight.shape[:2]
+        else:
+            if conv.kernel_size not in ((1, 1, 1), (3, 3, 3)) or conv.padding != (k // 2,) * 3 or conv.stride not in ((1, 1, 1), (2, 2, 2)):
+                raise NotImplementedError("3-D conv (B200 path): only k in {1,3}, pad=k//2, stride in {1,2}")
+            cout, cin = conv.weight.shape[:2]
+        scale, shift = mod._packed.get(src, "affine", lambda: hotpath.bn_affine(bn)) if bn is not None else (None, None)
+        x = _c(x)
+        kind = tc.T2 if transposed else (tc.K1 if k == 1 else (tc.S2 if st == 2 else tc.S1))
+        if _PRECISION == "bf16" and cin % 8 == 0 and tc.ntile(kind, cin, cout) and (kind != tc.S2 or all(v % 2 == 0 for v in x.shape[2:])):
+            w = mod._packed.get(src, "tc", lambda: tc.pack_weight(conv.weight.detach().float(), kind))
+            return tc.conv3d_tc(kind, tc.to_blocked_bf16(x, s2d=(kind == tc.S2)), w, cout, scale, shift, relu=relu, out_mode=tc.F32)
+        w = mod._packed.get(src, "f32", lambda: ops.pack_conv3d_weight(conv.weight.detach().float(), transposed))
+        return ops.conv3d_f32(x, w, scale, shift, k=k, stride=st, transposed=transposed, relu=relu)
+
     class _ConvBN3d(nn.Sequential):
         """convbn_3d: keys '0' (Conv3d) and '1' (BatchNorm3d); forward = fused conv + folded eval-BN."""
 
-        @torch.no_grad()
         def forward(self, x):
             conv, bn = self[0], self[1]
             if bn.training:
                 raise NotImplementedError("convbn_3d (B200 path) folds eval-mode BatchNorm; call .eval()")
-            k, s = conv.kernel_size[0], conv.stride[0]
-            if conv.kernel_size not in ((1, 1, 1), (3, 3, 3)) or conv.padding != (k // 2,) * 3 or conv.stride not in ((1, 1, 1), (2, 2, 2)):
-                raise NotImplementedError("convbn_3d (B200 path): only k in {1,3}, pad=k//2, stride in {1,2}")
-            scale, shift = hotpath.bn_affine(bn)
-            return ops.conv3d_f32(_c(x), ops.pack_conv3d_weight(conv.weight.detach().float()), scale, shift, k=k, stride=s)
+            _no_grad_path(self, x)
+            with torch.no_grad():
+                return _conv3d(self, conv, bn, x, relu=False)
 
     def convbn_3d(in_planes, out_planes, kernel_size, stride, pad):
         return _ConvBN3d(nn.Conv3d(in_planes, out_planes, kernel_size=kernel_size, padding=pad, stride=stride, bias=False),
@@ -149,12 +211,18 @@ def make_surface(signed: bool) -> dict:
             super().__init__(channels_3d)
             self.block, self.num_heads = block, num_heads
 
-        @torch.no_grad()
         def forward(self, x):
+            _no_grad_path(self, x)
+            if not hasattr(self, "_packed"):
+                object.__setattr__(self, "_packed", _Packed())
             f = self.final1x1
-            return ops.window_attention3d(_c(x), self.qkv_3d.weight.detach().float().t().contiguous(), self.qkv_3d.bias.detach().float(),
-                                          f.weight.detach().float().reshape(f.out_channels, -1).t().contiguous(), f.bias.detach().float(),
-                                          self.block, self.num_heads)
+            src = [self.qkv_3d.weight, self.qkv_3d.bias, f.weight, f.bias]
+            wq, bq, wo, bo = self._packed.get(src, "att", lambda: (
+                self.qkv_3d.weight.detach().float().t().contiguous(), self.qkv_3d.bias.detach().float().contiguous(),
+                f.weight.detach().float().reshape(f.out_channels, -1).t().contiguous(), f.bias.detach().float().contiguous()))
+            block = self.block if isinstance(self.block, (tuple, list)) else (self.block,) * 3
+            with torch.no_grad():
+                return ops.window_attention3d(_c(x), wq, bq, wo, bo, block, self.num_heads)
 
     class BasicConv(nn.Module):
         """BasicConv (submodule.py:89-116).  The 3-D flavours run on the B200 kernels; the 2-D flavours are outside the
@@ -180,19 +248,133 @@ def make_surface(signed: bool) -> dict:
                 return torch.relu(x) if self.relu else x
             if self.bn.training and self.use_bn:
                 raise NotImplementedError("BasicConv 3-D (B200 path) folds eval-mode BatchNorm; call .eval()")
-            conv = self.conv
-            k, s = conv.kernel_size[0], conv.stride[0]
-            scale, shift = hotpath.bn_affine(self.bn) if self.use_bn else (None, None)
+            _no_grad_path(self, x)
             with torch.no_grad():
-                if self.deconv:
-                    if not (k == 3 and s == 2 and conv.padding == (1, 1, 1) and conv.output_padding == (1, 1, 1)):
-                        raise NotImplementedError("BasicConv 3-D deconv (B200 path): only k3 s2 p1 op1")
-                    return ops.conv3d_f32(_c(x), ops.pack_conv3d_weight(conv.weight.detach().float(), True), scale, shift,
-                                          k=3, stride=2, transposed=True, relu=self.relu)
-                if conv.padding != (k // 2,) * 3 or k not in (1, 3) or s not in (1, 2):
-                    raise NotImplementedError("BasicConv 3-D (B200 path): only k in {1,3}, pad=k//2, stride in {1,2}")
-                return ops.conv3d_f32(_c(x), ops.pack_conv3d_weight(conv.weight.detach().float()), scale, shift, k=k, stride=s,
-                                      relu=self.relu)
+                return _conv3d(self, self.conv, self.bn if self.use_bn else None, x, relu=self.relu, transposed=self.deconv)
+
+    # ---- 2-D modules the reference models take from the same file (SemStereo.py:59-86, 200-211 use Conv2x and segmenthead;
+    # Fusion, DWConv2d/3d, Propagation2, Propagation_prob2, ConvSelfAttention are defined but never instantiated).  They are
+    # outside the hot path (the accelerated decoder is semstereo_b200.decoder / patch_model) and are ordinary
+    # torch modules here, with the reference's constructor signatures, state_dict keys and forward semantics, so that
+    # `from models.submodule import *` gives SemStereo.py / SemStereo_WHU.py every name they use. ----
+    class segmenthead(nn.Module):
+        """models/submodule.py:31-52: BasicConv 3x3 -> Conv2d 1x1 (+bias) -> optional bilinear upsampling by scale_factor."""
+
+        def __init__(self, inplanes, interplanes, outplanes, scale_factor=None):
+            super().__init__()
+            self.conv1 = BasicConv(inplanes, interplanes, kernel_size=3, padding=1)
+            self.conv2 = nn.Conv2d(interplanes, outplanes, kernel_size=1, padding=0, bias=True)
+            self.scale_factor = scale_factor
+
+        def forward(self, x):
+            x = self.conv1(x)
+            out = self.conv2(x)
+            if self.scale_factor is not None:
+                size = [x.shape[-2] * self.scale_factor, x.shape[-1] * self.scale_factor]
+                out = nn.functional.interpolate(out, size=size, mode="bilinear", align_corners=False)
+            return out
+
+    class Conv2x(nn.Module):
+        """models/submodule.py:119-161: stride-2 (de)conv, then concat with (or add to) the skip tensor, then a 3x3 conv."""
+
+        def __init__(self, in_channels, out_channels, deconv=False, is_3d=False, concat=True, keep_concat=True, bn=True, relu=True,
+                     keep_dispc=False):
+            super().__init__()
+            self.concat, self.is_3d = concat, is_3d
+            if deconv and is_3d and keep_dispc:
+                geo = dict(kernel_size=(1, 4, 4), stride=(1, 2, 2), padding=(0, 1, 1))
+            else:
+                geo = dict(kernel_size=((4, 4, 4) if is_3d else 4) if deconv else 3, stride=2, padding=1)
+            self.conv1 = BasicConv(in_channels, out_channels, deconv, is_3d, bn=True, relu=True, **geo)
+            c2_in = out_channels * 2 if concat else out_channels
+            c2_out = out_channels * (2 if keep_concat else 1) if concat else out_channels
+            self.conv2 = BasicConv(c2_in, c2_out, False, is_3d, bn, relu, kernel_size=3, stride=1, padding=1)
+
+        def forward(self, x, rem):
+            x = self.conv1(x)
+            if x.shape != rem.shape:
+                x = nn.functional.interpolate(x, size=(rem.shape[-2], rem.shape[-1]), mode="bilinear")
+            x = torch.cat((x, rem), 1) if self.concat else x + rem
+            return self.conv2(x)
+
+    class Fusion(nn.Module):
+        """models/submodule.py:10-29 (never instantiated by the models)."""
+
+        def __init__(self, inplanes, interplanes_x, interplanes_y, mid_channels):
+            super().__init__()
+            half = interplanes_x // 2
+            self.conv_y = nn.Sequential(nn.Conv2d(interplanes_y, half, kernel_size=1, padding=0, bias=True), nn.BatchNorm2d(half))
+            self.conv_x = nn.Sequential(nn.Conv2d(interplanes_x, half, kernel_size=1, padding=0, bias=True), nn.BatchNorm2d(half))
+            self.conv = BasicConv(interplanes_x, interplanes_x, kernel_size=3, stride=1, padding=1)
+
+        def forward(self, x, y):
+            size = x.shape[-2:]
+            y, x = self.conv_y(y), self.conv_x(x)
+            if y.shape != x.shape:
+                y = nn.functional.interpolate(y, tuple(size), mode="bilinear", align_corners=False)
+            w = torch.softmax(self.conv(torch.cat((x, y), 1)), dim=1) + 1
+            return x * w, y * w
+
+    def _dwconv(conv_cls, bn_cls):
+        class DW(nn.Module):
+            def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1):
+                super().__init__()
+                self.depthwise = conv_cls(in_channels, in_channels, kernel_size=kernel_size, stride=stride, padding=padding, groups=in_channels)
+                self.bn1 = bn_cls(in_channels)
+                self.relu = nn.ReLU(inplace=True)
+                self.pointwise = conv_cls(in_channels, out_channels, kernel_size=1, stride=1, padding=0)
+                self.bn2 = bn_cls(out_channels)
+
+            def forward(self, x):
+                return self.bn2(self.pointwise(self.relu(self.bn1(self.depthwise(x)))))
+        return DW
+
+    DWConv2d = _dwconv(nn.Conv2d, nn.BatchNorm2d)     # models/submodule.py:54-70
+    DWConv3d = _dwconv(nn.Conv3d, nn.BatchNorm3d)     # models/submodule.py:72-87
+    DWConv2d.__name__, DWConv3d.__name__ = "DWConv2d", "DWConv3d"
+
+    def _one_hot_taps(taps, radius, ndim):
+        class P(nn.Module):
+            """One-hot 5x5 tap gather with replicate padding (models/submodule.py:309-359; never instantiated by the models)."""
+
+            def forward(self, x):
+                k = 2 * radius + 1
+                f = torch.zeros((len(taps), 1) + ((1, k, k) if ndim == 3 else (k, k)), device=x.device)
+                for i, (r, c) in enumerate(taps):
+                    f[(i, 0, 0, r, c) if ndim == 3 else (i, 0, r, c)] = 1.0
+                if ndim == 3:
+                    return nn.functional.conv3d(nn.functional.pad(x, (radius,) * 4 + (0, 0), mode="replicate"), f)
+                return nn.functional.conv2d(nn.functional.pad(x, (radius,) * 4, mode="replicate"), f)
+        return P
+
+    _TAPS9 = ((0, 2), (2, 0), (2, 2), (2, 4), (4, 2), (1, 1), (3, 3), (1, 3), (3, 1))
+    Propagation2 = _one_hot_taps(_TAPS9, 2, 2)                                   # models/submodule.py:309-332
+    # Propagation_prob2 (:334-359) sets taps 0-4 twice; the later assignments ADD ones (the earlier stay set): reproduce both
+    class Propagation_prob2(nn.Module):
+        def forward(self, prob_volume):
+            f = torch.zeros(9, 1, 1, 5, 5, device=prob_volume.device)
+            for i, (r, c) in enumerate(((0, 0), (1, 1), (2, 2), (2, 0), (0, 2))):
+                f[i, 0, 0, r, c] = 1.0
+            for i, (r, c) in enumerate(_TAPS9):
+                f[i, 0, 0, r, c] = 1.0
+            return nn.functional.conv3d(nn.functional.pad(prob_volume, (2, 2, 2, 2, 0, 0), mode="replicate"), f)
+    Propagation2.__name__ = "Propagation2"
+
+    class ConvSelfAttention(nn.Module):
+        """models/submodule.py:379-410 (never instantiated by the models): global dot-product self-attention over pixels."""
+
+        def __init__(self, in_channels, out_channels):
+            super().__init__()
+            self.query_conv = nn.Conv2d(in_channels, out_channels, kernel_size=1, padding=0)
+            self.key_conv = nn.Conv2d(in_channels, out_channels, kernel_size=1, padding=0)
+            self.value_conv = nn.Conv2d(in_channels, out_channels, kernel_size=1, padding=0)
+            self.gamma = nn.Parameter(torch.zeros(1))
+
+        def forward(self, x):
+            q, k, v = self.query_conv(x), self.key_conv(x), self.value_conv(x)
+            b, c, h, w = q.shape
+            att = torch.softmax(torch.bmm(q.view(b, c, -1).permute(0, 2, 1), k.view(b, c, -1)), dim=2)
+            return self.gamma * torch.bmm(att, v.view(b, c, -1)).view(b, c, h, w) + x
 
     for k, v in list(locals().items()):
         if k not in ("ns", "signed", "dmin") and not k.startswith("_"):

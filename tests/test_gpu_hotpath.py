@@ -22,7 +22,7 @@ if torch.cuda.is_available():
 
 
 def build(maxdisp, signed, att_only, peaked, seed=1):
-    m = DisparityHotPath(maxdisp, att_only, signed)
+    m = DisparityHotPath(maxdisp, att_only, signed, precision="fp32")
     m.load_state_dict(make_params(seed=seed, peaked=peaked), strict=True)
     return m.to(DEV)
 
@@ -84,7 +84,7 @@ def test_against_oracle_other_shapes(signed, maxdisp, B, H, W):
     p = make_params(seed=9, peaked=20.0, gamma=0.1)
     inp = make_inputs(11, B, H, W)
     ref = oh.forward(p, inp, maxdisp, signed=signed, keep=True)
-    m = DisparityHotPath(maxdisp, False, signed)
+    m = DisparityHotPath(maxdisp, False, signed, precision="fp32")
     m.load_state_dict(p, strict=True)
     out = run(m.to(DEV), inp)
     same = (out["ind_k"] == ref["ind_k"]).all(dim=2)
@@ -150,7 +150,7 @@ def test_concat_feature_inside_the_path():
     oracle's concat features in, and the whole path still matches the oracle run that computes them itself."""
     p = make_params(seed=9, peaked=20.0, gamma=0.1)
     inp = make_inputs(11, 1, 128, 128)
-    m = DisparityHotPath(64, False, True)
+    m = DisparityHotPath(64, False, True, precision="fp32")
     m.load_state_dict(p, strict=True)
     m = m.to(DEV)
     cf = m._concat_feature(m._packed(), inp["f4_l"].to(DEV)).cpu()
@@ -193,7 +193,7 @@ def test_other_disparity_ranges(signed, maxdisp):
     p = make_params(seed=9, peaked=20.0, gamma=0.1)
     inp = make_inputs(13, 1, 128, 128)
     ref = oh.forward(p, inp, maxdisp, signed=signed, keep=True)
-    m = DisparityHotPath(maxdisp, False, signed)
+    m = DisparityHotPath(maxdisp, False, signed, precision="fp32")
     m.load_state_dict(p, strict=True)
     out = run(m.to(DEV), inp)
     same = (out["ind_k"] == ref["ind_k"]).all(dim=2)
@@ -232,7 +232,7 @@ def test_full_size_against_oracle(signed, maxdisp, H, W):
     p = make_params(seed=1, peaked=20.0)
     inp = make_inputs(5, 1, H, W)
     ref = oh.forward(p, inp, maxdisp, signed=signed, keep=True)
-    m = DisparityHotPath(maxdisp, False, signed)
+    m = DisparityHotPath(maxdisp, False, signed, precision="fp32")
     m.load_state_dict(p, strict=True)
     out = run(m.to(DEV), inp)
     same = (out["ind_k"] == ref["ind_k"]).all(dim=2)                       # (1,1,H/4,W/4)

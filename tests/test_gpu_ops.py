@@ -165,7 +165,7 @@ def test_conv3d_cout1():
 def test_hourglass_block_against_reference_golden(golden_dir):
     from semstereo_b200.hotpath import DisparityHotPath
     g = dict(np.load(os.path.join(golden_dir, "ops_signed.npz")))
-    m = DisparityHotPath(64)
+    m = DisparityHotPath(64, precision="fp32")
     m.load_state_dict(make_params(seed=2))
     m.to(DEV)
     out = m._hourglass(m._packed(), "hourglass_att", cu(op_inputs()["hg_in"]))
@@ -231,7 +231,7 @@ def test_ssr_upsample2_equals_two_calls():
     """The fused two-map SSR_upsample (SemStereo.py:312 + :324) is bit-identical to two single-map calls."""
     from semstereo_b200.hotpath import DisparityHotPath, pack_ssr
     from semstereo_b200.params import make_params
-    m = DisparityHotPath(64, False, True)
+    m = DisparityHotPath(64, False, True, precision="fp32")
     m.load_state_dict(make_params(seed=4), strict=True)
     packed = pack_ssr(m.ssr_upsample)
     g = torch.Generator().manual_seed(8)

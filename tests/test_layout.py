@@ -88,6 +88,8 @@ inp = {k: torch.randn(B, 3, 4, 5, generator=g) for k in names}
 full = FakePath()(*[inp[k] for k in names])["pred_up"]
 got = sd.ShardedHotPath(FakePath())(inp)
 assert got.shape == full.shape and torch.equal(got, full), (rank, got.shape)
+got0 = sd.ShardedHotPath(FakePath(), dst=0)(inp)          # DataParallel semantics: only rank 0 receives the batch
+assert (got0 is None) if rank != 0 else torch.equal(got0, full), rank
 class RowPath:             # row-local stand-in: row tiles with any halo must reproduce the untiled result exactly
     att_weights_only = False
     def __call__(self, f8_l, f8_r, f4_l, f4_r, cf_l, cf_r, spx, lab):
@@ -108,7 +110,7 @@ print("ok", rank)
 '''
 
 
-@pytest.mark.parametrize("B", [4, 5])
+@pytest.mark.parametrize("B", [4, 5, 1])          # even, ragged, and batch < world (rank 1 has an empty shard)
 def test_sharded_gather_world2_gloo(tmp_path, B):
     script = tmp_path / "w.py"
     script.write_text(WORKER)
