@@ -70,6 +70,8 @@ SS_API int ss_conv3d_cout1_f32(const float* in, const float* weight, float* out,
  * [B][8 = (d&1,h&1,w&1)][C/8][D/2][H/2][W/2][8] that the stride-2 layer reads and the transposed layer's residual uses.
  * Converters: fp32 NCDHW -> blocked (s2d = 1: phase-split), blocked -> fp32 NCDHW, blocked -> phase-split. */
 SS_API int ss_to_blocked_bf16(const float* in_ncdhw, void* out_blocked, int B, int C, int D, int H, int W, int s2d, void* stream);
+/* bf16 -> fp32 widening of n elements (n % 8 == 0): host boundary helper, see pipeline.HostPipeline(host_dtype=bfloat16). */
+SS_API int ss_widen_bf16(const void* in_bf16, float* out_f32, long long n, void* stream);
 SS_API int ss_from_blocked_bf16(const void* in_blocked, float* out_ncdhw, int B, int C, int D, int H, int W, void* stream);
 SS_API int ss_blocked_to_s2d(const void* in_blocked, void* out_s2d, int B, int C, int D, int H, int W, void* stream);
 /* The 3-D layers of the hourglass stack (same layers as ss_conv3d_f32) + folded eval-BN + residual + ReLU + channelAtt gate.

@@ -28,6 +28,7 @@ SIGNATURES = {
     "ss_conv3d_f32": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "ss_conv3d_cout1_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "ss_to_blocked_bf16": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ss_widen_bf16": [_P, _P, ctypes.c_longlong, _P],
     "ss_from_blocked_bf16": [_P, _P, _I, _I, _I, _I, _I, _P],
     "ss_blocked_to_s2d": [_P, _P, _I, _I, _I, _I, _I, _P],
     "ss_window_attention_core_blocked": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],

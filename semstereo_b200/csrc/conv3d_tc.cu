@@ -1198,6 +1198,15 @@ __global__ void __launch_bounds__(256) blocked_to_s2d_kernel(const uint4* __rest
       in[((size_t)b * C8 + chunk) * S + v];
 }
 
+// bf16 -> fp32, 8 elements per thread (host boundary: features shipped over PCIe as bf16 are widened on the device)
+__global__ void __launch_bounds__(256) widen_bf16_kernel(const uint4* __restrict__ in, float4* __restrict__ out, size_t n8) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 q = __ldcs(in + i);
+  out[2 * i] = make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u), __uint_as_float(q.y << 16), __uint_as_float(q.y & 0xffff0000u));
+  out[2 * i + 1] = make_float4(__uint_as_float(q.z << 16), __uint_as_float(q.z & 0xffff0000u), __uint_as_float(q.w << 16), __uint_as_float(q.w & 0xffff0000u));
+}
+
 // dims: (W*8, H, D, outer) ; box (80, 18, 1, box_outer)
 int make_act_tmap(CUtensorMap* tm, const void* base, int W, int H, int D, long long outer, int box_outer) {
   ss_encode_tiled_fn enc = ss_get_encode_tiled();
@@ -1524,6 +1533,18 @@ extern "C" int ss_to_blocked_bf16_ex(const float* in_ncdhw, void* out_blocked, i
   to_blocked_kernel<<<dim3((unsigned)ceil_div64(S, 256), C / 8, B), 256, 0, (cudaStream_t)stream>>>(
       in_ncdhw, reinterpret_cast<uint4*>(out_blocked), C, D, H, W, s2d, split == 1 ? (size_t)B * (C / 8) * S : (size_t)0, split == 2);
   SS_CHECK_LAUNCH("ss_to_blocked_bf16");
+  return SS_OK;
+}
+
+extern "C" int ss_widen_bf16(const void* in_bf16, float* out_f32, long long n, void* stream) {
+  SS_REQUIRE(in_bf16 && out_f32 && n > 0, "ss_widen_bf16: bad argument");
+  SS_REQUIRE(n % 8 == 0 && ((reinterpret_cast<uintptr_t>(in_bf16) | reinterpret_cast<uintptr_t>(out_f32)) & 15) == 0,
+             "ss_widen_bf16: element count must be a multiple of 8 and the pointers 16-byte aligned");
+  const size_t n8 = (size_t)n / 8;
+  SS_UNSUPPORTED(ceil_div64(n8, 256) > 0x7fffffffLL, "ss_widen_bf16: too many elements");
+  widen_bf16_kernel<<<(unsigned)ceil_div64(n8, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(in_bf16),
+                                                                                    reinterpret_cast<float4*>(out_f32), n8);
+  SS_CHECK_LAUNCH("ss_widen_bf16");
   return SS_OK;
 }
 

@@ -54,6 +54,16 @@ def pointwise_split(x_tri, w_tri, cout, scale=None, shift=None, relu=False):
     return conv2d_tc(CONV1, x_tri, w_tri, cout, scale, shift, relu=relu, out_f32=True)
 
 
+def widen_bf16(x, out=None):
+    """bf16 tensor -> fp32 tensor of the same shape (our kernel; used where features cross PCIe as bf16)."""
+    if not x.is_cuda or x.dtype != torch.bfloat16 or not x.is_contiguous() or x.numel() % 8:
+        raise ValueError("widen_bf16: contiguous CUDA bf16 tensor with a multiple of 8 elements expected")
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    _call("ss_widen_bf16", x.device, _ptr(x), _ptr(out), x.numel())
+    return out
+
+
 def from_blocked_bf16(xb):
     dev = _require_bf16(xb, 6)
     B, C8, D, H, W, _ = xb.shape

@@ -18,8 +18,12 @@ class HostPipeline:
     def __init__(self, path, depth: int = 2, post=None, keys=ORDER, call=None):
         """path: a DisparityHotPath (or, with `keys` / `call`, any module of this package, e.g. decoder.StereoHead) on a CUDA
         device.  keys: the batch-dict entries staged on the device; call(staged_dict) -> device result tensor (default: the hot
-        path's full-resolution disparity).  post(device_result) -> device tensor to return (e.g. an all-gather)."""
+        path's full-resolution disparity).  post(device_result) -> device tensor to return (e.g. an all-gather).
+        Host tensors may be fp32 or bf16 (per entry): bf16 entries cross PCIe at half the bytes and are widened to fp32 on the
+        device by ss_widen_bf16 -- lossless for features that are bf16-valued to begin with (e.g. produced by a bf16 decoder), a
+        rounding of the INPUTS otherwise (the caller's choice; the path itself computes the same either way)."""
         self.path, self.depth, self.post, self.keys = path, depth, post, tuple(keys)
+        self._wide = [None] * depth           # fp32 copies of bf16-staged entries
         self.dev = next(path.parameters()).device
         self.copy_stream = torch.cuda.Stream(self.dev)
         if call is None:
@@ -37,9 +41,13 @@ class HostPipeline:
     def _staging(self, i, batch):
         st = self._stage[i]
         keys = [k for k in self.keys if batch.get(k) is not None]      # cf_l / cf_r are optional (computed on the device if absent)
-        if st is None or set(st) != set(keys) or any(st[k].shape != batch[k].shape for k in keys):
-            st = {k: torch.empty(batch[k].shape, dtype=torch.float32, device=self.dev) for k in keys}
+        if st is None or set(st) != set(keys) or any(st[k].shape != batch[k].shape or st[k].dtype != batch[k].dtype for k in keys):
+            for k in keys:
+                if batch[k].dtype not in (torch.float32, torch.bfloat16):
+                    raise TypeError(f"HostPipeline: entry '{k}' must be float32 or bfloat16, got {batch[k].dtype}")
+            st = {k: torch.empty(batch[k].shape, dtype=batch[k].dtype, device=self.dev) for k in keys}
             self._stage[i] = st
+            self._wide[i] = {k: torch.empty(batch[k].shape, dtype=torch.float32, device=self.dev) for k in keys if batch[k].dtype == torch.bfloat16}
             # the caching allocator may hand out blocks that kernels already queued on the compute stream still use
             # (stream-ordered reuse): order the first copy into a fresh staging set after that work, once
             self.copy_stream.wait_stream(torch.cuda.current_stream(self.dev))
@@ -64,8 +72,13 @@ class HostPipeline:
                 for k in st:
                     st[k].copy_(batch[k], non_blocking=True)
                 self._copied[i].record(self.copy_stream)
-            self.h2d_bytes += sum(batch[k].numel() * 4 for k in st)
+            self.h2d_bytes += sum(batch[k].numel() * batch[k].element_size() for k in st)
             compute.wait_event(self._copied[i])
+            if self._wide[i]:
+                from . import ops_tc
+                st = dict(st)
+                for k, w in self._wide[i].items():
+                    st[k] = ops_tc.widen_bf16(st[k], w)
             out = self.call(st)
             self._consumed[i].record(compute)
             if self.post is not None:
