@@ -178,16 +178,25 @@ def cpu_reference(H, W, maxdisp, steps, warmup, signed=True, att_only=False, ext
     torch.set_num_threads(os.cpu_count() or 1)
     p = make_params(seed=1, peaked=20.0)
     inp = drop_cf(make_inputs(3, 1, H, W), external_cf)
-    if stage == "head":
+    if stage in ("head", "full"):
         from oracle import decoder as od
         from semstereo_b200.params import make_backbone_features, make_decoder_params
         p = dict(p)
         p.update(make_decoder_params(seed=2))
         fl, fr = make_backbone_features(3, 1, H, W)
+    if stage == "full":
+        from oracle import backbone as ob
+        from semstereo_b200.params import make_backbone_params, make_images
+        hf = ob.build(make_backbone_params(seed=4))
+        left, right = make_images(3, 1, H, W)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        if stage == "head":
+        if stage == "full":
+            with torch.no_grad():
+                fl = list(hf(left, output_hidden_states=True).hidden_states)
+                fr = list(hf(right, output_hidden_states=True).hidden_states)
+        if stage in ("head", "full"):
             d = od.forward(p, fl, fr, right_label=False)
             inp = {k: d[k] for k in ("f8_l", "f8_r", "f4_l", "f4_r", "spx_pred", "pred_label")}
         oh.forward(p, inp, maxdisp, signed=signed, att_weights_only=att_only)
@@ -216,9 +225,10 @@ def main():
                     help="us3d: SemStereo, signed, 1024x1024, maxdisp 64 (configs #1/#3); whu: SemStereo_WHU + submodule_.py, unsigned, "
                          "384x768, maxdisp 128 (config #4)")
     ap.add_argument("--att-only", action="store_true", help="attention_weights_only forward (the forward half of config #5)")
-    ap.add_argument("--stage", default="path", choices=["path", "head"],
+    ap.add_argument("--stage", default="path", choices=["path", "head", "full"],
                     help="path: the disparity hot path (forward:273-324, BASELINE north_star; default).  head: everything after the "
-                         "backbone (forward:249-346): the 2-D decoder (SURVEY 8(f) rank 1) + the path; inputs are the backbone pyramids")
+                         "backbone (forward:249-346): the 2-D decoder (SURVEY 8(f) rank 1) + the path; inputs are the backbone pyramids.  "
+                         "full: the whole SemStereo.forward from the two images (MobileViTv2 backbone, SURVEY 8(f) rank 2, + decoder + path)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches in region 1 instead of CUDA-graph replays")
     ap.add_argument("--external-cf", action="store_true",
                     help="hand concat_feature(f4_*) in as inputs (round-1 boundary) instead of computing it inside the path")
@@ -231,13 +241,14 @@ def main():
             a.maxdisp = 128
     H, W, md = a.height, a.width, a.maxdisp
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    head = a.stage == "head"
+    head = a.stage in ("head", "full")
+    full = a.stage == "full"
     if head:
         if a.att_only:
             raise SystemExit("--stage head runs the full forward")
         a.precision = "bf16"                   # the decoder has no fp32-accurate mode yet
     workload = (f"{'SemStereo' if signed else 'SemStereo_WHU'} "
-                f"{'decoder + disparity path = everything after the backbone (forward:249-346)' if head else 'disparity hot path (forward:273-324)'}, {H}x{W} "
+                f"{'whole forward from the images: MobileViTv2 backbone + decoder + disparity path (forward:246-346)' if a.stage == 'full' else ('decoder + disparity path = everything after the backbone (forward:249-346)' if head else 'disparity hot path (forward:273-324)')}, {H}x{W} "
                 f"{'US3D' if signed else 'WHU'}-shaped pairs, maxdisp {md}, {'signed' if signed else 'unsigned'}"
                 f"{', attention_weights_only' if a.att_only else ''}"
                 f"{'' if a.external_cf or a.att_only else ', concat_feature (:314-315) computed inside the path'}")
@@ -269,7 +280,18 @@ def main():
     dev = torch.device("cuda", local)
     B = a.batch
     okey = "pred_att_up" if a.att_only else "pred_up"
-    if head:
+    if full:
+        from semstereo_b200.backbone import SemStereoB200
+        from semstereo_b200.params import make_backbone_params, make_decoder_params, make_images
+        model = SemStereoB200(md, False, signed)
+        sd = dict(make_params(seed=1, peaked=20.0))
+        sd.update(make_decoder_params(seed=2))
+        sd.update({"feature." + k: v for k, v in make_backbone_params(seed=4).items()})
+        model.load_state_dict(sd, strict=True)
+        left, right = make_images(100 + rank, B, H, W)
+        host = {"left": left.pin_memory(), "right": right.pin_memory()}
+        call = lambda st: model(st["left"], st["right"])[okey]      # noqa: E731
+    elif head:
         from semstereo_b200.decoder import StereoHead
         from semstereo_b200.params import make_backbone_features, make_decoder_params
         model = StereoHead(md, False, signed)
@@ -468,12 +490,13 @@ def main():
                                     "note": "same pipeline, f8_*/f4_* shipped as bf16 (HostPipeline widens on the device); informative only -- "
                                             "`e2e` above ships every input as fp32"}
     # whole-step tensor-core fraction: algorithmic FLOPs of every 3-D conv (Table A of SURVEY 8a) + concat_feature, over the step
-    step_flops = B * (sum(v for k, v in flops.items() if not (a.att_only and not k.startswith(("hourglass_att", "classif_att_"))))
+    step_flops = 0 if head else B * (sum(v for k, v in flops.items() if not (a.att_only and not k.startswith(("hourglass_att", "classif_att_"))))
                       + (0 if a.att_only or a.external_cf else 2 * 2 * 9 * (128 * 64 + 64 * 32) * (H // 4) * (W // 4)))
     ach = step_flops / (ms_total / a.steps * 1e-3) / 1e12
-    res["tensor_step"] = {"algorithmic_tflop_per_step": round(step_flops / 1e12, 4), "achieved": round(ach, 1), "unit": "TFLOP/s",
-                          "frac_of_sustained_peak": round(ach / pk["tf_sust"], 4), "frac_of_burst_peak": round(ach / pk["tf_burst"], 4),
-                          "note": "algorithmic FLOPs only: the bf16x3 attention branch executes 3x its share on the tensor cores"}
+    if not head:
+        res["tensor_step"] = {"algorithmic_tflop_per_step": round(step_flops / 1e12, 4), "achieved": round(ach, 1), "unit": "TFLOP/s",
+                              "frac_of_sustained_peak": round(ach / pk["tf_sust"], 4), "frac_of_burst_peak": round(ach / pk["tf_burst"], 4),
+                              "note": "algorithmic FLOPs only: the bf16x3 attention branch executes 3x its share on the tensor cores"}
     res["host"] = {"numa_bound_cpus": len(numa_cpus) if numa_cpus else None}
     res["launch_mode"] = {"value_region": "cuda graph replay per step (+ NCCL gather to rank 0 on a side stream)" if graph_used else
                           ("eager" + (f" (graph capture failed: {graph_err})" if graph_err else "")),

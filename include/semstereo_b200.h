@@ -156,6 +156,31 @@ SS_API int ss_conv2d_tc_ntile(int mode, int Cin, int Cout);
 SS_API int ss_conv2d_tc(int mode, const void* in0_blocked, int C0, const void* in1_blocked_or_null, int C1, const void* weight_packed,
                         const float* scale_or_null, const float* shift_or_null, void* out, int out_mode, int B, int Cout, int H, int W,
                         int relu, void* stream);
+/* ss_conv2d_tc with the epilogue the MobileViTv2 backbone needs (mode 1 only): act 0 none / 1 ReLU / 2 SiLU, and a bf16 blocked
+ * residual (B,Cout/8,H,W,8) added after the activation (inverted-residual and transformer skip connections). */
+SS_API int ss_conv2d_tc_ex(int mode, const void* in0_blocked, int C0, const void* in1_blocked_or_null, int C1, const void* weight_packed,
+                           const float* scale_or_null, const float* shift_or_null, const void* residual_blocked_or_null, void* out,
+                           int out_mode, int B, int Cout, int H, int W, int act, void* stream);
+/* ---- backbone `Feature` (SemStereo.py:33-56 = timm mobilevitv2_100; architecture restated in semstereo_b200/backbone.py) --------
+ * Everything that is not a 1x1 convolution, on the bf16 blocked layout (B,C/8,H,W,8):
+ * stem: Conv2d(3,32,3,s2,p1) + folded BN + SiLU from the fp32 NCHW image (weight fp32 (32,3,3,3)); the output has Cout_padded
+ *   channels (>= 32, the rest zero) so that the next 1x1 conv sees a multiple of 64 input channels.
+ * dwconv: depthwise Conv2d 3x3 p1, stride 1 or 2 (weight fp32 (C,9)) + folded BN + act (0 none, 1 ReLU, 2 SiLU).
+ * groupnorm1: nn.GroupNorm(1, C) (mean / variance over C*H*W per sample, fp32 statistics, deterministic two-pass);
+ *   workspace: ss_groupnorm1_workspace_floats(B) floats.
+ * linear_attention: MobileViTv2 separable self-attention core between qkv_proj and out_proj.  qkv blocked with 2d/8 + 1 chunks:
+ *   [0,d/8) key, [d/8,2d/8) value, chunk 2d/8 lane 0 = query.  The softmax runs over the 2x2-patch index for each of the 4 patch
+ *   positions = over the pixels of one (y&1, x&1) parity class, so no unfold/fold is materialised.  out = relu(value) * context,
+ *   (B,d/8,H,W,8).  workspace: ss_linear_attention_workspace_floats(B, d) floats. */
+SS_API int ss_stem_conv3x3_s2(const float* image, const float* weight, const float* scale, const float* shift, void* out_blocked, int B,
+                              int H, int W, int Cout_padded, void* stream);
+SS_API int ss_dwconv3x3_blocked(const void* in_blocked, const float* weight, const float* scale, const float* shift, void* out_blocked,
+                                int B, int C, int H, int W, int stride, int act, void* stream);
+SS_API int ss_groupnorm1_workspace_floats(int B);
+SS_API int ss_groupnorm1_blocked(const void* in_blocked, const float* gamma, const float* beta, void* out_blocked, float* workspace, int B,
+                                 int C, int H, int W, float eps, void* stream);
+SS_API int ss_linear_attention_workspace_floats(int B, int d);
+SS_API int ss_linear_attention_blocked(const void* qkv_blocked, void* out_blocked, float* workspace, int B, int d, int H, int W, void* stream);
 /* F.interpolate(scale 2, bilinear, align_corners=False) of `planes` fp32 (h,w) planes (segmenthead, submodule.py:46-51). */
 SS_API int ss_bilinear_up2(const float* in, float* out, int planes, int h, int w, void* stream);
 /* segmenthead.conv2 (submodule.py:36,44): Conv2d 1x1 + bias, Cout <= 8, from blocked bf16 (B,C/8,H,W,8) to fp32 (B,Cout,H,W);

@@ -48,6 +48,13 @@ SIGNATURES = {
     "ss_spatial_transformer_grid_backward": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "ss_conv2d_tc_ntile": [_I, _I, _I],
     "ss_conv2d_tc": [_I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ss_conv2d_tc_ex": [_I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ss_stem_conv3x3_s2": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "ss_dwconv3x3_blocked": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ss_groupnorm1_workspace_floats": [_I],
+    "ss_groupnorm1_blocked": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "ss_linear_attention_workspace_floats": [_I, _I],
+    "ss_linear_attention_blocked": [_P, _P, _P, _I, _I, _I, _I, _P],
     "ss_bilinear_up2": [_P, _P, _I, _I, _I, _P],
     "ss_pointwise_blocked_small": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "ss_conv3d_tc": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],

@@ -139,11 +139,11 @@ __global__ void __launch_bounds__(256) window_attention3d_kernel(const AttnP p) 
   }
 }
 
-// The softmax(q k^T * scale) v core alone, fp32, for the bf16x3 split route: the qkv Linear and the final 1x1x1 conv run as
+// GENERIC fallback (any window with T <= 96).  The softmax(q k^T * scale) v core alone, fp32, for the bf16x3 split route: the qkv Linear and the final 1x1x1 conv run as
 // fp32-accurate tensor-core GEMMs around it (ss_conv2d_tc over the [hi | lo | hi] K-concat form), so this kernel reads the fp32
 // qkv volume (B,3C,D,H,W; channel = which*C + head*hd + j) and writes the head outputs directly in that K-concat form:
 // bf16 (B, 3*C/8, D, H, W, 8) -- a head (hd = 8 channels) is exactly one 16-byte channel chunk.
-__global__ void __launch_bounds__(256) window_attention_core_f32_kernel(const float* __restrict__ qkv, uint4* __restrict__ out, int D,
+__global__ void __launch_bounds__(256) window_attention_core_f32_generic_kernel(const float* __restrict__ qkv, uint4* __restrict__ out, int D,
                                                                        int H, int W, int bd, int bh, int bw, int nd, int nh, int nw, int T) {
   extern __shared__ __align__(16) float smem[];        // [3][heads][T][hd]
   int wid = blockIdx.x;
@@ -215,6 +215,91 @@ __global__ void __launch_bounds__(256) window_attention_core_f32_kernel(const fl
   }
 }
 
+// Fast variant for the model's windows (bw == 4, T = bd*bh*bw in {64, 96}): 128-bit window gathers (a window row is 4 contiguous
+// floats), and per (head, query) task all T scores are computed first into registers (T independent 8-term dot products), then
+// max / exp / weighted sum -- no serial online-softmax chain (the generic kernel below was latency-bound: 92 us for 128 windows).
+template <int T>
+__global__ void __launch_bounds__(256, 2) window_attention_core_f32_kernel(const float* __restrict__ qkv, uint4* __restrict__ out, int D,
+                                                                          int H, int W, int bd, int bh, int nd, int nh, int nw) {
+  extern __shared__ __align__(16) float smem[];        // [3][heads][T][hd]
+  constexpr int BW = 4;
+  int wid = blockIdx.x;
+  const int wx = wid % nw;  wid /= nw;
+  const int wy = wid % nh;  wid /= nh;
+  const int wz = wid % nd;
+  const int b = wid / nd;
+  const size_t cs = (size_t)D * H * W;
+  const size_t wbase = ((size_t)wz * bd * H + (size_t)wy * bh) * W + (size_t)wx * BW;
+  const float* src = qkv + (size_t)b * 3 * kC * cs + wbase;
+  // gather: one float4 = the 4 tokens of one (dd, hh) row of the window for one channel
+  constexpr int ROWS = T / BW;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < 3 * kC * ROWS; i += 256) {
+    const int c = i / ROWS, r = i - c * ROWS;            // c = which*C + head*hd + j ; r = dd*bh + hh
+    const int dd = r / bh, hh = r - dd * bh;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)c * cs + ((size_t)dd * H + hh) * W));
+    float* dst = smem + ((size_t)(c >> 3) * T + r * BW) * kHd + (c & 7);
+    dst[0] = v.x; dst[kHd] = v.y; dst[2 * kHd] = v.z; dst[3 * kHd] = v.w;
+  }
+  __syncthreads();
+  const float scale = 0.35355339059327379f;             // hd^-0.5 with hd = 8
+  const float* Q = smem;
+  const float* Km = smem + (size_t)kHeads * T * kHd;
+  const float* V = smem + (size_t)2 * kHeads * T * kHd;
+  uint4* ob = out + (size_t)b * 3 * kHeads * cs + wbase;
+#pragma unroll 1
+  for (int id = threadIdx.x; id < kHeads * T; id += 256) {
+    const int tq = id % T, h = id / T;                  // T is a multiple of 32: the lanes of a warp share the head -> broadcasts
+    float q[kHd];
+    {
+      const float4* qp = reinterpret_cast<const float4*>(Q + ((size_t)h * T + tq) * kHd);
+      const float4 a = qp[0], c = qp[1];
+      q[0] = a.x * scale; q[1] = a.y * scale; q[2] = a.z * scale; q[3] = a.w * scale;
+      q[4] = c.x * scale; q[5] = c.y * scale; q[6] = c.z * scale; q[7] = c.w * scale;
+    }
+    const float4* kp = reinterpret_cast<const float4*>(Km + (size_t)h * T * kHd);
+    const float4* vp = reinterpret_cast<const float4*>(V + (size_t)h * T * kHd);
+    float sc[T];
+    float m = -INFINITY;
+#pragma unroll
+    for (int tk = 0; tk < T; ++tk) {
+      const float4 a = kp[2 * tk], c = kp[2 * tk + 1];
+      float x = q[0] * a.x;
+      x = fmaf(q[1], a.y, x); x = fmaf(q[2], a.z, x); x = fmaf(q[3], a.w, x);
+      x = fmaf(q[4], c.x, x); x = fmaf(q[5], c.y, x); x = fmaf(q[6], c.z, x); x = fmaf(q[7], c.w, x);
+      sc[tk] = x;
+      m = fmaxf(m, x);
+    }
+    float l = 0.0f, o[kHd];
+#pragma unroll
+    for (int j = 0; j < kHd; ++j) o[j] = 0.0f;
+#pragma unroll
+    for (int tk = 0; tk < T; ++tk) {
+      const float pe = expf(sc[tk] - m);
+      l += pe;
+      const float4 va = vp[2 * tk], vc = vp[2 * tk + 1];
+      o[0] = fmaf(pe, va.x, o[0]); o[1] = fmaf(pe, va.y, o[1]); o[2] = fmaf(pe, va.z, o[2]); o[3] = fmaf(pe, va.w, o[3]);
+      o[4] = fmaf(pe, vc.x, o[4]); o[5] = fmaf(pe, vc.y, o[5]); o[6] = fmaf(pe, vc.z, o[6]); o[7] = fmaf(pe, vc.w, o[7]);
+    }
+    const float inv = 1.0f / l;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float x0 = o[2 * j] * inv, x1 = o[2 * j + 1] * inv;
+      __nv_bfloat162 hv = __floats2bfloat162_rn(x0, x1);
+      hi[j] = *reinterpret_cast<uint32_t*>(&hv);
+      __nv_bfloat162 lv = __floats2bfloat162_rn(x0 - __uint_as_float(hi[j] << 16), x1 - __uint_as_float(hi[j] & 0xffff0000u));
+      lo[j] = *reinterpret_cast<uint32_t*>(&lv);
+    }
+    const int dd = tq / (bh * BW), rr = tq - dd * bh * BW, hh = rr / BW, ww = rr - hh * BW;
+    const size_t vo = ((size_t)dd * H + hh) * W + ww;
+    const uint4 qh = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    ob[(size_t)h * cs + vo] = qh;
+    ob[(size_t)(kHeads + h) * cs + vo] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    ob[(size_t)(2 * kHeads + h) * cs + vo] = qh;
+  }
+}
+
 }  // namespace
 
 extern "C" int ss_window_attention_core_f32(const float* qkv, void* out_tri, int B, int C, int D, int H, int W, int bd, int bh, int bw,
@@ -229,9 +314,20 @@ extern "C" int ss_window_attention_core_f32(const float* qkv, void* out_tri, int
   const size_t smem = (size_t)3 * kC * T * sizeof(float);
   const long long nwin = (long long)B * (D / bd) * (H / bh) * (W / bw);
   SS_UNSUPPORTED(nwin > 0x7fffffffLL, "ss_window_attention_core_f32: too many windows");
-  SS_CUDA(ss_allow_smem(window_attention_core_f32_kernel, smem));
-  window_attention_core_f32_kernel<<<(unsigned)nwin, 256, smem, (cudaStream_t)stream>>>(qkv, reinterpret_cast<uint4*>(out_tri), D, H, W,
-                                                                                        bd, bh, bw, D / bd, H / bh, W / bw, T);
+  const bool fast = bw == 4 && W % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (T == 64 || T == 96);
+  if (fast && T == 64) {
+    SS_CUDA(ss_allow_smem(window_attention_core_f32_kernel<64>, smem));
+    window_attention_core_f32_kernel<64><<<(unsigned)nwin, 256, smem, (cudaStream_t)stream>>>(qkv, reinterpret_cast<uint4*>(out_tri), D, H, W, bd,
+                                                                                              bh, D / bd, H / bh, W / bw);
+  } else if (fast) {
+    SS_CUDA(ss_allow_smem(window_attention_core_f32_kernel<96>, smem));
+    window_attention_core_f32_kernel<96><<<(unsigned)nwin, 256, smem, (cudaStream_t)stream>>>(qkv, reinterpret_cast<uint4*>(out_tri), D, H, W, bd,
+                                                                                              bh, D / bd, H / bh, W / bw);
+  } else {
+    SS_CUDA(ss_allow_smem(window_attention_core_f32_generic_kernel, smem));
+    window_attention_core_f32_generic_kernel<<<(unsigned)nwin, 256, smem, (cudaStream_t)stream>>>(qkv, reinterpret_cast<uint4*>(out_tri), D, H,
+                                                                                                  W, bd, bh, bw, D / bd, H / bh, W / bw, T);
+  }
   SS_CHECK_LAUNCH("ss_window_attention_core_f32");
   return SS_OK;
 }

@@ -25,8 +25,10 @@ struct C2P {
   const __nv_bfloat16* w;
   const float* scale;   // [Cout] or null (1)
   const float* shift;   // [Cout] or null (0)
+  const __nv_bfloat16* residual;   // 1x1 mode only: bf16 blocked tensor shaped like the output, added after the activation, or null
   void* out;
   int out_mode;         // 0: bf16 blocked, 1: fp32 NCHW
+  int act;              // 1x1 mode only (else `relu`): 0 none, 1 ReLU, 2 SiLU
   int cout;             // channels stored
   int B, H, W;          // input dims (conv: also output dims; deconv writes 2H x 2W)
   int relu;
@@ -94,7 +96,9 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 // =====================================================================================================================
 // conv: TAPS = 9 (3x3, pad 1) or 1 (1x1).  Weights: [n_tiles][ncb][TAPS][CB/8][N][8].
 // =====================================================================================================================
-template <int N, int TAPS, int NS, int NWS>
+// EXT (1x1 mode; compile time so that the 3x3 decoder kernels keep their registers): SiLU activation and a residual input in
+// the epilogue -- the inverted-residual / transformer blocks of the MobileViTv2 backbone.
+template <int N, int TAPS, int NS, int NWS, bool EXT = false>
 __global__ void __launch_bounds__(256, 1) conv2d_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                                                            const C2P p) {
   constexpr uint32_t TAPB = CB * N * 2;
@@ -196,8 +200,29 @@ __global__ void __launch_bounds__(256, 1) conv2d_tc_kernel(const __grid_constant
         }
         const int co0 = nt * N + j * 32;
         if (!valid || co0 >= p.cout) continue;
-        affine_relu32(v, s_scale + (N < 32 ? 0 : j * 32), s_shift + (N < 32 ? 0 : j * 32), p.relu);
         const size_t HW = (size_t)p.H * p.W, sp = (size_t)h * p.W + w;
+        if (!EXT) affine_relu32(v, s_scale + (N < 32 ? 0 : j * 32), s_shift + (N < 32 ? 0 : j * 32), p.relu);
+        else {
+          affine_relu32(v, s_scale + (N < 32 ? 0 : j * 32), s_shift + (N < 32 ? 0 : j * 32), p.act == 1);
+          if (p.act == 2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __fdividef(v[i], 1.0f + __expf(-v[i]));
+          }
+          if (p.residual) {
+            const uint4* r = reinterpret_cast<const uint4*>(p.residual) + ((size_t)b * (p.cout / 8) + co0 / 8) * HW + sp;
+#pragma unroll
+            for (int c8 = 0; c8 < (N < 32 ? N / 8 : 4); ++c8)
+              if (co0 + 8 * c8 < p.cout) {
+                const uint4 q = __ldg(r + (size_t)c8 * HW);
+                const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  v[8 * c8 + 2 * i] += __uint_as_float(u[i] << 16);
+                  v[8 * c8 + 2 * i + 1] += __uint_as_float(u[i] & 0xffff0000u);
+                }
+              }
+          }
+        }
         if (p.out_mode == 1) {
           float* o = reinterpret_cast<float*>(p.out) + ((size_t)b * p.cout + co0) * HW + sp;
 #pragma unroll
@@ -459,6 +484,8 @@ int launch_conv(const CUtensorMap& t0, const CUtensorMap& t1, const C2P& p, cuda
   constexpr int NS = 4, NWS = N >= 128 ? 4 : 6;
   constexpr size_t smem = (size_t)NS * SLICE + (size_t)NWS * CB * N * 2;
   static_assert(smem <= 227 * 1024 - 2048, "shared memory budget");
+  if (TAPS == 1 && (p.act == 2 || p.residual))
+    return launch2d(conv2d_tc_kernel<N, TAPS, NS, NWS, TAPS == 1>, smem, t0, t1, p, st, "ss_conv2d_tc(conv, ext)");
   return launch2d(conv2d_tc_kernel<N, TAPS, NS, NWS>, smem, t0, t1, p, st, "ss_conv2d_tc(conv)");
 }
 template <int NP>
@@ -482,6 +509,19 @@ extern "C" int ss_conv2d_tc_ntile(int mode, int Cin, int Cout) {
 extern "C" int ss_conv2d_tc(int mode, const void* in0_blocked, int C0, const void* in1_blocked_or_null, int C1, const void* weight_packed,
                             const float* scale_or_null, const float* shift_or_null, void* out, int out_mode, int B, int Cout, int H, int W,
                             int relu, void* stream) {
+  return ss_conv2d_tc_ex(mode, in0_blocked, C0, in1_blocked_or_null, C1, weight_packed, scale_or_null, shift_or_null, nullptr, out, out_mode,
+                         B, Cout, H, W, relu ? 1 : 0, stream);
+}
+
+// act: 0 none, 1 ReLU, 2 SiLU (mode 1 only); residual_blocked: bf16 blocked (B,Cout/8,H,W,8) added after the activation (mode 1 only).
+extern "C" int ss_conv2d_tc_ex(int mode, const void* in0_blocked, int C0, const void* in1_blocked_or_null, int C1, const void* weight_packed,
+                               const float* scale_or_null, const float* shift_or_null, const void* residual_blocked_or_null, void* out,
+                               int out_mode, int B, int Cout, int H, int W, int act, void* stream) {
+  const int relu = act == 1;
+  SS_REQUIRE(act >= 0 && act <= 2, "ss_conv2d_tc: act must be 0 (none), 1 (ReLU) or 2 (SiLU)");
+  SS_UNSUPPORTED(mode != 1 && (act == 2 || residual_blocked_or_null), "ss_conv2d_tc: SiLU / residual epilogue exists for the 1x1 mode only");
+  SS_REQUIRE(!residual_blocked_or_null || (Cout % 8 == 0 && (reinterpret_cast<uintptr_t>(residual_blocked_or_null) & 15) == 0),
+             "ss_conv2d_tc: the residual is a 16-byte aligned bf16 blocked tensor (Cout %% 8 == 0)");
   SS_REQUIRE(in0_blocked && weight_packed && out, "ss_conv2d_tc: null pointer");
   SS_REQUIRE(B > 0 && H > 0 && W > 0 && Cout > 0 && C0 > 0 && C1 >= 0, "ss_conv2d_tc: non-positive dimension");
   SS_REQUIRE((in1_blocked_or_null != nullptr) == (C1 > 0), "ss_conv2d_tc: second input and its channel count must come together");
@@ -496,6 +536,7 @@ extern "C" int ss_conv2d_tc(int mode, const void* in0_blocked, int C0, const voi
   C2P p;
   p.w = reinterpret_cast<const __nv_bfloat16*>(weight_packed);
   p.scale = scale_or_null; p.shift = shift_or_null; p.out = out; p.out_mode = out_mode; p.cout = Cout;
+  p.act = act; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual_blocked_or_null);
   p.B = B; p.H = H; p.W = W; p.relu = relu;
   p.ncb0 = C0 / CB; p.ncb = (C0 + C1) / CB;
   p.n_tiles = ceil_div(Cout, N);

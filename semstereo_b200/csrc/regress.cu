@@ -260,7 +260,8 @@ __global__ void __launch_bounds__(128) topk_select_kernel(const float* __restric
   }
   // Keep the K largest probabilities, ties broken toward the lower index (total order: p descending, index ascending).
   // The model keeps 24 of 32 bins, so it is cheaper to DROP the nb-K last elements of that order one by one (minimum p,
-  // among equals the highest index: `<=` lets a later index win) than to rank all bins against each other.
+  // among equals the highest index: `<=` lets a later index win) than to rank all bins against each other (a rank-by-count
+  // variant with NB*NB independent comparisons was measured slower, 0.27 vs 0.22 ms at batch 8: round 2).
   unsigned long long keep = nb >= 64 ? ~0ull : ((1ull << nb) - 1ull);
 #pragma unroll 1
   for (int r = 0; r < nb - K; ++r) {

@@ -50,8 +50,16 @@ class _SegHeadParams(nn.Module):
 
 
 class Decoder2D(nn.Module):
-    def __init__(self, num_classes: int = 6):
+    def __init__(self, num_classes: int = 6, precision: str = "bf16"):
+        """precision "bf16": every conv with bf16 operands.  "split": the convs that feed the disparity path's sample selection --
+        FeatUp and chal_1 / chal_2 (f4_*, f8_*) -- with fp32-accurate bf16x3 products (each conv is one GEMM over the
+        [hi | lo | hi] K-concat form, ops_tc.pack_weight2d_split; 3x the MMAs, fp32 activations between layers), the segmentation
+        heads and the spx chain (they only feed SSR_upsample) stay bf16.  With DisparityHotPath(precision="split") behind it the
+        top-k sample sets equal the fp32 oracle's end to end from fp32 backbone features."""
         super().__init__()
+        if precision not in ("bf16", "split"):
+            raise ValueError("Decoder2D precision must be 'bf16' or 'split'")
+        self.precision = precision
         self.num_classes = num_classes
         self.feature_up = _FeatUpParams()
         self.head_l = _SegHeadParams(CHANS[0], CHANS[0] // 4, num_classes)
@@ -105,6 +113,10 @@ class Decoder2D(nn.Module):
         def conv2x(name, m):
             convbn(name + ".conv1", m.conv1, tc.DECONV4)
             convbn(name + ".conv2", m.conv2, tc.CONV3)
+            if self.precision == "split" and name.startswith("feature_up."):
+                half = m.conv2.conv.weight.shape[1] // 2
+                c[name + ".conv1.ws"] = tc.pack_weight2d_split(m.conv1.conv.weight, tc.DECONV4)
+                c[name + ".conv2.ws"] = tc.pack_weight2d_split(m.conv2.conv.weight, tc.CONV3, (half, half))
 
         for n in ("deconv32_16", "deconv16_8", "deconv8_4", "deconv4_2"):
             conv2x("feature_up." + n, getattr(self.feature_up, n))
@@ -121,6 +133,8 @@ class Decoder2D(nn.Module):
             m = getattr(self, f"chal_{i}")
             s, t = bn_affine(m[1])
             c[f"chal_{i}.w"] = tc.pack_weight2d(m[0].weight, tc.CONV1)
+            if self.precision == "split" and i in (1, 2):
+                c[f"chal_{i}.ws"] = tc.pack_weight2d_split(m[0].weight, tc.CONV1)
             c[f"chal_{i}.s"] = s
             c[f"chal_{i}.t"] = (t + s * m[0].bias.detach().float()).contiguous()       # BN(conv + b) = s*conv + (s*b + t)
         self._cache = c
@@ -136,6 +150,26 @@ class Decoder2D(nn.Module):
             raise NotImplementedError("Decoder2D: feature sizes must halve exactly between levels (H, W multiples of 32)")
         with ops.label(name + ".conv2"):
             return tc.conv2d_tc(tc.CONV3, y, c[name + ".conv2.w"], 2 * cout, c[name + ".conv2.s"], c[name + ".conv2.t"], relu=True, x1=rem)
+
+    def _conv2x_split(self, c, name, x, rem):
+        """Conv2x with fp32-accurate products: x, rem fp32 NCHW -> fp32 NCHW."""
+        cout = rem.shape[1]
+        with ops.label(name + ".conv1"):
+            y = tc.conv2d_tc(tc.DECONV4, tc.to_blocked_tri(x), c[name + ".conv1.ws"], cout, c[name + ".conv1.s"], c[name + ".conv1.t"], relu=True,
+                             out_f32=True)
+        if y.shape != rem.shape:
+            raise NotImplementedError("Decoder2D: feature sizes must halve exactly between levels (H, W multiples of 32)")
+        with ops.label(name + ".conv2"):
+            return tc.conv2d_tc(tc.CONV3, tc.to_blocked_tri(y), c[name + ".conv2.ws"], 2 * cout, c[name + ".conv2.s"], c[name + ".conv2.t"],
+                                relu=True, out_f32=True, x1=tc.to_blocked_tri(rem))
+
+    def _feat_up_split(self, c, f):
+        x2, x4, x8, x16, x32 = f
+        x16 = self._conv2x_split(c, "feature_up.deconv32_16", x32, x16)
+        x8 = self._conv2x_split(c, "feature_up.deconv16_8", x16, x8)
+        x4 = self._conv2x_split(c, "feature_up.deconv8_4", x8, x4)
+        x2 = self._conv2x_split(c, "feature_up.deconv4_2", x4, x2)
+        return [x2, x4, x8, x16, x32]
 
     def _feat_up(self, c, f):
         x2, x4, x8, x16, x32 = f
@@ -156,24 +190,49 @@ class Decoder2D(nn.Module):
 
     @torch.no_grad()
     def forward(self, feat_l, feat_r, right_label: bool = False):
-        """feat_l / feat_r: the five fp32 NCHW maps of `Feature` (SemStereo.py:47-56) for the left / right image.
+        """feat_l / feat_r: the five maps of `Feature` (SemStereo.py:47-56) for the left / right image, fp32 NCHW or (from
+        backbone.MobileViTv2Backbone) bf16 blocked.
         Returns the inputs of DisparityHotPath (fp32 NCHW) plus `f4_l_blocked` (bf16) so the path does not convert f4_l again."""
         c = self._packed()
+        blocked = feat_l[0].dtype == torch.bfloat16      # straight from MobileViTv2Backbone: already (B,C/8,H,W,8) bf16
         for f in (feat_l, feat_r):
-            if len(f) != 5 or any(t.shape[1] != ch for t, ch in zip(f, BACKBONE_CHANS)):
+            if len(f) != 5 or any(t.shape[1] * (8 if blocked else 1) != ch for t, ch in zip(f, BACKBONE_CHANS)):
                 raise ValueError(f"Decoder2D: five backbone maps with {BACKBONE_CHANS} channels expected")
-        with ops.label("to_blocked"):
-            bl = [tc.to_blocked2d(t) for t in feat_l]
-            br = [tc.to_blocked2d(t) for t in feat_r]
-        fl, fr = self._feat_up(c, bl), self._feat_up(c, br)
+        split = self.precision == "split"
+        if split and blocked:
+            raise ValueError("Decoder2D(precision='split') takes fp32 backbone features (bf16 inputs have already lost the low bits)")
+        if split:
+            # fp32-accurate FeatUp + chal_1 / chal_2; bf16 blocked copies of its outputs feed the heads and the spx chain
+            sl, sr = self._feat_up_split(c, [t.contiguous().float() for t in feat_l]), self._feat_up_split(c, [t.contiguous().float() for t in feat_r])
+            with ops.label("to_blocked"):
+                fl = [tc.to_blocked2d(t) for t in sl]
+                fr = [None, None, None, None, None]
+                if right_label:
+                    fr[0] = tc.to_blocked2d(sr[0])
+        else:
+            if blocked:
+                bl, br = [t.contiguous() for t in feat_l], [t.contiguous() for t in feat_r]
+            else:
+                with ops.label("to_blocked"):
+                    bl = [tc.to_blocked2d(t) for t in feat_l]
+                    br = [tc.to_blocked2d(t) for t in feat_r]
+            fl, fr = self._feat_up(c, bl), self._feat_up(c, br)
         out = {"pred_label": self._head(c, "head_l", fl[0])}
         if right_label:
             out["pred_label_r"] = self._head(c, "head_r", fr[0])
         cl = [self._chal(c, i, fl[i]) for i in range(5)]
-        with ops.label("from_blocked"):
-            out["f4_l"], out["f8_l"] = tc.from_blocked2d(cl[1]), tc.from_blocked2d(cl[2])
-        out["f4_r"], out["f8_r"] = self._chal(c, 1, fr[1], out_f32=True), self._chal(c, 2, fr[2], out_f32=True)
-        out["f4_l_blocked"] = cl[1]
+        if split:
+            for i, k in ((1, "f4"), (2, "f8")):
+                with ops.label(f"chal_{i}"):
+                    for side, src in (("_l", sl), ("_r", sr)):
+                        out[k + side] = tc.conv2d_tc(tc.CONV1, tc.to_blocked_tri(src[i]), c[f"chal_{i}.ws"], CHANS2[i], c[f"chal_{i}.s"], c[f"chal_{i}.t"],
+                                                     out_f32=True)
+            out["f4_l_blocked"] = None      # the path converts its own copy from the fp32-accurate f4_l
+        else:
+            with ops.label("from_blocked"):
+                out["f4_l"], out["f8_l"] = tc.from_blocked2d(cl[1]), tc.from_blocked2d(cl[2])
+            out["f4_r"], out["f8_r"] = self._chal(c, 1, fr[1], out_f32=True), self._chal(c, 2, fr[2], out_f32=True)
+            out["f4_l_blocked"] = cl[1]
         x = self._conv2x(c, "spx32_16", cl[4], cl[3])
         x = self._conv2x(c, "spx16_8", x, cl[2])
         x = self._conv2x(c, "spx8_4", x, cl[1])
@@ -187,10 +246,17 @@ class StereoHead(nn.Module):
     """Everything of SemStereo.forward after `self.feature` (models/SemStereo.py:249-346): Decoder2D + DisparityHotPath.
     state_dict keys are the reference's (both sub-modules register their containers at the top level of this module)."""
 
-    def __init__(self, maxdisp: int, att_weights_only: bool = False, signed: bool = True, num_classes: int = 6):
+    def __init__(self, maxdisp: int, att_weights_only: bool = False, signed: bool = True, num_classes: int = 6, precision: str = "bf16"):
+        """precision "bf16" (default, fastest): bf16 operands everywhere -- statistical parity only (top-24 sample sets agree with
+        the fp32 oracle on ~96 % of the pixels, median |disparity error| ~0.03 px in 1/4-res units; tests/test_gpu_decoder.py).
+        "split": fp32-accurate bf16x3 products in FeatUp, chal_1/2 and the attention branch (Decoder2D / DisparityHotPath
+        precision="split"): the sample sets equal the oracle's (>= 99.9 %), the aggregation stays bf16; ~2x slower."""
         super().__init__()
-        self.decoder = Decoder2D(num_classes)
-        self.path = DisparityHotPath(maxdisp, att_weights_only, signed, num_classes, precision="bf16")
+        if precision not in ("bf16", "split"):
+            raise ValueError("StereoHead precision must be 'bf16' or 'split'")
+        self.precision = precision
+        self.decoder = Decoder2D(num_classes, precision)
+        self.path = DisparityHotPath(maxdisp, att_weights_only, signed, num_classes, precision=precision)
 
     def load_state_dict(self, state_dict, strict=False, **kw):
         a = self.decoder.load_state_dict(state_dict, strict=strict, **kw)

@@ -443,19 +443,29 @@ class DisparityHotPath(nn.Module):
         # --- sparse concat volume + aggregation (SemStereo.py:314-324) ---
         main_bf16 = self._is_bf16("hourglass")
         f4l_b = None                            # bf16 blocked copy of f4_l: feeds concat_feature and the gate convs
-        if main_bf16:
-            f4l_b = (f4_l_blocked.view(f4_l.shape[0], 16, 1, *f4_l.shape[2:], 8) if f4_l_blocked is not None
-                     else tc.to_blocked_bf16(f4_l.unsqueeze(2)))
         # bf16 mode without kept intermediates: the sparse concat volume is generated inside the concat_stem kernel (never in HBM)
         nbins = (2 if self.signed else 1) * m4
         fused = main_bf16 and not keep and nbins == 32
+        if fused and cf_l is None and cf_r is None and f4_l_blocked is None:
+            # concat_feature of BOTH images as one batch of 2B through its two tensor-core layers (2 launches instead of 4)
+            Bn = f4_l.shape[0]
+            both = torch.empty((2 * Bn, 16, 1, *f4_l.shape[2:], 8), device=f4_l.device, dtype=torch.bfloat16)
+            with ops.label("concat_feature"):
+                tc.to_blocked_bf16(f4_l.unsqueeze(2), out=both[:Bn])
+                tc.to_blocked_bf16(f4_r.unsqueeze(2), out=both[Bn:])
+                y = tc.conv3d_tc(tc.C2D, both, c["cf0.tc"], 64, c["cf0.scale"], c["cf0.shift"], relu=True)
+                cf = tc.conv3d_tc(tc.C2D, y, c["cf1.tc"], 32)
+            f4l_b, cf_l, cf_r = both[:Bn], cf[:Bn], cf[Bn:]
+        elif main_bf16:
+            f4l_b = (f4_l_blocked.view(f4_l.shape[0], 16, 1, *f4_l.shape[2:], 8) if f4_l_blocked is not None
+                     else tc.to_blocked_bf16(f4_l.unsqueeze(2)))
         if cf_l is None:
             cf_l = self._concat_feature(c, f4_l, f4l_b, blocked=fused)
-        elif fused:
+        elif fused and cf_l.dtype != torch.bfloat16:
             cf_l = tc.to_blocked2d(cf_l)
         if cf_r is None:
             cf_r = self._concat_feature(c, f4_r, blocked=fused)
-        elif fused:
+        elif fused and cf_r.dtype != torch.bfloat16:
             cf_r = tc.to_blocked2d(cf_r)
         gate4 = self._gate_logits(c, "concat_feature_att_4", f4_l, f4l_b)
         if fused:

@@ -5,6 +5,8 @@ phase = 4*(d&1) + 2*(h&1) + (w&1).  See include/semstereo_b200.h and csrc/conv3d
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib
@@ -21,13 +23,17 @@ def _require_bf16(t, ndim):
     return t.device
 
 
-def to_blocked_bf16(x, s2d=False, split=False):
-    """split=True: the hi/lo pair of the bf16x3 route stacked on the batch axis -> batch 2B (see conv3d_tc_split)."""
+def to_blocked_bf16(x, s2d=False, split=False, out=None):
+    """split=True: the hi/lo pair of the bf16x3 route stacked on the batch axis -> batch 2B (see conv3d_tc_split).
+    out: write into this (contiguous, right-shaped) tensor, e.g. one half of a batch-stacked buffer."""
     dev = _require_cuda(x)
     B, C, D, H, W = x.shape
     nb = 2 * B if split else B
     shape = (nb, 8, C // 8, D // 2, H // 2, W // 2, 8) if s2d else (nb, C // 8, D, H, W, 8)
-    out = torch.empty(shape, device=dev, dtype=torch.bfloat16)
+    if out is None:
+        out = torch.empty(shape, device=dev, dtype=torch.bfloat16)
+    elif tuple(out.shape) != shape or out.dtype != torch.bfloat16 or not out.is_contiguous() or out.device != dev:
+        raise ValueError("to_blocked_bf16: `out` must be a contiguous bf16 tensor of shape %s" % (shape,))
     _call("ss_to_blocked_bf16_ex", dev, _ptr(x), _ptr(out), B, C, D, H, W, int(s2d), int(split))
     return out
 
@@ -378,9 +384,33 @@ def pack_weight2d(w, mode):
     return t.contiguous().to(torch.bfloat16)
 
 
-def conv2d_tc(mode, x0, w_packed, cout, scale=None, shift=None, relu=False, out_f32=False, x1=None):
+def pack_weight2d_split(w, mode, groups=None):
+    """bf16x3 split of a 2-D conv as ONE GEMM over K-concat operands: every input tensor of the (virtual) channel concat is given
+    in the [hi | lo | hi] form of to_blocked_tri, and the weight columns of each input group are laid out [w_hi | w_hi | w_lo]
+    to match.  groups: channel counts of the concatenated inputs (default: one input).  w as for pack_weight2d."""
+    w = w.detach().float()
+    cdim = 0 if mode == DECONV4 else 1
+    cin = w.shape[cdim]
+    groups = [cin] if groups is None else list(groups)
+    if sum(groups) != cin:
+        raise ValueError("pack_weight2d_split: groups must sum to the input channel count")
+    hi, lo = split_f32(w)
+    parts, o = [], 0
+    for gch in groups:
+        sl = [slice(None)] * w.dim()
+        sl[cdim] = slice(o, o + gch)
+        parts += [hi[tuple(sl)], hi[tuple(sl)], lo[tuple(sl)]]
+        o += gch
+    return pack_weight2d(torch.cat(parts, cdim), mode)
+
+
+NONE, RELU, SILU = 0, 1, 2          # act of conv2d_tc (1x1 mode) / dwconv3x3
+
+
+def conv2d_tc(mode, x0, w_packed, cout, scale=None, shift=None, relu=False, out_f32=False, x1=None, act=None, residual=None):
     """x0 (and optionally x1, concatenated after it along channels) blocked bf16 (B,C/8,H,W,8).  Returns blocked bf16
-    (B,Cout/8,OH,OW,8) or fp32 NCHW; OH,OW = H,W (conv) or 2H,2W (DECONV4)."""
+    (B,Cout/8,OH,OW,8) or fp32 NCHW; OH,OW = H,W (conv) or 2H,2W (DECONV4).  1x1 mode only: act (NONE / RELU / SILU, overrides
+    `relu`) and residual (bf16 blocked, shaped like the output, added after the activation)."""
     dev = _require_bf16(x0, 5)
     B, C80, H, W, _ = x0.shape
     c0, c1 = C80 * 8, 0
@@ -404,8 +434,62 @@ def conv2d_tc(mode, x0, w_packed, cout, scale=None, shift=None, relu=False, out_
         out = torch.empty((B, cout, OH, OW), device=dev, dtype=torch.float32)
     else:
         out = torch.empty((B, cout // 8, OH, OW, 8), device=dev, dtype=torch.bfloat16)
-    _call("ss_conv2d_tc", dev, int(mode), _ptr(x0), c0, _ptr(x1), c1, _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(out),
-          int(out_f32), B, cout, H, W, int(relu))
+    if residual is not None:
+        _require_bf16(residual, 5)
+        if out_f32 or tuple(residual.shape) != tuple(out.shape):
+            raise ValueError("conv2d_tc: the residual must be bf16 blocked with the shape of the (bf16) output")
+    _call("ss_conv2d_tc_ex", dev, int(mode), _ptr(x0), c0, _ptr(x1), c1, _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(residual), _ptr(out),
+          int(out_f32), B, cout, H, W, int(relu) if act is None else int(act))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# backbone kernels (csrc/backbone.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+def stem_conv(image, weight, scale, shift, cout_padded=64):
+    """Conv2d(3,32,3,s2,p1) + folded BN + SiLU: fp32 (B,3,H,W) -> bf16 blocked (B,cout_padded/8,H/2,W/2,8), channels >= 32 zero."""
+    dev = _require_cuda(image, weight, scale, shift)
+    B, C, H, W = image.shape
+    if C != 3 or tuple(weight.shape) != (32, 3, 3, 3):
+        raise ValueError("stem_conv: (B,3,H,W) image and (32,3,3,3) weight expected")
+    out = torch.empty((B, cout_padded // 8, H // 2, W // 2, 8), device=dev, dtype=torch.bfloat16)
+    _call("ss_stem_conv3x3_s2", dev, _ptr(image), _ptr(weight), _ptr(scale), _ptr(shift), _ptr(out), B, H, W, int(cout_padded))
+    return out
+
+
+def dwconv3x3(xb, weight, scale, shift, stride=1, act=SILU):
+    """Depthwise Conv2d 3x3 p1 (+ folded BN + act) on blocked bf16; weight fp32 (C,9)."""
+    dev = _require_bf16(xb, 5)
+    _require_cuda(weight, scale, shift)
+    B, C8, H, W, _ = xb.shape
+    if weight.numel() != C8 * 8 * 9:
+        raise ValueError("dwconv3x3: weight (C,9) expected")
+    out = torch.empty((B, C8, H // stride, W // stride, 8), device=dev, dtype=torch.bfloat16)
+    _call("ss_dwconv3x3_blocked", dev, _ptr(xb), _ptr(weight), _ptr(scale), _ptr(shift), _ptr(out), B, C8 * 8, H, W, int(stride), int(act))
+    return out
+
+
+def groupnorm1(xb, gamma, beta, eps=1e-5):
+    """nn.GroupNorm(1, C) on blocked bf16 (statistics in fp32)."""
+    dev = _require_bf16(xb, 5)
+    _require_cuda(gamma, beta)
+    B, C8, H, W, _ = xb.shape
+    ws = torch.empty(_lib.load().ss_groupnorm1_workspace_floats(B), device=dev, dtype=torch.float32)
+    out = torch.empty_like(xb)
+    _call("ss_groupnorm1_blocked", dev, _ptr(xb), _ptr(gamma), _ptr(beta), _ptr(out), _ptr(ws), B, C8 * 8, H, W, ctypes.c_float(eps))
+    return out
+
+
+def linear_attention(qkv_b, d):
+    """MobileViTv2 separable self-attention core: qkv blocked (B, 2d/8 + 1, H, W, 8) [key | value | query in lane 0 of the last
+    chunk] -> relu(value) * context, blocked (B, d/8, H, W, 8)."""
+    dev = _require_bf16(qkv_b, 5)
+    B, CH, H, W, _ = qkv_b.shape
+    if CH != 2 * (d // 8) + 1:
+        raise ValueError("linear_attention: qkv must have 2d/8 + 1 channel chunks")
+    ws = torch.empty(_lib.load().ss_linear_attention_workspace_floats(B, d), device=dev, dtype=torch.float32)
+    out = torch.empty((B, d // 8, H, W, 8), device=dev, dtype=torch.bfloat16)
+    _call("ss_linear_attention_blocked", dev, _ptr(qkv_b), _ptr(out), _ptr(ws), B, int(d), H, W)
     return out
 
 

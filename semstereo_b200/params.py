@@ -218,3 +218,48 @@ def make_backbone_features(seed: int, B: int, H: int, W: int, max_shift: int = 3
         fl.append(l.contiguous())
         fr.append(r.contiguous())
     return fl, fr
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# backbone: MobileViTv2-1.0, HuggingFace parameter names (semstereo_b200/backbone.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def make_backbone_params(seed: int = 4) -> "OrderedDict[str, torch.Tensor]":
+    """Seeded parameters of MobileViTv2Backbone (= a MobileViTV2Model state_dict): unit-gain conv weights, non-trivial
+    BatchNorm statistics / GroupNorm affines / biases, so that every folded constant is exercised and activations stay O(1)."""
+    from .backbone import MobileViTv2Backbone
+    g = torch.Generator().manual_seed(seed)
+    p: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for name, t in MobileViTv2Backbone().state_dict().items():
+        shape = tuple(t.shape)
+        if name.endswith("num_batches_tracked"):
+            continue
+        if name.endswith("running_var"):
+            v = torch.rand(shape, generator=g) + 0.5
+        elif name.endswith("running_mean"):
+            v = 0.1 * torch.randn(shape, generator=g)
+        elif len(shape) == 1 and name.endswith(".weight"):        # BatchNorm / GroupNorm gamma
+            v = torch.rand(shape, generator=g) + 0.5
+        elif len(shape) == 1:                                      # biases, betas
+            v = 0.1 * torch.randn(shape, generator=g)
+        else:                                                      # conv weights (Cout, Cin/groups, k, k)
+            fan_in = shape[1] * shape[2] * shape[3]
+            v = (torch.rand(shape, generator=g) * 2 - 1) * (3.0 / fan_in) ** 0.5 * 1.4
+        p[name] = v.contiguous()
+    return p
+
+
+def make_images(seed: int, B: int, H: int, W: int, max_shift: int = 12):
+    """Seeded synthetic stereo pair, ImageNet-normalised like datasets/data_io.py:6-13: smooth random texture, the right image is
+    the left one displaced along x by a row-block-dependent shift plus noise (CPU fp32, (B,3,H,W) each)."""
+    g = torch.Generator().manual_seed(seed)
+    base = torch.rand(B, 3, H // 4, W // 4, generator=g)
+    left = torch.nn.functional.interpolate(base, size=(H, W), mode="bilinear", align_corners=False) + 0.1 * torch.rand(B, 3, H, W, generator=g)
+    left = left.clamp(0, 1)
+    right = torch.empty_like(left)
+    for i in range(4):
+        ys = slice(i * H // 4, (i + 1) * H // 4)
+        right[:, :, ys] = torch.roll(left[:, :, ys], shifts=-((i * 7) % (2 * max_shift + 1) - max_shift), dims=-1)
+    right = (right + 0.02 * torch.randn(B, 3, H, W, generator=g)).clamp(0, 1)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    return ((left - mean) / std).contiguous(), ((right - mean) / std).contiguous()

@@ -44,7 +44,7 @@ def test_decoder_against_oracle(B, H, W):
         assert got.shape == ref[k].shape, k
         rmax, rmean = rel(got, ref[k])
         print(f"\n[decoder bf16] {k}: max err / max|ref| = {rmax:.4f}, mean err / mean|ref| = {rmean:.4f}")
-        assert rmax <= 4e-2 and rmean <= 1.5e-2, (k, rmax, rmean)
+        assert rmax <= 1e-2 and rmean <= 1e-2, (k, rmax, rmean)          # measured 0.4-0.5 % (bf16 operands through <= 10 layers)
     assert torch.equal(tc_from_blocked(out["f4_l_blocked"]), out["f4_l"].cpu())
 
 
@@ -62,7 +62,7 @@ def test_decoder_against_reference_golden(golden_dir):
     out = m.to(DEV)([t.to(DEV) for t in fl], [t.to(DEV) for t in fr], right_label=True)
     for k in ("f4_l", "f8_r", "spx_pred", "pred_label", "pred_label_r"):
         rmax, rmean = rel(out[k].cpu(), torch.from_numpy(g[k]))
-        assert rmax <= 4e-2 and rmean <= 1.5e-2, (k, rmax, rmean)
+        assert rmax <= 1e-2 and rmean <= 1e-2, (k, rmax, rmean)          # measured 0.4-0.5 %
 
 
 def test_stereo_head_against_oracle():
@@ -186,8 +186,33 @@ def test_stereo_head_full_size_against_oracle():
     torch.cuda.synchronize()
     for k in ("pred_label", "spx_pred", "f4_l", "f8_r"):
         rmax, rmean = rel(out[k].cpu(), d[k])
-        assert rmax <= 4e-2 and rmean <= 1.5e-2, (k, rmax, rmean)
+        assert rmax <= 1e-2 and rmean <= 1e-2, (k, rmax, rmean)          # measured 0.4-0.5 %
     agree = (out["ind_k"].cpu() == ref["ind_k"]).all(dim=2).float().mean().item()
     e = (out["pred_up"].cpu() - ref["pred_up"]).abs().flatten()
     print(f"\n[stereo head 1024x1024] top-24 agreement {agree:.4f}; pred_up median {e.median():.4f} p90 {e.quantile(0.9):.4f} (1/4-res px)")
     assert agree >= 0.85 and e.median().item() <= 0.06 and e.quantile(0.9).item() <= 0.8
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 128, 256)])
+def test_split_precision_decoder_and_head_select_the_oracle_samples(B, H, W):
+    """precision="split": FeatUp + chal_1/2 with fp32-accurate bf16x3 products (K-concat GEMMs) -> the path's inputs match the
+    oracle decoder to ~1e-5, and with the split attention branch behind it the top-24 sample sets equal the oracle's END TO END
+    from the backbone features (StereoHead precision)."""
+    p = params()
+    fl, fr = make_backbone_features(11, B, H, W)
+    d = od.forward(p, fl, fr, right_label=False)
+    ref = oh.forward(p, {k: d[k] for k in ("f8_l", "f8_r", "f4_l", "f4_r", "spx_pred", "pred_label")}, 64, signed=True, keep=True)
+    head = StereoHead(64, precision="split")
+    head.load_state_dict(p, strict=True)
+    out = head.to(DEV)([t.to(DEV) for t in fl], [t.to(DEV) for t in fr], keep=True)
+    torch.cuda.synchronize()
+    for k in ("f4_l", "f4_r", "f8_l", "f8_r"):
+        rmax, _ = rel(out[k].cpu(), d[k])
+        print(f"[decoder split] {k}: max err / max|ref| = {rmax:.2e}")
+        assert rmax <= 5e-5, (k, rmax)
+    agree = (out["ind_k"].cpu() == ref["ind_k"]).all(dim=2).float().mean().item()
+    med = (out["pred_up"].cpu() - ref["pred_up"]).abs().median().item()
+    print(f"[stereo head split] top-24 sample-set agreement {agree:.6f}; median |pred_up - oracle| {med:.4f} px (1/4-res units)")
+    assert agree >= 0.999 and med <= 0.05
+    with pytest.raises(ValueError):
+        StereoHead(64, precision="fp32")

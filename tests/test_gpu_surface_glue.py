@@ -18,6 +18,15 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True)
+def true_fp32_torch_convs():
+    """torch's own GPU convolutions default to TF32; the comparisons here are against fp32 references."""
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
 def build_glue(ns, other, maxdisp, signed, num_classes=6):
     """The hot-path half of SemStereo.__init__ (SemStereo.py:204-239) from the surface names."""
     convbn_3d, attention_block, BasicConv = other["convbn_3d"], other["attention_block"], ns["BasicConv"]
