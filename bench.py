@@ -116,13 +116,18 @@ def hbm_bytes(H, W, maxdisp, signed=True):
 
 
 def ncu_traffic(kernel, precision, batch):
-    """DRAM bytes (read + write) per launch of `kernel` from the committed `ncu --set full` capture (profiles/r01_traffic.json:
+    """DRAM bytes (read + write) per launch of `kernel` from the committed `ncu --set full` capture (profiles/r0N_traffic.json:
     bytes per stereo pair, measured at the batch stated there), scaled to this run's batch; None when no capture exists."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if not os.path.exists(p):
-        return None
-    ent = json.load(open(p)).get(precision, {}).get(kernel)
-    return None if ent is None else int(ent["dram_bytes_per_pair"] * batch)
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(p):
+            continue
+        tab = json.load(open(p))
+        # the aggregation branch (incl. the dominant concat_stem kernel) is the same bf16 kernel in the "split" and "mixed" modes
+        ent = tab.get(precision, {}).get(kernel) or (tab.get("bf16", {}).get(kernel) if precision in ("split", "mixed") else None)
+        if ent is not None:
+            return int(ent["dram_bytes_per_pair"] * batch)
+    return None
 
 
 class ClockSampler:

@@ -289,4 +289,22 @@ SS_API int ss_spatial_transformer_grid_backward(const float* y, const float* dis
                                                 const float* grad_x_rep_or_null, float* grad_x_or_null, float* grad_y, float* grad_disp,
                                                 int B, int C, int K, int H, int W, void* stream);
 
+/* ---- training closure of the 3-D conv stack (BASELINE config #5; convbn_3d / BasicConv(is_3d) in training mode) -----------------
+ * Conv3d weight gradient: x (B,Cin,Di,Hi,Wi), grad_out (B,Cout,Do,Ho,Wo) -> grad_weight_packed [K^3][Cin][Cout] (the packing of
+ * ss_conv3d_f32; MUST be zero on entry, accumulated with atomics).  K in {1,3}, pad K/2, stride in {1,2}.  The INPUT gradient
+ * needs no entry point of its own: it is ss_conv3d_f32 on grad_out with a re-packed weight (flipped k3 s1 / transposed-conv k3 s2 /
+ * W^T k1; semstereo_b200/train_ops.py). */
+SS_API int ss_conv3d_wgrad_f32(const float* x, const float* grad_out, float* grad_weight_packed, int B, int Cin, int Cout, int Di, int Hi,
+                               int Wi, int K, int stride, void* stream);
+/* BatchNorm{2,3}d with BATCH statistics over (B, S = spatial size) per channel (training mode of nn.BatchNorm, appendix C of
+ * SURVEY.md): batch_mean / batch_var (biased) are outputs of the forward (the caller updates running_mean / running_var with
+ * momentum and the unbiased variance) and inputs of the backward.  out = (x - mean) * rsqrt(var + eps) * weight + bias (-> ReLU).
+ * backward: grad_weight = sum(dy * xhat), grad_bias = sum(dy), grad_x = w * rstd * (dy - (grad_bias + xhat * grad_weight) / N);
+ * with relu = 1 in the forward the caller masks grad_out with (out > 0) first. */
+SS_API int ss_bn_train_forward(const float* x, const float* weight_or_null, const float* bias_or_null, float* out, float* batch_mean,
+                               float* batch_var, int B, int C, long long S, float eps, int relu, void* stream);
+SS_API int ss_bn_train_backward(const float* x, const float* grad_out, const float* batch_mean, const float* batch_var,
+                                const float* weight_or_null, float* grad_x, float* grad_weight, float* grad_bias, int B, int C, long long S,
+                                float eps, void* stream);
+
 #endif /* SEMSTEREO_B200_H */

@@ -1,0 +1,193 @@
+// Training closure of the 3-D convolution stack (BASELINE config #5): what convbn_3d /
+// BasicConv(is_3d) (models/submodule_other.py:845-848, models/submodule.py:89-116) need beyond the inference kernels when the
+// model trains (main_us3d.py:186-222): the weight gradient of Conv3d, and BatchNorm3d with BATCH statistics, forward and backward.
+//   * input gradient of Conv3d: no new kernel -- dX of a k3 s1 conv is the k3 s1 conv of dY with the flipped / transposed weight,
+//     dX of a k3 s2 p1 conv is ConvTranspose3d(k3, s2, p1, op1) of dY with the same weight, dX of a k1 conv is the k1 conv with
+//     W^T: all three are launches of ss_conv3d_f32 (csrc/conv3d_f32.cu) with a re-packed weight (semstereo_b200/train_ops.py);
+//   * conv3d_wgrad: dW[tap][ci][co] = sum over (b, output voxel o) of dY[b,co,o] * X[b,ci, o*stride - pad + tap]
+//     -- a GEMM with K = B * output voxels, split over CTAs along K, fp32 FFMA, atomic accumulation into a zeroed dW;
+//   * bn_stats / bn_apply / bn_backward: per-channel batch mean and biased variance over (B, D, H, W), normalise + affine
+//     (+ ReLU), and the standard BatchNorm VJP  dx = w * rstd / N * (N dy - sum(dy) - xhat * sum(dy xhat)).
+// fp32 throughout (the reference trains in fp32); deterministic except for the order of the wgrad atomics.
+#include "common.cuh"
+
+namespace {
+
+// ---- Conv3d weight gradient -----------------------------------------------------------------------------------------------
+constexpr int WG_T = 32, WG_V = 32, WG_CHUNK = 4096;      // 32 ci x 32 co tile, 32 voxels per smem step, voxels per CTA
+
+struct WgP {
+  const float* x;      // (B,Cin,Di,Hi,Wi)
+  const float* dy;     // (B,Cout,Do,Ho,Wo)
+  float* dw;           // [K^3][Cin][Cout], zeroed by the caller
+  int B, Cin, Cout, Di, Hi, Wi, Do, Ho, Wo, K, stride, pad;
+  long long M;         // B*Do*Ho*Wo
+  int tiles_co;
+};
+
+__global__ void __launch_bounds__(256) conv3d_wgrad_kernel(const WgP p) {
+  __shared__ float Xs[WG_T][WG_V + 1];
+  __shared__ float Ys[WG_T][WG_V + 1];
+  const int tap = blockIdx.y;
+  const int kd = tap / (p.K * p.K), kh = (tap / p.K) % p.K, kw = tap % p.K;
+  const int ci0 = (blockIdx.z / p.tiles_co) * WG_T, co0 = (blockIdx.z % p.tiles_co) * WG_T;
+  const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;          // thread owns ci {ti, ti+16} x co {tj, tj+16}
+  const long long m0 = (long long)blockIdx.x * WG_CHUNK, m1 = min(p.M, m0 + WG_CHUNK);
+  const size_t in_cs = (size_t)p.Di * p.Hi * p.Wi, out_cs = (size_t)p.Do * p.Ho * p.Wo;
+  const int lv = tid & 31, lc = tid >> 5;                              // loader: voxel lv, channels lc, lc+8, lc+16, lc+24
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (long long mb = m0; mb < m1; mb += WG_V) {
+    const long long m = mb + lv;
+    bool ok = m < m1;
+    long long r = ok ? m : 0;
+    const int ow = (int)(r % p.Wo); r /= p.Wo;
+    const int oh = (int)(r % p.Ho); r /= p.Ho;
+    const int od = (int)(r % p.Do);
+    const int b = (int)(r / p.Do);
+    const int di = od * p.stride - p.pad + kd, hi = oh * p.stride - p.pad + kh, wi = ow * p.stride - p.pad + kw;
+    const bool xin = ok && di >= 0 && di < p.Di && hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi;
+    const size_t xo = ((size_t)(xin ? di : 0) * p.Hi + (xin ? hi : 0)) * p.Wi + (xin ? wi : 0);
+    const size_t yo = ((size_t)od * p.Ho + oh) * p.Wo + ow;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = lc + 8 * q;
+      Xs[c][lv] = (xin && ci0 + c < p.Cin) ? __ldg(p.x + ((size_t)b * p.Cin + ci0 + c) * in_cs + xo) : 0.0f;
+      Ys[c][lv] = (ok && co0 + c < p.Cout) ? __ldg(p.dy + ((size_t)b * p.Cout + co0 + c) * out_cs + yo) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < WG_V; ++v) {
+      const float x0 = Xs[ti][v], x1 = Xs[ti + 16][v], y0 = Ys[tj][v], y1 = Ys[tj + 16][v];
+      acc[0][0] = fmaf(x0, y0, acc[0][0]); acc[0][1] = fmaf(x0, y1, acc[0][1]);
+      acc[1][0] = fmaf(x1, y0, acc[1][0]); acc[1][1] = fmaf(x1, y1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int ci = ci0 + ti + 16 * a, co = co0 + tj + 16 * c;
+      if (ci < p.Cin && co < p.Cout) atomicAdd(p.dw + ((size_t)tap * p.Cin + ci) * p.Cout + co, acc[a][c]);
+    }
+}
+
+// ---- BatchNorm with batch statistics ------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_d(double v, double* red) {      // 256 threads
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < 8; ++i) t += red[i];
+  return t;
+}
+
+// one CTA per channel: mean and biased variance over B*S elements (two passes over the channel: exact centred variance)
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ var, int B, int C,
+                                                       size_t S) {
+  __shared__ double red[8];
+  const int c = blockIdx.x;
+  const size_t n = (size_t)B * S;
+  float s = 0.f;
+  for (size_t i = threadIdx.x; i < n; i += 256) s += __ldg(x + ((i / S) * C + c) * S + i % S);
+  const double mu = block_sum_d((double)s, red) / (double)n;
+  const float muf = (float)mu;
+  float q = 0.f;
+  for (size_t i = threadIdx.x; i < n; i += 256) { const float d = __ldg(x + ((i / S) * C + c) * S + i % S) - muf; q = fmaf(d, d, q); }
+  const double v = block_sum_d((double)q, red) / (double)n;
+  if (threadIdx.x == 0) { mean[c] = muf; var[c] = (float)v; }
+}
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ var,
+                                                       const float* __restrict__ weight, const float* __restrict__ bias, float* __restrict__ out,
+                                                       int C, size_t S, size_t total, float eps, int relu) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)((i / S) % C);
+  const float rstd = rsqrtf(__ldg(var + c) + eps);
+  float y = (x[i] - __ldg(mean + c)) * rstd * (weight ? __ldg(weight + c) : 1.0f) + (bias ? __ldg(bias + c) : 0.0f);
+  out[i] = relu ? fmaxf(y, 0.0f) : y;
+}
+
+// per channel: dbias = sum(dy), dweight = sum(dy * xhat)
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ mean,
+                                                            const float* __restrict__ var, float* __restrict__ dweight, float* __restrict__ dbias,
+                                                            int B, int C, size_t S, float eps) {
+  __shared__ double red[8];
+  const int c = blockIdx.x;
+  const size_t n = (size_t)B * S;
+  const float mu = __ldg(mean + c), rstd = rsqrtf(__ldg(var + c) + eps);
+  float s = 0.f, q = 0.f;
+  for (size_t i = threadIdx.x; i < n; i += 256) {
+    const size_t o = ((i / S) * C + c) * S + i % S;
+    const float g = __ldg(dy + o);
+    s += g;
+    q = fmaf(g, (__ldg(x + o) - mu) * rstd, q);
+  }
+  const double sd = block_sum_d((double)s, red);
+  const double qd = block_sum_d((double)q, red);
+  if (threadIdx.x == 0) { dbias[c] = (float)sd; dweight[c] = (float)qd; }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ mean,
+                                                        const float* __restrict__ var, const float* __restrict__ weight,
+                                                        const float* __restrict__ dweight, const float* __restrict__ dbias, float* __restrict__ dx,
+                                                        int C, size_t S, size_t total, float inv_n, float eps) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)((i / S) % C);
+  const float rstd = rsqrtf(__ldg(var + c) + eps), xhat = (x[i] - __ldg(mean + c)) * rstd;
+  const float w = weight ? __ldg(weight + c) : 1.0f;
+  dx[i] = w * rstd * (dy[i] - inv_n * (__ldg(dbias + c) + xhat * __ldg(dweight + c)));
+}
+
+}  // namespace
+
+extern "C" int ss_conv3d_wgrad_f32(const float* x, const float* grad_out, float* grad_weight_packed, int B, int Cin, int Cout, int Di, int Hi,
+                                   int Wi, int K, int stride, void* stream) {
+  SS_REQUIRE(x && grad_out && grad_weight_packed, "ss_conv3d_wgrad_f32: null pointer");
+  SS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Di > 0 && Hi > 0 && Wi > 0, "ss_conv3d_wgrad_f32: non-positive dimension");
+  SS_UNSUPPORTED(!(K == 1 || K == 3) || !(stride == 1 || stride == 2), "ss_conv3d_wgrad_f32: K in {1,3}, stride in {1,2} (got K=%d, stride=%d)", K, stride);
+  WgP p;
+  p.x = x; p.dy = grad_out; p.dw = grad_weight_packed;
+  p.B = B; p.Cin = Cin; p.Cout = Cout; p.Di = Di; p.Hi = Hi; p.Wi = Wi; p.K = K; p.stride = stride; p.pad = K / 2;
+  p.Do = (Di + 2 * p.pad - K) / stride + 1; p.Ho = (Hi + 2 * p.pad - K) / stride + 1; p.Wo = (Wi + 2 * p.pad - K) / stride + 1;
+  p.M = (long long)B * p.Do * p.Ho * p.Wo;
+  p.tiles_co = ceil_div(Cout, WG_T);
+  const long long chunks = ceil_div64(p.M, WG_CHUNK);
+  const int tiles = ceil_div(Cin, WG_T) * p.tiles_co;
+  SS_UNSUPPORTED(chunks > 0x7fffffffLL || tiles > 65535, "ss_conv3d_wgrad_f32: grid dimension too large");
+  conv3d_wgrad_kernel<<<dim3((unsigned)chunks, K * K * K, tiles), 256, 0, (cudaStream_t)stream>>>(p);
+  SS_CHECK_LAUNCH("ss_conv3d_wgrad_f32");
+  return SS_OK;
+}
+
+extern "C" int ss_bn_train_forward(const float* x, const float* weight_or_null, const float* bias_or_null, float* out, float* batch_mean,
+                                   float* batch_var, int B, int C, long long S, float eps, int relu, void* stream) {
+  SS_REQUIRE(x && out && batch_mean && batch_var && B > 0 && C > 0 && S > 0, "ss_bn_train_forward: bad argument");
+  SS_UNSUPPORTED((long long)B * S < 2, "ss_bn_train_forward: batch statistics need more than one value per channel");
+  cudaStream_t st = (cudaStream_t)stream;
+  bn_stats_kernel<<<C, 256, 0, st>>>(x, batch_mean, batch_var, B, C, (size_t)S);
+  SS_CHECK_LAUNCH("ss_bn_train_forward(stats)");
+  const size_t total = (size_t)B * C * S;
+  bn_apply_kernel<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(x, batch_mean, batch_var, weight_or_null, bias_or_null, out, C, (size_t)S,
+                                                                           total, eps, relu);
+  SS_CHECK_LAUNCH("ss_bn_train_forward(apply)");
+  return SS_OK;
+}
+
+extern "C" int ss_bn_train_backward(const float* x, const float* grad_out, const float* batch_mean, const float* batch_var,
+                                    const float* weight_or_null, float* grad_x, float* grad_weight, float* grad_bias, int B, int C, long long S,
+                                    float eps, void* stream) {
+  SS_REQUIRE(x && grad_out && batch_mean && batch_var && grad_x && grad_weight && grad_bias && B > 0 && C > 0 && S > 0,
+             "ss_bn_train_backward: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  bn_bwd_reduce_kernel<<<C, 256, 0, st>>>(x, grad_out, batch_mean, batch_var, grad_weight, grad_bias, B, C, (size_t)S, eps);
+  SS_CHECK_LAUNCH("ss_bn_train_backward(reduce)");
+  const size_t total = (size_t)B * C * S;
+  bn_bwd_dx_kernel<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(x, grad_out, batch_mean, batch_var, weight_or_null, grad_weight, grad_bias,
+                                                                            grad_x, C, (size_t)S, total, 1.0f / (float)((double)B * (double)S), eps);
+  SS_CHECK_LAUNCH("ss_bn_train_backward(dx)");
+  return SS_OK;
+}
