@@ -237,7 +237,15 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches in region 1 instead of CUDA-graph replays")
     ap.add_argument("--external-cf", action="store_true",
                     help="hand concat_feature(f4_*) in as inputs (round-1 boundary) instead of computing it inside the path")
+    ap.add_argument("--train", action="store_true",
+                    help="BASELINE config #5: attention_weights_only TRAINING step (forward + losses + backward + gradient all-reduce + Adam), "
+                         "--batch pairs per GPU (default 2 => 16 on 8 GPUs); delegates to tools/train_step.py")
     a = ap.parse_args()
+    if a.train:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import train_step
+        return train_step.main(["--gpus", str(a.gpus), "--steps", str(a.steps), "--warmup", str(a.warmup), "--height", str(a.height),
+                                "--width", str(a.width), "--maxdisp", str(a.maxdisp), "--batch", str(2 if a.batch == 8 else a.batch)])
     signed = a.variant == "us3d"
     if a.variant == "whu":
         if a.height == 1024 and a.width == 1024:

@@ -301,10 +301,23 @@ SS_API int ss_conv3d_wgrad_f32(const float* x, const float* grad_out, float* gra
  * momentum and the unbiased variance) and inputs of the backward.  out = (x - mean) * rsqrt(var + eps) * weight + bias (-> ReLU).
  * backward: grad_weight = sum(dy * xhat), grad_bias = sum(dy), grad_x = w * rstd * (dy - (grad_bias + xhat * grad_weight) / N);
  * with relu = 1 in the forward the caller masks grad_out with (out > 0) first. */
+SS_API int ss_bn_workspace_bytes(int C);          /* device scratch for the per-channel reductions (64 partial sums per channel) */
 SS_API int ss_bn_train_forward(const float* x, const float* weight_or_null, const float* bias_or_null, float* out, float* batch_mean,
-                               float* batch_var, int B, int C, long long S, float eps, int relu, void* stream);
+                               float* batch_var, void* workspace, int B, int C, long long S, float eps, int relu, void* stream);
 SS_API int ss_bn_train_backward(const float* x, const float* grad_out, const float* batch_mean, const float* batch_var,
-                                const float* weight_or_null, float* grad_x, float* grad_weight, float* grad_bias, int B, int C, long long S,
-                                float eps, void* stream);
+                                const float* weight_or_null, float* grad_x, float* grad_weight, float* grad_bias, void* workspace, int B, int C,
+                                long long S, float eps, void* stream);
+
+/* attention_block in training mode (submodule_other.py:805-837): the qkv Linear and the final 1x1x1 conv are k = 1 layers of the
+ * differentiable conv above; in between, the fp32 softmax core with an fp32 NCDHW output (qkv (B,3C,D,H,W) -> (B,C,D,H,W)) and its
+ * backward (grad_out (B,C,D,H,W) -> grad_qkv (B,3C,D,H,W)).  C = 128, 16 heads, windows <= 96 tokens (forward: 64 / 96, bw = 4). */
+SS_API int ss_window_attention_core_f32_out(const float* qkv, float* out_f32, int B, int C, int D, int H, int W, int bd, int bh, int bw,
+                                            int num_heads, void* stream);
+SS_API int ss_window_attention_core_backward(const float* qkv, const float* grad_out, float* grad_qkv, int B, int C, int D, int H, int W,
+                                             int bd, int bh, int bw, int num_heads, void* stream);
+/* F.interpolate(scale_factor 4, bilinear, align_corners=False) of `planes` fp32 (h,w) planes and its VJP (SSR_upsample in training
+ * mode, submodule.py:424, composed from differentiable kernels because its BatchNorm layers then need batch statistics). */
+SS_API int ss_bilinear_up4(const float* in, float* out, int planes, int h, int w, void* stream);
+SS_API int ss_bilinear_up4_backward(const float* grad_out, float* grad_in, int planes, int h, int w, void* stream);
 
 #endif /* SEMSTEREO_B200_H */

@@ -46,9 +46,14 @@ SIGNATURES = {
     "ss_propagation_backward": [_P, _P, _I, _I, _I, _I, _P],
     "ss_disparity_variance_backward": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "ss_spatial_transformer_grid_backward": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "ss_window_attention_core_f32_out": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "ss_window_attention_core_backward": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "ss_bilinear_up4": [_P, _P, _I, _I, _I, _P],
+    "ss_bilinear_up4_backward": [_P, _P, _I, _I, _I, _P],
     "ss_conv3d_wgrad_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
-    "ss_bn_train_forward": [_P, _P, _P, _P, _P, _P, _I, _I, ctypes.c_longlong, _F, _I, _P],
-    "ss_bn_train_backward": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, ctypes.c_longlong, _F, _P],
+    "ss_bn_workspace_bytes": [_I],
+    "ss_bn_train_forward": [_P, _P, _P, _P, _P, _P, _P, _I, _I, ctypes.c_longlong, _F, _I, _P],
+    "ss_bn_train_backward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, ctypes.c_longlong, _F, _P],
     "ss_conv2d_tc_ntile": [_I, _I, _I],
     "ss_conv2d_tc": [_I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ss_conv2d_tc_ex": [_I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

@@ -219,8 +219,9 @@ __global__ void __launch_bounds__(256) window_attention_core_f32_generic_kernel(
 // floats), and per (head, query) task all T scores are computed first into registers (T independent 8-term dot products), then
 // max / exp / weighted sum -- no serial online-softmax chain (the generic kernel below was latency-bound: 92 us for 128 windows).
 template <int T>
-__global__ void __launch_bounds__(256, 2) window_attention_core_f32_kernel(const float* __restrict__ qkv, uint4* __restrict__ out, int D,
-                                                                          int H, int W, int bd, int bh, int nd, int nh, int nw) {
+__global__ void __launch_bounds__(256, 2) window_attention_core_f32_kernel(const float* __restrict__ qkv, uint4* __restrict__ out,
+                                                                          float* __restrict__ out_f32, int D, int H, int W, int bd, int bh,
+                                                                          int nd, int nh, int nw) {
   extern __shared__ __align__(16) float smem[];        // [3][heads][T][hd]
   constexpr int BW = 4;
   int wid = blockIdx.x;
@@ -282,6 +283,14 @@ __global__ void __launch_bounds__(256, 2) window_attention_core_f32_kernel(const
       o[4] = fmaf(pe, vc.x, o[4]); o[5] = fmaf(pe, vc.y, o[5]); o[6] = fmaf(pe, vc.z, o[6]); o[7] = fmaf(pe, vc.w, o[7]);
     }
     const float inv = 1.0f / l;
+    const int dd = tq / (bh * BW), rr = tq - dd * bh * BW, hh = rr / BW, ww = rr - hh * BW;
+    const size_t vo = ((size_t)dd * H + hh) * W + ww;
+    if (out_f32) {                      // training / plain fp32 consumers: (B,C,D,H,W), channel = head*hd + j
+      float* of = out_f32 + ((size_t)b * kC + h * kHd) * cs + wbase + vo;
+#pragma unroll
+      for (int j = 0; j < kHd; ++j) of[(size_t)j * cs] = o[j] * inv;
+      continue;
+    }
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -291,8 +300,6 @@ __global__ void __launch_bounds__(256, 2) window_attention_core_f32_kernel(const
       __nv_bfloat162 lv = __floats2bfloat162_rn(x0 - __uint_as_float(hi[j] << 16), x1 - __uint_as_float(hi[j] & 0xffff0000u));
       lo[j] = *reinterpret_cast<uint32_t*>(&lv);
     }
-    const int dd = tq / (bh * BW), rr = tq - dd * bh * BW, hh = rr / BW, ww = rr - hh * BW;
-    const size_t vo = ((size_t)dd * H + hh) * W + ww;
     const uint4 qh = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     ob[(size_t)h * cs + vo] = qh;
     ob[(size_t)(kHeads + h) * cs + vo] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -300,7 +307,142 @@ __global__ void __launch_bounds__(256, 2) window_attention_core_f32_kernel(const
   }
 }
 
+// Backward of the core (training, BASELINE config #5): one CTA per (window, head), thread i = query i (then key/value column i).
+//   S = scale q k^T, P = softmax_j(S), O = P v;   dV_j = sum_i P_ij dO_i;  dP_ij = dO_i . v_j;  dS_ij = P_ij (dP_ij - sum_j P_ij dP_ij);
+//   dQ_i = scale sum_j dS_ij k_j;  dK_j = scale sum_i dS_ij q_i.        qkv, dqkv (B,3C,D,H,W); dO (B,C,D,H,W).
+__global__ void __launch_bounds__(96) window_attention_core_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_out,
+                                                                       float* __restrict__ d_qkv, int D, int H, int W, int bd, int bh, int bw,
+                                                                       int nd, int nh, int nw, int T) {
+  extern __shared__ __align__(16) float smem[];
+  float* Qs = smem;                    // [T][8]
+  float* Ks = Qs + T * kHd;
+  float* Vs = Ks + T * kHd;
+  float* Gs = Vs + T * kHd;            // dO
+  float* Ps = Gs + T * kHd;            // [T][T+1]
+  float* Ss = Ps + T * (T + 1);        // dS [T][T+1]
+  const int h = blockIdx.x % kHeads;
+  int wid = blockIdx.x / kHeads;
+  const int wx = wid % nw;  wid /= nw;
+  const int wy = wid % nh;  wid /= nh;
+  const int wz = wid % nd;
+  const int b = wid / nd;
+  const size_t cs = (size_t)D * H * W;
+  const size_t wbase = ((size_t)wz * bd * H + (size_t)wy * bh) * W + (size_t)wx * bw;
+  const int bhw = bh * bw;
+  const int i = threadIdx.x;
+  size_t vo = 0;
+  if (i < T) {
+    const int dd = i / bhw, r = i - dd * bhw, hh = r / bw, ww = r - hh * bw;
+    vo = wbase + ((size_t)dd * H + hh) * W + ww;
+#pragma unroll
+    for (int j = 0; j < kHd; ++j) {
+      const size_t c = (size_t)h * kHd + j;
+      Qs[i * kHd + j] = __ldg(qkv + ((size_t)b * 3 * kC + c) * cs + vo);
+      Ks[i * kHd + j] = __ldg(qkv + ((size_t)b * 3 * kC + kC + c) * cs + vo);
+      Vs[i * kHd + j] = __ldg(qkv + ((size_t)b * 3 * kC + 2 * kC + c) * cs + vo);
+      Gs[i * kHd + j] = __ldg(d_out + ((size_t)b * kC + c) * cs + vo);
+    }
+  }
+  __syncthreads();
+  const float scale = 0.35355339059327379f;
+  if (i < T) {
+    float q[kHd], g[kHd];
+#pragma unroll
+    for (int j = 0; j < kHd; ++j) { q[j] = Qs[i * kHd + j]; g[j] = Gs[i * kHd + j]; }
+    float m = -INFINITY;
+    for (int t = 0; t < T; ++t) {
+      float x = 0.f;
+#pragma unroll
+      for (int j = 0; j < kHd; ++j) x = fmaf(q[j], Ks[t * kHd + j], x);
+      x *= scale;
+      Ps[i * (T + 1) + t] = x;
+      m = fmaxf(m, x);
+    }
+    float l = 0.f;
+    for (int t = 0; t < T; ++t) { const float e = expf(Ps[i * (T + 1) + t] - m); Ps[i * (T + 1) + t] = e; l += e; }
+    const float inv = 1.0f / l;
+    float dsum = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const float pr = Ps[i * (T + 1) + t] * inv;
+      float dp = 0.f;
+#pragma unroll
+      for (int j = 0; j < kHd; ++j) dp = fmaf(g[j], Vs[t * kHd + j], dp);
+      Ps[i * (T + 1) + t] = pr;
+      Ss[i * (T + 1) + t] = dp;
+      dsum = fmaf(pr, dp, dsum);
+    }
+    float dq[kHd];
+#pragma unroll
+    for (int j = 0; j < kHd; ++j) dq[j] = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const float ds = Ps[i * (T + 1) + t] * (Ss[i * (T + 1) + t] - dsum);
+      Ss[i * (T + 1) + t] = ds;
+#pragma unroll
+      for (int j = 0; j < kHd; ++j) dq[j] = fmaf(ds, Ks[t * kHd + j], dq[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < kHd; ++j) d_qkv[((size_t)b * 3 * kC + (size_t)h * kHd + j) * cs + vo] = dq[j] * scale;
+  }
+  __syncthreads();
+  if (i < T) {                         // column i: dK_i, dV_i
+    float dk[kHd], dv[kHd];
+#pragma unroll
+    for (int j = 0; j < kHd; ++j) { dk[j] = 0.f; dv[j] = 0.f; }
+    for (int t = 0; t < T; ++t) {
+      const float ds = Ss[t * (T + 1) + i], pr = Ps[t * (T + 1) + i];
+#pragma unroll
+      for (int j = 0; j < kHd; ++j) { dk[j] = fmaf(ds, Qs[t * kHd + j], dk[j]); dv[j] = fmaf(pr, Gs[t * kHd + j], dv[j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < kHd; ++j) {
+      d_qkv[((size_t)b * 3 * kC + kC + (size_t)h * kHd + j) * cs + vo] = dk[j] * scale;
+      d_qkv[((size_t)b * 3 * kC + 2 * kC + (size_t)h * kHd + j) * cs + vo] = dv[j];
+    }
+  }
+}
+
 }  // namespace
+
+// fp32 output variant of the core (training forward) and its backward.
+extern "C" int ss_window_attention_core_f32_out(const float* qkv, float* out_f32, int B, int C, int D, int H, int W, int bd, int bh, int bw,
+                                                int num_heads, void* stream) {
+  SS_REQUIRE(qkv && out_f32, "ss_window_attention_core_f32_out: null pointer");
+  SS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && bd > 0 && bh > 0 && bw > 0, "ss_window_attention_core_f32_out: non-positive dimension");
+  SS_UNSUPPORTED(C != kC || num_heads != kHeads, "ss_window_attention_core_f32_out: only C=128 with 16 heads is supported");
+  SS_UNSUPPORTED(D % bd || H % bh || W % bw, "ss_window_attention_core_f32_out: D,H,W must be multiples of the window");
+  const int T = bd * bh * bw;
+  SS_UNSUPPORTED(!(bw == 4 && W % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (T == 64 || T == 96)),
+                 "ss_window_attention_core_f32_out: windows of 64 / 96 tokens with bw = 4 only");
+  const size_t smem = (size_t)3 * kC * T * sizeof(float);
+  const long long nwin = (long long)B * (D / bd) * (H / bh) * (W / bw);
+  if (T == 64) {
+    SS_CUDA(ss_allow_smem(window_attention_core_f32_kernel<64>, smem));
+    window_attention_core_f32_kernel<64><<<(unsigned)nwin, 256, smem, (cudaStream_t)stream>>>(qkv, nullptr, out_f32, D, H, W, bd, bh, D / bd, H / bh, W / bw);
+  } else {
+    SS_CUDA(ss_allow_smem(window_attention_core_f32_kernel<96>, smem));
+    window_attention_core_f32_kernel<96><<<(unsigned)nwin, 256, smem, (cudaStream_t)stream>>>(qkv, nullptr, out_f32, D, H, W, bd, bh, D / bd, H / bh, W / bw);
+  }
+  SS_CHECK_LAUNCH("ss_window_attention_core_f32_out");
+  return SS_OK;
+}
+
+extern "C" int ss_window_attention_core_backward(const float* qkv, const float* grad_out, float* grad_qkv, int B, int C, int D, int H, int W,
+                                                 int bd, int bh, int bw, int num_heads, void* stream) {
+  SS_REQUIRE(qkv && grad_out && grad_qkv, "ss_window_attention_core_backward: null pointer");
+  SS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && bd > 0 && bh > 0 && bw > 0, "ss_window_attention_core_backward: non-positive dimension");
+  SS_UNSUPPORTED(C != kC || num_heads != kHeads, "ss_window_attention_core_backward: only C=128 with 16 heads is supported");
+  SS_UNSUPPORTED(D % bd || H % bh || W % bw, "ss_window_attention_core_backward: D,H,W must be multiples of the window");
+  const int T = bd * bh * bw;
+  SS_UNSUPPORTED(T > 96, "ss_window_attention_core_backward: window of %d tokens unsupported (<= 96)", T);
+  const size_t smem = ((size_t)4 * T * kHd + (size_t)2 * T * (T + 1)) * sizeof(float);
+  const long long nblk = (long long)B * (D / bd) * (H / bh) * (W / bw) * kHeads;
+  SS_UNSUPPORTED(nblk > 0x7fffffffLL, "ss_window_attention_core_backward: too many windows");
+  SS_CUDA(ss_allow_smem(window_attention_core_bwd_kernel, smem));
+  window_attention_core_bwd_kernel<<<(unsigned)nblk, 96, smem, (cudaStream_t)stream>>>(qkv, grad_out, grad_qkv, D, H, W, bd, bh, bw, D / bd, H / bh,
+                                                                                      W / bw, T);
+  SS_CHECK_LAUNCH("ss_window_attention_core_backward");
+  return SS_OK;
+}
 
 extern "C" int ss_window_attention_core_f32(const float* qkv, void* out_tri, int B, int C, int D, int H, int W, int bd, int bh, int bw,
                                             int num_heads, void* stream) {
@@ -317,12 +459,12 @@ extern "C" int ss_window_attention_core_f32(const float* qkv, void* out_tri, int
   const bool fast = bw == 4 && W % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (T == 64 || T == 96);
   if (fast && T == 64) {
     SS_CUDA(ss_allow_smem(window_attention_core_f32_kernel<64>, smem));
-    window_attention_core_f32_kernel<64><<<(unsigned)nwin, 256, smem, (cudaStream_t)stream>>>(qkv, reinterpret_cast<uint4*>(out_tri), D, H, W, bd,
-                                                                                              bh, D / bd, H / bh, W / bw);
+    window_attention_core_f32_kernel<64><<<(unsigned)nwin, 256, smem, (cudaStream_t)stream>>>(qkv, reinterpret_cast<uint4*>(out_tri), nullptr, D, H, W,
+                                                                                              bd, bh, D / bd, H / bh, W / bw);
   } else if (fast) {
     SS_CUDA(ss_allow_smem(window_attention_core_f32_kernel<96>, smem));
-    window_attention_core_f32_kernel<96><<<(unsigned)nwin, 256, smem, (cudaStream_t)stream>>>(qkv, reinterpret_cast<uint4*>(out_tri), D, H, W, bd,
-                                                                                              bh, D / bd, H / bh, W / bw);
+    window_attention_core_f32_kernel<96><<<(unsigned)nwin, 256, smem, (cudaStream_t)stream>>>(qkv, reinterpret_cast<uint4*>(out_tri), nullptr, D, H, W,
+                                                                                              bd, bh, D / bd, H / bh, W / bw);
   } else {
     SS_CUDA(ss_allow_smem(window_attention_core_f32_generic_kernel, smem));
     window_attention_core_f32_generic_kernel<<<(unsigned)nwin, 256, smem, (cudaStream_t)stream>>>(qkv, reinterpret_cast<uint4*>(out_tri), D, H,

@@ -83,20 +83,52 @@ __device__ __forceinline__ double block_sum_d(double v, double* red) {      // 2
   return t;
 }
 
-// one CTA per channel: mean and biased variance over B*S elements (two passes over the channel: exact centred variance)
-__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ var, int B, int C,
-                                                       size_t S) {
+// Per-channel reductions over the B*S elements of a channel, split over BN_SPLIT CTAs per channel (a full-resolution SSR map has
+// 1-6 channels of 2M elements: one CTA per channel left the GPU empty).  Partials are doubles; a finalize kernel combines them.
+constexpr int BN_SPLIT = 64;
+
+// partial[c][s] = (sum a, sum b) with (a, b) = (x, x^2) [MODE 0]  or  (dy, dy * xhat) [MODE 1]
+template <int MODE>
+__global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ mean,
+                                                         const float* __restrict__ var, double2* __restrict__ partial, int B, int C, size_t S,
+                                                         float eps) {
   __shared__ double red[8];
-  const int c = blockIdx.x;
+  const int c = blockIdx.y, sp = blockIdx.x;
   const size_t n = (size_t)B * S;
-  float s = 0.f;
-  for (size_t i = threadIdx.x; i < n; i += 256) s += __ldg(x + ((i / S) * C + c) * S + i % S);
-  const double mu = block_sum_d((double)s, red) / (double)n;
-  const float muf = (float)mu;
-  float q = 0.f;
-  for (size_t i = threadIdx.x; i < n; i += 256) { const float d = __ldg(x + ((i / S) * C + c) * S + i % S) - muf; q = fmaf(d, d, q); }
-  const double v = block_sum_d((double)q, red) / (double)n;
-  if (threadIdx.x == 0) { mean[c] = muf; var[c] = (float)v; }
+  const size_t per = (n + BN_SPLIT - 1) / BN_SPLIT, lo = sp * per, hi = min(n, lo + per);
+  float mu = 0.f, rstd = 1.f;
+  if (MODE == 1) { mu = __ldg(mean + c); rstd = rsqrtf(__ldg(var + c) + eps); }
+  double a = 0.0, b2 = 0.0;
+  float fa = 0.f, fb = 0.f;
+  int cnt = 0;
+  for (size_t i = lo + threadIdx.x; i < hi; i += 256) {
+    const size_t o = ((i / S) * C + c) * S + i % S;
+    const float xv = __ldg(x + o);
+    if (MODE == 0) { fa += xv; fb = fmaf(xv, xv, fb); }
+    else { const float g = __ldg(dy + o); fa += g; fb = fmaf(g, (xv - mu) * rstd, fb); }
+    if (++cnt == 64) { a += fa; b2 += fb; fa = fb = 0.f; cnt = 0; }      // flush the fp32 partials into doubles every 64 elements
+  }
+  a += fa; b2 += fb;
+  const double sa = block_sum_d(a, red);
+  const double sb = block_sum_d(b2, red);
+  if (threadIdx.x == 0) partial[(size_t)c * BN_SPLIT + sp] = make_double2(sa, sb);
+}
+
+// MODE 0: mean, biased variance.  MODE 1: out_a = sum dy (grad_bias), out_b = sum dy * xhat (grad_weight)
+template <int MODE>
+__global__ void __launch_bounds__(64) bn_finalize_kernel(const double2* __restrict__ partial, float* __restrict__ out_a, float* __restrict__ out_b,
+                                                         double n) {
+  const int c = blockIdx.x;
+  double2 v = threadIdx.x < BN_SPLIT ? partial[(size_t)c * BN_SPLIT + threadIdx.x] : make_double2(0.0, 0.0);
+  for (int o = 16; o > 0; o >>= 1) { v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o); }
+  __shared__ double2 r[2];
+  if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double a = r[0].x + r[1].x, b = r[0].y + r[1].y;
+    if (MODE == 0) { const double mu = a / n; out_a[c] = (float)mu; out_b[c] = (float)fmax(b / n - mu * mu, 0.0); }
+    else { out_a[c] = (float)a; out_b[c] = (float)b; }
+  }
 }
 
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ var,
@@ -108,26 +140,6 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
   const float rstd = rsqrtf(__ldg(var + c) + eps);
   float y = (x[i] - __ldg(mean + c)) * rstd * (weight ? __ldg(weight + c) : 1.0f) + (bias ? __ldg(bias + c) : 0.0f);
   out[i] = relu ? fmaxf(y, 0.0f) : y;
-}
-
-// per channel: dbias = sum(dy), dweight = sum(dy * xhat)
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ mean,
-                                                            const float* __restrict__ var, float* __restrict__ dweight, float* __restrict__ dbias,
-                                                            int B, int C, size_t S, float eps) {
-  __shared__ double red[8];
-  const int c = blockIdx.x;
-  const size_t n = (size_t)B * S;
-  const float mu = __ldg(mean + c), rstd = rsqrtf(__ldg(var + c) + eps);
-  float s = 0.f, q = 0.f;
-  for (size_t i = threadIdx.x; i < n; i += 256) {
-    const size_t o = ((i / S) * C + c) * S + i % S;
-    const float g = __ldg(dy + o);
-    s += g;
-    q = fmaf(g, (__ldg(x + o) - mu) * rstd, q);
-  }
-  const double sd = block_sum_d((double)s, red);
-  const double qd = block_sum_d((double)q, red);
-  if (threadIdx.x == 0) { dbias[c] = (float)sd; dweight[c] = (float)qd; }
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ mean,
@@ -163,12 +175,18 @@ extern "C" int ss_conv3d_wgrad_f32(const float* x, const float* grad_out, float*
   return SS_OK;
 }
 
+extern "C" int ss_bn_workspace_bytes(int C) { return C * BN_SPLIT * (int)sizeof(double2); }
+
 extern "C" int ss_bn_train_forward(const float* x, const float* weight_or_null, const float* bias_or_null, float* out, float* batch_mean,
-                                   float* batch_var, int B, int C, long long S, float eps, int relu, void* stream) {
+                                   float* batch_var, void* workspace, int B, int C, long long S, float eps, int relu, void* stream) {
   SS_REQUIRE(x && out && batch_mean && batch_var && B > 0 && C > 0 && S > 0, "ss_bn_train_forward: bad argument");
   SS_UNSUPPORTED((long long)B * S < 2, "ss_bn_train_forward: batch statistics need more than one value per channel");
   cudaStream_t st = (cudaStream_t)stream;
-  bn_stats_kernel<<<C, 256, 0, st>>>(x, batch_mean, batch_var, B, C, (size_t)S);
+  SS_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "ss_bn_train_forward: 16-byte aligned workspace required");
+  double2* part = reinterpret_cast<double2*>(workspace);
+  bn_partial_kernel<0><<<dim3(BN_SPLIT, C), 256, 0, st>>>(x, nullptr, nullptr, nullptr, part, B, C, (size_t)S, eps);
+  SS_CHECK_LAUNCH("ss_bn_train_forward(partial)");
+  bn_finalize_kernel<0><<<C, 64, 0, st>>>(part, batch_mean, batch_var, (double)B * (double)S);
   SS_CHECK_LAUNCH("ss_bn_train_forward(stats)");
   const size_t total = (size_t)B * C * S;
   bn_apply_kernel<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(x, batch_mean, batch_var, weight_or_null, bias_or_null, out, C, (size_t)S,
@@ -178,12 +196,16 @@ extern "C" int ss_bn_train_forward(const float* x, const float* weight_or_null, 
 }
 
 extern "C" int ss_bn_train_backward(const float* x, const float* grad_out, const float* batch_mean, const float* batch_var,
-                                    const float* weight_or_null, float* grad_x, float* grad_weight, float* grad_bias, int B, int C, long long S,
-                                    float eps, void* stream) {
+                                    const float* weight_or_null, float* grad_x, float* grad_weight, float* grad_bias, void* workspace, int B, int C,
+                                    long long S, float eps, void* stream) {
   SS_REQUIRE(x && grad_out && batch_mean && batch_var && grad_x && grad_weight && grad_bias && B > 0 && C > 0 && S > 0,
              "ss_bn_train_backward: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  bn_bwd_reduce_kernel<<<C, 256, 0, st>>>(x, grad_out, batch_mean, batch_var, grad_weight, grad_bias, B, C, (size_t)S, eps);
+  SS_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "ss_bn_train_backward: 16-byte aligned workspace required");
+  double2* part = reinterpret_cast<double2*>(workspace);
+  bn_partial_kernel<1><<<dim3(BN_SPLIT, C), 256, 0, st>>>(x, grad_out, batch_mean, batch_var, part, B, C, (size_t)S, eps);
+  SS_CHECK_LAUNCH("ss_bn_train_backward(partial)");
+  bn_finalize_kernel<1><<<C, 64, 0, st>>>(part, grad_bias, grad_weight, 1.0);
   SS_CHECK_LAUNCH("ss_bn_train_backward(reduce)");
   const size_t total = (size_t)B * C * S;
   bn_bwd_dx_kernel<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(x, grad_out, batch_mean, batch_var, weight_or_null, grad_weight, grad_bias,

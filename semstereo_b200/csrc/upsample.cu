@@ -156,7 +156,62 @@ __global__ void __launch_bounds__(256) context_upsample_kernel(const float* __re
   out[(size_t)b * HW + pix] = acc;
 }
 
+// F.interpolate(scale_factor=4, mode='bilinear', align_corners=False) of fp32 planes and its VJP (gather form, deterministic):
+// the unfused pieces SSR_upsample needs in TRAINING mode (its BatchNorm layers then use batch statistics, so the fused inference
+// kernel above does not apply; semstereo_b200/train_ops.py composes the module from differentiable kernels).
+__global__ void __launch_bounds__(256) bilinear_up4_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w) {
+  const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y;
+  const size_t plane = blockIdx.z;
+  if (X >= 4 * w) return;
+  int y0, y1, x0, x1;
+  float hy0, hy1, wx0, wx1;
+  lin4(Y, h, y0, y1, hy0, hy1);
+  lin4(X, w, x0, x1, wx0, wx1);
+  const float* s = in + plane * h * w;
+  out[plane * 16 * h * w + (size_t)Y * 4 * w + X] = hy0 * (wx0 * __ldg(s + y0 * w + x0) + wx1 * __ldg(s + y0 * w + x1)) +
+                                                    hy1 * (wx0 * __ldg(s + y1 * w + x0) + wx1 * __ldg(s + y1 * w + x1));
+}
+
+__global__ void __launch_bounds__(256) bilinear_up4_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, int h, int w) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  const size_t plane = blockIdx.z;
+  if (x >= w) return;
+  const float* g = gout + plane * 16 * h * w;
+  float acc = 0.0f;
+  for (int Y = max(4 * y - 4, 0); Y <= min(4 * y + 7, 4 * h - 1); ++Y) {
+    int y0, y1;
+    float hy0, hy1;
+    lin4(Y, h, y0, y1, hy0, hy1);
+    const float wy = (y0 == y ? hy0 : 0.0f) + (y1 == y ? hy1 : 0.0f);
+    if (wy == 0.0f) continue;
+    for (int X = max(4 * x - 4, 0); X <= min(4 * x + 7, 4 * w - 1); ++X) {
+      int x0, x1;
+      float wx0, wx1;
+      lin4(X, w, x0, x1, wx0, wx1);
+      const float wxx = (x0 == x ? wx0 : 0.0f) + (x1 == x ? wx1 : 0.0f);
+      if (wxx != 0.0f) acc = fmaf(wy * wxx, __ldg(g + (size_t)Y * 4 * w + X), acc);
+    }
+  }
+  gin[plane * h * w + (size_t)y * w + x] = acc;
+}
+
 }  // namespace
+
+extern "C" int ss_bilinear_up4(const float* in, float* out, int planes, int h, int w, void* stream) {
+  SS_REQUIRE(in && out && planes > 0 && h > 0 && w > 0, "ss_bilinear_up4: bad argument");
+  SS_UNSUPPORTED(4 * h > 65535 || planes > 65535, "ss_bilinear_up4: grid dimension exceeds 65535");
+  bilinear_up4_kernel<<<dim3(ceil_div(4 * w, 256), 4 * h, planes), 256, 0, (cudaStream_t)stream>>>(in, out, h, w);
+  SS_CHECK_LAUNCH("ss_bilinear_up4");
+  return SS_OK;
+}
+
+extern "C" int ss_bilinear_up4_backward(const float* grad_out, float* grad_in, int planes, int h, int w, void* stream) {
+  SS_REQUIRE(grad_out && grad_in && planes > 0 && h > 0 && w > 0, "ss_bilinear_up4_backward: bad argument");
+  SS_UNSUPPORTED(h > 65535 || planes > 65535, "ss_bilinear_up4_backward: grid dimension exceeds 65535");
+  bilinear_up4_bwd_kernel<<<dim3(ceil_div(w, 256), h, planes), 256, 0, (cudaStream_t)stream>>>(grad_out, grad_in, h, w);
+  SS_CHECK_LAUNCH("ss_bilinear_up4_backward");
+  return SS_OK;
+}
 
 // `packed` is a HOST array of ss_ssr_param_count(num_classes) floats in the order of SsrPacked (see include/semstereo_b200.h).
 extern "C" int ss_ssr_param_count(int num_classes) { return 2 + num_classes * (9 + 1 + 2 + 2 * (num_classes + 3) + 1) + 1; }

@@ -156,8 +156,9 @@ def make_surface(signed: bool) -> dict:
             self.num_classes = num_classes
 
         def forward(self, depth_low, weights, pred_label):
-            if self.training:
-                raise NotImplementedError("SSR_upsample (B200 path) folds eval-mode BatchNorm; call .eval()")
+            if self.training:      # batch statistics in the four BatchNorm2d layers: differentiable composition (train_ops.py)
+                from . import train_ops
+                return train_ops.ssr_upsample_train(self, depth_low, weights, pred_label)
             _no_grad_path(self, depth_low, weights, pred_label)
             if not hasattr(self, "_packed"):
                 object.__setattr__(self, "_packed", _Packed())
@@ -196,8 +197,9 @@ def make_surface(signed: bool) -> dict:
 
         def forward(self, x):
             conv, bn = self[0], self[1]
-            if bn.training:
-                raise NotImplementedError("convbn_3d (B200 path) folds eval-mode BatchNorm; call .eval()")
+            if bn.training:      # training mode (BASELINE config #5): Conv3d and BatchNorm3d with batch statistics, forward and
+                from . import train_ops      # backward on the CUDA kernels (csrc/train.cu); differentiable, running stats updated
+                return train_ops.batch_norm_train(train_ops.conv3d(x, conv.weight, conv.stride[0]), bn)
             _no_grad_path(self, x)
             with torch.no_grad():
                 return _conv3d(self, conv, bn, x, relu=False)
@@ -212,6 +214,9 @@ def make_surface(signed: bool) -> dict:
             self.block, self.num_heads = block, num_heads
 
         def forward(self, x):
+            if self.training:      # differentiable route (train_ops.py): k = 1 convs + the fp32 softmax core with its backward kernel
+                from . import train_ops
+                return train_ops.attention_block_train(self, x)
             _no_grad_path(self, x)
             if not hasattr(self, "_packed"):
                 object.__setattr__(self, "_packed", _Packed())
@@ -246,8 +251,14 @@ def make_surface(signed: bool) -> dict:
                 if self.use_bn:
                     x = self.bn(x)
                 return torch.relu(x) if self.relu else x
-            if self.bn.training and self.use_bn:
-                raise NotImplementedError("BasicConv 3-D (B200 path) folds eval-mode BatchNorm; call .eval()")
+            if self.training and not self.deconv:      # training mode: native Conv3d / BatchNorm3d forward + backward (csrc/train.cu)
+                from . import train_ops
+                y = train_ops.conv3d(x, self.conv.weight, self.conv.stride[0])
+                if self.use_bn:
+                    y = train_ops.batch_norm_train(y, self.bn)
+                return torch.relu(y) if self.relu else y
+            if self.training:
+                raise NotImplementedError("BasicConv 3-D deconv (B200 path) has no training mode; the models use nn.ConvTranspose3d directly")
             _no_grad_path(self, x)
             with torch.no_grad():
                 return _conv3d(self, self.conv, self.bn if self.use_bn else None, x, relu=self.relu, transposed=self.deconv)

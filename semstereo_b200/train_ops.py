@@ -9,9 +9,14 @@
   batch_norm    forward / backward ss_bn_train_forward / ss_bn_train_backward, running statistics updated like nn.BatchNorm3d
                 (momentum, unbiased variance)
 
+  attention     qkv Linear / final 1x1x1 conv = k = 1 convs above; softmax core ss_window_attention_core_f32_out / _backward
+  SSR_upsample  bilinear x4 (ss_bilinear_up4 / _backward), 2-D convs through the 3-D kernels, batch_norm; pointwise glue in torch
+
 The stateless operators of the surface (volume builders, regression, warps, propagation) already carry their backward kernels
-(torch_ops.py / csrc/backward.cu).  NOT native yet in training mode: `attention_block` and `SSR_upsample` (they raise), so a
-full training step of the reference model still needs torch modules for those two (tools/train_step.py states which)."""
+(torch_ops.py / csrc/backward.cu).  With these the reference model TRAINS through the level-1 drop-in: every module /
+function it takes from models.submodule(_other) is differentiable on the CUDA kernels; what the model does inline
+(nn.ConvTranspose3d, the `patch` / classifier nn.Conv3d, interpolate, softmax, sort, gather, the 2-D decoder) is torch, as in the
+reference.  fp32 FFMA kernels: a first correct training path, not a fast one (tools/train_step.py measures it)."""
 from __future__ import annotations
 
 import ctypes
@@ -67,6 +72,11 @@ def conv3d(x, weight, stride=1):
     return _Conv3dFn.apply(x, weight, stride)
 
 
+def _ws_bytes(C):
+    from . import _lib
+    return _lib.load().ss_bn_workspace_bytes(int(C))
+
+
 class _BatchNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, eps):
@@ -79,7 +89,8 @@ class _BatchNormFn(torch.autograd.Function):
         var = torch.empty(C, device=dev, dtype=torch.float32)
         wd = None if weight is None else weight.detach().float().contiguous()
         bd = None if bias is None else bias.detach().float().contiguous()
-        _call("ss_bn_train_forward", dev, _ptr(x), _ptr(wd), _ptr(bd), _ptr(out), _ptr(mean), _ptr(var), B, C, ctypes.c_longlong(S),
+        ws = torch.empty(_ws_bytes(C), device=dev, dtype=torch.uint8)
+        _call("ss_bn_train_forward", dev, _ptr(x), _ptr(wd), _ptr(bd), _ptr(out), _ptr(mean), _ptr(var), _ptr(ws), B, C, ctypes.c_longlong(S),
               ctypes.c_float(eps), 0)
         ctx.save_for_backward(x, mean, var, wd if wd is not None else x.new_empty(0))
         ctx.eps, ctx.has_w, ctx.has_b = eps, weight is not None, bias is not None
@@ -96,8 +107,9 @@ class _BatchNormFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         dw = torch.empty(C, device=dev, dtype=torch.float32)
         db = torch.empty(C, device=dev, dtype=torch.float32)
+        ws = torch.empty(_ws_bytes(C), device=dev, dtype=torch.uint8)
         _call("ss_bn_train_backward", dev, _ptr(x), _ptr(dy), _ptr(mean), _ptr(var), _ptr(wd if ctx.has_w else None), _ptr(dx), _ptr(dw), _ptr(db),
-              B, C, ctypes.c_longlong(S), ctypes.c_float(ctx.eps))
+              _ptr(ws), B, C, ctypes.c_longlong(S), ctypes.c_float(ctx.eps))
         return dx, (dw if ctx.has_w else None), (db if ctx.has_b else None), None
 
 
@@ -113,3 +125,83 @@ def batch_norm_train(x, bn: torch.nn.modules.batchnorm._BatchNorm):
             bn.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
             bn.running_var.mul_(1 - mom).add_(var * (n / max(n - 1, 1)), alpha=mom)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# attention_block and SSR_upsample in training mode: compositions of differentiable kernels
+# ---------------------------------------------------------------------------------------------------------------------
+class _AttnCoreFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, block, heads):
+        dev = _require_cuda(qkv)
+        qkv = qkv.contiguous()
+        B, C3, D, H, W = qkv.shape
+        out = torch.empty((B, C3 // 3, D, H, W), device=dev, dtype=torch.float32)
+        _call("ss_window_attention_core_f32_out", dev, _ptr(qkv), _ptr(out), B, C3 // 3, D, H, W, int(block[0]), int(block[1]), int(block[2]), int(heads))
+        ctx.save_for_backward(qkv)
+        ctx.block, ctx.heads = tuple(int(v) for v in block), int(heads)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (qkv,) = ctx.saved_tensors
+        B, C3, D, H, W = qkv.shape
+        dq = torch.empty_like(qkv)
+        _call("ss_window_attention_core_backward", qkv.device, _ptr(qkv), _ptr(dout.contiguous().float()), _ptr(dq), B, C3 // 3, D, H, W,
+              ctx.block[0], ctx.block[1], ctx.block[2], ctx.heads)
+        return dq, None, None
+
+
+def attention_block_train(mod, x):
+    """attention_block.forward (submodule_other.py:805-837) with gradients: the qkv Linear and the final 1x1x1 conv are k = 1 layers
+    of the differentiable conv3d above (+ bias), the softmax core in between has its own forward / backward kernels."""
+    block = mod.block if isinstance(mod.block, (tuple, list)) else (mod.block,) * 3
+    C = mod.qkv_3d.in_features
+    qkv = conv3d(x, mod.qkv_3d.weight.view(3 * C, C, 1, 1, 1), 1) + mod.qkv_3d.bias.view(1, -1, 1, 1, 1)
+    o = _AttnCoreFn.apply(qkv, block, mod.num_heads)
+    return conv3d(o, mod.final1x1.weight, 1) + mod.final1x1.bias.view(1, -1, 1, 1, 1)
+
+
+class _Up4Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        dev = _require_cuda(x)
+        x = x.contiguous()
+        h, w = x.shape[-2:]
+        planes = x.numel() // (h * w)
+        out = torch.empty(tuple(x.shape[:-2]) + (4 * h, 4 * w), device=dev, dtype=torch.float32)
+        _call("ss_bilinear_up4", dev, _ptr(x), _ptr(out), planes, h, w)
+        ctx.shape = tuple(x.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h, w = ctx.shape[-2:]
+        gin = torch.empty(ctx.shape, device=g.device, dtype=torch.float32)
+        _call("ss_bilinear_up4_backward", g.device, _ptr(g.contiguous().float()), _ptr(gin), gin.numel() // (h * w), h, w)
+        return gin
+
+
+def conv2d(x, weight, bias=None):
+    """Differentiable Conv2d (k in {1,3}, stride 1, padding k//2) through the 3-D kernels: the image is a depth-1 volume, a 3x3
+    kernel is the centre depth plane of a 3x3x3 one."""
+    k = weight.shape[-1]
+    w3 = weight.unsqueeze(2)
+    if k == 3:
+        w3 = torch.nn.functional.pad(w3, (0, 0, 0, 0, 1, 1))
+    y = conv3d(x.unsqueeze(2), w3, 1).squeeze(2)
+    return y if bias is None else y + bias.view(1, -1, 1, 1)
+
+
+def ssr_upsample_train(mod, depth_low, weights, pred_label):
+    """SSR_upsample.forward (submodule.py:421-431) in TRAINING mode (its four BatchNorm2d layers use batch statistics, which rules
+    out the fused inference kernel): bilinear x4, the convolutions and the BatchNorms are differentiable kernels of this file, the
+    pointwise glue (softmax over the 6 classes, sigmoids, products) is torch, as in the reference."""
+    lab = torch.softmax(pred_label, dim=1)
+    d_up = _Up4Fn.apply(depth_low.float())
+    d = batch_norm_train(d_up, mod.conv[0])
+    d = batch_norm_train(conv2d(d, mod.conv[1].weight, mod.conv[1].bias), mod.conv[2])
+    g = torch.sigmoid(batch_norm_train(conv2d(lab * weights, mod.conv1[0].weight, mod.conv1[0].bias), mod.conv1[1]))
+    g = torch.sigmoid(batch_norm_train(conv2d(g * weights, mod.conv2[0].weight, mod.conv2[0].bias), mod.conv2[1]))
+    res = conv2d(d * g, mod.conv3.weight, mod.conv3.bias)
+    return (d_up + res).squeeze(1)
