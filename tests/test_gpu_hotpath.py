@@ -241,6 +241,39 @@ def test_full_size_against_oracle(signed, maxdisp, H, W):
     good = torch.nn.functional.max_pool2d((~up).float()[None, None], 9, 1, 4)[0, 0] == 0     # away from pixels whose samples differ
     assert maxerr(out["pred_att_up"][0][good], ref["pred_att_up"][0][good]) <= 1e-3
     assert maxerr(out["cost_att"], ref["cost_att"]) <= 2e-2
+    # the aggregation branch in fp32 at the full size: cost volume and final disparity.  A flipped sample set
+    # changes the aggregation input in its whole receptive field, and regression_topk keeps the 2 largest costs: pixels whose
+    # 2nd / 3rd costs are closer than the fp32 noise of the 3-D stack are ill-conditioned (any tied candidate is legal).
+    if bool(same.all()):
+        cerr = maxerr(out["cost"], ref["cost"])
+        assert cerr <= 2e-2
+        srt = ref["cost"].squeeze(1).sort(1, descending=True)[0]
+        bad = torch.nn.functional.max_pool2d(((srt[:, 1] - srt[:, 2]) <= 4 * cerr).float().unsqueeze(1), 3, 1, 1)
+        good4 = bad[:, 0] == 0
+        assert good4.float().mean().item() > 0.85
+        assert maxerr(out["pred"].squeeze(1)[good4], ref["pred"].squeeze(1)[good4]) <= 1e-3
+        goodf = torch.nn.functional.interpolate(bad, scale_factor=4, mode="nearest")[:, 0] == 0
+        assert maxerr(out["pred_up"][goodf], ref["pred_up"][goodf]) <= 1e-3
+        print(f"\n[{H}x{W}] fp32 mode: max |cost - oracle| {cerr:.2e}; pred_up within 1e-3 px on the {goodf.float().mean().item():.3f} well-conditioned pixels")
+    else:
+        assert (out["pred_up"] - ref["pred_up"]).abs().median().item() <= 1e-3
+    # the BENCHMARKED default mode (precision="split": attention branch with fp32-accurate bf16x3 tensor-core products): the top-24
+    # sample sets equal the oracle's on >= 99.9 % of the pixels and the kept probabilities agree to 2e-5 there
+    ms = DisparityHotPath(maxdisp, False, signed)
+    assert ms.precision == "split"
+    ms.load_state_dict(p, strict=True)
+    outs = run(ms.to(DEV), inp)
+    same_s = (outs["ind_k"] == ref["ind_k"]).all(dim=2)
+    sel = same_s.unsqueeze(2).expand_as(ref["att_topk"])
+    e_att = (outs["att_topk"].reshape(ref["att_topk"].shape) - ref["att_topk"]).abs()[sel].max().item()
+    ups = torch.nn.functional.interpolate(same_s.float(), scale_factor=4, mode="nearest")[0, 0] == 1
+    goods = torch.nn.functional.max_pool2d((~ups).float()[None, None], 9, 1, 4)[0, 0] == 0
+    e_pa = maxerr(outs["pred_att_up"][0][goods], ref["pred_att_up"][0][goods])
+    es = (outs["pred_up"] - ref["pred_up"]).abs().flatten()
+    print(f"[{H}x{W}] split mode (bench default): sample-set agreement {same_s.float().mean().item():.6f}, max |att_topk - oracle| {e_att:.2e}, "
+          f"max |pred_att_up - oracle| {e_pa:.2e} px, pred_up median {es.median():.4f} p90 {es.quantile(0.9):.4f} (bf16 aggregation)")
+    assert same_s.float().mean().item() >= 0.999 and e_att <= 2e-5 and e_pa <= 1e-3
+    assert es.median().item() <= 0.05 and es.quantile(0.9).item() <= 0.5
     mb = DisparityHotPath(maxdisp, False, signed, precision="bf16")
     mb.load_state_dict(p, strict=True)
     outb = run(mb.to(DEV), inp, keep=False)

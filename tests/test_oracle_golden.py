@@ -84,6 +84,8 @@ def test_hotpath_matches_reference_forward(golden_dir, name, maxdisp, signed, pe
     inp = make_inputs(seed, 1, H, W)
     for k, v in inp.items():
         assert abs(v.double().abs().sum().item() - g["chk_" + k]) <= 1e-9 * g["chk_" + k], f"RNG drift in {k}"
+    chk_p = sum(v.double().abs().sum().item() for v in p.values())          # the weights too (goldens regenerated in round 2)
+    assert abs(chk_p - float(g["chk_params"])) <= 1e-9 * float(g["chk_params"]), "RNG drift in the seeded parameters"
     out = oh.forward(p, inp, maxdisp, signed=signed, att_weights_only=att_only, keep=True)
     close(out["corr_volume"].reshape(-1)[::5], g["corr_volume_sub"], 1e-6, "corr_volume")
     close(out["cost_att"], g["cost_att"], 5e-4 * peaked, "cost_att")

@@ -90,7 +90,7 @@ def main(argv=None):
         for d, h in zip(stage, host):
             d.copy_(h, non_blocking=True)
         l = step((stage[:5], stage[5:10], stage[10], stage[11], stage[12]))
-        lv = float(l)                                    # D2H read of the loss
+        lv = float(l.detach())                           # D2H read of the loss
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
