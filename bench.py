@@ -521,7 +521,7 @@ def main():
         os.sched_setaffinity(0, all_cpus)           # the CPU baseline gets every host core again
         times = cpu_reference(H, W, md, a.cpu_steps, 1, signed, a.att_only, a.external_cf, a.stage)
         res["cpu_baseline"] = {"value": len(times) / sum(times), "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
-                               "sample": f"{len(times)} pairs at {H}x{W} through {'oracle/decoder.py + ' if head else ''}oracle/hotpath.py (torch CPU fp32), 1 warm-up"}
+                               "sample": f"{len(times)} pairs at {H}x{W} through {'oracle/backbone.py (HF MobileViTV2) + ' if full else ''}{'oracle/decoder.py + ' if head else ''}oracle/hotpath.py (torch CPU fp32), 1 warm-up"}
     print(json.dumps(res))
     if world > 1:
         tdist.destroy_process_group()

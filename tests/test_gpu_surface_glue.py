@@ -167,12 +167,14 @@ def test_surface_caches_follow_the_parameters_and_bf16_route():
         finally:
             sf.set_precision("fp32")
         assert 1e-6 < (c - b).abs().max().item() <= 3e-2 * b.abs().max().item()              # tensor-core route: bf16 operands
-    # training / grad-requiring calls refuse instead of silently dropping the graph
+    # no silently dropped graphs: training mode takes the differentiable kernels (tests/test_gpu_train.py), the fused
+    # inference kernels refuse inputs that require grad
     att = other["attention_block"](128, 16, (4, 4, 4)).to(DEV)
-    with pytest.raises(NotImplementedError):
-        att.train()(torch.randn(1, 128, 4, 8, 8, device=DEV))
+    y = att.train()(torch.randn(1, 128, 4, 8, 8, device=DEV))
+    assert y.requires_grad and y.grad_fn is not None
     with pytest.raises(NotImplementedError):
         att.eval()(torch.randn(1, 128, 4, 8, 8, device=DEV, requires_grad=True))
     bc = ns["BasicConv"](32, 32, is_3d=True, bn=False, kernel_size=3, stride=1, padding=1).to(DEV)
+    assert bc.train()(torch.randn(1, 32, 4, 8, 8, device=DEV)).requires_grad
     with pytest.raises(NotImplementedError):
-        bc.train()(torch.randn(1, 32, 4, 8, 8, device=DEV))
+        bc.eval()(torch.randn(1, 32, 4, 8, 8, device=DEV, requires_grad=True))
