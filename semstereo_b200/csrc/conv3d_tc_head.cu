@@ -23,7 +23,8 @@ constexpr int CIN = 32, C8 = CIN / 8, NT = 16, NROW = 3 * NT;               // 9
 constexpr uint32_t SLICE = C8 * TILE_B;                                     // 11520 B
 constexpr uint32_t WBYTES = C8 * NROW * 16;                                 // 3072 B of weights
 constexpr int NS = 4;                                                       // input-slice ring
-constexpr uint32_t NB = 16;                                                 // accumulator ring: output depths in flight
+constexpr uint32_t NB = 8;                                                  // accumulator ring: output depths in flight
+constexpr uint32_t RB_COLS = NB * 16;                                       // TMEM columns of one 128-row block (NB depths x 16 columns)
 constexpr int QSTRIDE = 9;                                                  // floats per halo voxel in the smem copy of Q
 constexpr int ROWB = NV - 128;                                              // first halo voxel of the second 128-row block (52)
 
@@ -48,11 +49,13 @@ __device__ __forceinline__ void decode_item(const HeadP& p, int s, int& b, int& 
 // SP (in-kernel bf16x3 split): split input tensor (hi batches | lo batches), slice = [hi chunks][lo chunks], weights [hi][lo],
 // three MMAs per K step: x_hi*w_hi + x_lo*w_hi + x_hi*w_lo.
 template <bool SP>
-__global__ void __launch_bounds__(256, 1) conv3d_tc_head_kernel(const __grid_constant__ CUtensorMap tmA, const HeadP p) {
+__global__ void __launch_bounds__(256, 2) conv3d_tc_head_kernel(const __grid_constant__ CUtensorMap tmA, const HeadP p) {
   constexpr uint32_t HALF_A = C8 * TILE_B, HALF_B = C8 * NROW * 16;
   constexpr uint32_t SLICE = (SP ? 2 : 1) * HALF_A, WBYTES = (SP ? 2 : 1) * HALF_B;      // shadow the single-operand sizes
   constexpr uint32_t LBO_A = TILE_B, SBO_A = 128, LBO_B = NROW * 16, SBO_B = 128;
-  constexpr uint32_t TMEM_COLS = 512;                               // 2 row blocks x NB depths x 16 columns
+  // 2 row blocks x NB depths x 16 columns = 256 of the SM's 512 TMEM columns: TWO CTAs per SM, so that one CTA's epilogue chain
+  // (TMEM -> smem copy of Q -> barrier -> 9-term gather -> store, ~0.45 us per depth) overlaps the other's (round 1: 1 CTA/SM).
+  constexpr uint32_t TMEM_COLS = 2 * RB_COLS;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t a_full[NS], a_empty[NS], acc_full[NB], acc_empty[NB], w_full;
   __shared__ uint32_t tmem_base_s;
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_head_kernel(const __grid_con
   const uint32_t tmem_base = tmem_base_s;
   if (warp >= 4) {                                                  // all accumulator blocks start out zero
 #pragma unroll 1
-    for (uint32_t c = 0; c < 512; c += 32) tc::tmem_zero32(tmem_base + ((uint32_t)((warp - 4) * 32) << 16) + c);
+    for (uint32_t c = 0; c < TMEM_COLS; c += 32) tc::tmem_zero32(tmem_base + ((uint32_t)((warp - 4) * 32) << 16) + c);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -135,13 +138,13 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_head_kernel(const __grid_con
             for (int ks = 0; ks < 2; ++ks) {
               const uint32_t a = a_lo + (uint32_t)(rb * ROWB) + (uint32_t)(ks * 2 * LBO_A) / 16;
               const uint32_t bb = b_lo0 + (uint32_t)(ks * 2 * LBO_B) / 16;
-              tc::mma_bf16_lohi(tmem_base + rb * 256 + blk * NT, a, a_hi, bb + brow1, b_hi, id1, 1u);
-              if (n2) tc::mma_bf16_lohi(tmem_base + rb * 256, a, a_hi, bb + brow2, b_hi, id2, 1u);
+              tc::mma_bf16_lohi(tmem_base + rb * RB_COLS + blk * NT, a, a_hi, bb + brow1, b_hi, id1, 1u);
+              if (n2) tc::mma_bf16_lohi(tmem_base + rb * RB_COLS, a, a_hi, bb + brow2, b_hi, id2, 1u);
               if (SP) {
-                tc::mma_bf16_lohi(tmem_base + rb * 256 + blk * NT, a + (HALF_A >> 4), a_hi, bb + brow1, b_hi, id1, 1u);
-                if (n2) tc::mma_bf16_lohi(tmem_base + rb * 256, a + (HALF_A >> 4), a_hi, bb + brow2, b_hi, id2, 1u);
-                tc::mma_bf16_lohi(tmem_base + rb * 256 + blk * NT, a, a_hi, bb + (HALF_B >> 4) + brow1, b_hi, id1, 1u);
-                if (n2) tc::mma_bf16_lohi(tmem_base + rb * 256, a, a_hi, bb + (HALF_B >> 4) + brow2, b_hi, id2, 1u);
+                tc::mma_bf16_lohi(tmem_base + rb * RB_COLS + blk * NT, a + (HALF_A >> 4), a_hi, bb + brow1, b_hi, id1, 1u);
+                if (n2) tc::mma_bf16_lohi(tmem_base + rb * RB_COLS, a + (HALF_A >> 4), a_hi, bb + brow2, b_hi, id2, 1u);
+                tc::mma_bf16_lohi(tmem_base + rb * RB_COLS + blk * NT, a, a_hi, bb + (HALF_B >> 4) + brow1, b_hi, id1, 1u);
+                if (n2) tc::mma_bf16_lohi(tmem_base + rb * RB_COLS, a, a_hi, bb + (HALF_B >> 4) + brow2, b_hi, id2, 1u);
               }
             }
           tc::mma_commit(&a_empty[slot]);
@@ -173,8 +176,8 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_head_kernel(const __grid_con
         tc::tmem_zero16(ta);
 #pragma unroll
         for (int t = 0; t < 9; ++t) dst[m * QSTRIDE + t] = v[t];
-        tc::tmem_ld16(ta + 256, v);                               // row block B: halo voxel ROWB + m
-        tc::tmem_zero16(ta + 256);
+        tc::tmem_ld16(ta + RB_COLS, v);                           // row block B: halo voxel ROWB + m
+        tc::tmem_zero16(ta + RB_COLS);
         tc::fence_before_sync();
         tc::mbar_arrive(&acc_empty[blk]);
         if (ROWB + m >= 128) {
@@ -238,7 +241,7 @@ extern "C" int ss_conv3d_tc_head_ex(const void* in_blocked, const void* weight_p
   p.out = out; p.acc_in = acc_in_or_null; p.acc_in2 = acc_in2_or_null;
   p.B = B; p.D = D; p.H = H; p.W = W;
   p.HT = ceil_div(H, TH); p.WT = ceil_div(W, TW);
-  int grid = ss_num_sms();
+  int grid = 2 * ss_num_sms();             // two persistent CTAs per SM (256 TMEM columns each)
   const int spatial = B * p.HT * p.WT;
   int best = D;
   double best_cost = 1e30;

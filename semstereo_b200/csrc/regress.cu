@@ -96,15 +96,23 @@ __global__ void __launch_bounds__(128) att_stats_kernel(const float* __restrict_
 // ~75 % of the rows and that row is then not even loaded.  A hypothesis then costs 2 shared loads per channel instead of 4,
 // and the left value is read once for all 5.  Hypotheses whose corners leave the window (|disparity| > PAD-2) read global memory.
 // ---------------------------------------------------------------------------------------------
-constexpr int SS_TX = 128, SS_PAD = 24, SS_WW = SS_TX + 2 * SS_PAD, SS_CK = 32;
+// Round 2 (ncu r02_three: 160 M instructions for 42 M FP32 + 21 M shared loads -- index arithmetic and predicates of the staging
+// loops dominated, at 23 % occupancy): 256 threads per CTA, the two halves of the CTA take the two halves of every staged
+// 32-channel chunk for the same 128 pixels (partial sums combined through shared memory at the end).  The left features are NOT
+// staged: a thread is the only reader of its pixel's left value, so it loads its 16 channels straight into registers (coalesced
+// 512-byte rows) before the right rows are staged, which hides their latency.  Staging is per warp and per channel (warp w takes
+// channels w, w+8, ...; a lane owns the same one or two 128-bit columns of every row, so bounds and offsets are computed once).
+// The x weights are applied AFTER the channel sum (sum_c l*r0 and sum_c l*r1 are accumulated separately: 2 FMAs per channel and
+// hypothesis instead of 3 operations).
+constexpr int SS_TX = 128, SS_NT = 256, SS_PAD = 24, SS_WW = SS_TX + 2 * SS_PAD, SS_CK = 32, SS_Q = SS_WW / 4;
 
-__global__ void __launch_bounds__(SS_TX) sample_strength_kernel(const float* __restrict__ fl, const float* __restrict__ fr,
-                                                                const float* __restrict__ mu, const float* __restrict__ gate,
-                                                                float* __restrict__ strength, int B, int C, int H, int W) {
-  __shared__ __align__(16) float Ls[SS_CK][SS_TX];
+template <bool VEC4>
+__global__ void __launch_bounds__(SS_NT, 4) sample_strength_kernel(const float* __restrict__ fl, const float* __restrict__ fr,
+                                                                   const float* __restrict__ mu, const float* __restrict__ gate,
+                                                                   float* __restrict__ strength, int B, int C, int H, int W) {
   __shared__ __align__(16) float Rc[SS_CK][SS_WW];
-  const bool vec4 = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(fl) | reinterpret_cast<uintptr_t>(fr)) & 15) == 0;
-  const int tx = threadIdx.x;
+  __shared__ float Part[5][SS_TX];
+  const int tid = threadIdx.x, tx = tid & (SS_TX - 1), half = tid >> 7, warp = tid >> 5, lane = tid & 31;
   const int x0 = blockIdx.x * SS_TX, x = x0 + tx, y = blockIdx.y, b = blockIdx.z;
   const size_t HW = (size_t)H * W;
   const float iy = warp_coord((float)y, (float)(H - 1));
@@ -113,61 +121,75 @@ __global__ void __launch_bounds__(SS_TX) sample_strength_kernel(const float* __r
   const float wy0 = vy0 ? fy1 - iy : 0.0f, wy1 = vy1 ? iy - fy0 : 0.0f;      // uniform over the row
   const int y0 = vy0 ? (int)fy0 : 0, y1 = vy1 ? (int)fy1 : 0;
   const bool active = x < W;
-  float g[5], wx0[5], wx1[5], ixs[5];
-  int j0[5];
-  bool in_win[5];
-#pragma unroll
-  for (int s = 0; s < 5; ++s) {
+  // hypothesis s: the disparity / gate of the pixel's s-th propagation neighbour; only the window offset stays live across the
+  // channel loop (the rest is recomputed after it: registers decide this kernel's occupancy)
+  auto hypothesis = [&](int s, float& gs, float& ix, bool& inw, int& j, float& fx0) {
     float d = 0.0f;
-    g[s] = 0.0f;
+    gs = 0.0f;
     if (active) {
       const int ty = min(max(y + kPropDy[s], 0), H - 1), txx = min(max(x + kPropDx[s], 0), W - 1);
       d = __ldg(mu + (size_t)b * HW + (size_t)ty * W + txx);
-      g[s] = __ldg(gate + (size_t)b * HW + (size_t)ty * W + txx);
+      gs = __ldg(gate + (size_t)b * HW + (size_t)ty * W + txx);
     }
-    const float ix = warp_coord((float)x - d, (float)(W - 1));
-    ixs[s] = ix;
-    const float fx0 = floorf(ix), fx1 = fx0 + 1.0f;
+    ix = warp_coord((float)x - d, (float)(W - 1));
+    fx0 = floorf(ix);
     const float jf = fx0 - (float)(x0 - SS_PAD);
-    in_win[s] = jf >= 0.0f && jf <= (float)(SS_WW - 2);      // both corners inside the staged window (zeros outside the image)
-    j0[s] = in_win[s] ? (int)jf : 0;
-    wx0[s] = in_win[s] ? fx1 - ix : 0.0f;         // out-of-window hypotheses add 0 in the staged loop and are done below
-    wx1[s] = in_win[s] ? ix - fx0 : 0.0f;
+    inw = jf >= 0.0f && jf <= (float)(SS_WW - 2);            // both corners inside the staged window (zeros outside the image)
+    j = inw ? (int)jf : 0;                                    // out-of-window hypotheses are redone from global memory below
+  };
+  int j0[5];
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    float gs, ix, fx0;
+    bool inw;
+    hypothesis(s, gs, ix, inw, j0[s], fx0);
   }
+  // staging geometry of this lane: 128-bit columns lane and lane + 32 of the 44-column window; columns outside the image (or past
+  // the window) load a clamped address and are replaced by zeros, so the loop body is branch-free
+  const int xa = x0 - SS_PAD + 4 * lane, xb = xa + 128;
+  const bool oka = xa >= 0 && xa < W, okb = lane + 32 < SS_Q && xb < W;      // xb >= 0 always
+  const int cola = oka ? xa : 0, offb = okb ? xb - cola : 0;
+  const float* r0p = fr + (size_t)b * C * HW + (size_t)y0 * W + (size_t)warp * HW + cola;      // rows y0 / y1 of channel `warp`
+  const float* r1p = fr + (size_t)b * C * HW + (size_t)y1 * W + (size_t)warp * HW + cola;
+  const float* lp = fl + (size_t)b * C * HW + (size_t)y * W + (size_t)(half * (SS_CK / 2)) * HW + (active ? x : 0);
   const float* lb = fl + (size_t)b * C * HW + (size_t)y * W;
   const float* rb = fr + (size_t)b * C * HW;
-  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  const bool two_rows = wy1 != 0.0f;                   // CTA-uniform
+  float a0[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, a1[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   for (int c0 = 0; c0 < C; c0 += SS_CK) {
-    if (vec4) {        // rows are 16-byte aligned: x0 and x0 - PAD are multiples of 4
-      for (int i = tx; i < SS_CK * (SS_TX / 4); i += SS_TX) {
-        const int c = i / (SS_TX / 4), j = (i - c * (SS_TX / 4)) * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c0 + c < C && x0 + j < W) v = __ldg(reinterpret_cast<const float4*>(lb + (size_t)(c0 + c) * HW + x0 + j));
-        *reinterpret_cast<float4*>(&Ls[c][j]) = v;
-      }
-      for (int i = tx; i < SS_CK * (SS_WW / 4); i += SS_TX) {
-        const int c = i / (SS_WW / 4), j = (i - c * (SS_WW / 4)) * 4;
-        const int xx = x0 - SS_PAD + j;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c0 + c < C && xx >= 0 && xx < W) {
-          const float* rp = rb + (size_t)(c0 + c) * HW + xx;
-          if (wy0 != 0.0f) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(rp + (size_t)y0 * W));
-            v = make_float4(a.x * wy0, a.y * wy0, a.z * wy0, a.w * wy0);
+    float l[SS_CK / 2];                                // this thread's left values of its half of the chunk
+    if (c0 + SS_CK <= C) {
+#pragma unroll
+      for (int c = 0; c < SS_CK / 2; ++c) l[c] = __ldg(lp + (size_t)c * HW);
+    } else {
+#pragma unroll
+      for (int c = 0; c < SS_CK / 2; ++c) l[c] = c0 + half * (SS_CK / 2) + c < C ? __ldg(lp + (size_t)c * HW) : 0.0f;
+    }
+    lp += (size_t)SS_CK * HW;
+    if (VEC4) {        // rows are 16-byte aligned: x0 - PAD is a multiple of 4
+#pragma unroll
+      for (int k = 0; k < SS_CK / 8; ++k) {            // channel c0 + warp + 8k (warp-uniform)
+        float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+        if (c0 + warp + 8 * k < C) {
+          va = __ldg(reinterpret_cast<const float4*>(r0p));
+          vb = __ldg(reinterpret_cast<const float4*>(r0p + offb));
+          va.x *= wy0; va.y *= wy0; va.z *= wy0; va.w *= wy0;
+          vb.x *= wy0; vb.y *= wy0; vb.z *= wy0; vb.w *= wy0;
+          if (two_rows) {
+            const float4 ta = __ldg(reinterpret_cast<const float4*>(r1p)), tb = __ldg(reinterpret_cast<const float4*>(r1p + offb));
+            va.x = fmaf(ta.x, wy1, va.x); va.y = fmaf(ta.y, wy1, va.y); va.z = fmaf(ta.z, wy1, va.z); va.w = fmaf(ta.w, wy1, va.w);
+            vb.x = fmaf(tb.x, wy1, vb.x); vb.y = fmaf(tb.y, wy1, vb.y); vb.z = fmaf(tb.z, wy1, vb.z); vb.w = fmaf(tb.w, wy1, vb.w);
           }
-          if (wy1 != 0.0f) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(rp + (size_t)y1 * W));
-            v.x = fmaf(a.x, wy1, v.x); v.y = fmaf(a.y, wy1, v.y); v.z = fmaf(a.z, wy1, v.z); v.w = fmaf(a.w, wy1, v.w);
-          }
+          if (!oka) va = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!okb) vb = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        *reinterpret_cast<float4*>(&Rc[c][j]) = v;
+        *reinterpret_cast<float4*>(&Rc[warp + 8 * k][4 * lane]) = va;
+        if (lane + 32 < SS_Q) *reinterpret_cast<float4*>(&Rc[warp + 8 * k][4 * lane + 128]) = vb;
+        r0p += 8 * HW;
+        r1p += 8 * HW;
       }
     } else {
-      for (int i = tx; i < SS_CK * SS_TX; i += SS_TX) {
-        const int c = i / SS_TX, j = i - c * SS_TX;
-        Ls[c][j] = (c0 + c < C && x0 + j < W) ? __ldg(lb + (size_t)(c0 + c) * HW + x0 + j) : 0.0f;
-      }
-      for (int i = tx; i < SS_CK * SS_WW; i += SS_TX) {
+      for (int i = tid; i < SS_CK * SS_WW; i += SS_NT) {
         const int c = i / SS_WW, j = i - c * SS_WW;
         const int xx = x0 - SS_PAD + j;
         float v = 0.0f;
@@ -180,31 +202,52 @@ __global__ void __launch_bounds__(SS_TX) sample_strength_kernel(const float* __r
       }
     }
     __syncthreads();
-    if (active) {
-      const int nc = min(SS_CK, C - c0);
-#pragma unroll 4
-      for (int c = 0; c < nc; ++c) {
-        const float l = Ls[c][tx];
 #pragma unroll
-        for (int s = 0; s < 5; ++s) acc[s] = fmaf(l, fmaf(Rc[c][j0[s] + 1], wx1[s], Rc[c][j0[s]] * wx0[s]), acc[s]);
+    for (int c = 0; c < SS_CK / 2; ++c) {              // channels past C hold zeros on both sides
+      const float* rc = Rc[half * (SS_CK / 2) + c];
+#pragma unroll
+      for (int s = 0; s < 5; ++s) {
+        a0[s] = fmaf(l[c], rc[j0[s]], a0[s]);
+        a1[s] = fmaf(l[c], rc[j0[s] + 1], a1[s]);
       }
     }
     __syncthreads();
   }
-  if (active) {
+  // combine the two channel halves: the upper half hands its partial sums to the lower half, which finishes the pixel
+  float acc[5];
 #pragma unroll
-    for (int s = 0; s < 5; ++s) {
-      if (in_win[s]) continue;                      // rare: wild disparity, corners outside the staged window
-      const Bilin q = make_bilin(ixs[s], iy, H, W);
-      float a = 0.0f;
-      for (int c = 0; c < C; ++c) a += __ldg(lb + (size_t)c * HW + x) * bilin_fetch(rb + (size_t)c * HW, q);
-      acc[s] = a;
-    }
+  for (int s = 0; s < 5; ++s) {
+    float gs, ix, fx0;
+    bool inw;
+    int j;
+    hypothesis(s, gs, ix, inw, j, fx0);
+    acc[s] = inw ? fmaf(a1[s], ix - fx0, a0[s] * (fx0 + 1.0f - ix)) : 0.0f;
   }
+  if (half == 1) {
+#pragma unroll
+    for (int s = 0; s < 5; ++s) Part[s][tx] = acc[s];
+  }
+  __syncthreads();
+  if (half == 1) return;
+#pragma unroll
+  for (int s = 0; s < 5; ++s) acc[s] += Part[s][tx];
   if (active) {
     float logit[5], m = -INFINITY;
 #pragma unroll
-    for (int s = 0; s < 5; ++s) { logit[s] = (acc[s] / (float)C) * g[s]; m = fmaxf(m, logit[s]); }
+    for (int s = 0; s < 5; ++s) {
+      float gs, ix, fx0;
+      bool inw;
+      int j;
+      hypothesis(s, gs, ix, inw, j, fx0);
+      if (!inw) {                                   // rare: wild disparity, corners outside the staged window
+        const Bilin q = make_bilin(ix, iy, H, W);
+        float a = 0.0f;
+        for (int c = 0; c < C; ++c) a += __ldg(lb + (size_t)c * HW + x) * bilin_fetch(rb + (size_t)c * HW, q);
+        acc[s] = a;
+      }
+      logit[s] = (acc[s] / (float)C) * gs;
+      m = fmaxf(m, logit[s]);
+    }
     float e[5], sum = 0.0f;
 #pragma unroll
     for (int s = 0; s < 5; ++s) { e[s] = expf(logit[s] - m); sum += e[s]; }
@@ -403,7 +446,10 @@ extern "C" int ss_sample_strength(const float* feat_l, const float* feat_r, cons
   SS_REQUIRE(B > 0 && C > 0 && H > 1 && W > 1, "ss_sample_strength: bad dimension");
   SS_GRID_LIMIT(H <= 65535 && B <= 65535, "ss_sample_strength");
   dim3 grid(ceil_div(W, SS_TX), H, B);
-  sample_strength_kernel<<<grid, SS_TX, 0, (cudaStream_t)stream>>>(feat_l, feat_r, mu, gate, strength, B, C, H, W);
+  if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(feat_r) & 15) == 0)
+    sample_strength_kernel<true><<<grid, SS_NT, 0, (cudaStream_t)stream>>>(feat_l, feat_r, mu, gate, strength, B, C, H, W);
+  else
+    sample_strength_kernel<false><<<grid, SS_NT, 0, (cudaStream_t)stream>>>(feat_l, feat_r, mu, gate, strength, B, C, H, W);
   SS_CHECK_LAUNCH("ss_sample_strength");
   return SS_OK;
 }

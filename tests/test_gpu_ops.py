@@ -196,6 +196,21 @@ def test_attention_stats_strength_topk_concat():
         assert err(ops.sparse_concat_volume(cu(cfl), cu(cfr), dtk, atk), vol) <= 5e-6
 
 
+def test_sample_strength_wide_rows():
+    """Row widths that take the 128-bit staging path (W % 4 == 0): two full pixel blocks, a ragged second block, one short block;
+    channel counts that are not a multiple of the 32-channel chunk; disparities that leave the +-24 column window (global-memory
+    fallback) and the image (zero padding)."""
+    from oracle import hotpath as oh
+    g = torch.Generator().manual_seed(41)
+    for C, H, W in ((128, 6, 256), (40, 5, 136), (24, 4, 20), (32, 3, 260)):
+        f4l, f4r = torch.randn(2, C, H, W, generator=g), torch.randn(2, C, H, W, generator=g)
+        mu = 12 * torch.randn(2, H, W, generator=g)
+        gate = torch.rand(2, 1, H, W, generator=g)
+        st = oh.sample_strength(f4l, f4r, mu, gate)
+        st2 = ops.sample_strength(cu(f4l), cu(f4r), cu(mu), cu(gate))
+        assert err(st2, st) <= 2e-5, (C, H, W)
+
+
 def oh_stats(p, cost_att, maxdisp, signed):
     from oracle import hotpath as oh
     return oh.attention_stats(p, cost_att, maxdisp, (2 * cost_att.shape[3], 2 * cost_att.shape[4]), signed)
