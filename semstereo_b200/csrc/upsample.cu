@@ -47,36 +47,34 @@ __global__ void __launch_bounds__(128) ssr_upsample_kernel(const float* __restri
   if (x >= w) return;
   const int X0 = 4 * x;
   const int cx0 = max(x - 1, 0), cx1 = x, cx2 = min(x + 1, w - 1);
-  // bilinear x4 of the low-res disparity on rows Y-1..Y+1, columns X0-1..X0+4 (zero outside: the conv pads the BN output)
+  // bilinear x4 of the low-res disparity on rows Y-1..Y+1, columns X0-1..X0+4 (zero outside: the conv pads the BN output).
+  // Column X0-1+j of an x4 align_corners=False upsample always blends the same low-res pair with the same weight: source position
+  // x + (j - 2.5) / 4, i.e. (x-1, x) with fractions 3/8, 5/8, 7/8 for j = 0..2 and (x, x+1) with 1/8, 3/8, 5/8 for j = 3..5 (exact in
+  // fp32, the values lin4() computes).  The clamped neighbour loads reproduce the right border; at the left border PyTorch clamps
+  // the source position to 0, i.e. fraction 0.  (Round 2: the per-column index / select arithmetic was ~1/3 of the instructions.)
+  const bool left_edge = x == 0, right_edge = x == w - 1;
+  const float f1l[3] = {left_edge ? 0.0f : 0.375f, left_edge ? 0.0f : 0.625f, left_edge ? 0.0f : 0.875f};
   float v[ND][3][6], centre[ND][4];
 #pragma unroll
-  for (int n = 0; n < ND; ++n) {
-    const float* dl = (n == 0 ? depth_low_a : depth_low_b) + (size_t)b * h * w;
+  for (int r = 0; r < 3; ++r) {
+    const int yy = Y + r - 1;
+    const bool yin = yy >= 0 && yy < H;
+    int y0 = 0, y1 = 0;
+    float hy0 = 0.f, hy1 = 0.f;
+    if (yin) lin4(yy, h, y0, y1, hy0, hy1);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) centre[n][j] = 0.f;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int yy = Y + r - 1;
-      const bool yin = yy >= 0 && yy < H;
-      int y0 = 0, y1 = 0;
-      float hy0 = 0.f, hy1 = 0.f;
-      if (yin) lin4(yy, h, y0, y1, hy0, hy1);
+    for (int n = 0; n < ND; ++n) {
+      const float* dl = (n == 0 ? depth_low_a : depth_low_b) + (size_t)b * h * w;
       const float a0 = __ldg(dl + y0 * w + cx0), a1 = __ldg(dl + y0 * w + cx1), a2 = __ldg(dl + y0 * w + cx2);
       const float c0 = __ldg(dl + y1 * w + cx0), c1 = __ldg(dl + y1 * w + cx1), c2 = __ldg(dl + y1 * w + cx2);
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
-        const int xx = X0 - 1 + j;
-        float val = 0.0f;
-        if (yin && xx >= 0 && xx < W) {
-          int x0, x1;
-          float wx0, wx1;
-          lin4(xx, w, x0, x1, wx0, wx1);
-          const float up = hy0 * (wx0 * sel3(a0, a1, a2, x0, cx0, cx1) + wx1 * sel3(a0, a1, a2, x1, cx0, cx1)) +
-                           hy1 * (wx0 * sel3(c0, c1, c2, x0, cx0, cx1) + wx1 * sel3(c0, c1, c2, x1, cx0, cx1));
-          if (r == 1 && j >= 1 && j <= 4) centre[n][j - 1] = up;
-          val = fmaf(P.a0, up, P.b0);
-        }
-        v[n][r][j] = val;
+        const float wx1 = j < 3 ? f1l[j] : 0.125f + 0.25f * (float)(j - 3), wx0 = 1.0f - wx1;
+        const float al = j < 3 ? a0 : a1, ar = j < 3 ? a1 : a2, cl = j < 3 ? c0 : c1, cr = j < 3 ? c1 : c2;
+        const float up = hy0 * (wx0 * al + wx1 * ar) + hy1 * (wx0 * cl + wx1 * cr);
+        const bool in = yin && !(j == 0 && left_edge) && !(j == 5 && right_edge);
+        if (r == 1 && j >= 1 && j <= 4) centre[n][j - 1] = up;
+        v[n][r][j] = in ? fmaf(P.a0, up, P.b0) : 0.0f;
       }
     }
   }
