@@ -6,6 +6,8 @@
 //   regression_topk      : models/submodule.py:434-442
 //   disparity_regression / disparity_variance : models/submodule.py:164-170, 257-263
 //   propagation / propagation_prob / spatial_transformer_grid : models/submodule.py:265-307, 361-377
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -259,85 +261,94 @@ __global__ void __launch_bounds__(SS_NT, 4) sample_strength_kernel(const float* 
 // ---------------------------------------------------------------------------------------------
 // K8
 // ---------------------------------------------------------------------------------------------
-template <int NB>
+// Round 2 (ncu r02_three: ~6000 instructions per pixel, most of them 64-bit address arithmetic and per-bin `k < nb` branches):
+// block-uniform base pointers + 32-bit element offsets, a FULL instantiation for nb == NB (the model's 32 bins), one running
+// output offset, and the renormalised expectation as (sum e*d) / (sum e) -- one division instead of one per kept bin.
+template <int NB, bool FULL>
 __global__ void __launch_bounds__(128) topk_select_kernel(const float* __restrict__ att, const float* __restrict__ strength,
                                                           long long* __restrict__ ind_k, float* __restrict__ att_topk,
                                                           float* __restrict__ disp_topk, float* __restrict__ pred_att,
-                                                          float* __restrict__ prob_out, int B, int nb, int K, int H, int W,
+                                                          float* __restrict__ prob_out, int B, int nb_, int K, int H, int W,
                                                           float disp_offset) {
+  using mask_t = typename std::conditional<(NB <= 32), unsigned, unsigned long long>::type;
+  const int nb = FULL ? NB : nb_;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, b = blockIdx.z;
   if (x >= W) return;
-  const size_t HW = (size_t)H * W, pix = (size_t)y * W + x;
-  size_t tap[5];
+  const unsigned HW = (unsigned)H * (unsigned)W, pix = (unsigned)y * W + x;      // nb * HW < 2^32 (checked by the launcher)
+  const float* sb = strength + (size_t)b * 5 * HW;
+  const float* ab = att + (size_t)b * nb * HW;
+  const unsigned HW4 = HW * 4u;                         // bytes of one bin plane (< 2^32, checked by the launcher)
+  const char* ap[5];
   float st[5];
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
     const int ty = min(max(y + kPropDy[s], 0), H - 1), tx = min(max(x + kPropDx[s], 0), W - 1);
-    tap[s] = (size_t)ty * W + tx;
-    st[s] = __ldg(strength + ((size_t)b * 5 + s) * HW + pix);
+    ap[s] = reinterpret_cast<const char*>(ab + ((unsigned)ty * W + tx));
+    st[s] = __ldg(sb + ((unsigned)s * HW + pix));
   }
-  const float* ab = att + (size_t)b * nb * HW;
   float mix[NB], p[NB];
   float m = -INFINITY;
 #pragma unroll
   for (int k = 0; k < NB; ++k) {
-    if (k < nb) {
-      const float* a = ab + (size_t)k * HW;
-      float acc = __fmul_rn(__ldg(a + tap[0]), st[0]);       // products then a sequential sum, as torch.sum(dim=1)
+    if (FULL || k < nb) {
+      // address = tap pointer + k * (HW * 4): one 32 x 32 -> 64-bit multiply-add per load
+      float acc = __fmul_rn(__ldg(reinterpret_cast<const float*>(ap[0] + (unsigned long long)HW4 * (unsigned)k)), st[0]);
 #pragma unroll
-      for (int s = 1; s < 5; ++s) acc = __fadd_rn(acc, __fmul_rn(__ldg(a + tap[s]), st[s]));
+      for (int s = 1; s < 5; ++s)           // products then a sequential sum, as torch.sum(dim=1)
+        acc = __fadd_rn(acc, __fmul_rn(__ldg(reinterpret_cast<const float*>(ap[s] + (unsigned long long)HW4 * (unsigned)k)), st[s]));
       mix[k] = acc;
       m = fmaxf(m, acc);
     } else mix[k] = -INFINITY;
   }
   float sum = 0.0f;
 #pragma unroll
-  for (int k = 0; k < NB; ++k) { p[k] = (k < nb) ? expf(mix[k] - m) : 0.0f; sum += p[k]; }
+  for (int k = 0; k < NB; ++k) { p[k] = (FULL || k < nb) ? expf(mix[k] - m) : 0.0f; sum += p[k]; }
 #pragma unroll
-  for (int k = 0; k < NB; ++k) p[k] = (k < nb) ? p[k] / sum : -1.0f;
+  for (int k = 0; k < NB; ++k) p[k] = (FULL || k < nb) ? p[k] / sum : -1.0f;
   if (prob_out) {
+    float* po = prob_out + (size_t)b * nb * HW;
 #pragma unroll
     for (int k = 0; k < NB; ++k)
-      if (k < nb) prob_out[((size_t)b * nb + k) * HW + pix] = p[k];
+      if (FULL || k < nb) po[(unsigned)k * HW + pix] = p[k];
   }
   // Keep the K largest probabilities, ties broken toward the lower index (total order: p descending, index ascending).
   // The model keeps 24 of 32 bins, so it is cheaper to DROP the nb-K last elements of that order one by one (minimum p,
   // among equals the highest index: `<=` lets a later index win) than to rank all bins against each other (a rank-by-count
   // variant with NB*NB independent comparisons was measured slower, 0.27 vs 0.22 ms at batch 8: round 2).
-  unsigned long long keep = nb >= 64 ? ~0ull : ((1ull << nb) - 1ull);
+  mask_t keep = nb >= (int)(8 * sizeof(mask_t)) ? ~(mask_t)0 : (((mask_t)1 << nb) - 1);
 #pragma unroll 1
   for (int r = 0; r < nb - K; ++r) {
     float mn = INFINITY;
     int mi = 0;
 #pragma unroll
     for (int k = 0; k < NB; ++k)
-      if (((keep >> k) & 1ull) && p[k] <= mn) { mn = p[k]; mi = k; }
-    keep &= ~(1ull << mi);
+      if (((keep >> k) & 1) && p[k] <= mn) { mn = p[k]; mi = k; }
+    keep &= ~((mask_t)1 << mi);
   }
   float m2 = -INFINITY;
 #pragma unroll
   for (int k = 0; k < NB; ++k)
-    if ((keep >> k) & 1ull) m2 = fmaxf(m2, mix[k]);
-  float s2 = 0.0f;
-#pragma unroll
-  for (int k = 0; k < NB; ++k)
-    if ((keep >> k) & 1ull) s2 += expf(mix[k] - m2);
-  float pred = 0.0f;
-  int j = 0;
-  const size_t obase = (size_t)b * K * HW + pix;
+    if ((keep >> k) & 1) m2 = fmaxf(m2, mix[k]);
+  float num = 0.0f, den = 0.0f;
+  unsigned o = pix;                                    // + j * HW for the j-th kept bin
+  long long* ik = ind_k ? ind_k + (size_t)b * K * HW : nullptr;
+  float* at = att_topk + (size_t)b * K * HW;
+  float* dt = disp_topk + (size_t)b * K * HW;
 #pragma unroll
   for (int k = 0; k < NB; ++k) {
-    if ((keep >> k) & 1ull) {
+    if ((keep >> k) & 1) {
       const float d = (float)k - disp_offset;
-      if (ind_k) ind_k[obase + (size_t)j * HW] = k;
-      att_topk[obase + (size_t)j * HW] = p[k];
-      disp_topk[obase + (size_t)j * HW] = d;
-      pred += (expf(mix[k] - m2) / s2) * d;
-      ++j;
+      if (ik) ik[o] = k;
+      at[o] = p[k];
+      dt[o] = d;
+      const float e = expf(mix[k] - m2);
+      den += e;
+      num = fmaf(e, d, num);
+      o += HW;
     }
   }
-  pred_att[(size_t)b * HW + pix] = pred;
+  pred_att[(size_t)b * HW + pix] = num / den;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -461,13 +472,16 @@ extern "C" int ss_topk_select(const float* att_up, const float* strength, long l
   SS_REQUIRE(B > 0 && nbins > 0 && K > 0 && K <= nbins && H > 0 && W > 0, "ss_topk_select: need 0 < K <= nbins");
   SS_UNSUPPORTED(nbins > 64, "ss_topk_select: more than 64 disparity bins (%d) unsupported", nbins);
   SS_GRID_LIMIT(H <= 65535 && B <= 65535, "ss_topk_select");
+  SS_GRID_LIMIT((unsigned long long)nbins * H * W < (1ull << 32) && (unsigned long long)5 * H * W < (1ull << 32), "ss_topk_select");
   dim3 grid(ceil_div(W, 128), H, B);
-  if (nbins <= 32)
-    topk_select_kernel<32><<<grid, 128, 0, (cudaStream_t)stream>>>(att_up, strength, ind_k, att_topk, disp_topk, pred_att,
-                                                                    prob_or_null, B, nbins, K, H, W, disp_offset);
-  else
-    topk_select_kernel<64><<<grid, 128, 0, (cudaStream_t)stream>>>(att_up, strength, ind_k, att_topk, disp_topk, pred_att,
-                                                                    prob_or_null, B, nbins, K, H, W, disp_offset);
+#define SS_TOPK(NB, FULL)                                                                                                     \
+  topk_select_kernel<NB, FULL><<<grid, 128, 0, (cudaStream_t)stream>>>(att_up, strength, ind_k, att_topk, disp_topk, pred_att, \
+                                                                        prob_or_null, B, nbins, K, H, W, disp_offset)
+  if (nbins == 32) SS_TOPK(32, true);
+  else if (nbins < 32) SS_TOPK(32, false);
+  else if (nbins == 64) SS_TOPK(64, true);
+  else SS_TOPK(64, false);
+#undef SS_TOPK
   SS_CHECK_LAUNCH("ss_topk_select");
   return SS_OK;
 }
