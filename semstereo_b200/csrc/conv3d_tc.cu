@@ -21,6 +21,8 @@
 //   t2 : ConvTranspose3d k3 s2 p1 op1 as 8 sub-pixel output phases (1/2/4/8 taps each, no zero insertion); the hourglass
 //        skip connection (redir conv output, stored phase-split) is added in the epilogue before the ReLU.
 // Epilogue: y = acc*scale[co] + shift[co] (+ residual) -> ReLU -> * gate[b,co,h,w] -> bf16 blocked / phase-split, or fp32 NCDHW.
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -358,8 +360,10 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_const
 // SP (bf16x3 split route, in-kernel): the input is a split tensor (hi batches [0,B) | lo batches [B,2B)), a staged slice holds the
 // hi chunks followed by the lo chunks (two TMA boxes), the weights of a tap are [hi: CIN/8 chunks][lo: CIN/8 chunks], and every
 // K step issues three MMAs into the same accumulator: x_hi*w_hi + x_lo*w_hi + x_hi*w_lo (fp32-accurate product, fp32 accumulation).
-template <int CIN, int N, int NS, int NWS, bool SP = false>
-__global__ void __launch_bounds__(256, 1) conv3d_tc_s1f_kernel(const __grid_constant__ CUtensorMap tmA, const TcP p) {
+// EPG: epilogue warp groups (4 warps each, 128 + 128*EPG threads): with EPG = 2 the groups drain alternate accumulator blocks, so the
+// TMEM load -> affine -> store latency of one output slice overlaps the next one's.
+template <int CIN, int N, int NS, int NWS, bool SP = false, int EPG = 1>
+__global__ void __launch_bounds__(128 + 128 * EPG, 1) conv3d_tc_s1f_kernel(const __grid_constant__ CUtensorMap tmA, const TcP p) {
   constexpr bool kResident = (NWS == 9);
   constexpr uint32_t HALF_A = (CIN / 8) * TILE_B, HALF_B = CIN * 3 * N * 2;      // one operand half (hi or lo) of a slice / tap
   constexpr uint32_t SLICE = (SP ? 2 : 1) * HALF_A;
@@ -371,7 +375,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1f_kernel(const __grid_cons
   TC_KERNEL_PROLOGUE_N(NS, NWS, kResident, NB)
   uint8_t* Abase = smem;
   uint8_t* Wbase = smem + NS * SLICE;
-  if (warp >= 4) {                                     // all accumulator blocks start out zero
+  if (warp >= 4 && warp < 8) {                         // all accumulator blocks start out zero
 #pragma unroll 1
     for (uint32_t c = 0; c < 512; c += 32) tc::tmem_zero32(tmem_base + ((uint32_t)((warp - 4) * 32) << 16) + c);
   }
@@ -447,35 +451,43 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1f_kernel(const __grid_cons
         const uint32_t d1 = tmem_base + blk * N, d2 = tmem_base;
         const uint32_t a_lo = a_lo0 + slot * (SLICE >> 4);
         const uint32_t brow1 = (uint32_t)j0 * (N / 8) * (SBO_B >> 4), brow2 = (uint32_t)(j0 + n1) * (N / 8) * (SBO_B >> 4);
+        // The issuing thread's instruction stream bounds these kernels (ncu r02_s1f: the MMA warp never waits, ~400 SASS
+        // instructions per slice for 18 MMAs of ~56 cycles each): the ring-wrap case, which doubles every MMA, is a separate
+        // copy of the loop so that the common case carries no second descriptor set.
+        auto issue = [&](auto wrap_tag) {
+          constexpr bool WRAP = decltype(wrap_tag)::value;
 #pragma unroll
-        for (int t9 = 0; t9 < 9; ++t9) {
-          const int kh = t9 / 3, kw = t9 - 3 * kh;
-          uint32_t b_lo, wslot = 0;
-          if (kResident) b_lo = b_lo0 + (uint32_t)t9 * (TAPB >> 4);
-          else {
-            wslot = wc % NWS;
-            tc::mbar_wait(&w_full[wslot], (wc / NWS) & 1);
-            tc::fence_after_sync();
-            b_lo = b_lo0 + wslot * (TAPB >> 4);
-          }
-          if (leader) {
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-              const uint32_t a = a_lo + (uint32_t)((kh * WW + kw) * 16 + ks * 2 * LBO_A) / 16;
-              const uint32_t bb = b_lo + (uint32_t)(ks * 2 * LBO_B) / 16;
-              tc::mma_bf16_lohi(d1, a, a_hi, bb + brow1, b_hi, id1, 1u);
-              if (n2) tc::mma_bf16_lohi(d2, a, a_hi, bb + brow2, b_hi, id2, 1u);
-              if (SP) {
-                tc::mma_bf16_lohi(d1, a + (HALF_A >> 4), a_hi, bb + brow1, b_hi, id1, 1u);
-                if (n2) tc::mma_bf16_lohi(d2, a + (HALF_A >> 4), a_hi, bb + brow2, b_hi, id2, 1u);
-                tc::mma_bf16_lohi(d1, a, a_hi, bb + (HALF_B >> 4) + brow1, b_hi, id1, 1u);
-                if (n2) tc::mma_bf16_lohi(d2, a, a_hi, bb + (HALF_B >> 4) + brow2, b_hi, id2, 1u);
-              }
+          for (int t9 = 0; t9 < 9; ++t9) {
+            const int kh = t9 / 3, kw = t9 - 3 * kh;
+            uint32_t b_lo, wslot = 0;
+            if (kResident) b_lo = b_lo0 + (uint32_t)t9 * (TAPB >> 4);
+            else {
+              wslot = wc % NWS;
+              tc::mbar_wait(&w_full[wslot], (wc / NWS) & 1);
+              tc::fence_after_sync();
+              b_lo = b_lo0 + wslot * (TAPB >> 4);
             }
-            if (!kResident) tc::mma_commit(&w_empty[wslot]);
+            if (leader) {
+#pragma unroll
+              for (int ks = 0; ks < KS; ++ks) {
+                const uint32_t a = a_lo + (uint32_t)((kh * WW + kw) * 16 + ks * 2 * LBO_A) / 16;
+                const uint32_t bb = b_lo + (uint32_t)(ks * 2 * LBO_B) / 16;
+                tc::mma_bf16_lohi(d1, a, a_hi, bb + brow1, b_hi, id1, 1u);
+                if (WRAP) tc::mma_bf16_lohi(d2, a, a_hi, bb + brow2, b_hi, id2, 1u);
+                if (SP) {
+                  tc::mma_bf16_lohi(d1, a + (HALF_A >> 4), a_hi, bb + brow1, b_hi, id1, 1u);
+                  if (WRAP) tc::mma_bf16_lohi(d2, a + (HALF_A >> 4), a_hi, bb + brow2, b_hi, id2, 1u);
+                  tc::mma_bf16_lohi(d1, a, a_hi, bb + (HALF_B >> 4) + brow1, b_hi, id1, 1u);
+                  if (WRAP) tc::mma_bf16_lohi(d2, a, a_hi, bb + (HALF_B >> 4) + brow2, b_hi, id2, 1u);
+                }
+              }
+              if (!kResident) tc::mma_commit(&w_empty[wslot]);
+            }
+            if (!kResident) ++wc;
           }
-          if (!kResident) ++wc;
-        }
+        };
+        if (n2) issue(std::true_type{});
+        else issue(std::false_type{});
         if (leader) {
           tc::mma_commit(&a_empty[slot]);
           if (d_in - 1 >= dlo) tc::mma_commit(&acc_full[(acc_base + (uint32_t)(d_in - 1 - dlo)) % NB]);
@@ -486,8 +498,8 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1f_kernel(const __grid_cons
       acc_base += (uint32_t)(dhi - dlo);
     }
   } else if (warp >= 4) {
-    // ===== epilogue =====
-    const int e = warp - 4, m = e * 32 + lane, hh = m >> 3, ww = m & 7;
+    // ===== epilogue (warp & 3 = the TMEM lane quarter this warp may read) =====
+    const int e = warp & 3, eg = (warp - 4) >> 2, m = e * 32 + lane, hh = m >> 3, ww = m & 7;
     uint32_t u = 0;
     for (int s = cta_s; s < p.items; s += cta_stride) {
       int b, h0, w0, dlo, dhi;
@@ -495,6 +507,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1f_kernel(const __grid_cons
       const int h = h0 + hh, w = w0 + ww;
       const bool valid = h < p.H && w < p.W;
       for (int d_out = dlo; d_out < dhi; ++d_out, ++u) {
+        if (EPG > 1 && (int)(u % EPG) != eg) continue;
         const uint32_t blk = u % NB;
         tc::mbar_wait(&acc_full[blk], (u / NB) & 1);
         tc::fence_after_sync();
@@ -693,19 +706,24 @@ __global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_con
         const uint32_t d1 = tmem_base + blk * N, d2 = tmem_base;
         const uint32_t a_lo = a_lo0 + slot * (K9_SLICE >> 4);
         const uint32_t brow1 = (uint32_t)j0 * (N / 8) * (SBO_B >> 4), brow2 = (uint32_t)(j0 + n1) * (N / 8) * (SBO_B >> 4);
+        auto issue = [&](auto wrap_tag) {              // the ring-wrap case is a separate copy of the loop (see s1f)
+          constexpr bool WRAP = decltype(wrap_tag)::value;
 #pragma unroll
-        for (int t9 = 0; t9 < 9; ++t9) {
-          const int kh = t9 / 3, kw = t9 - 3 * kh;
-          const uint32_t b_lo = b_lo0 + (uint32_t)t9 * (K9_TAPB >> 4);
-          if (leader) {
+          for (int t9 = 0; t9 < 9; ++t9) {
+            const int kh = t9 / 3, kw = t9 - 3 * kh;
+            const uint32_t b_lo = b_lo0 + (uint32_t)t9 * (K9_TAPB >> 4);
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
               const uint32_t a = a_lo + (uint32_t)((kh * WW + kw) * 16 + ks * 2 * LBO_A) / 16;
               const uint32_t bb = b_lo + (uint32_t)(ks * 2 * LBO_B) / 16;
               tc::mma_bf16_lohi(d1, a, a_hi, bb + brow1, b_hi, id1, 1u);
-              if (n2) tc::mma_bf16_lohi(d2, a, a_hi, bb + brow2, b_hi, id2, 1u);
+              if (WRAP) tc::mma_bf16_lohi(d2, a, a_hi, bb + brow2, b_hi, id2, 1u);
             }
           }
+        };
+        if (leader) {
+          if (n2) issue(std::true_type{});
+          else issue(std::false_type{});
         }
         if (leader) {
           tc::mma_commit(&a_empty[slot]);
@@ -1247,11 +1265,11 @@ void plan_tc(TcP& p, double halo_cost, int& grid) {
 }
 
 template <typename K>
-int launch_tc(K kernel, size_t smem, const CUtensorMap& tm, TcP p, double halo_cost, cudaStream_t st, const char* name) {
+int launch_tc(K kernel, size_t smem, const CUtensorMap& tm, TcP p, double halo_cost, cudaStream_t st, const char* name, int threads = 256) {
   SS_CUDA(ss_allow_smem(kernel, smem));
   int grid;
   plan_tc(p, halo_cost, grid);
-  kernel<<<grid, 256, smem, st>>>(tm, p);
+  kernel<<<grid, threads, smem, st>>>(tm, p);
   SS_CHECK_LAUNCH(name);
   return SS_OK;
 }
@@ -1262,11 +1280,11 @@ int launch_s1(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
   static_assert(smem <= 227 * 1024 - 2048, "shared memory budget");
   return launch_tc(conv3d_tc_s1_kernel<CIN, N, NS, NWS, TAPS, EPI>, smem, tm, p, TAPS == 27 ? 0.35 : 0.0, st, "ss_conv3d_tc(s1)");
 }
-template <int CIN, int N, int NS, int NWS, bool SP = false>
+template <int CIN, int N, int NS, int NWS, bool SP = false, int EPG = 1>
 int launch_s1f(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
   constexpr size_t smem = (SP ? 2 : 1) * ((size_t)NS * (CIN / 8) * TILE_B + (size_t)NWS * CIN * 3 * N * 2);
   static_assert(smem <= 227 * 1024 - 2048, "shared memory budget");
-  return launch_tc(conv3d_tc_s1f_kernel<CIN, N, NS, NWS, SP>, smem, tm, p, 1.4, st, "ss_conv3d_tc(s1f)");
+  return launch_tc(conv3d_tc_s1f_kernel<CIN, N, NS, NWS, SP, EPG>, smem, tm, p, 1.4, st, "ss_conv3d_tc(s1f)", 128 + 128 * EPG);
 }
 template <int CIN, int N, int NS, int NWS, bool SP = false, int EPI = 0>
 int launch_s2(const CUtensorMap& tm, const TcP& p, cudaStream_t st) {
@@ -1455,7 +1473,7 @@ extern "C" int ss_conv3d_tc_ex(int kind, const void* in_blocked, const void* wei
       if (Cin == 128) return launch_s1<128, 64, 3, 2, 9>(tm, p, st);
       return launch_s1<64, 32, 4, 9, 9>(tm, p, st);
     case 5:
-      if (Cin == 32 && Cout == 32) return launch_s1f<32, 32, 6, 9>(tm, p, st);
+      if (Cin == 32 && Cout == 32) return launch_s1f<32, 32, 6, 9, false, 2>(tm, p, st);
       if (Cin == 64 && Cout == 32) return launch_s1f<64, 32, 4, 9>(tm, p, st);
       if (Cin == 32 && Cout == 64) return launch_s1f<32, 64, 6, 9>(tm, p, st);
       return launch_s1f<64, 64, 4, 4>(tm, p, st);
