@@ -427,6 +427,8 @@ __global__ void __launch_bounds__(128 + 128 * EPG, 1) conv3d_tc_s1f_kernel(const
     const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(Abase), LBO_A), a_hi = tc::desc_hi(SBO_A);
     const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(Wbase), LBO_B), b_hi = tc::desc_hi(SBO_B);
     if (kResident && cta_s < p.items) tc::mbar_wait(&w_full[0], 0);
+    const uint32_t bar_af = tc::smem_u32(&a_full[0]), bar_ae = tc::smem_u32(&a_empty[0]), bar_wf = tc::smem_u32(&w_full[0]),
+                   bar_we = tc::smem_u32(&w_empty[0]), bar_cf = tc::smem_u32(&acc_full[0]), bar_ce = tc::smem_u32(&acc_empty[0]);
     uint32_t g = 0, wc = 0;
     uint32_t acc_base = 0;       // unwrapped ring index of the accumulator of (this item, dlo)
     uint32_t acquired = 0;       // accumulator blocks handed to the MMAs so far (unwrapped)
@@ -439,11 +441,11 @@ __global__ void __launch_bounds__(128 + 128 * EPG, 1) conv3d_tc_s1f_kernel(const
         const int j0 = max(0, dlo - d_in + 1), j1 = min(3, dhi - d_in + 1);       // column blocks [j0, j1) exist
         const uint32_t u0 = acc_base + (uint32_t)(d_in - 1 + j0 - dlo), nb = (uint32_t)(j1 - j0);
         while (acquired < u0 + nb) {
-          tc::mbar_wait(&acc_empty[acquired % NB], ((acquired / NB) & 1) ^ 1);
+          tc::mbar_wait_a(bar_ce + (acquired % NB) * 8, ((acquired / NB) & 1) ^ 1);
           ++acquired;
         }
         const uint32_t slot = g % NS;
-        tc::mbar_wait(&a_full[slot], (g / NS) & 1);
+        tc::mbar_wait_a(bar_af + slot * 8, (g / NS) & 1);
         tc::fence_after_sync();
         const uint32_t blk = u0 % NB, n1 = min(nb, NB - blk), n2 = nb - n1;
         const uint32_t id1 = n1 == 1 ? tc::make_idesc_bf16(128, N) : n1 == 2 ? tc::make_idesc_bf16(128, 2 * N) : tc::make_idesc_bf16(128, 3 * N);
@@ -463,7 +465,7 @@ __global__ void __launch_bounds__(128 + 128 * EPG, 1) conv3d_tc_s1f_kernel(const
             if (kResident) b_lo = b_lo0 + (uint32_t)t9 * (TAPB >> 4);
             else {
               wslot = wc % NWS;
-              tc::mbar_wait(&w_full[wslot], (wc / NWS) & 1);
+              tc::mbar_wait_a(bar_wf + wslot * 8, (wc / NWS) & 1);
               tc::fence_after_sync();
               b_lo = b_lo0 + wslot * (TAPB >> 4);
             }
@@ -481,7 +483,7 @@ __global__ void __launch_bounds__(128 + 128 * EPG, 1) conv3d_tc_s1f_kernel(const
                   if (WRAP) tc::mma_bf16_lohi(d2, a, a_hi, bb + (HALF_B >> 4) + brow2, b_hi, id2, 1u);
                 }
               }
-              if (!kResident) tc::mma_commit(&w_empty[wslot]);
+              if (!kResident) tc::mma_commit_a(bar_we + wslot * 8);
             }
             if (!kResident) ++wc;
           }
@@ -489,9 +491,9 @@ __global__ void __launch_bounds__(128 + 128 * EPG, 1) conv3d_tc_s1f_kernel(const
         if (n2) issue(std::true_type{});
         else issue(std::false_type{});
         if (leader) {
-          tc::mma_commit(&a_empty[slot]);
-          if (d_in - 1 >= dlo) tc::mma_commit(&acc_full[(acc_base + (uint32_t)(d_in - 1 - dlo)) % NB]);
-          if (d_in == din1 && din1 == dhi - 1) tc::mma_commit(&acc_full[(acc_base + (uint32_t)(d_in - dlo)) % NB]);
+          tc::mma_commit_a(bar_ae + slot * 8);
+          if (d_in - 1 >= dlo) tc::mma_commit_a(bar_cf + ((acc_base + (uint32_t)(d_in - 1 - dlo)) % NB) * 8);
+          if (d_in == din1 && din1 == dhi - 1) tc::mma_commit_a(bar_cf + ((acc_base + (uint32_t)(d_in - dlo)) % NB) * 8);
         }
         __syncwarp();
       }
@@ -684,6 +686,8 @@ __global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_con
     const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(Abase), LBO_A), a_hi = tc::desc_hi(SBO_A);
     const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(Wbase), LBO_B), b_hi = tc::desc_hi(SBO_B);
     if (cta_s < p.items) tc::mbar_wait(&w_full, 0);
+    const uint32_t bar_af = tc::smem_u32(&a_full[0]), bar_ae = tc::smem_u32(&a_empty[0]), bar_cf = tc::smem_u32(&acc_full[0]),
+                   bar_ce = tc::smem_u32(&acc_empty[0]);
     uint32_t g = 0, acc_base = 0, acquired = 0;
     for (int s = cta_s; s < p.items; s += cta_stride) {
       int b, h0, w0, dlo, dhi;
@@ -694,11 +698,11 @@ __global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_con
         const int j0 = max(0, dlo - d_in + 1), j1 = min(3, dhi - d_in + 1);
         const uint32_t u0 = acc_base + (uint32_t)(d_in - 1 + j0 - dlo), nb = (uint32_t)(j1 - j0);
         while (acquired < u0 + nb) {
-          tc::mbar_wait(&acc_empty[acquired % NB], ((acquired / NB) & 1) ^ 1);
+          tc::mbar_wait_a(bar_ce + (acquired % NB) * 8, ((acquired / NB) & 1) ^ 1);
           ++acquired;
         }
         const uint32_t slot = g % K9_NS;
-        tc::mbar_wait(&a_full[slot], (g / K9_NS) & 1);
+        tc::mbar_wait_a(bar_af + slot * 8, (g / K9_NS) & 1);
         tc::fence_after_sync();
         const uint32_t blk = u0 % NB, n1 = min(nb, NB - blk), n2 = nb - n1;
         const uint32_t id1 = n1 == 1 ? tc::make_idesc_bf16(128, N) : n1 == 2 ? tc::make_idesc_bf16(128, 2 * N) : tc::make_idesc_bf16(128, 3 * N);
@@ -726,9 +730,9 @@ __global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_con
           else issue(std::false_type{});
         }
         if (leader) {
-          tc::mma_commit(&a_empty[slot]);
-          if (d_in - 1 >= dlo) tc::mma_commit(&acc_full[(acc_base + (uint32_t)(d_in - 1 - dlo)) % NB]);
-          if (d_in == din1 && din1 == dhi - 1) tc::mma_commit(&acc_full[(acc_base + (uint32_t)(d_in - dlo)) % NB]);
+          tc::mma_commit_a(bar_ae + slot * 8);
+          if (d_in - 1 >= dlo) tc::mma_commit_a(bar_cf + ((acc_base + (uint32_t)(d_in - 1 - dlo)) % NB) * 8);
+          if (d_in == din1 && din1 == dhi - 1) tc::mma_commit_a(bar_cf + ((acc_base + (uint32_t)(d_in - dlo)) % NB) * 8);
         }
         __syncwarp();
       }
@@ -1473,7 +1477,7 @@ extern "C" int ss_conv3d_tc_ex(int kind, const void* in_blocked, const void* wei
       if (Cin == 128) return launch_s1<128, 64, 3, 2, 9>(tm, p, st);
       return launch_s1<64, 32, 4, 9, 9>(tm, p, st);
     case 5:
-      if (Cin == 32 && Cout == 32) return launch_s1f<32, 32, 6, 9, false, 2>(tm, p, st);
+      if (Cin == 32 && Cout == 32) return launch_s1f<32, 32, 6, 9>(tm, p, st);
       if (Cin == 64 && Cout == 32) return launch_s1f<64, 32, 4, 9>(tm, p, st);
       if (Cin == 32 && Cout == 64) return launch_s1f<32, 64, 6, 9>(tm, p, st);
       return launch_s1f<64, 64, 4, 4>(tm, p, st);

@@ -46,6 +46,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same on a shared-window address computed once with smem_u32 (ptxas re-derives the address of a __shared__ symbol at every use:
+// S2UR CgaCtaId + ULEA; the MMA issuer's loop cannot afford that, see conv3d_tc.cu s1f).
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_a(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_a(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
 // ---- TMA ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -107,6 +128,9 @@ __device__ __forceinline__ bool elect_one() {
 // arrives on `bar` once every previously issued tcgen05.mma of this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mma_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
