@@ -1474,13 +1474,13 @@ extern "C" int ss_conv3d_tc_ex(int kind, const void* in_blocked, const void* wei
       if (Cin == 32) return launch_s2<32, 64, 2, 27>(tm, p, st);
       return ex ? launch_s2<64, 128, 2, 2, false, 3>(tm, p, st) : launch_s2<64, 128, 2, 2>(tm, p, st);
     case 4:
-      if (Cin == 128) return launch_s1<128, 64, 3, 2, 9>(tm, p, st);
+      if (Cin == 128) return launch_s1<128, 64, 2, 8, 9>(tm, p, st);      // 8-deep tap ring: a 2-deep one exposes the 16 KB reload latency
       return launch_s1<64, 32, 4, 9, 9>(tm, p, st);
     case 5:
       if (Cin == 32 && Cout == 32) return launch_s1f<32, 32, 6, 9>(tm, p, st);
       if (Cin == 64 && Cout == 32) return launch_s1f<64, 32, 4, 9>(tm, p, st);
       if (Cin == 32 && Cout == 64) return launch_s1f<32, 64, 6, 9>(tm, p, st);
-      return launch_s1f<64, 64, 4, 4>(tm, p, st);
+      return launch_s1f<64, 64, 2, 7>(tm, p, st);
     default:
       if (Cin == 128) return ex ? launch_t2<128, 64, 3, 2, 2, false, 3>(tm, p, st) : launch_t2<128, 64, 3, 2, 2>(tm, p, st);
       return launch_t2<64, 32, 3, 27, 4>(tm, p, st);
