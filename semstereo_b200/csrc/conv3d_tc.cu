@@ -1482,7 +1482,7 @@ extern "C" int ss_conv3d_tc_ex(int kind, const void* in_blocked, const void* wei
       if (Cin == 32 && Cout == 64) return launch_s1f<32, 64, 6, 9>(tm, p, st);
       return launch_s1f<64, 64, 2, 7>(tm, p, st);
     default:
-      if (Cin == 128) return ex ? launch_t2<128, 64, 3, 2, 2, false, 3>(tm, p, st) : launch_t2<128, 64, 3, 2, 2>(tm, p, st);
+      if (Cin == 128) return ex ? launch_t2<128, 64, 2, 5, 2, false, 3>(tm, p, st) : launch_t2<128, 64, 2, 5, 2>(tm, p, st);
       return launch_t2<64, 32, 3, 27, 4>(tm, p, st);
   }
 }
