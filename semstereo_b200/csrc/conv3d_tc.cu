@@ -372,9 +372,16 @@ __global__ void __launch_bounds__(128 + 128 * EPG, 1) conv3d_tc_s1f_kernel(const
   constexpr uint32_t LBO_A = TILE_B, SBO_A = WW * 16, LBO_B = 3 * N * 16, SBO_B = 128;
   constexpr uint32_t TMEM_COLS = 512;
   constexpr uint32_t NB = 512 / N;                     // accumulator blocks in the TMEM ring
+  constexpr uint32_t PLN = 4;                          // slice records in flight between the planner and the MMA issuer
+  __shared__ __align__(16) uint32_t plan[PLN][12];
+  __shared__ __align__(8) uint64_t plan_full[PLN], plan_empty[PLN];
   TC_KERNEL_PROLOGUE_N(NS, NWS, kResident, NB)
   uint8_t* Abase = smem;
   uint8_t* Wbase = smem + NS * SLICE;
+  if (threadIdx.x == 0) {
+    for (uint32_t i = 0; i < PLN; ++i) { tc::mbar_init(&plan_full[i], 1); tc::mbar_init(&plan_empty[i], 1); }
+    tc::fence_barrier_init();
+  }
   if (warp >= 4 && warp < 8) {                         // all accumulator blocks start out zero
 #pragma unroll 1
     for (uint32_t c = 0; c < 512; c += 32) tc::tmem_zero32(tmem_base + ((uint32_t)((warp - 4) * 32) << 16) + c);
@@ -421,15 +428,17 @@ __global__ void __launch_bounds__(128 + 128 * EPG, 1) conv3d_tc_s1f_kernel(const
           }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    const bool leader = tc::elect_one();
-    const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(Abase), LBO_A), a_hi = tc::desc_hi(SBO_A);
-    const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(Wbase), LBO_B), b_hi = tc::desc_hi(SBO_B);
-    if (kResident && cta_s < p.items) tc::mbar_wait(&w_full[0], 0);
-    const uint32_t bar_af = tc::smem_u32(&a_full[0]), bar_ae = tc::smem_u32(&a_empty[0]), bar_wf = tc::smem_u32(&w_full[0]),
-                   bar_we = tc::smem_u32(&w_empty[0]), bar_cf = tc::smem_u32(&acc_full[0]), bar_ce = tc::smem_u32(&acc_empty[0]);
-    uint32_t g = 0, wc = 0;
+  } else if (warp == 2) {
+    // ===== planner: everything the MMA issuer needs to know about a slice, and every wait it would have to do =====
+    // (ncu r02_s1f / r02_k9: the issuing thread never waited on a barrier, yet the tensor pipe idled a third of the time.  A
+    // register read by a queued tcgen05.mma cannot be rewritten before that MMA is dispatched, so the issuer's own per-slice
+    // bookkeeping -- ring indices, descriptor selection, barrier addresses, ~190 instructions -- only started once the queue of
+    // ~7 pending MMAs had drained, and the pipe then sat idle behind it.  This warp does that work one or more slices ahead and
+    // hands the issuer a 48-byte record; the issuer's path between two batches of MMAs shrinks to one wait and three loads.)
+    const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(Abase), LBO_A);
+    const uint32_t bar_af = tc::smem_u32(&a_full[0]), bar_ae = tc::smem_u32(&a_empty[0]), bar_cf = tc::smem_u32(&acc_full[0]),
+                   bar_ce = tc::smem_u32(&acc_empty[0]), bar_pf = tc::smem_u32(&plan_full[0]), bar_pe = tc::smem_u32(&plan_empty[0]);
+    uint32_t g = 0, k = 0;
     uint32_t acc_base = 0;       // unwrapped ring index of the accumulator of (this item, dlo)
     uint32_t acquired = 0;       // accumulator blocks handed to the MMAs so far (unwrapped)
     for (int s = cta_s; s < p.items; s += cta_stride) {
@@ -437,7 +446,7 @@ __global__ void __launch_bounds__(128 + 128 * EPG, 1) conv3d_tc_s1f_kernel(const
       decode_item(p, s, b, h0, w0, dlo, dhi);
       const int din0 = max(dlo - 1, 0), din1 = min(dhi, p.D - 1);
 #pragma unroll 1
-      for (int d_in = din0; d_in <= din1; ++d_in, ++g) {
+      for (int d_in = din0; d_in <= din1; ++d_in, ++g, ++k) {
         const int j0 = max(0, dlo - d_in + 1), j1 = min(3, dhi - d_in + 1);       // column blocks [j0, j1) exist
         const uint32_t u0 = acc_base + (uint32_t)(d_in - 1 + j0 - dlo), nb = (uint32_t)(j1 - j0);
         while (acquired < u0 + nb) {
@@ -446,58 +455,94 @@ __global__ void __launch_bounds__(128 + 128 * EPG, 1) conv3d_tc_s1f_kernel(const
         }
         const uint32_t slot = g % NS;
         tc::mbar_wait_a(bar_af + slot * 8, (g / NS) & 1);
-        tc::fence_after_sync();
         const uint32_t blk = u0 % NB, n1 = min(nb, NB - blk), n2 = nb - n1;
-        const uint32_t id1 = n1 == 1 ? tc::make_idesc_bf16(128, N) : n1 == 2 ? tc::make_idesc_bf16(128, 2 * N) : tc::make_idesc_bf16(128, 3 * N);
-        const uint32_t id2 = n2 == 1 ? tc::make_idesc_bf16(128, N) : tc::make_idesc_bf16(128, 2 * N);
-        const uint32_t d1 = tmem_base + blk * N, d2 = tmem_base;
-        const uint32_t a_lo = a_lo0 + slot * (SLICE >> 4);
-        const uint32_t brow1 = (uint32_t)j0 * (N / 8) * (SBO_B >> 4), brow2 = (uint32_t)(j0 + n1) * (N / 8) * (SBO_B >> 4);
-        // The issuing thread's instruction stream bounds these kernels (ncu r02_s1f: the MMA warp never waits, ~400 SASS
-        // instructions per slice for 18 MMAs of ~56 cycles each): the ring-wrap case, which doubles every MMA, is a separate
-        // copy of the loop so that the common case carries no second descriptor set.
-        auto issue = [&](auto wrap_tag) {
-          constexpr bool WRAP = decltype(wrap_tag)::value;
-#pragma unroll
-          for (int t9 = 0; t9 < 9; ++t9) {
-            const int kh = t9 / 3, kw = t9 - 3 * kh;
-            uint32_t b_lo, wslot = 0;
-            if (kResident) b_lo = b_lo0 + (uint32_t)t9 * (TAPB >> 4);
-            else {
-              wslot = wc % NWS;
-              tc::mbar_wait_a(bar_wf + wslot * 8, (wc / NWS) & 1);
-              tc::fence_after_sync();
-              b_lo = b_lo0 + wslot * (TAPB >> 4);
-            }
-            if (leader) {
-#pragma unroll
-              for (int ks = 0; ks < KS; ++ks) {
-                const uint32_t a = a_lo + (uint32_t)((kh * WW + kw) * 16 + ks * 2 * LBO_A) / 16;
-                const uint32_t bb = b_lo + (uint32_t)(ks * 2 * LBO_B) / 16;
-                tc::mma_bf16_lohi(d1, a, a_hi, bb + brow1, b_hi, id1, 1u);
-                if (WRAP) tc::mma_bf16_lohi(d2, a, a_hi, bb + brow2, b_hi, id2, 1u);
-                if (SP) {
-                  tc::mma_bf16_lohi(d1, a + (HALF_A >> 4), a_hi, bb + brow1, b_hi, id1, 1u);
-                  if (WRAP) tc::mma_bf16_lohi(d2, a + (HALF_A >> 4), a_hi, bb + brow2, b_hi, id2, 1u);
-                  tc::mma_bf16_lohi(d1, a, a_hi, bb + (HALF_B >> 4) + brow1, b_hi, id1, 1u);
-                  if (WRAP) tc::mma_bf16_lohi(d2, a, a_hi, bb + (HALF_B >> 4) + brow2, b_hi, id2, 1u);
-                }
-              }
-              if (!kResident) tc::mma_commit_a(bar_we + wslot * 8);
-            }
-            if (!kResident) ++wc;
-          }
-        };
-        if (n2) issue(std::true_type{});
-        else issue(std::false_type{});
-        if (leader) {
-          tc::mma_commit_a(bar_ae + slot * 8);
-          if (d_in - 1 >= dlo) tc::mma_commit_a(bar_cf + ((acc_base + (uint32_t)(d_in - 1 - dlo)) % NB) * 8);
-          if (d_in == din1 && din1 == dhi - 1) tc::mma_commit_a(bar_cf + ((acc_base + (uint32_t)(d_in - dlo)) % NB) * 8);
+        const uint32_t pk = k % PLN;
+        tc::mbar_wait_a(bar_pe + pk * 8, ((k / PLN) & 1) ^ 1);
+        if (lane == 0) {
+          uint32_t* r = plan[pk];
+          r[0] = tmem_base + blk * N;
+          r[1] = n1 == 1 ? tc::make_idesc_bf16(128, N) : n1 == 2 ? tc::make_idesc_bf16(128, 2 * N) : tc::make_idesc_bf16(128, 3 * N);
+          r[2] = a_lo0 + slot * (SLICE >> 4);
+          r[3] = (uint32_t)j0 * (N / 8) * (SBO_B >> 4);
+          r[4] = n2;
+          r[5] = n2 == 1 ? tc::make_idesc_bf16(128, N) : tc::make_idesc_bf16(128, 2 * N);
+          r[6] = (uint32_t)(j0 + n1) * (N / 8) * (SBO_B >> 4);
+          r[7] = bar_ae + slot * 8;
+          r[8] = d_in - 1 >= dlo ? bar_cf + ((acc_base + (uint32_t)(d_in - 1 - dlo)) % NB) * 8 : 0u;
+          r[9] = (d_in == din1 && din1 == dhi - 1) ? bar_cf + ((acc_base + (uint32_t)(d_in - dlo)) % NB) * 8 : 0u;
+          r[10] = 1u;
+          tc::mbar_arrive(&plan_full[pk]);             // release: the record, and the a_full / acc_empty phases observed above
         }
         __syncwarp();
       }
       acc_base += (uint32_t)(dhi - dlo);
+    }
+    const uint32_t pk = k % PLN;                         // end marker
+    tc::mbar_wait_a(bar_pe + pk * 8, ((k / PLN) & 1) ^ 1);
+    if (lane == 0) {
+      plan[pk][10] = 0u;
+      tc::mbar_arrive(&plan_full[pk]);
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const bool leader = tc::elect_one();
+    const uint32_t a_hi = tc::desc_hi(SBO_A);
+    const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(Wbase), LBO_B), b_hi = tc::desc_hi(SBO_B);
+    if (kResident && cta_s < p.items) tc::mbar_wait(&w_full[0], 0);
+    const uint32_t bar_wf = tc::smem_u32(&w_full[0]), bar_we = tc::smem_u32(&w_empty[0]), bar_pf = tc::smem_u32(&plan_full[0]),
+                   bar_pe = tc::smem_u32(&plan_empty[0]);
+    uint32_t wc = 0;
+#pragma unroll 1
+    for (uint32_t k = 0;; ++k) {
+      const uint32_t pk = k % PLN;
+      tc::mbar_wait_a(bar_pf + pk * 8, (k / PLN) & 1);
+      const uint4 r0 = *reinterpret_cast<const uint4*>(&plan[pk][0]), r1 = *reinterpret_cast<const uint4*>(&plan[pk][4]),
+                  r2 = *reinterpret_cast<const uint4*>(&plan[pk][8]);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive_a(bar_pe + pk * 8);
+      if (r2.z == 0u) break;
+      tc::fence_after_sync();
+      const uint32_t d1 = r0.x, id1 = r0.y, a_lo = r0.z, brow1 = r0.w, n2 = r1.x, id2 = r1.y, brow2 = r1.z, d2 = tmem_base;
+      auto issue = [&](auto wrap_tag) {                // the ring-wrap case, which doubles every MMA, is a separate copy of the loop
+        constexpr bool WRAP = decltype(wrap_tag)::value;
+#pragma unroll
+        for (int t9 = 0; t9 < 9; ++t9) {
+          const int kh = t9 / 3, kw = t9 - 3 * kh;
+          uint32_t b_lo, wslot = 0;
+          if (kResident) b_lo = b_lo0 + (uint32_t)t9 * (TAPB >> 4);
+          else {
+            wslot = wc % NWS;
+            tc::mbar_wait_a(bar_wf + wslot * 8, (wc / NWS) & 1);
+            tc::fence_after_sync();
+            b_lo = b_lo0 + wslot * (TAPB >> 4);
+          }
+          if (leader) {
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+              const uint32_t a = a_lo + (uint32_t)((kh * WW + kw) * 16 + ks * 2 * LBO_A) / 16;
+              const uint32_t bb = b_lo + (uint32_t)(ks * 2 * LBO_B) / 16;
+              tc::mma_bf16_lohi(d1, a, a_hi, bb + brow1, b_hi, id1, 1u);
+              if (WRAP) tc::mma_bf16_lohi(d2, a, a_hi, bb + brow2, b_hi, id2, 1u);
+              if (SP) {
+                tc::mma_bf16_lohi(d1, a + (HALF_A >> 4), a_hi, bb + brow1, b_hi, id1, 1u);
+                if (WRAP) tc::mma_bf16_lohi(d2, a + (HALF_A >> 4), a_hi, bb + brow2, b_hi, id2, 1u);
+                tc::mma_bf16_lohi(d1, a, a_hi, bb + (HALF_B >> 4) + brow1, b_hi, id1, 1u);
+                if (WRAP) tc::mma_bf16_lohi(d2, a, a_hi, bb + (HALF_B >> 4) + brow2, b_hi, id2, 1u);
+              }
+            }
+            if (!kResident) tc::mma_commit_a(bar_we + wslot * 8);
+          }
+          if (!kResident) ++wc;
+        }
+      };
+      if (n2) issue(std::true_type{});
+      else issue(std::false_type{});
+      if (leader) {
+        tc::mma_commit_a(r1.w);
+        if (r2.x) tc::mma_commit_a(r2.x);
+        if (r2.y) tc::mma_commit_a(r2.y);
+      }
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ===== epilogue (warp & 3 = the TMEM lane quarter this warp may read) =====
@@ -1457,7 +1502,7 @@ extern "C" int ss_conv3d_tc_ex(int kind, const void* in_blocked, const void* wei
   if (rc != SS_OK) return rc;
   p.HT = ceil_div(p.H, TH); p.WT = ceil_div(p.W, TW);
   if (in_split) {
-    if (kind == 5) return Cin == 32 ? launch_s1f<32, 32, 4, 9, true>(tm, p, st) : launch_s1f<64, 64, 2, 2, true>(tm, p, st);
+    if (kind == 5) return Cin == 32 ? launch_s1f<32, 32, 4, 9, true, 2>(tm, p, st) : launch_s1f<64, 64, 2, 2, true, 2>(tm, p, st);
     if (kind == 2) return launch_s2<32, 64, 2, 4, true>(tm, p, st);
     return launch_t2<64, 32, 3, 4, 2, true>(tm, p, st);
   }
@@ -1477,10 +1522,10 @@ extern "C" int ss_conv3d_tc_ex(int kind, const void* in_blocked, const void* wei
       if (Cin == 128) return launch_s1<128, 64, 2, 8, 9>(tm, p, st);      // 8-deep tap ring: a 2-deep one exposes the 16 KB reload latency
       return launch_s1<64, 32, 4, 9, 9>(tm, p, st);
     case 5:
-      if (Cin == 32 && Cout == 32) return launch_s1f<32, 32, 6, 9>(tm, p, st);
-      if (Cin == 64 && Cout == 32) return launch_s1f<64, 32, 4, 9>(tm, p, st);
-      if (Cin == 32 && Cout == 64) return launch_s1f<32, 64, 6, 9>(tm, p, st);
-      return launch_s1f<64, 64, 2, 7>(tm, p, st);
+      if (Cin == 32 && Cout == 32) return launch_s1f<32, 32, 6, 9, false, 2>(tm, p, st);
+      if (Cin == 64 && Cout == 32) return launch_s1f<64, 32, 4, 9, false, 2>(tm, p, st);
+      if (Cin == 32 && Cout == 64) return launch_s1f<32, 64, 6, 9, false, 2>(tm, p, st);
+      return launch_s1f<64, 64, 2, 7, false, 2>(tm, p, st);
     default:
       if (Cin == 128) return ex ? launch_t2<128, 64, 2, 5, 2, false, 3>(tm, p, st) : launch_t2<128, 64, 2, 5, 2>(tm, p, st);
       return launch_t2<64, 32, 3, 27, 4>(tm, p, st);
