@@ -159,7 +159,8 @@ __device__ __forceinline__ void epilogue_store32(const TcP& p, float (&v)[32], c
 
 // Common prologue: barriers, TMEM, folded-BN staging.
 #define TC_KERNEL_PROLOGUE(NSLOTS, NWSLOTS, RESIDENT) TC_KERNEL_PROLOGUE_N(NSLOTS, NWSLOTS, RESIDENT, 2)
-#define TC_KERNEL_PROLOGUE_N(NSLOTS, NWSLOTS, RESIDENT, NACC)                                                              \
+#define TC_KERNEL_PROLOGUE_N(NSLOTS, NWSLOTS, RESIDENT, NACC) TC_KERNEL_PROLOGUE_NF(NSLOTS, NWSLOTS, RESIDENT, NACC, 1)
+#define TC_KERNEL_PROLOGUE_NF(NSLOTS, NWSLOTS, RESIDENT, NACC, FULLCNT)                                                    \
   extern __shared__ __align__(1024) uint8_t smem[];                                                                        \
   __shared__ __align__(8) uint64_t a_full[NSLOTS], a_empty[NSLOTS], w_full[NWSLOTS], w_empty[NWSLOTS], acc_full[NACC], acc_empty[NACC]; \
   __shared__ uint32_t tmem_base_s;                                                                                         \
@@ -175,7 +176,7 @@ __device__ __forceinline__ void epilogue_store32(const TcP& p, float (&v)[32], c
     tc::prefetch_tmap(&tmA);                                                                                               \
     for (int i = 0; i < NSLOTS; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1); }                      \
     for (int i = 0; i < ((RESIDENT) ? 1 : NWSLOTS); ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }  \
-    for (int i = 0; i < NACC; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }                  \
+    for (int i = 0; i < NACC; ++i) { tc::mbar_init(&acc_full[i], FULLCNT); tc::mbar_init(&acc_empty[i], 128); }            \
     tc::fence_barrier_init();                                                                                              \
   }                                                                                                                        \
   if (warp == 2) tc::tmem_alloc(&tmem_base_s, TMEM_COLS);                                                                  \
@@ -362,7 +363,14 @@ __global__ void __launch_bounds__(256, 1) conv3d_tc_s1_kernel(const __grid_const
 // K step issues three MMAs into the same accumulator: x_hi*w_hi + x_lo*w_hi + x_hi*w_lo (fp32-accurate product, fp32 accumulation).
 // EPG: epilogue warp groups (4 warps each, 128 + 128*EPG threads): with EPG = 2 the groups drain alternate accumulator blocks, so the
 // TMEM load -> affine -> store latency of one output slice overlaps the next one's.
-template <int CIN, int N, int NS, int NWS, bool SP = false, int EPG = 1>
+// NISS = 2 (resident weights): two issuer warps take alternate slices IN TURN (a turn barrier keeps the MMAs in slice order, so the
+// accumulation order and the results are those of one issuer).  A register read by a queued tcgen05.mma cannot be rewritten before
+// that MMA is dispatched, so a lone issuer reaches its commits and its next record only once its ~7 queued MMAs have drained, and the
+// pipe idles behind it (ncu: tensor data pipe 72 % busy); with two warps (two uniform-register files) one loads and converts its next
+// record while the other's MMAs execute.  A commit covers only the committing thread's MMAs, so an accumulator block is full after
+// ONE arrival from each issuer (acc_full count 2): from the owner of slice d, and from the owner of the block's last other
+// contributor (slice d+1, or d-1 where the volume ends at d).
+template <int CIN, int N, int NS, int NWS, bool SP = false, int EPG = 1, int NISS = (NWS == 9 ? 2 : 1)>
 __global__ void __launch_bounds__(128 + 128 * EPG, 1) conv3d_tc_s1f_kernel(const __grid_constant__ CUtensorMap tmA, const TcP p) {
   constexpr bool kResident = (NWS == 9);
   constexpr uint32_t HALF_A = (CIN / 8) * TILE_B, HALF_B = CIN * 3 * N * 2;      // one operand half (hi or lo) of a slice / tap
@@ -373,13 +381,15 @@ __global__ void __launch_bounds__(128 + 128 * EPG, 1) conv3d_tc_s1f_kernel(const
   constexpr uint32_t TMEM_COLS = 512;
   constexpr uint32_t NB = 512 / N;                     // accumulator blocks in the TMEM ring
   constexpr uint32_t PLN = 4;                          // slice records in flight between the planner and the MMA issuer
-  __shared__ __align__(16) uint32_t plan[PLN][12];
-  __shared__ __align__(8) uint64_t plan_full[PLN], plan_empty[PLN];
-  TC_KERNEL_PROLOGUE_N(NS, NWS, kResident, NB)
+  static_assert(NISS == 1 || NWS == 9, "two issuers need resident weights (the streamed tap ring has one consumer)");
+  __shared__ __align__(16) uint32_t plan[NISS][PLN][12];
+  __shared__ __align__(8) uint64_t plan_full[NISS][PLN], plan_empty[NISS][PLN], turn[2];
+  TC_KERNEL_PROLOGUE_NF(NS, NWS, kResident, NB, NISS)
   uint8_t* Abase = smem;
   uint8_t* Wbase = smem + NS * SLICE;
   if (threadIdx.x == 0) {
-    for (uint32_t i = 0; i < PLN; ++i) { tc::mbar_init(&plan_full[i], 1); tc::mbar_init(&plan_empty[i], 1); }
+    for (uint32_t i = 0; i < NISS * PLN; ++i) { tc::mbar_init(&plan_full[0][i], 1); tc::mbar_init(&plan_empty[0][i], 1); }
+    tc::mbar_init(&turn[0], 1); tc::mbar_init(&turn[1], 1);
     tc::fence_barrier_init();
   }
   if (warp >= 4 && warp < 8) {                         // all accumulator blocks start out zero
@@ -390,6 +400,14 @@ __global__ void __launch_bounds__(128 + 128 * EPG, 1) conv3d_tc_s1f_kernel(const
   __syncthreads();
   tc::fence_after_sync();
 
+  if (kResident && warp == 3) {                        // resident weights: loaded once; warp 3 then becomes the second MMA issuer
+    if (lane == 0 && cta_s < p.items) {
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w);
+      tc::mbar_expect_tx(&w_full[0], 9 * TAPB);
+      for (int t9 = 0; t9 < 9; ++t9) tc::bulk_load(Wbase + t9 * TAPB, wsrc + (size_t)t9 * TAPB, TAPB, &w_full[0]);
+    }
+    __syncwarp();
+  }
   if (warp == 0 && lane == 0) {
     // ===== input-slice producer =====
     uint32_t g = 0;
@@ -405,15 +423,10 @@ __global__ void __launch_bounds__(128 + 128 * EPG, 1) conv3d_tc_s1f_kernel(const
         if (SP) tc::tma_load_4d(Abase + slot * SLICE + HALF_A, &tmA, &a_full[slot], (w0 - 1) * 8, h0 - 1, d_in, (b + p.B) * (CIN / 8));
       }
     }
-  } else if (warp == 3 && lane == 0) {
-    // ===== weight producer =====
+  } else if (!kResident && warp == 3 && lane == 0) {
+    // ===== weight producer (streamed tap ring) =====
     const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w);
-    if (kResident) {
-      if (cta_s < p.items) {
-        tc::mbar_expect_tx(&w_full[0], 9 * TAPB);
-        for (int t9 = 0; t9 < 9; ++t9) tc::bulk_load(Wbase + t9 * TAPB, wsrc + (size_t)t9 * TAPB, TAPB, &w_full[0]);
-      }
-    } else {
+    {
       uint32_t wc = 0;
       for (int s = cta_s; s < p.items; s += cta_stride) {
         int b, h0, w0, dlo, dhi;
@@ -437,8 +450,8 @@ __global__ void __launch_bounds__(128 + 128 * EPG, 1) conv3d_tc_s1f_kernel(const
     // hands the issuer a 48-byte record; the issuer's path between two batches of MMAs shrinks to one wait and three loads.)
     const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(Abase), LBO_A);
     const uint32_t bar_af = tc::smem_u32(&a_full[0]), bar_ae = tc::smem_u32(&a_empty[0]), bar_cf = tc::smem_u32(&acc_full[0]),
-                   bar_ce = tc::smem_u32(&acc_empty[0]), bar_pf = tc::smem_u32(&plan_full[0]), bar_pe = tc::smem_u32(&plan_empty[0]);
-    uint32_t g = 0, k = 0;
+                   bar_ce = tc::smem_u32(&acc_empty[0]), bar_pf = tc::smem_u32(&plan_full[0][0]), bar_pe = tc::smem_u32(&plan_empty[0][0]);
+    uint32_t g = 0;              // slice counter: slice g belongs to issuer g % NISS, as record g / NISS of its ring
     uint32_t acc_base = 0;       // unwrapped ring index of the accumulator of (this item, dlo)
     uint32_t acquired = 0;       // accumulator blocks handed to the MMAs so far (unwrapped)
     for (int s = cta_s; s < p.items; s += cta_stride) {
@@ -446,7 +459,7 @@ __global__ void __launch_bounds__(128 + 128 * EPG, 1) conv3d_tc_s1f_kernel(const
       decode_item(p, s, b, h0, w0, dlo, dhi);
       const int din0 = max(dlo - 1, 0), din1 = min(dhi, p.D - 1);
 #pragma unroll 1
-      for (int d_in = din0; d_in <= din1; ++d_in, ++g, ++k) {
+      for (int d_in = din0; d_in <= din1; ++d_in, ++g) {
         const int j0 = max(0, dlo - d_in + 1), j1 = min(3, dhi - d_in + 1);       // column blocks [j0, j1) exist
         const uint32_t u0 = acc_base + (uint32_t)(d_in - 1 + j0 - dlo), nb = (uint32_t)(j1 - j0);
         while (acquired < u0 + nb) {
@@ -456,10 +469,11 @@ __global__ void __launch_bounds__(128 + 128 * EPG, 1) conv3d_tc_s1f_kernel(const
         const uint32_t slot = g % NS;
         tc::mbar_wait_a(bar_af + slot * 8, (g / NS) & 1);
         const uint32_t blk = u0 % NB, n1 = min(nb, NB - blk), n2 = nb - n1;
-        const uint32_t pk = k % PLN;
-        tc::mbar_wait_a(bar_pe + pk * 8, ((k / PLN) & 1) ^ 1);
+        const uint32_t own = g % NISS, q = g / NISS, pk = own * PLN + q % PLN;
+        tc::mbar_wait_a(bar_pe + pk * 8, ((q / PLN) & 1) ^ 1);
         if (lane == 0) {
-          uint32_t* r = plan[pk];
+          uint32_t* r = plan[0][pk];
+          auto full_of = [&](int d) { return bar_cf + ((acc_base + (uint32_t)(d - dlo)) % NB) * 8; };     // acc_full of output depth d
           r[0] = tmem_base + blk * N;
           r[1] = n1 == 1 ? tc::make_idesc_bf16(128, N) : n1 == 2 ? tc::make_idesc_bf16(128, 2 * N) : tc::make_idesc_bf16(128, 3 * N);
           r[2] = a_lo0 + slot * (SLICE >> 4);
@@ -468,39 +482,51 @@ __global__ void __launch_bounds__(128 + 128 * EPG, 1) conv3d_tc_s1f_kernel(const
           r[5] = n2 == 1 ? tc::make_idesc_bf16(128, N) : tc::make_idesc_bf16(128, 2 * N);
           r[6] = (uint32_t)(j0 + n1) * (N / 8) * (SBO_B >> 4);
           r[7] = bar_ae + slot * 8;
-          r[8] = d_in - 1 >= dlo ? bar_cf + ((acc_base + (uint32_t)(d_in - 1 - dlo)) % NB) * 8 : 0u;
-          r[9] = (d_in == din1 && din1 == dhi - 1) ? bar_cf + ((acc_base + (uint32_t)(d_in - dlo)) % NB) * 8 : 0u;
+          if (NISS == 1) {       // block d-1 is complete after slice d; the last block also after the last slice of a volume's end
+            r[8] = d_in - 1 >= dlo ? full_of(d_in - 1) : 0u;
+            r[9] = (d_in == din1 && din1 == dhi - 1) ? full_of(d_in) : 0u;
+            r[11] = 0u;
+          } else {               // one arrival per issuer and block (see the kernel comment); a one-slice item arrives twice
+            r[8] = (d_in >= dlo && d_in < dhi) ? full_of(d_in) : 0u;
+            r[9] = d_in - 1 >= dlo ? full_of(d_in - 1) : 0u;
+            r[11] = (din1 == dhi - 1 && ((d_in == dhi - 2 && d_in >= din0) || (d_in == dhi - 1 && dhi - 2 < din0))) ? full_of(dhi - 1) : 0u;
+          }
           r[10] = 1u;
-          tc::mbar_arrive(&plan_full[pk]);             // release: the record, and the a_full / acc_empty phases observed above
+          tc::mbar_arrive_a(bar_pf + pk * 8);          // release: the record, and the a_full / acc_empty phases observed above
         }
         __syncwarp();
       }
       acc_base += (uint32_t)(dhi - dlo);
     }
-    const uint32_t pk = k % PLN;                         // end marker
-    tc::mbar_wait_a(bar_pe + pk * 8, ((k / PLN) & 1) ^ 1);
-    if (lane == 0) {
-      plan[pk][10] = 0u;
-      tc::mbar_arrive(&plan_full[pk]);
+    for (uint32_t e = 0; e < (uint32_t)NISS; ++e, ++g) {      // end markers, one per issuer
+      const uint32_t own = g % NISS, q = g / NISS, pk = own * PLN + q % PLN;
+      tc::mbar_wait_a(bar_pe + pk * 8, ((q / PLN) & 1) ^ 1);
+      if (lane == 0) {
+        plan[0][pk][10] = 0u;
+        tc::mbar_arrive_a(bar_pf + pk * 8);
+      }
+      __syncwarp();
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
+  } else if (warp == 1 || (NISS == 2 && warp == 3)) {
+    // ===== MMA issuer(s) =====
+    const uint32_t me = warp == 1 ? 0u : 1u;
     const bool leader = tc::elect_one();
     const uint32_t a_hi = tc::desc_hi(SBO_A);
     const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(Wbase), LBO_B), b_hi = tc::desc_hi(SBO_B);
     if (kResident && cta_s < p.items) tc::mbar_wait(&w_full[0], 0);
-    const uint32_t bar_wf = tc::smem_u32(&w_full[0]), bar_we = tc::smem_u32(&w_empty[0]), bar_pf = tc::smem_u32(&plan_full[0]),
-                   bar_pe = tc::smem_u32(&plan_empty[0]);
+    const uint32_t bar_wf = tc::smem_u32(&w_full[0]), bar_we = tc::smem_u32(&w_empty[0]), bar_pf = tc::smem_u32(&plan_full[me][0]),
+                   bar_pe = tc::smem_u32(&plan_empty[me][0]), bar_turn = tc::smem_u32(&turn[0]);
     uint32_t wc = 0;
 #pragma unroll 1
     for (uint32_t k = 0;; ++k) {
       const uint32_t pk = k % PLN;
       tc::mbar_wait_a(bar_pf + pk * 8, (k / PLN) & 1);
-      const uint4 r0 = *reinterpret_cast<const uint4*>(&plan[pk][0]), r1 = *reinterpret_cast<const uint4*>(&plan[pk][4]),
-                  r2 = *reinterpret_cast<const uint4*>(&plan[pk][8]);
+      const uint4 r0 = *reinterpret_cast<const uint4*>(&plan[me][pk][0]), r1 = *reinterpret_cast<const uint4*>(&plan[me][pk][4]),
+                  r2 = *reinterpret_cast<const uint4*>(&plan[me][pk][8]);
       __syncwarp();
       if (lane == 0) tc::mbar_arrive_a(bar_pe + pk * 8);
       if (r2.z == 0u) break;
+      if (NISS == 2) tc::mbar_wait_a(bar_turn + me * 8, (k & 1) ^ (me ^ 1));      // issuer 0 starts; then strictly alternating
       tc::fence_after_sync();
       const uint32_t d1 = r0.x, id1 = r0.y, a_lo = r0.z, brow1 = r0.w, n2 = r1.x, id2 = r1.y, brow2 = r1.z, d2 = tmem_base;
       auto issue = [&](auto wrap_tag) {                // the ring-wrap case, which doubles every MMA, is a separate copy of the loop
@@ -538,13 +564,15 @@ __global__ void __launch_bounds__(128 + 128 * EPG, 1) conv3d_tc_s1f_kernel(const
       if (n2) issue(std::true_type{});
       else issue(std::false_type{});
       if (leader) {
+        if (NISS == 2) tc::mbar_arrive_a(bar_turn + (me ^ 1) * 8);     // this slice's MMAs are in the queue: the other issuer's turn
         tc::mma_commit_a(r1.w);
         if (r2.x) tc::mma_commit_a(r2.x);
         if (r2.y) tc::mma_commit_a(r2.y);
+        if (NISS == 2 && r2.w) tc::mma_commit_a(r2.w);
       }
       __syncwarp();
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + 4 * EPG) {
     // ===== epilogue (warp & 3 = the TMEM lane quarter this warp may read) =====
     const int e = warp & 3, eg = (warp - 4) >> 2, m = e * 32 + lane, hh = m >> 3, ww = m & 7;
     uint32_t u = 0;
