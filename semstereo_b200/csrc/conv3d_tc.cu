@@ -729,9 +729,9 @@ __global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_con
           na0 = in0 ? __ldg(kp.att + o0 + ko) : 0.0f; nd0 = in0 ? __ldg(kp.disp + o0 + ko) : 0.0f;
           na1 = in1 ? __ldg(kp.att + o1 + ko) : 0.0f; nd1 = in1 ? __ldg(kp.disp + o1 + ko) : 0.0f;
         }
-        const uint32_t slot = g % K9_NS;
-        tc::mbar_wait(&a_empty[slot], ((g / K9_NS) & 1) ^ 1);
-        uint4* At = reinterpret_cast<uint4*>(Abase + slot * K9_SLICE);       // [8][180]
+        // The two A slots ping-pong between these warps and the tensor core, so the time from "slot free" to "slot full" is on the
+        // kernel's critical path: the slice is computed into registers BEFORE the wait, and only the 16 stores follow it.
+        uint4 v[2][8];
 #pragma unroll
         for (int rep = 0; rep < 2; ++rep) {
           const int px = rep ? px1 : pt, r = rep ? r1 : r0, c = rep ? c1 : c0;
@@ -743,9 +743,20 @@ __global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_con
             const float ar = ok ? a : 0.0f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              At[j * (HH * WW) + px] = scale8(Ls[j * (HH * WW) + px], a);
-              At[(4 + j) * (HH * WW) + px] = scale8(Rs[(j * HH + r) * K9_RW + cs], ar);
+              v[rep][j] = scale8(Ls[j * (HH * WW) + px], a);
+              v[rep][4 + j] = scale8(Rs[(j * HH + r) * K9_RW + cs], ar);
             }
+          }
+        }
+        const uint32_t slot = g % K9_NS;
+        tc::mbar_wait(&a_empty[slot], ((g / K9_NS) & 1) ^ 1);
+        uint4* At = reinterpret_cast<uint4*>(Abase + slot * K9_SLICE);       // [8][180]
+#pragma unroll
+        for (int rep = 0; rep < 2; ++rep) {
+          const int px = rep ? px1 : pt;
+          if (px < HH * WW) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) At[j * (HH * WW) + px] = v[rep][j];
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic stores -> visible to the tensor core's reads
