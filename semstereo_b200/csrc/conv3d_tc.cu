@@ -619,15 +619,15 @@ __global__ void __launch_bounds__(128 + 128 * EPG, 1) conv3d_tc_s1f_kernel(const
 // the convolution and of grid_sample.  Disparity samples are the integer bins dmin .. dmin+31 (disparity_sample_topk, :305);
 // the reference's bilinear weights differ from this integer shift by the 1e-6 of its fp32 grid round trip, below bf16 resolution.
 // =====================================================================================================================
-constexpr int K9_NS = 2, K9_RW = 41, K9_BINS = 32;
+constexpr int K9_NS = 3, K9_RW = 41, K9_BINS = 32;
 constexpr uint32_t K9_SLICE = 8 * TILE_B, K9_TAPB = 64 * 96 * 2;
-constexpr uint32_t K9_OFF_W = K9_NS * K9_SLICE, K9_OFF_L = K9_OFF_W + 9 * K9_TAPB, K9_OFF_R = K9_OFF_L + 4 * HH * WW * 16,
-                   K9_SMEM = K9_OFF_R + 4 * HH * K9_RW * 16;
-static_assert(K9_OFF_L % 128 == 0 && K9_OFF_R % 128 == 0, "TMA destinations");
+constexpr uint32_t K9_OFF_W = K9_NS * K9_SLICE, K9_OFF_R = K9_OFF_W + 9 * K9_TAPB, K9_SMEM = K9_OFF_R + 4 * HH * K9_RW * 16;
+static_assert(K9_OFF_W % 128 == 0 && K9_OFF_R % 128 == 0, "TMA destinations");
 static_assert(K9_SMEM <= 227 * 1024 - 2048, "shared memory budget");
 
 struct K9P {
   TcP t;              // the conv part (w = s1f-packed weights [9][8][96][8]); t.D = number of samples K
+  const uint4* cf_l;  // bf16 blocked (B,4,H,W,8): read directly by the producer threads (their pixels' 64 bytes, once per item)
   const float* disp;  // (B,K,H,W) integer-valued samples
   const float* att;   // (B,K,H,W)
   int dmin;           // lowest disparity bin (-(maxdisp/4) signed, 0 unsigned); samples are integers in [dmin, dmin + 31]
@@ -641,8 +641,7 @@ __device__ __forceinline__ uint4 scale8(const uint4 q, float a) {
   return make_uint4(r[0], r[1], r[2], r[3]);
 }
 
-__global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR,
-                                                                const K9P kp) {
+__global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_constant__ CUtensorMap tmR, const K9P kp) {
   constexpr int N = 32, KS = 4;
   constexpr uint32_t LBO_A = TILE_B, SBO_A = WW * 16, LBO_B = 3 * N * 16, SBO_B = 128;
   constexpr uint32_t NB = 512 / N;
@@ -658,7 +657,7 @@ __global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_con
     s_shift[i] = p.shift ? __ldg(p.shift + i) : 0.0f;
   }
   if (threadIdx.x == 0) {
-    tc::prefetch_tmap(&tmL); tc::prefetch_tmap(&tmR);
+    tc::prefetch_tmap(&tmR);
     for (int i = 0; i < K9_NS; ++i) { tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1); }
     tc::mbar_init(&w_full, 1);
     for (uint32_t i = 0; i < NB; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
@@ -688,8 +687,7 @@ __global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_con
       int b, h0, w0, dlo, dhi;
       decode_item(p, s, b, h0, w0, dlo, dhi);
       tc::mbar_wait(&st_empty, (it & 1) ^ 1);
-      tc::mbar_expect_tx(&st_full, K9_SMEM - K9_OFF_L);
-      tc::tma_load_4d(smem + K9_OFF_L, &tmL, &st_full, 0, w0 - 1, h0 - 1, b * 4);
+      tc::mbar_expect_tx(&st_full, K9_SMEM - K9_OFF_R);
       tc::tma_load_4d(smem + K9_OFF_R, &tmR, &st_full, 0, w0 - 1 - dhi_bin, h0 - 1, b * 4);
     }
   } else if (warp == 3 && lane == 0) {
@@ -702,7 +700,6 @@ __global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_con
   } else if (warp >= 8) {
     // ===== A producers: the slice k of the sparse concat volume for the 180 halo pixels =====
     const int pt = threadIdx.x - 256;
-    const uint4* Ls = reinterpret_cast<const uint4*>(smem + K9_OFF_L);     // [4][180]
     const uint4* Rs = reinterpret_cast<const uint4*>(smem + K9_OFF_R);     // [4][18][41]
     const size_t HW = (size_t)p.H * p.W;
     const int px1 = pt + 128;                                                // this thread's halo pixels: pt and (if < 180) pt + 128
@@ -720,6 +717,15 @@ __global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_con
       const size_t o1 = (size_t)b * p.D * HW + (size_t)(in1 ? y1 : 0) * p.W + (in1 ? x1 : 0);
       float na0 = in0 ? __ldg(kp.att + o0 + (size_t)din0 * HW) : 0.0f, nd0 = in0 ? __ldg(kp.disp + o0 + (size_t)din0 * HW) : 0.0f;
       float na1 = in1 ? __ldg(kp.att + o1 + (size_t)din0 * HW) : 0.0f, nd1 = in1 ? __ldg(kp.disp + o1 + (size_t)din0 * HW) : 0.0f;
+      // the left features of this thread's pixels stay in registers for the whole item (they are the same for every sample k): the
+      // 11.5 KB shared-memory tile they used to be staged in is what pays for the third A slot
+      uint4 Lr[2][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const size_t cj = ((size_t)b * 4 + j) * HW;
+        Lr[0][j] = in0 ? __ldg(kp.cf_l + cj + (size_t)y0 * p.W + x0) : make_uint4(0u, 0u, 0u, 0u);
+        Lr[1][j] = in1 ? __ldg(kp.cf_l + cj + (size_t)y1 * p.W + x1) : make_uint4(0u, 0u, 0u, 0u);
+      }
       tc::mbar_wait(&st_full, it & 1);
 #pragma unroll 1
       for (int d_in = din0; d_in <= din1; ++d_in, ++g) {
@@ -729,9 +735,9 @@ __global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_con
           na0 = in0 ? __ldg(kp.att + o0 + ko) : 0.0f; nd0 = in0 ? __ldg(kp.disp + o0 + ko) : 0.0f;
           na1 = in1 ? __ldg(kp.att + o1 + ko) : 0.0f; nd1 = in1 ? __ldg(kp.disp + o1 + ko) : 0.0f;
         }
-        // The two A slots ping-pong between these warps and the tensor core, so the time from "slot free" to "slot full" is on the
-        // kernel's critical path: the slice is computed into registers BEFORE the wait, and only the 16 stores follow it.
-        uint4 v[2][8];
+        const uint32_t slot = g % K9_NS;
+        tc::mbar_wait(&a_empty[slot], ((g / K9_NS) & 1) ^ 1);
+        uint4* At = reinterpret_cast<uint4*>(Abase + slot * K9_SLICE);       // [8][180]
 #pragma unroll
         for (int rep = 0; rep < 2; ++rep) {
           const int px = rep ? px1 : pt, r = rep ? r1 : r0, c = rep ? c1 : c0;
@@ -743,20 +749,9 @@ __global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_con
             const float ar = ok ? a : 0.0f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              v[rep][j] = scale8(Ls[j * (HH * WW) + px], a);
-              v[rep][4 + j] = scale8(Rs[(j * HH + r) * K9_RW + cs], ar);
+              At[j * (HH * WW) + px] = scale8(Lr[rep][j], a);
+              At[(4 + j) * (HH * WW) + px] = scale8(Rs[(j * HH + r) * K9_RW + cs], ar);
             }
-          }
-        }
-        const uint32_t slot = g % K9_NS;
-        tc::mbar_wait(&a_empty[slot], ((g / K9_NS) & 1) ^ 1);
-        uint4* At = reinterpret_cast<uint4*>(Abase + slot * K9_SLICE);       // [8][180]
-#pragma unroll
-        for (int rep = 0; rep < 2; ++rep) {
-          const int px = rep ? px1 : pt;
-          if (px < HH * WW) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) At[j * (HH * WW) + px] = v[rep][j];
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic stores -> visible to the tensor core's reads
@@ -1594,8 +1589,8 @@ extern "C" int ss_concat_stem_fused(const void* cf_l_blocked, const void* cf_r_b
   p.B = B; p.D = K; p.H = H; p.W = W; p.relu = relu;
   p.n_tiles = 1; p.HT = ceil_div(H, TH); p.WT = ceil_div(W, TW);
   p.DC = 1; p.n_dc = 1; p.items = 0;
-  kp.dmin = dmin; kp.disp = disp_topk; kp.att = att_topk;
-  CUtensorMap tmL, tmR;
+  kp.dmin = dmin; kp.disp = disp_topk; kp.att = att_topk; kp.cf_l = reinterpret_cast<const uint4*>(cf_l_blocked);
+  CUtensorMap tmR;
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   auto encode = [&](CUtensorMap* tm, CUtensorMapDataType dt, const void* base, const cuuint64_t* dims, const cuuint64_t* strides,
                     const cuuint32_t* box) -> int {
@@ -1611,15 +1606,14 @@ extern "C" int ss_concat_stem_fused(const void* cf_l_blocked, const void* cf_r_b
     // (8 channels, x, y, chunk): a box dimension may not exceed 256 elements, so the 41-pixel window cannot be 328 bf16 in one dim
     const cuuint64_t dims[4] = {8u, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * 4};
     const cuuint64_t strides[3] = {16u, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
-    const cuuint32_t boxl[4] = {8u, (cuuint32_t)WW, (cuuint32_t)HH, 4u}, boxr[4] = {8u, (cuuint32_t)K9_RW, (cuuint32_t)HH, 4u};
-    int rc = encode(&tmL, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, cf_l_blocked, dims, strides, boxl);
+    const cuuint32_t boxr[4] = {8u, (cuuint32_t)K9_RW, (cuuint32_t)HH, 4u};
+    int rc = encode(&tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, cf_r_blocked, dims, strides, boxr);
     if (rc != SS_OK) return rc;
-    if ((rc = encode(&tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, cf_r_blocked, dims, strides, boxr)) != SS_OK) return rc;
   }
   SS_CUDA(ss_allow_smem(concat_stem_k9_kernel, K9_SMEM));
   int grid;
   plan_tc(p, 1.4, grid);
-  concat_stem_k9_kernel<<<grid, 384, K9_SMEM, (cudaStream_t)stream>>>(tmL, tmR, kp);
+  concat_stem_k9_kernel<<<grid, 384, K9_SMEM, (cudaStream_t)stream>>>(tmR, kp);
   SS_CHECK_LAUNCH("ss_concat_stem_fused");
   return SS_OK;
 }
