@@ -647,7 +647,10 @@ __global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_con
   constexpr uint32_t NB = 512 / N;
   const TcP& p = kp.t;
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr uint32_t PLN = 4;                          // planner -> issuer records in flight, per issuer (see s1f)
+  __shared__ __align__(16) uint32_t plan[2][PLN][12];
   __shared__ __align__(8) uint64_t a_full[K9_NS], a_empty[K9_NS], w_full, acc_full[NB], acc_empty[NB], st_full, st_empty;
+  __shared__ __align__(8) uint64_t plan_full[2][PLN], plan_empty[2][PLN], turn[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_scale[N], s_shift[N];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -660,8 +663,10 @@ __global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_con
     tc::prefetch_tmap(&tmR);
     for (int i = 0; i < K9_NS; ++i) { tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1); }
     tc::mbar_init(&w_full, 1);
-    for (uint32_t i = 0; i < NB; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
+    for (uint32_t i = 0; i < NB; ++i) { tc::mbar_init(&acc_full[i], 2); tc::mbar_init(&acc_empty[i], 128); }      // one arrival per issuer
     tc::mbar_init(&st_full, 1); tc::mbar_init(&st_empty, 128);
+    for (uint32_t i = 0; i < 2 * PLN; ++i) { tc::mbar_init(&plan_full[0][i], 1); tc::mbar_init(&plan_empty[0][i], 1); }
+    tc::mbar_init(&turn[0], 1); tc::mbar_init(&turn[1], 1);
     tc::fence_barrier_init();
   }
   if (warp == 2) tc::tmem_alloc(&tmem_base_s, 512);
@@ -680,8 +685,16 @@ __global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_con
   uint8_t* Wbase = smem + K9_OFF_W;
   const int dhi_bin = kp.dmin + K9_BINS - 1;                 // largest disparity a sample can take
 
+  if (warp == 3) {                                       // resident weights, one bulk copy per tap; warp 3 then is the second MMA issuer
+    if (lane == 0 && cta_s < p.items) {
+      tc::mbar_expect_tx(&w_full, 9 * K9_TAPB);
+      for (int t9 = 0; t9 < 9; ++t9)
+        tc::bulk_load(Wbase + t9 * K9_TAPB, reinterpret_cast<const uint8_t*>(p.w) + (size_t)t9 * K9_TAPB, K9_TAPB, &w_full);
+    }
+    __syncwarp();
+  }
   if (warp == 0 && lane == 0) {
-    // ===== stager: per item, the cf_l tile, the cf_r window and the sample columns =====
+    // ===== stager: per item, the cf_r window =====
     uint32_t it = 0;
     for (int s = cta_s; s < p.items; s += cta_stride, ++it) {
       int b, h0, w0, dlo, dhi;
@@ -689,13 +702,6 @@ __global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_con
       tc::mbar_wait(&st_empty, (it & 1) ^ 1);
       tc::mbar_expect_tx(&st_full, K9_SMEM - K9_OFF_R);
       tc::tma_load_4d(smem + K9_OFF_R, &tmR, &st_full, 0, w0 - 1 - dhi_bin, h0 - 1, b * 4);
-    }
-  } else if (warp == 3 && lane == 0) {
-    // ===== weights: resident, one bulk copy per tap =====
-    if (cta_s < p.items) {
-      tc::mbar_expect_tx(&w_full, 9 * K9_TAPB);
-      for (int t9 = 0; t9 < 9; ++t9)
-        tc::bulk_load(Wbase + t9 * K9_TAPB, reinterpret_cast<const uint8_t*>(p.w) + (size_t)t9 * K9_TAPB, K9_TAPB, &w_full);
     }
   } else if (warp >= 8) {
     // ===== A producers: the slice k of the sparse concat volume for the 180 halo pixels =====
@@ -759,14 +765,11 @@ __global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_con
       }
       tc::mbar_arrive(&st_empty);                                            // the staged item is no longer needed by this thread
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer (as s1f, weights resident) =====
-    const bool leader = tc::elect_one();
-    const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(Abase), LBO_A), a_hi = tc::desc_hi(SBO_A);
-    const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(Wbase), LBO_B), b_hi = tc::desc_hi(SBO_B);
-    if (cta_s < p.items) tc::mbar_wait(&w_full, 0);
+  } else if (warp == 2) {
+    // ===== planner (as s1f): waits and per-slice bookkeeping, one 48-byte record per slice for the issuer that owns it =====
+    const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(Abase), LBO_A);
     const uint32_t bar_af = tc::smem_u32(&a_full[0]), bar_ae = tc::smem_u32(&a_empty[0]), bar_cf = tc::smem_u32(&acc_full[0]),
-                   bar_ce = tc::smem_u32(&acc_empty[0]);
+                   bar_ce = tc::smem_u32(&acc_empty[0]), bar_pf = tc::smem_u32(&plan_full[0][0]), bar_pe = tc::smem_u32(&plan_empty[0][0]);
     uint32_t g = 0, acc_base = 0, acquired = 0;
     for (int s = cta_s; s < p.items; s += cta_stride) {
       int b, h0, w0, dlo, dhi;
@@ -782,40 +785,84 @@ __global__ void __launch_bounds__(384, 1) concat_stem_k9_kernel(const __grid_con
         }
         const uint32_t slot = g % K9_NS;
         tc::mbar_wait_a(bar_af + slot * 8, (g / K9_NS) & 1);
-        tc::fence_after_sync();
         const uint32_t blk = u0 % NB, n1 = min(nb, NB - blk), n2 = nb - n1;
-        const uint32_t id1 = n1 == 1 ? tc::make_idesc_bf16(128, N) : n1 == 2 ? tc::make_idesc_bf16(128, 2 * N) : tc::make_idesc_bf16(128, 3 * N);
-        const uint32_t id2 = n2 == 1 ? tc::make_idesc_bf16(128, N) : tc::make_idesc_bf16(128, 2 * N);
-        const uint32_t d1 = tmem_base + blk * N, d2 = tmem_base;
-        const uint32_t a_lo = a_lo0 + slot * (K9_SLICE >> 4);
-        const uint32_t brow1 = (uint32_t)j0 * (N / 8) * (SBO_B >> 4), brow2 = (uint32_t)(j0 + n1) * (N / 8) * (SBO_B >> 4);
-        auto issue = [&](auto wrap_tag) {              // the ring-wrap case is a separate copy of the loop (see s1f)
-          constexpr bool WRAP = decltype(wrap_tag)::value;
-#pragma unroll
-          for (int t9 = 0; t9 < 9; ++t9) {
-            const int kh = t9 / 3, kw = t9 - 3 * kh;
-            const uint32_t b_lo = b_lo0 + (uint32_t)t9 * (K9_TAPB >> 4);
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-              const uint32_t a = a_lo + (uint32_t)((kh * WW + kw) * 16 + ks * 2 * LBO_A) / 16;
-              const uint32_t bb = b_lo + (uint32_t)(ks * 2 * LBO_B) / 16;
-              tc::mma_bf16_lohi(d1, a, a_hi, bb + brow1, b_hi, id1, 1u);
-              if (WRAP) tc::mma_bf16_lohi(d2, a, a_hi, bb + brow2, b_hi, id2, 1u);
-            }
-          }
-        };
-        if (leader) {
-          if (n2) issue(std::true_type{});
-          else issue(std::false_type{});
-        }
-        if (leader) {
-          tc::mma_commit_a(bar_ae + slot * 8);
-          if (d_in - 1 >= dlo) tc::mma_commit_a(bar_cf + ((acc_base + (uint32_t)(d_in - 1 - dlo)) % NB) * 8);
-          if (d_in == din1 && din1 == dhi - 1) tc::mma_commit_a(bar_cf + ((acc_base + (uint32_t)(d_in - dlo)) % NB) * 8);
+        const uint32_t own = g & 1u, q = g >> 1, pk = own * PLN + q % PLN;
+        tc::mbar_wait_a(bar_pe + pk * 8, ((q / PLN) & 1) ^ 1);
+        if (lane == 0) {
+          uint32_t* r = plan[0][pk];
+          auto full_of = [&](int d) { return bar_cf + ((acc_base + (uint32_t)(d - dlo)) % NB) * 8; };
+          r[0] = tmem_base + blk * N;
+          r[1] = n1 == 1 ? tc::make_idesc_bf16(128, N) : n1 == 2 ? tc::make_idesc_bf16(128, 2 * N) : tc::make_idesc_bf16(128, 3 * N);
+          r[2] = a_lo0 + slot * (K9_SLICE >> 4);
+          r[3] = (uint32_t)j0 * (N / 8) * (SBO_B >> 4);
+          r[4] = n2;
+          r[5] = n2 == 1 ? tc::make_idesc_bf16(128, N) : tc::make_idesc_bf16(128, 2 * N);
+          r[6] = (uint32_t)(j0 + n1) * (N / 8) * (SBO_B >> 4);
+          r[7] = bar_ae + slot * 8;
+          r[8] = (d_in >= dlo && d_in < dhi) ? full_of(d_in) : 0u;
+          r[9] = d_in - 1 >= dlo ? full_of(d_in - 1) : 0u;
+          r[10] = 1u;
+          r[11] = (din1 == dhi - 1 && ((d_in == dhi - 2 && d_in >= din0) || (d_in == dhi - 1 && dhi - 2 < din0))) ? full_of(dhi - 1) : 0u;
+          tc::mbar_arrive_a(bar_pf + pk * 8);
         }
         __syncwarp();
       }
       acc_base += (uint32_t)(dhi - dlo);
+    }
+    for (uint32_t e = 0; e < 2u; ++e, ++g) {             // end markers, one per issuer
+      const uint32_t own = g & 1u, q = g >> 1, pk = own * PLN + q % PLN;
+      tc::mbar_wait_a(bar_pe + pk * 8, ((q / PLN) & 1) ^ 1);
+      if (lane == 0) {
+        plan[0][pk][10] = 0u;
+        tc::mbar_arrive_a(bar_pf + pk * 8);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1 || warp == 3) {
+    // ===== MMA issuers (as s1f: alternate slices, in turn; weights resident) =====
+    const uint32_t me = warp == 1 ? 0u : 1u;
+    const bool leader = tc::elect_one();
+    const uint32_t a_hi = tc::desc_hi(SBO_A);
+    const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(Wbase), LBO_B), b_hi = tc::desc_hi(SBO_B);
+    if (cta_s < p.items) tc::mbar_wait(&w_full, 0);
+    const uint32_t bar_pf = tc::smem_u32(&plan_full[me][0]), bar_pe = tc::smem_u32(&plan_empty[me][0]), bar_turn = tc::smem_u32(&turn[0]);
+#pragma unroll 1
+    for (uint32_t k = 0;; ++k) {
+      const uint32_t pk = k % PLN;
+      tc::mbar_wait_a(bar_pf + pk * 8, (k / PLN) & 1);
+      const uint4 r0 = *reinterpret_cast<const uint4*>(&plan[me][pk][0]), r1 = *reinterpret_cast<const uint4*>(&plan[me][pk][4]),
+                  r2 = *reinterpret_cast<const uint4*>(&plan[me][pk][8]);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive_a(bar_pe + pk * 8);
+      if (r2.z == 0u) break;
+      tc::mbar_wait_a(bar_turn + me * 8, (k & 1) ^ (me ^ 1));
+      tc::fence_after_sync();
+      const uint32_t d1 = r0.x, id1 = r0.y, a_lo = r0.z, brow1 = r0.w, n2 = r1.x, id2 = r1.y, brow2 = r1.z, d2 = tmem_base;
+      auto issue = [&](auto wrap_tag) {              // the ring-wrap case is a separate copy of the loop (see s1f)
+        constexpr bool WRAP = decltype(wrap_tag)::value;
+#pragma unroll
+        for (int t9 = 0; t9 < 9; ++t9) {
+          const int kh = t9 / 3, kw = t9 - 3 * kh;
+          const uint32_t b_lo = b_lo0 + (uint32_t)t9 * (K9_TAPB >> 4);
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+            const uint32_t a = a_lo + (uint32_t)((kh * WW + kw) * 16 + ks * 2 * LBO_A) / 16;
+            const uint32_t bb = b_lo + (uint32_t)(ks * 2 * LBO_B) / 16;
+            tc::mma_bf16_lohi(d1, a, a_hi, bb + brow1, b_hi, id1, 1u);
+            if (WRAP) tc::mma_bf16_lohi(d2, a, a_hi, bb + brow2, b_hi, id2, 1u);
+          }
+        }
+      };
+      if (leader) {
+        if (n2) issue(std::true_type{});
+        else issue(std::false_type{});
+        tc::mbar_arrive_a(bar_turn + (me ^ 1) * 8);    // this slice's MMAs are in the queue: the other issuer's turn
+        tc::mma_commit_a(r1.w);
+        if (r2.x) tc::mma_commit_a(r2.x);
+        if (r2.y) tc::mma_commit_a(r2.y);
+        if (r2.w) tc::mma_commit_a(r2.w);
+      }
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ===== epilogue (as s1f) =====
