@@ -484,9 +484,12 @@ def main():
     roof = {"kernel": dom["name"], "bound": dom["bound"], "achieved": dom["achieved"],
             "peak": pk["tf_sust"] if dom["bound"] == "tensor" else pk["hbm"], "unit": dom["unit"], "frac": dom["frac"],
             "traffic": ncu_traffic(dom["name"], a.precision, B),
+            **({"frac_of_burst_peak": round(dom["achieved"] / pk["tf_burst"], 4), "burst_peak": pk["tf_burst"]} if dom["bound"] == "tensor" else {}),
             "peak_source": pk["src"] + (" (sustained bf16 cuBLAS)" if dom["bound"] == "tensor" else " (copy)"),
             "note": ("tcgen05 bf16 implicit GEMM, fp32 accumulation in TMEM; achieved = Table-A FLOPs of the layer x batch / CUDA-event "
-                     "time of the launch inside the timed region" if a.precision != "fp32"
+                     "time of the launch inside the timed region; `peak` is the SUSTAINED cuBLAS rate (8192^3 back to back for 4 s, "
+                     "power-capped) as the contract asks for a kernel timed inside a long step -- a fraction above 1 means the kernel "
+                     "sustains more than cuBLAS does under the same cap; frac_of_burst_peak is against cuBLAS' best-of-10" if a.precision != "fp32"
                      else "fp32-accurate FFMA mode; fraction is against the bf16 tensor peak")}
     value = world * B * a.steps / (ms_total * 1e-3)
     e2e_v = world * B * a.steps / (ms_e2e * 1e-3)

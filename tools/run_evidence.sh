@@ -15,6 +15,8 @@ b r02_bench_fp32 --steps 5 --warmup 3 --precision fp32 --batch 2 --no-cpu-baseli
 b r02_bench_head_b8 --steps 10 --warmup 3 --stage head --cpu-steps 1
 b r02_bench_full_b8 --steps 10 --warmup 3 --stage full --cpu-steps 1
 b r02_bench_reference_arm --impl reference --steps 2 --warmup 1
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I semstereo_b200/csrc -I include tools/probes/probe_mma_align.cu -o /tmp/probe_mma 2>/dev/null && timeout 120 /tmp/probe_mma > gpurun_out/r02_probe_mma_rate.txt
+timeout 200 python tools/probes/power_probe.py 2>/dev/null | tail -5 > gpurun_out/r02_power_probe.txt
 timeout 400 python tools/bench_volumes.py > gpurun_out/bench_volumes.log 2>&1; cp gpurun_out/bench_volumes.json gpurun_out/r02_bench_volumes_config2.json
 timeout 200 python tools/bench_conv.py > gpurun_out/r02_bench_conv.log 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches_split_batch2.csv python tools/ncu_path_once.py 2 split 2 > /dev/null 2>&1
