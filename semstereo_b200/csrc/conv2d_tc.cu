@@ -59,7 +59,7 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 
 #define C2_PROLOGUE(NSLOTS, NWSLOTS, NSTAGE, TMEM_COLS)                                                                    \
   extern __shared__ __align__(1024) uint8_t smem[];                                                                        \
-  __shared__ __align__(8) uint64_t a_full[NSLOTS], a_empty[NSLOTS], w_full[NWSLOTS], w_empty[NWSLOTS], acc_full[2], acc_empty[2]; \
+  __shared__ __align__(8) uint64_t a_full[NSLOTS], a_empty[NSLOTS], w_full[NWSLOTS], w_empty[NWSLOTS], acc_full[4], acc_empty[4]; \
   __shared__ uint32_t tmem_base_s;                                                                                         \
   __shared__ float s_scale[NSTAGE], s_shift[NSTAGE];                                                                       \
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;                                                              \
@@ -68,7 +68,7 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
     tc::prefetch_tmap(&tm1);                                                                                               \
     for (int i = 0; i < NSLOTS; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1); }                      \
     for (int i = 0; i < NWSLOTS; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }                     \
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }                     \
+    for (int i = 0; i < 4; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }                     \
     tc::fence_barrier_init();                                                                                              \
   }                                                                                                                        \
   if (warp == 2) tc::tmem_alloc(&tmem_base_s, TMEM_COLS);                                                                  \
@@ -98,15 +98,22 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 // =====================================================================================================================
 // EXT (1x1 mode; compile time so that the 3x3 decoder kernels keep their registers): SiLU activation and a residual input in
 // the epilogue -- the inverted-residual / transformer blocks of the MobileViTv2 backbone.
-template <int N, int TAPS, int NS, int NWS, bool EXT = false>
-__global__ void __launch_bounds__(256, 1) conv2d_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+// EPG: epilogue warp groups.  A 1x1 conv with few input channels does 4-16 MMAs per 128-pixel tile but a 128-channel affine + SiLU
+// + pack + store epilogue: with one group of 4 warps the epilogue, not the tensor core or HBM, bounds the layer (the backbone's 512^2
+// expand convs ran at 1/3 of their HBM time).  With EPG = 2 each group owns one of the two accumulator stages.
+template <int N, int TAPS, int NS, int NWS, bool EXT = false, int EPG = 1>
+__global__ void __launch_bounds__(128 + 128 * EPG, 1) conv2d_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                                                            const C2P p) {
   constexpr uint32_t TAPB = CB * N * 2;
   constexpr int KS = CB / 16;
   constexpr uint32_t LBO_A = TILE_B, SBO_A = WW * 16, LBO_B = N * 16, SBO_B = 128;
   constexpr uint32_t ACC = N < 32 ? 32 : N;            // accumulator stride in TMEM columns
   constexpr uint32_t IDESC = tc::make_idesc_bf16(128, N);
-  C2_PROLOGUE(NS, NWS, (N < 32 ? 32 : N), 2 * ACC)
+  constexpr int NST = (N < 32 ? 32 : N);
+  constexpr uint32_t NACC = EPG > 1 ? EPG : 2;         // accumulator stages in TMEM: one per epilogue group
+  constexpr uint32_t TCOLS = NACC * ACC <= 32 ? 32 : NACC * ACC <= 64 ? 64 : NACC * ACC <= 128 ? 128 : NACC * ACC <= 256 ? 256 : 512;
+  static_assert(NACC * ACC <= 512 && NACC <= 4, "TMEM columns");
+  C2_PROLOGUE(NS, NWS, EPG * NST, TCOLS)
   uint8_t* Abase = smem;
   uint8_t* Wbase = smem + NS * SLICE;
   const int total = p.items * p.n_tiles;
@@ -114,11 +121,26 @@ __global__ void __launch_bounds__(256, 1) conv2d_tc_kernel(const __grid_constant
   if (warp == 0 && lane == 0) {
     C2_TILE_PRODUCER(NS)
   } else if (warp == 3 && lane == 0) {
-    uint32_t wc = 0;
+    // 1x1 convs whose K blocks all fit in the slab ring keep their weights RESIDENT while the Cout tile does not change (the backbone's
+    // 512^2 layers do 4 MMAs per tile: re-streaming 16 KB per tile through the ring cost 3x the layer's HBM time, round 2)
+    const bool resident = TAPS == 1 && p.ncb <= NWS;
+    uint32_t wc = 0, reloads = 0;
+    int nt_loaded = -1;
     for (int s = blockIdx.x; s < total; s += gridDim.x) {
       int nt, b, h0, w0;
       decode(p, s, nt, b, h0, w0);
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)nt * p.ncb * TAPS * TAPB;
+      if (resident) {
+        if (nt == nt_loaded) continue;
+        for (int i = 0; i < p.ncb; ++i) {
+          tc::mbar_wait(&w_empty[i], (reloads & 1) ^ 1);
+          tc::mbar_expect_tx(&w_full[i], TAPB);
+          tc::bulk_load(Wbase + i * TAPB, wsrc + (size_t)i * TAPB, TAPB, &w_full[i]);
+        }
+        nt_loaded = nt;
+        ++reloads;
+        continue;
+      }
       for (int i = 0; i < p.ncb * TAPS; ++i, ++wc) {
         const uint32_t slot = wc % NWS;
         tc::mbar_wait(&w_empty[slot], ((wc / NWS) & 1) ^ 1);
@@ -128,12 +150,25 @@ __global__ void __launch_bounds__(256, 1) conv2d_tc_kernel(const __grid_constant
     }
   } else if (warp == 1) {
     const bool leader = tc::elect_one();
+    const bool resident = TAPS == 1 && p.ncb <= NWS;
     const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(Abase), LBO_A), a_hi = tc::desc_hi(SBO_A);
     const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(Wbase), LBO_B), b_hi = tc::desc_hi(SBO_B);
-    uint32_t g = 0, wc = 0, acc_it = 0;
+    uint32_t g = 0, wc = 0, acc_it = 0, reloads = 0;
+    int nt_loaded = -1;
     for (int s = blockIdx.x; s < total; s += gridDim.x, ++acc_it) {
-      const uint32_t as = acc_it & 1;
-      tc::mbar_wait(&acc_empty[as], ((acc_it >> 1) & 1) ^ 1);
+      int nt = 0, nt_next = -1;
+      if (resident) {                        // nt is the slowest index of s: it changes at most n_tiles - 1 times per CTA
+        nt = s / p.items;
+        nt_next = s + (int)gridDim.x < total ? (s + (int)gridDim.x) / p.items : -1;
+        if (nt != nt_loaded) {
+          for (int i = 0; i < p.ncb; ++i) tc::mbar_wait(&w_full[i], reloads & 1);
+          tc::fence_after_sync();
+          nt_loaded = nt;
+          ++reloads;
+        }
+      }
+      const uint32_t as = acc_it % NACC;
+      tc::mbar_wait(&acc_empty[as], ((acc_it / NACC) & 1) ^ 1);
       tc::fence_after_sync();
       const uint32_t tmem_d = tmem_base + as * ACC;
       uint32_t accumulate = 0;
@@ -146,9 +181,11 @@ __global__ void __launch_bounds__(256, 1) conv2d_tc_kernel(const __grid_constant
 #pragma unroll
         for (int t = 0; t < TAPS; ++t, ++wc) {
           const int kh = TAPS == 9 ? t / 3 : 1, kw = TAPS == 9 ? t % 3 : 1;
-          const uint32_t wslot = wc % NWS;
-          tc::mbar_wait(&w_full[wslot], (wc / NWS) & 1);
-          tc::fence_after_sync();
+          const uint32_t wslot = resident ? (uint32_t)cb : wc % NWS;
+          if (!resident) {
+            tc::mbar_wait(&w_full[wslot], (wc / NWS) & 1);
+            tc::fence_after_sync();
+          }
           const uint32_t b_lo = b_lo0 + wslot * (TAPB >> 4);
           if (leader) {
 #pragma unroll
@@ -157,7 +194,7 @@ __global__ void __launch_bounds__(256, 1) conv2d_tc_kernel(const __grid_constant
                                 b_lo + (uint32_t)(ks * 2 * LBO_B) / 16, b_hi, IDESC, accumulate);
               accumulate = 1;
             }
-            tc::mma_commit(&w_empty[wslot]);
+            if (!resident || nt_next != nt) tc::mma_commit(&w_empty[wslot]);      // resident: released after the tile's last item
           }
           accumulate = 1;
         }
@@ -168,26 +205,29 @@ __global__ void __launch_bounds__(256, 1) conv2d_tc_kernel(const __grid_constant
       __syncwarp();
     }
   } else if (warp >= 4) {
-    const int e = warp - 4, m = e * 32 + lane, hh = m >> 3, ww = m & 7;
+    const int e = warp & 3, eg = (warp - 4) >> 2, m = e * 32 + lane, hh = m >> 3, ww = m & 7;
+    float* const s_scale_g = s_scale + eg * NST;       // each epilogue group stages its own copy (named barrier 1 + group)
+    float* const s_shift_g = s_shift + eg * NST;
     uint32_t acc_it = 0;
     int nt_staged = -1;
     for (int s = blockIdx.x; s < total; s += gridDim.x, ++acc_it) {
+      if (EPG > 1 && (int)(acc_it % NACC) != eg) continue;   // group g drains accumulator stage g
       int nt, b, h0, w0;
       decode(p, s, nt, b, h0, w0);
-      if (nt != nt_staged) {                 // folded-BN constants of this Cout tile (epilogue warps only: named barrier 1)
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = threadIdx.x - 128; i < N; i += 128) {
+      if (nt != nt_staged) {                 // folded-BN constants of this Cout tile
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+        for (int i = (threadIdx.x & 127); i < N; i += 128) {
           const int co = nt * N + i;
-          s_scale[i] = (p.scale && co < p.cout) ? __ldg(p.scale + co) : 1.0f;
-          s_shift[i] = (p.shift && co < p.cout) ? __ldg(p.shift + co) : 0.0f;
+          s_scale_g[i] = (p.scale && co < p.cout) ? __ldg(p.scale + co) : 1.0f;
+          s_shift_g[i] = (p.shift && co < p.cout) ? __ldg(p.shift + co) : 0.0f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
         nt_staged = nt;
       }
       const int h = h0 + hh, w = w0 + ww;
       const bool valid = h < p.H && w < p.W;
-      const uint32_t as = acc_it & 1;
-      tc::mbar_wait(&acc_full[as], (acc_it >> 1) & 1);
+      const uint32_t as = acc_it % NACC;
+      tc::mbar_wait(&acc_full[as], (acc_it / NACC) & 1);
       tc::fence_after_sync();
       constexpr int NJ = (N + 31) / 32;
 #pragma unroll 1
@@ -201,9 +241,9 @@ __global__ void __launch_bounds__(256, 1) conv2d_tc_kernel(const __grid_constant
         const int co0 = nt * N + j * 32;
         if (!valid || co0 >= p.cout) continue;
         const size_t HW = (size_t)p.H * p.W, sp = (size_t)h * p.W + w;
-        if (!EXT) affine_relu32(v, s_scale + (N < 32 ? 0 : j * 32), s_shift + (N < 32 ? 0 : j * 32), p.relu);
+        if (!EXT) affine_relu32(v, s_scale_g + (N < 32 ? 0 : j * 32), s_shift_g + (N < 32 ? 0 : j * 32), p.relu);
         else {
-          affine_relu32(v, s_scale + (N < 32 ? 0 : j * 32), s_shift + (N < 32 ? 0 : j * 32), p.act == 1);
+          affine_relu32(v, s_scale_g + (N < 32 ? 0 : j * 32), s_shift_g + (N < 32 ? 0 : j * 32), p.act == 1);
           if (p.act == 2) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __fdividef(v[i], 1.0f + __expf(-v[i]));
@@ -239,7 +279,7 @@ __global__ void __launch_bounds__(256, 1) conv2d_tc_kernel(const __grid_constant
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 2) tc::tmem_dealloc(tmem_base, 2 * ACC);
+  if (warp == 2) tc::tmem_dealloc(tmem_base, TCOLS);
 }
 
 // =====================================================================================================================
@@ -470,11 +510,11 @@ int make_tmap2d(CUtensorMap* tm, const void* base, int W, int H, long long outer
 }
 
 template <typename K>
-int launch2d(K kernel, size_t smem, const CUtensorMap& t0, const CUtensorMap& t1, const C2P& p, cudaStream_t st, const char* name) {
+int launch2d(K kernel, size_t smem, const CUtensorMap& t0, const CUtensorMap& t1, const C2P& p, cudaStream_t st, const char* name, int threads = 256) {
   SS_CUDA(ss_allow_smem(kernel, smem));
   const long long total = (long long)p.items * p.n_tiles;
   const int grid = (int)(total < ss_num_sms() ? total : ss_num_sms());
-  kernel<<<grid, 256, smem, st>>>(t0, t1, p);
+  kernel<<<grid, threads, smem, st>>>(t0, t1, p);
   SS_CHECK_LAUNCH(name);
   return SS_OK;
 }
@@ -484,9 +524,10 @@ int launch_conv(const CUtensorMap& t0, const CUtensorMap& t1, const C2P& p, cuda
   constexpr int NS = 4, NWS = N >= 128 ? 4 : 6;
   constexpr size_t smem = (size_t)NS * SLICE + (size_t)NWS * CB * N * 2;
   static_assert(smem <= 227 * 1024 - 2048, "shared memory budget");
+  constexpr int EPG = TAPS == 1 ? (N >= 64 ? 3 : 2) : 1;
   if (TAPS == 1 && (p.act == 2 || p.residual))
-    return launch2d(conv2d_tc_kernel<N, TAPS, NS, NWS, TAPS == 1>, smem, t0, t1, p, st, "ss_conv2d_tc(conv, ext)");
-  return launch2d(conv2d_tc_kernel<N, TAPS, NS, NWS>, smem, t0, t1, p, st, "ss_conv2d_tc(conv)");
+    return launch2d(conv2d_tc_kernel<N, TAPS, NS, NWS, TAPS == 1, EPG>, smem, t0, t1, p, st, "ss_conv2d_tc(conv, ext)", 128 + 128 * EPG);
+  return launch2d(conv2d_tc_kernel<N, TAPS, NS, NWS, false, EPG>, smem, t0, t1, p, st, "ss_conv2d_tc(conv)", 128 + 128 * EPG);
 }
 template <int NP>
 int launch_deconv(const CUtensorMap& t0, const CUtensorMap& t1, const C2P& p, cudaStream_t st) {
