@@ -282,3 +282,22 @@ def test_full_size_against_oracle(signed, maxdisp, H, W):
     print(f"\n[{H}x{W}] fp32 index agreement {same.float().mean().item():.6f}; bf16 top-24 agreement {agree:.4f}, "
           f"pred_up median {e.median():.4f} p90 {e.quantile(0.9):.4f} (1/4-res px)")
     assert agree >= 0.90 and e.median().item() <= 0.05 and e.quantile(0.9).item() <= 0.5
+
+
+@pytest.mark.parametrize("precision", ["split", "bf16"])
+def test_path_is_bitwise_reproducible(precision):
+    """The tensor-core kernels with two MMA issuer warps (s1f, concat_stem) issue their slices strictly in turn, so the fp32
+    accumulation order -- and with it every output bit -- is the same from run to run (and equal to the single-issuer order)."""
+    from semstereo_b200.hotpath import DisparityHotPath
+    m = DisparityHotPath(64, False, True, precision=precision)
+    m.load_state_dict(make_params(seed=1, peaked=20.0), strict=True)
+    m = m.to(DEV)
+    inp = {k: v.to(DEV) for k, v in make_inputs(7, 2, 256, 512).items() if k not in ("cf_l", "cf_r")}
+    outs = []
+    for _ in range(3):
+        o = m(*[inp.get(k) for k in ORDER])
+        torch.cuda.synchronize()
+        outs.append({k: o[k].clone() for k in ("pred_up", "pred_att", "disp_topk", "att_topk", "cost_att")})
+    for o in outs[1:]:
+        for k, v in o.items():
+            assert torch.equal(v, outs[0][k]), k
