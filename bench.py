@@ -235,6 +235,8 @@ def main():
                          "backbone (forward:249-346): the 2-D decoder (SURVEY 8(f) rank 1) + the path; inputs are the backbone pyramids.  "
                          "full: the whole SemStereo.forward from the two images (MobileViTv2 backbone, SURVEY 8(f) rank 2, + decoder + path)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches in region 1 instead of CUDA-graph replays")
+    ap.add_argument("--no-full-model", action="store_true",
+                    help="skip the `full_model` sub-measurement (the whole model from the images, --stage full) of the default line")
     ap.add_argument("--external-cf", action="store_true",
                     help="hand concat_feature(f4_*) in as inputs (round-1 boundary) instead of computing it inside the path")
     ap.add_argument("--train", action="store_true",
@@ -525,6 +527,23 @@ def main():
         times = cpu_reference(H, W, md, a.cpu_steps, 1, signed, a.att_only, a.external_cf, a.stage)
         res["cpu_baseline"] = {"value": len(times) / sum(times), "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
                                "sample": f"{len(times)} pairs at {H}x{W} through {'oracle/backbone.py (HF MobileViTV2) + ' if full else ''}{'oracle/decoder.py + ' if head else ''}oracle/hotpath.py (torch CPU fp32), 1 warm-up"}
+    # The default line also carries the whole model from the IMAGES (backbone + decoder + this path: `--stage full`), measured by a
+    # short run of this same script in a child process: with the host boundary at the images a step ships 201 MB instead of 1.2 GB,
+    # so its end-to-end rate is not PCIe-bound ("report --stage full beside --stage path").
+    if (world == 1 and a.stage == "path" and a.precision == "split" and not a.att_only and not a.external_cf and not a.no_full_model
+            and a.variant == "us3d" and a.batch == 8 and (H, W) == (1024, 1024)):
+        import subprocess
+        try:
+            torch.cuda.empty_cache()
+            cp = subprocess.run([sys.executable, os.path.abspath(__file__), "--stage", "full", "--steps", "5", "--warmup", "3", "--no-cpu-baseline",
+                                 "--batch", str(a.batch)], capture_output=True, text=True, timeout=240)
+            line = [ln for ln in cp.stdout.splitlines() if ln.startswith("{")][-1]
+            fm = json.loads(line)
+            res["full_model"] = {"value": fm["value"], "unit": fm["unit"], "ms_per_step": fm["ms_per_step"], "e2e": fm["e2e"],
+                                 "dtype": fm["dtype"], "clocks": fm["clocks"], "workload": fm["config"]["workload"],
+                                 "note": "python bench.py --stage full --steps 5 --warmup 3 (child process, same GPU, after the path run)"}
+        except Exception as e:                          # informative only: never let it break the contract line
+            res["full_model"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     print(json.dumps(res))
     if world > 1:
         tdist.destroy_process_group()
