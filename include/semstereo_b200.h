@@ -296,6 +296,16 @@ SS_API int ss_spatial_transformer_grid_backward(const float* y, const float* dis
  * W^T k1; semstereo_b200/train_ops.py). */
 SS_API int ss_conv3d_wgrad_f32(const float* x, const float* grad_out, float* grad_weight_packed, int B, int Cin, int Cout, int Di, int Hi,
                                int Wi, int K, int stride, void* stream);
+
+/* Small-channel 2-D convolutions in training mode (Cin, Cout <= 8, k in {1, 3}, stride 1, zero padding k/2): the convs of
+ * SSR_upsample (models/submodule.py:394-431: Conv2d(1,6,3,1,1), Conv2d(6,6,1), Conv2d(6,1,1)) at full image resolution.
+ * in (B,Cin,H,W), weight (Cout,Cin,k,k), out (B,Cout,H,W), all fp32; the input gradient is the same call on dY with the flipped,
+ * channel-transposed weight.  ss_conv2d_small_wgrad_f32 ACCUMULATES into grad_weight (Cout,Cin,k,k) (zero it first); it exists for
+ * the three SSR shapes (ss_conv2d_small_wgrad_supported). */
+SS_API int ss_conv2d_small_f32(const float* in, const float* weight, float* out, int B, int Cin, int Cout, int H, int W, int k, void* stream);
+SS_API int ss_conv2d_small_wgrad_supported(int Cin, int Cout, int k);
+SS_API int ss_conv2d_small_wgrad_f32(const float* x, const float* grad_out, float* grad_weight, int B, int Cin, int Cout, int H, int W, int k,
+                                     void* stream);
 /* BatchNorm{2,3}d with BATCH statistics over (B, S = spatial size) per channel (training mode of nn.BatchNorm, appendix C of
  * SURVEY.md): batch_mean / batch_var (biased) are outputs of the forward (the caller updates running_mean / running_var with
  * momentum and the unbiased variance) and inputs of the backward.  out = (x - mean) * rsqrt(var + eps) * weight + bias (-> ReLU).

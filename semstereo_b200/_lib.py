@@ -51,6 +51,9 @@ SIGNATURES = {
     "ss_bilinear_up4": [_P, _P, _I, _I, _I, _P],
     "ss_bilinear_up4_backward": [_P, _P, _I, _I, _I, _P],
     "ss_conv3d_wgrad_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "ss_conv2d_small_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ss_conv2d_small_wgrad_supported": [_I, _I, _I],
+    "ss_conv2d_small_wgrad_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ss_bn_workspace_bytes": [_I],
     "ss_bn_train_forward": [_P, _P, _P, _P, _P, _P, _P, _I, _I, ctypes.c_longlong, _F, _I, _P],
     "ss_bn_train_backward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, ctypes.c_longlong, _F, _P],

@@ -213,3 +213,122 @@ extern "C" int ss_bn_train_backward(const float* x, const float* grad_out, const
   SS_CHECK_LAUNCH("ss_bn_train_backward(dx)");
   return SS_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Small-channel 2-D convolutions (Cin, Cout <= 8; k in {1, 3}, stride 1, zero padding k/2): the four convs of SSR_upsample
+// (models/submodule.py:394-431: 1 -> 6 3x3, 6 -> 6 and 6 -> 1 1x1) at FULL image resolution in training mode.  Through the generic
+// implicit-GEMM kernels (a depth-1 volume, channels padded to the GEMM tile) they cost 2.3 ms per 3x3 launch and 7.6 ms for its
+// weight gradient at two 1024^2 images -- 20 % of the config-5 training step for 0.1 GFLOP.  Here: one thread per pixel, every output
+// channel in registers; dX is the same kernel on dY with flipped / transposed weights (done by the caller); dW accumulates all
+// Cout*Cin*k*k sums per thread over a strided set of pixels, then warp shuffles, shared memory and one atomicAdd per block and weight.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+template <int K>
+__global__ void __launch_bounds__(256) small_conv2d_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out,
+                                                           int Cin, int Cout, int H, int W) {
+  __shared__ float sw[8 * 8 * K * K];
+  for (int i = threadIdx.x; i < Cout * Cin * K * K; i += blockDim.x) sw[i] = __ldg(w + i);
+  __syncthreads();
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+  if (x >= W) return;
+  const size_t HW = (size_t)H * W;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int ci = 0; ci < Cin; ++ci) {
+    const float* ip = in + ((size_t)b * Cin + ci) * HW;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+      const int yy = y + ky - K / 2;
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const int xx = x + kx - K / 2;
+        const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(ip + (size_t)yy * W + xx) : 0.0f;
+#pragma unroll
+        for (int co = 0; co < 8; ++co)
+          if (co < Cout) acc[co] = fmaf(sw[((co * Cin + ci) * K + ky) * K + kx], v, acc[co]);
+      }
+    }
+  }
+  for (int co = 0; co < Cout; ++co) out[((size_t)b * Cout + co) * HW + (size_t)y * W + x] = acc[co];
+}
+
+template <int CIN, int COUT, int K>
+__global__ void __launch_bounds__(256) small_conv2d_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                                                                 int B, int H, int W) {
+  constexpr int NW = COUT * CIN * K * K;
+  __shared__ float red[8][NW];
+  const size_t HW = (size_t)H * W, total = (size_t)B * HW;
+  float acc[NW];
+#pragma unroll
+  for (int i = 0; i < NW; ++i) acc[i] = 0.f;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(p / HW);
+    const size_t pix = p - (size_t)b * HW;
+    const int yy0 = (int)(pix / W), xx0 = (int)(pix - (size_t)yy0 * W);
+    float g[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) g[co] = __ldg(dy + ((size_t)b * COUT + co) * HW + pix);
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      const float* ip = x + ((size_t)b * CIN + ci) * HW;
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky) {
+        const int yy = yy0 + ky - K / 2;
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          const int xx = xx0 + kx - K / 2;
+          const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(ip + (size_t)yy * W + xx) : 0.0f;
+#pragma unroll
+          for (int co = 0; co < COUT; ++co) acc[((co * CIN + ci) * K + ky) * K + kx] = fmaf(g[co], v, acc[((co * CIN + ci) * K + ky) * K + kx]);
+        }
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NW; ++i) {
+    float v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[wid][i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NW; i += blockDim.x) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += red[k][i];
+    atomicAdd(dw + i, v);
+  }
+}
+
+}  // namespace
+
+extern "C" int ss_conv2d_small_f32(const float* in, const float* weight, float* out, int B, int Cin, int Cout, int H, int W, int k, void* stream) {
+  SS_REQUIRE(in && weight && out && B > 0 && H > 0 && W > 0, "ss_conv2d_small_f32: bad argument");
+  SS_UNSUPPORTED(Cin < 1 || Cin > 8 || Cout < 1 || Cout > 8 || (k != 1 && k != 3), "ss_conv2d_small_f32: Cin, Cout in [1, 8] and k in {1, 3} only");
+  SS_UNSUPPORTED(H > 65535 || B > 65535, "ss_conv2d_small_f32: grid dimension exceeds 65535");
+  const dim3 grid(ceil_div(W, 256), H, B);
+  if (k == 3) small_conv2d_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(in, weight, out, Cin, Cout, H, W);
+  else small_conv2d_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(in, weight, out, Cin, Cout, H, W);
+  SS_CHECK_LAUNCH("ss_conv2d_small_f32");
+  return SS_OK;
+}
+
+// 1 when ss_conv2d_small_wgrad_f32 has an instantiation for this layer (the SSR_upsample shapes), else 0
+extern "C" int ss_conv2d_small_wgrad_supported(int Cin, int Cout, int k) {
+  return (Cin == 1 && Cout == 6 && k == 3) || (Cin == 6 && Cout == 6 && k == 1) || (Cin == 6 && Cout == 1 && k == 1) ? 1 : 0;
+}
+
+// grad_weight (Cout, Cin, k, k) is ACCUMULATED into (atomicAdd): zero it first
+extern "C" int ss_conv2d_small_wgrad_f32(const float* x, const float* grad_out, float* grad_weight, int B, int Cin, int Cout, int H, int W, int k,
+                                         void* stream) {
+  SS_REQUIRE(x && grad_out && grad_weight && B > 0 && H > 0 && W > 0, "ss_conv2d_small_wgrad_f32: bad argument");
+  SS_UNSUPPORTED(!ss_conv2d_small_wgrad_supported(Cin, Cout, k), "ss_conv2d_small_wgrad_f32: no instantiation for (Cin=%d, Cout=%d, k=%d)", Cin, Cout, k);
+  const int grid = ss_num_sms() * 4;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (k == 3) small_conv2d_wgrad_kernel<1, 6, 3><<<grid, 256, 0, st>>>(x, grad_out, grad_weight, B, H, W);
+  else if (Cout == 6) small_conv2d_wgrad_kernel<6, 6, 1><<<grid, 256, 0, st>>>(x, grad_out, grad_weight, B, H, W);
+  else small_conv2d_wgrad_kernel<6, 1, 1><<<grid, 256, 0, st>>>(x, grad_out, grad_weight, B, H, W);
+  SS_CHECK_LAUNCH("ss_conv2d_small_wgrad_f32");
+  return SS_OK;
+}

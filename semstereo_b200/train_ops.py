@@ -2,9 +2,11 @@
 `convbn_3d` / `BasicConv(is_3d)` (models/submodule_other.py:845-848, models/submodule.py:89-116) do when the reference trains
 (main_us3d.py:186-222) -- Conv3d and BatchNorm3d with batch statistics, forward AND backward on the CUDA kernels (fp32):
 
-  conv3d        forward  ss_conv3d_f32                       (csrc/conv3d_f32.cu, the inference kernel without the folded BN)
-                dX       ss_conv3d_f32 on dY with a re-packed weight: flipped taps + swapped channels (k3 s1), the
-                         ConvTranspose3d(k3,s2,p1,op1) phase GEMMs with the same weight (k3 s2), W^T (k1)
+  conv3d        forward  the bf16x3 tcgen05 kernels (ops_tc.conv3d_tc_split: fp32-accurate products, fp32 accumulation) for the k = 3
+                         layers that have such a configuration (32->32, 64->64, 128->128, s2 32->64 / 64->128), else ss_conv3d_f32
+                         (csrc/conv3d_f32.cu, the inference kernel without the folded BN)
+                dX       the same kernels on dY with a re-packed weight: flipped taps + swapped channels (k3 s1), the
+                         ConvTranspose3d(k3,s2,p1,op1) layer with the same weight (k3 s2: t2 64->32 / 128->64), W^T (k1)
                 dW       ss_conv3d_wgrad_f32                 (csrc/train.cu)
   batch_norm    forward / backward ss_bn_train_forward / ss_bn_train_backward, running statistics updated like nn.BatchNorm3d
                 (momentum, unbiased variance)
@@ -24,6 +26,7 @@ import ctypes
 import torch
 
 from . import ops
+from . import ops_tc as tc
 from .ops import _call, _ptr, _require_cuda
 
 
@@ -34,6 +37,35 @@ def _geometry(w, stride):
     return k
 
 
+_ROUTE = {"tensor_cores": True}
+
+
+def set_tensor_core_route(on: bool):
+    """Forward and dX of the k = 3 layers that have a bf16x3 split configuration run on the tcgen05 kernels (fp32-accurate products,
+    fp32 accumulation: ops_tc.conv3d_tc_split) by default; False forces the fp32 FFMA kernels everywhere."""
+    _ROUTE["tensor_cores"] = bool(on)
+
+
+def _tc_kind(cin, cout, k, stride, transposed=False):
+    """The tensor-core kind of a layer that has a bf16x3 split configuration (single launch, or the two-launch route of the
+    128-channel layers), else None."""
+    if k != 3 or not _ROUTE["tensor_cores"]:
+        return None
+    if transposed:
+        return tc.T2 if (cin, cout) in ((64, 32), (128, 64)) else None
+    if stride == 2:
+        return tc.S2 if (cin, cout) in ((32, 64), (64, 128)) else None
+    if (cin, cout) in ((32, 32), (64, 64)):
+        return tc.S1F
+    return tc.S1 if (cin, cout) == (128, 128) else None
+
+
+def _conv_tc(kind, x, w, cout):
+    """x (B,Cin,D,H,W) fp32, w in the layout pack_weight(kind) expects -> (B,Cout,...) fp32, on the tensor cores (bf16x3)."""
+    xs = tc.to_blocked_bf16(x, s2d=(kind == tc.S2), split=True)
+    return tc.conv3d_tc_split(kind, xs, tc.pack_weight_split(w, kind), cout, out_mode=tc.F32)
+
+
 class _Conv3dFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, stride):
@@ -41,6 +73,10 @@ class _Conv3dFn(torch.autograd.Function):
         x = x.contiguous().float()
         ctx.save_for_backward(x, w)
         ctx.stride, ctx.k = stride, k
+        cout, cin = w.shape[:2]
+        kind = _tc_kind(cin, cout, k, stride)
+        if kind is not None and not (stride == 2 and any(n % 2 for n in x.shape[2:])):
+            return _conv_tc(kind, x, w.detach().float(), cout)
         return ops.conv3d_f32(x, ops.pack_conv3d_weight(w.detach().float()), k=k, stride=stride)
 
     @staticmethod
@@ -49,14 +85,19 @@ class _Conv3dFn(torch.autograd.Function):
         k, stride = ctx.k, ctx.stride
         dy = dy.contiguous().float()
         wf = w.detach().float()
+        cout, cin = w.shape[:2]
         dx = dw = None
         if ctx.needs_input_grad[0]:
             if stride == 1:      # correlation with the flipped kernel, channels swapped: a plain k s1 conv of dY
-                dx = ops.conv3d_f32(dy, ops.pack_conv3d_weight(wf.flip(2, 3, 4).transpose(0, 1).contiguous()), k=k, stride=1)
+                wt = wf.flip(2, 3, 4).transpose(0, 1).contiguous()
+                kind = _tc_kind(cout, cin, k, 1)
+                dx = _conv_tc(kind, dy, wt, cin) if kind is not None else ops.conv3d_f32(dy, ops.pack_conv3d_weight(wt), k=k, stride=1)
             else:                # k3 s2 p1 on even dims: dX = conv_transpose3d(dY, W, 2, 1, output_padding 1); W already has that layout
                 if k != 3 or any(n % 2 for n in x.shape[2:]):
                     raise NotImplementedError("conv3d (training): stride 2 needs k = 3 and even input dims")
-                dx = ops.conv3d_f32(dy, ops.pack_conv3d_weight(wf, transposed=True), k=3, stride=2, transposed=True)
+                kind = _tc_kind(cout, cin, 3, 2, transposed=True)
+                dx = (_conv_tc(kind, dy, wf, cin) if kind is not None
+                      else ops.conv3d_f32(dy, ops.pack_conv3d_weight(wf, transposed=True), k=3, stride=2, transposed=True))
         if ctx.needs_input_grad[1]:
             dev = x.device
             B, Cin, Di, Hi, Wi = x.shape
@@ -182,10 +223,53 @@ class _Up4Fn(torch.autograd.Function):
         return gin
 
 
+class _SmallConv2dFn(torch.autograd.Function):
+    """Conv2d with Cin, Cout <= 8 (k in {1,3}, stride 1, pad k//2) on the small-channel kernels of csrc/train.cu."""
+
+    @staticmethod
+    def _run(x, w):
+        dev = _require_cuda(x, w)
+        B, Cin, H, W = x.shape
+        Cout, k = w.shape[0], w.shape[-1]
+        out = torch.empty((B, Cout, H, W), device=dev, dtype=torch.float32)
+        _call("ss_conv2d_small_f32", dev, _ptr(x), _ptr(w), _ptr(out), B, Cin, Cout, H, W, int(k))
+        return out
+
+    @staticmethod
+    def forward(ctx, x, w):
+        x = x.contiguous().float()
+        ctx.save_for_backward(x, w)
+        return _SmallConv2dFn._run(x, w.detach().float().contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous().float()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = _SmallConv2dFn._run(dy, w.detach().float().flip(2, 3).transpose(0, 1).contiguous())
+        if ctx.needs_input_grad[1]:
+            B, Cin, H, W = x.shape
+            Cout, k = w.shape[0], w.shape[-1]
+            dwf = torch.zeros((Cout, Cin, k, k), device=x.device, dtype=torch.float32)
+            _call("ss_conv2d_small_wgrad_f32", x.device, _ptr(x), _ptr(dy), _ptr(dwf), B, Cin, Cout, H, W, int(k))
+            dw = dwf.to(w.dtype)
+        return dx, dw
+
+
+def _small_conv_ok(cin, cout, k):
+    from . import _lib
+    return cin <= 8 and cout <= 8 and bool(_lib.load().ss_conv2d_small_wgrad_supported(int(cin), int(cout), int(k)))
+
+
 def conv2d(x, weight, bias=None):
-    """Differentiable Conv2d (k in {1,3}, stride 1, padding k//2) through the 3-D kernels: the image is a depth-1 volume, a 3x3
-    kernel is the centre depth plane of a 3x3x3 one."""
+    """Differentiable Conv2d (k in {1,3}, stride 1, padding k//2).  The SSR_upsample shapes (1 -> 6 3x3, 6 -> 6 / 6 -> 1 1x1) run on
+    the small-channel kernels; everything else goes through the 3-D kernels: the image is a depth-1 volume, a 3x3 kernel is the
+    centre depth plane of a 3x3x3 one."""
     k = weight.shape[-1]
+    if _small_conv_ok(weight.shape[1], weight.shape[0], k):
+        y = _SmallConv2dFn.apply(x, weight)
+        return y if bias is None else y + bias.view(1, -1, 1, 1)
     w3 = weight.unsqueeze(2)
     if k == 3:
         w3 = torch.nn.functional.pad(w3, (0, 0, 0, 0, 1, 1))

@@ -204,6 +204,44 @@ def test_training_step_of_the_model_glue():
         if n.startswith(("hourglass_att", "classif_att_", "corr_feature_att_8", "patch", "feature_up.deconv8_4")) and p.grad is not None:
             a, b = g_native[n], p.grad
             if b.abs().max().item() > 1e-6:       # fp32 rounding differs between the two routes and the forward has discontinuities
-                assert relerr(a, b) <= 2e-2, (n, relerr(a, b))      # (sort / top-k): measured <= 0.7 % on the upstream decoder weights
+                # (sort / top-k): a 1e-6 perturbation of the forward moves a few samples, measured 0.7 % - 3.5 % of max|grad| depending
+                # on which samples a run lands on (two runs of the same code differ by as much, see below)
+                assert relerr(a, b) <= 5e-2, (n, relerr(a, b))
                 checked += 1
     assert checked >= 20
+
+    # the tensor-core route (bf16x3 forward / dX) against the fp32 FFMA kernels on the same model and batch.  The glue's forward is
+    # not bitwise reproducible between two runs of the SAME route (its torch / cuDNN parts pick different algorithms on a first call:
+    # the loss toggles between 56.750996 and 56.750999), and one moved top-k sample shifts a weight gradient by up to 3.5 % of its
+    # maximum -- so this comparison can only be as tight as the one above; when both runs land on the same samples the two routes
+    # agree to 1e-5 (the tight, discontinuity-free gradient checks are test_conv3d_forward_and_gradients, per layer, <= 1e-4).
+    def native_grads(tc_on):
+        train_ops.set_tensor_core_route(tc_on)
+        try:
+            torch.manual_seed(3)
+            mm = SemStereoTrainGlue(64).to(DEV).train()
+            ls, _ = T.total_loss(mm(fl, fr), disp, disp4, label, 64)
+            ls.backward()
+            return {n: p.grad.clone() for n, p in mm.named_parameters() if p.grad is not None}
+        finally:
+            train_ops.set_tensor_core_route(True)
+    g_tc, g_f32 = native_grads(True), native_grads(False)
+    for n, b in g_f32.items():
+        if n.startswith(("hourglass_att", "classif_att_", "patch")) and b.abs().max().item() > 1e-6:
+            assert relerr(g_tc[n], b) <= 5e-2, (n, relerr(g_tc[n], b))
+
+
+@pytest.mark.parametrize("Cin,Cout,k", [(1, 6, 3), (6, 6, 1), (6, 1, 1)])
+def test_small_channel_conv2d_of_ssr_upsample(Cin, Cout, k):
+    """The SSR_upsample convs on the small-channel kernels (forward, dX = the same kernel with the flipped / transposed weight, dW)."""
+    g = torch.Generator().manual_seed(10 * Cin + Cout + k)
+    x = torch.randn(2, Cin, 37, 52, generator=g).to(DEV).requires_grad_(True)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(DEV).requires_grad_(True)
+    b = torch.randn(Cout, generator=g).to(DEV).requires_grad_(True)
+    y = train_ops.conv2d(x, w, b)
+    ref = F.conv2d(x, w, b, 1, k // 2)
+    assert relerr(y, ref) <= 1e-5
+    gy = torch.randn(ref.shape, generator=g).to(DEV)
+    gx, gw, gb = torch.autograd.grad(y, (x, w, b), gy)
+    rx, rw, rb = torch.autograd.grad(ref, (x, w, b), gy)
+    assert relerr(gx, rx) <= 1e-5 and relerr(gw, rw) <= 1e-4 and relerr(gb, rb) <= 1e-5, (relerr(gx, rx), relerr(gw, rw))
