@@ -25,17 +25,25 @@ struct WgP {
   int tiles_co;
 };
 
-__global__ void __launch_bounds__(256) conv3d_wgrad_kernel(const WgP p) {
+// 64 threads per CTA, each owns a 4 (ci) x 4 (co) register tile of the 32 x 32 block: per staged voxel a thread reads 4 + 4 shared
+// values (broadcast within the warp: 4 / 8 distinct addresses) for 16 FMAs.  (Round 1's version gave every one of 256 threads a 2 x 2
+// tile -- one FMA per shared load, 8 TFLOP/s on the 32 -> 32 layer; this one is still bound by the shared-memory pipe, at 2 FMAs per
+// load.)
+__global__ void __launch_bounds__(64) conv3d_wgrad_kernel(const WgP p) {
   __shared__ float Xs[WG_T][WG_V + 1];
   __shared__ float Ys[WG_T][WG_V + 1];
   const int tap = blockIdx.y;
   const int kd = tap / (p.K * p.K), kh = (tap / p.K) % p.K, kw = tap % p.K;
   const int ci0 = (blockIdx.z / p.tiles_co) * WG_T, co0 = (blockIdx.z % p.tiles_co) * WG_T;
-  const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;          // thread owns ci {ti, ti+16} x co {tj, tj+16}
+  const int tid = threadIdx.x, ti = tid >> 3, tj = tid & 7;            // thread owns ci 4*ti .. +3  x  co 4*tj .. +3
   const long long m0 = (long long)blockIdx.x * WG_CHUNK, m1 = min(p.M, m0 + WG_CHUNK);
   const size_t in_cs = (size_t)p.Di * p.Hi * p.Wi, out_cs = (size_t)p.Do * p.Ho * p.Wo;
-  const int lv = tid & 31, lc = tid >> 5;                              // loader: voxel lv, channels lc, lc+8, lc+16, lc+24
-  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  const int lv = tid & 31, lc = tid >> 5;                              // loader: voxel lv, channels lc, lc+2, ..., lc+30
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
   for (long long mb = m0; mb < m1; mb += WG_V) {
     const long long m = mb + lv;
     bool ok = m < m1;
@@ -48,26 +56,32 @@ __global__ void __launch_bounds__(256) conv3d_wgrad_kernel(const WgP p) {
     const bool xin = ok && di >= 0 && di < p.Di && hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi;
     const size_t xo = ((size_t)(xin ? di : 0) * p.Hi + (xin ? hi : 0)) * p.Wi + (xin ? wi : 0);
     const size_t yo = ((size_t)od * p.Ho + oh) * p.Wo + ow;
+    const float* xp = p.x + ((size_t)b * p.Cin + ci0 + lc) * in_cs + xo;
+    const float* yp = p.dy + ((size_t)b * p.Cout + co0 + lc) * out_cs + yo;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int c = lc + 8 * q;
-      Xs[c][lv] = (xin && ci0 + c < p.Cin) ? __ldg(p.x + ((size_t)b * p.Cin + ci0 + c) * in_cs + xo) : 0.0f;
-      Ys[c][lv] = (ok && co0 + c < p.Cout) ? __ldg(p.dy + ((size_t)b * p.Cout + co0 + c) * out_cs + yo) : 0.0f;
+    for (int q = 0; q < 16; ++q) {
+      const int c = lc + 2 * q;
+      Xs[c][lv] = (xin && ci0 + c < p.Cin) ? __ldg(xp + (size_t)(2 * q) * in_cs) : 0.0f;
+      Ys[c][lv] = (ok && co0 + c < p.Cout) ? __ldg(yp + (size_t)(2 * q) * out_cs) : 0.0f;
     }
     __syncthreads();
-#pragma unroll
+#pragma unroll 8
     for (int v = 0; v < WG_V; ++v) {
-      const float x0 = Xs[ti][v], x1 = Xs[ti + 16][v], y0 = Ys[tj][v], y1 = Ys[tj + 16][v];
-      acc[0][0] = fmaf(x0, y0, acc[0][0]); acc[0][1] = fmaf(x0, y1, acc[0][1]);
-      acc[1][0] = fmaf(x1, y0, acc[1][0]); acc[1][1] = fmaf(x1, y1, acc[1][1]);
+      float xv[4], yv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) { xv[a] = Xs[4 * ti + a][v]; yv[a] = Ys[4 * tj + a][v]; }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(xv[a], yv[c], acc[a][c]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int ci = ci0 + ti + 16 * a, co = co0 + tj + 16 * c;
+    for (int c = 0; c < 4; ++c) {
+      const int ci = ci0 + 4 * ti + a, co = co0 + 4 * tj + c;
       if (ci < p.Cin && co < p.Cout) atomicAdd(p.dw + ((size_t)tap * p.Cin + ci) * p.Cout + co, acc[a][c]);
     }
 }
@@ -170,7 +184,7 @@ extern "C" int ss_conv3d_wgrad_f32(const float* x, const float* grad_out, float*
   const long long chunks = ceil_div64(p.M, WG_CHUNK);
   const int tiles = ceil_div(Cin, WG_T) * p.tiles_co;
   SS_UNSUPPORTED(chunks > 0x7fffffffLL || tiles > 65535, "ss_conv3d_wgrad_f32: grid dimension too large");
-  conv3d_wgrad_kernel<<<dim3((unsigned)chunks, K * K * K, tiles), 256, 0, (cudaStream_t)stream>>>(p);
+  conv3d_wgrad_kernel<<<dim3((unsigned)chunks, K * K * K, tiles), 64, 0, (cudaStream_t)stream>>>(p);
   SS_CHECK_LAUNCH("ss_conv3d_wgrad_f32");
   return SS_OK;
 }
