@@ -3,7 +3,8 @@
 // model trains (main_us3d.py:186-222): the weight gradient of Conv3d, and BatchNorm3d with BATCH statistics, forward and backward.
 //   * input gradient of Conv3d: no new kernel -- dX of a k3 s1 conv is the k3 s1 conv of dY with the flipped / transposed weight,
 //     dX of a k3 s2 p1 conv is ConvTranspose3d(k3, s2, p1, op1) of dY with the same weight, dX of a k1 conv is the k1 conv with
-//     W^T: all three are launches of ss_conv3d_f32 (csrc/conv3d_f32.cu) with a re-packed weight (semstereo_b200/train_ops.py);
+//     W^T: all three are launches of the forward kernels with a re-packed weight (semstereo_b200/train_ops.py: the bf16x3
+//     tensor-core kernels where the layer has such a configuration, else ss_conv3d_f32 of csrc/conv3d_f32.cu);
 //   * conv3d_wgrad: dW[tap][ci][co] = sum over (b, output voxel o) of dY[b,co,o] * X[b,ci, o*stride - pad + tap]
 //     -- a GEMM with K = B * output voxels, split over CTAs along K, fp32 FFMA, atomic accumulation into a zeroed dW;
 //   * bn_stats / bn_apply / bn_backward: per-channel batch mean and biased variance over (B, D, H, W), normalise + affine

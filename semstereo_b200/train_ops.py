@@ -18,7 +18,8 @@ The stateless operators of the surface (volume builders, regression, warps, prop
 (torch_ops.py / csrc/backward.cu).  With these the reference model TRAINS through the level-1 drop-in: every module /
 function it takes from models.submodule(_other) is differentiable on the CUDA kernels; what the model does inline
 (nn.ConvTranspose3d, the `patch` / classifier nn.Conv3d, interpolate, softmax, sort, gather, the 2-D decoder) is torch, as in the
-reference.  fp32 FFMA kernels: a first correct training path, not a fast one (tools/train_step.py measures it)."""
+reference.  Forward and dX of the k = 3 layers run on the bf16x3 tensor-core kernels (fp32-accurate), dW and the rest are fp32 FFMA
+kernels; tools/train_step.py measures the step (config #5)."""
 from __future__ import annotations
 
 import ctypes
