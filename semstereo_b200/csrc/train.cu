@@ -28,11 +28,11 @@ struct WgP {
 
 // 64 threads per CTA, each owns a 4 (ci) x 4 (co) register tile of the 32 x 32 block: per staged voxel a thread reads 4 + 4 shared
 // values (broadcast within the warp: 4 / 8 distinct addresses) for 16 FMAs.  (Round 1's version gave every one of 256 threads a 2 x 2
-// tile -- one FMA per shared load, 8 TFLOP/s on the 32 -> 32 layer; this one is still bound by the shared-memory pipe, at 2 FMAs per
-// load.)
+// tile -- one FMA per shared load, 8 TFLOP/s on the 32 -> 32 layer.)  The staged tiles are [voxel][channel], so the 4 + 4 values are two
+// 128-bit loads for 16 FMAs.
 __global__ void __launch_bounds__(64) conv3d_wgrad_kernel(const WgP p) {
-  __shared__ float Xs[WG_T][WG_V + 1];
-  __shared__ float Ys[WG_T][WG_V + 1];
+  __shared__ __align__(16) float Xs[WG_V][WG_T + 4];                   // [voxel][channel]: a thread's 4 channels are one 128-bit load
+  __shared__ __align__(16) float Ys[WG_V][WG_T + 4];
   const int tap = blockIdx.y;
   const int kd = tap / (p.K * p.K), kh = (tap / p.K) % p.K, kw = tap % p.K;
   const int ci0 = (blockIdx.z / p.tiles_co) * WG_T, co0 = (blockIdx.z % p.tiles_co) * WG_T;
@@ -62,15 +62,14 @@ __global__ void __launch_bounds__(64) conv3d_wgrad_kernel(const WgP p) {
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
       const int c = lc + 2 * q;
-      Xs[c][lv] = (xin && ci0 + c < p.Cin) ? __ldg(xp + (size_t)(2 * q) * in_cs) : 0.0f;
-      Ys[c][lv] = (ok && co0 + c < p.Cout) ? __ldg(yp + (size_t)(2 * q) * out_cs) : 0.0f;
+      Xs[lv][c] = (xin && ci0 + c < p.Cin) ? __ldg(xp + (size_t)(2 * q) * in_cs) : 0.0f;
+      Ys[lv][c] = (ok && co0 + c < p.Cout) ? __ldg(yp + (size_t)(2 * q) * out_cs) : 0.0f;
     }
     __syncthreads();
 #pragma unroll 8
     for (int v = 0; v < WG_V; ++v) {
-      float xv[4], yv[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) { xv[a] = Xs[4 * ti + a][v]; yv[a] = Ys[4 * tj + a][v]; }
+      const float4 x4 = *reinterpret_cast<const float4*>(&Xs[v][4 * ti]), y4 = *reinterpret_cast<const float4*>(&Ys[v][4 * tj]);
+      const float xv[4] = {x4.x, x4.y, x4.z, x4.w}, yv[4] = {y4.x, y4.y, y4.z, y4.w};
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
