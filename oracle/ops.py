@@ -302,14 +302,21 @@ def deconv3d_bn(x, p, conv, bn):
 
 
 def window_attention3d(x, p, prefix, num_heads, block):
-    """attention_block.forward (submodule_other.py:805-837) for window-divisible H, W
-    (the padded/masked branch is not restated; H,W multiples of the window are required).
-    qkv output channel = which*C + head*hd + j; tokens of one (bd,bh,bw) window attend to
-    each other; output channel = head*hd + j; then 1x1x1 conv with bias; no residual."""
-    B, C, D, H, W = x.shape
+    """attention_block.forward (submodule_other.py:805-837), including its padded / masked branch (:809-812, :822-829, :835-836):
+    H and W are zero-padded (bottom / right) to multiples of the window BEFORE the qkv Linear (so a padded token carries the bias),
+    scores between a padded and a real token get -1000, and the padding is cropped before the final 1x1x1 conv.
+    Faithful to two quirks of the reference: D is never padded (it must divide), and the mask is built with
+    `mask[:, -pad_b:, :] = 1; mask[:, :, -pad_r:] = 1` -- when exactly one of pad_b / pad_r is 0, `-0:` selects EVERYTHING, the mask
+    is all ones and nothing is masked (the padded tokens then take part in the softmax of their window like real ones).
+    qkv output channel = which*C + head*hd + j; tokens of one (bd,bh,bw) window attend to each other; output channel = head*hd + j;
+    then 1x1x1 conv with bias; no residual."""
+    B, C, D, H0, W0 = x.shape
     bd, bh, bw = block
-    if D % bd or H % bh or W % bw:
-        raise ValueError("window_attention3d: D,H,W must be multiples of the window")
+    if D % bd:
+        raise ValueError("window_attention3d: D must be a multiple of the window depth (the reference does not pad it)")
+    pad_r, pad_b = (bw - W0 % bw) % bw, (bh - H0 % bh) % bh
+    x = F.pad(x, (0, pad_r, 0, pad_b))
+    H, W = H0 + pad_b, W0 + pad_r
     nd, nh, nw = D // bd, H // bh, W // bw
     hd = C // num_heads
     t = x.reshape(B, C, nd, bd, nh, bh, nw, bw).permute(0, 2, 4, 6, 3, 5, 7, 1)
@@ -317,10 +324,20 @@ def window_attention3d(x, p, prefix, num_heads, block):
     qkv = F.linear(t, p[prefix + ".qkv_3d.weight"], p[prefix + ".qkv_3d.bias"])
     qkv = qkv.reshape(B, -1, bd * bh * bw, 3, num_heads, hd).permute(3, 0, 1, 4, 2, 5)
     q, k, v = qkv[0], qkv[1], qkv[2]                                      # (B, win, head, tok, hd)
-    a = torch.softmax((q @ k.transpose(-2, -1)) * (hd ** -0.5), dim=-1)
+    s = (q @ k.transpose(-2, -1)) * (hd ** -0.5)
+    if pad_r > 0 or pad_b > 0:
+        mask = torch.zeros((H, W), device=x.device)
+        mask[H - pad_b if pad_b else 0:, :] = 1                           # `-0:` == everything
+        mask[:, W - pad_r if pad_r else 0:] = 1
+        mask = mask.reshape(nh, bh, nw, bw).permute(0, 2, 1, 3).reshape(nh * nw, bh * bw)          # (hw windows, hw tokens)
+        am = mask.unsqueeze(1) - mask.unsqueeze(2)
+        am = torch.where(am != 0, torch.full_like(am, -1000.0), torch.zeros_like(am))             # (nh*nw, bh*bw, bh*bw)
+        am = am.repeat(nd, bd, bd)                                                                  # (win, tok, tok): same for every depth
+        s = s + am.unsqueeze(0).unsqueeze(2)
+    a = torch.softmax(s, dim=-1)
     o = a @ v                                                             # (B, win, head, tok, hd)
     o = o.reshape(B, nd, nh, nw, num_heads, bd, bh, bw, hd).permute(0, 4, 8, 1, 5, 2, 6, 3, 7)
-    o = o.reshape(B, C, D, H, W)
+    o = o.reshape(B, C, D, H, W)[:, :, :, :H0, :W0]
     return F.conv3d(o, p[prefix + ".final1x1.weight"], p[prefix + ".final1x1.bias"])
 
 

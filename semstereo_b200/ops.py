@@ -185,13 +185,42 @@ def conv3d_cout1_f32(x, weight):
 
 
 # ---- K5 ----------------------------------------------------------------------------------------------
+def window_pad(t, block):
+    """Zero-pads axes 3 (H) and 4 (W) of a (B,C,D,H,W) / blocked (B,C/8,D,H,W,8) tensor to multiples of the window, as
+    attention_block.forward does before its qkv Linear (submodule_other.py:809-812).  Returns (tensor, H0, W0).
+    Supported: padding on ONE of the two axes -- the reference's mask `mask[:, -pad_b:, :] = 1; mask[:, :, -pad_r:] = 1` is all ones
+    when exactly one pad is 0 (`-0:` selects everything), so nothing is masked and the padded tokens (which carry the qkv bias) simply
+    take part in their window's softmax: the unmodified kernels on the padded volume, cropped afterwards, ARE that computation.
+    Padding on both axes needs the -1000 score mask between padded and real tokens, which the kernels do not have: refused."""
+    D, H, W = t.shape[2], t.shape[3], t.shape[4]
+    if D % block[0]:
+        raise NotImplementedError(f"window attention: depth {D} is not a multiple of the window depth {block[0]} (the reference does not pad D)")
+    pb, pr = (-H) % block[1], (-W) % block[2]
+    if pb and pr:
+        raise NotImplementedError(f"window attention: H = {H} and W = {W} both need padding to the window {tuple(block)[1:]}: the "
+                                  "reference's masked branch (submodule_other.py:822-829) is not implemented on the B200 path")
+    if not (pb or pr):
+        return t, H, W
+    shape = list(t.shape)
+    shape[3], shape[4] = H + pb, W + pr
+    out = t.new_zeros(shape)
+    out[:, :, :, :H, :W] = t
+    return out, H, W
+
+
+def window_crop(t, H0, W0):
+    """Inverse of window_pad on the output (submodule_other.py:835-836)."""
+    return t if (t.shape[3], t.shape[4]) == (H0, W0) else t[:, :, :, :H0, :W0].contiguous()
+
+
 def window_attention3d(x, wqkv_t, bqkv, wo_t, bo, block, num_heads=16):
     dev = _require_cuda(x, wqkv_t, bqkv, wo_t, bo)
+    x, H0, W0 = window_pad(x, block)
     B, C, D, H, W = x.shape
     out = torch.empty_like(x)
     _call("ss_window_attention3d", dev, _ptr(x), _ptr(wqkv_t), _ptr(bqkv), _ptr(wo_t), _ptr(bo), _ptr(out), B, C, D, H, W,
           int(block[0]), int(block[1]), int(block[2]), int(num_heads))
-    return out
+    return window_crop(out, H0, W0)            # the final 1x1x1 conv is position-wise: cropping after it equals cropping before it
 
 
 # ---- K6 / K7 / K8 ------------------------------------------------------------------------------------

@@ -114,9 +114,10 @@ def make_params(seed: int = 1, peaked: float = 1.0, gamma: float = 0.05) -> "Ord
 def make_inputs(seed: int, B: int, H: int, W: int, num_classes: int = 6, max_shift: int = 3):
     """Seeded synthetic inputs of the hot path for a (B,3,H,W) stereo pair (CPU fp32).
     Right features are the left ones displaced along x by a row-block-dependent shift plus noise,
-    so the cost volumes have real structure.  H, W must be multiples of 128 (the two
-    window-attention stages need H/32 % 4 == 0 and W/32 % 4 == 0)."""
-    assert H % 128 == 0 and W % 128 == 0, "H and W must be multiples of 128"
+    so the cost volumes have real structure.  H, W must be multiples of 64 (three stride-2 stages below 1/4 resolution, and the
+    4-wide attention window of the main hourglass at H/16); a multiple of 64 that is not one of 128 makes the attention-branch
+    hourglass pad its window at H/32 (attention_block's padded branch, submodule_other.py:809-836)."""
+    assert H % 64 == 0 and W % 64 == 0, "H and W must be multiples of 64"
     g = torch.Generator().manual_seed(seed)
 
     def pair(c, h, w, scale):

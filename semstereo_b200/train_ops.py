@@ -199,8 +199,14 @@ def attention_block_train(mod, x):
     of the differentiable conv3d above (+ bias), the softmax core in between has its own forward / backward kernels."""
     block = mod.block if isinstance(mod.block, (tuple, list)) else (mod.block,) * 3
     C = mod.qkv_3d.in_features
+    H0, W0 = x.shape[3], x.shape[4]
+    pb, pr = (-H0) % block[1], (-W0) % block[2]
+    if pb and pr:       # the reference's -1000 mask between padded and real tokens (submodule_other.py:822-829); see ops.window_pad
+        raise NotImplementedError("attention_block (training): H and W both need padding to the window: masked branch not implemented")
+    if pb or pr:        # one axis: zero-pad before the qkv Linear, crop before the final conv -- nothing is masked (ops.window_pad)
+        x = torch.nn.functional.pad(x, (0, pr, 0, pb))
     qkv = conv3d(x, mod.qkv_3d.weight.view(3 * C, C, 1, 1, 1), 1) + mod.qkv_3d.bias.view(1, -1, 1, 1, 1)
-    o = _AttnCoreFn.apply(qkv, block, mod.num_heads)
+    o = _AttnCoreFn.apply(qkv, block, mod.num_heads)[:, :, :, :H0, :W0]
     return conv3d(o, mod.final1x1.weight, 1) + mod.final1x1.bias.view(1, -1, 1, 1, 1)
 
 

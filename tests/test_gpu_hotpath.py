@@ -301,3 +301,23 @@ def test_path_is_bitwise_reproducible(precision):
     for o in outs[1:]:
         for k, v in o.items():
             assert torch.equal(v, outs[0][k]), k
+
+
+@pytest.mark.parametrize("precision", ["fp32", "split", "bf16"])
+def test_width_that_needs_window_padding(precision):
+    """128 x 192 images: the attention-branch hourglass reaches its attention block at W/32 = 6, not a multiple of the 4-wide window,
+    so the block zero-pads W to 8 (one axis: the reference masks nothing there) and crops afterwards (submodule_other.py:809-836).
+    The oracle restates that branch and is pinned to the reference module by tests/golden/att_padded.npz."""
+    p = make_params(seed=1, peaked=20.0)
+    inp = make_inputs(9, 1, 128, 192)
+    ref = oh.forward(p, inp, 64, signed=True, keep=True)
+    m = DisparityHotPath(64, False, True, precision=precision)
+    m.load_state_dict(p, strict=True)
+    out = run(m.to(DEV), inp)
+    if precision == "bf16":
+        e = (out["pred_up"] - ref["pred_up"]).abs().flatten()
+        assert e.median().item() <= 0.05 and maxerr(out["cost_att"], ref["cost_att"]) <= 0.5
+    else:
+        same = (out["ind_k"] == ref["ind_k"]).all(dim=2)
+        assert same.float().mean().item() >= 0.999
+        assert maxerr(out["cost_att"], ref["cost_att"]) <= (2e-4 if precision == "fp32" else 2e-3)

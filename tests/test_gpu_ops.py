@@ -266,3 +266,22 @@ def test_torch_library_ops_match_the_wrappers():
     assert torch.equal(torch.ops.semstereo_b200.concat_volume(l, r, 4, False), ops.concat_volume(l, r, 4, False))
     c, d = torch.randn(1, 24, 8, 32, generator=g).to(DEV), torch.randn(1, 24, 8, 32, generator=g).to(DEV)
     assert torch.equal(torch.ops.semstereo_b200.regression_topk(c, d, 2), ops.regression_topk(c, d, 2))
+
+
+def test_window_attention_on_padded_windows(golden_dir):
+    """attention_block on H / W that are not multiples of the window, against outputs of the unmodified reference module
+    (tests/golden/att_padded.npz): padding on one axis is supported (nothing is masked there, see ops.window_pad); padding on both
+    axes needs the reference's score mask and is refused loudly."""
+    from oracle.make_golden_attpad import CASES
+    g = dict(np.load(os.path.join(golden_dir, "att_padded.npz")))
+    p = make_params(seed=2)
+    wq = p["hourglass.attention_block.qkv_3d.weight"].t().contiguous()
+    wo = p["hourglass.attention_block.final1x1.weight"].reshape(128, 128).t().contiguous()
+    args = (cu(wq), cu(p["hourglass.attention_block.qkv_3d.bias"]), cu(wo), cu(p["hourglass.attention_block.final1x1.bias"]))
+    for name, (block, shape) in CASES.items():
+        x = cu(torch.from_numpy(g["in_" + name]))
+        if name.startswith("both"):
+            with pytest.raises(NotImplementedError):
+                ops.window_attention3d(x, *args, block, 16)
+        else:
+            assert err(ops.window_attention3d(x, *args, block, 16), g["out_" + name]) <= 5e-5, name

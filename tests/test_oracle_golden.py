@@ -132,3 +132,16 @@ def test_decoder_oracle_matches_reference_modules(golden_dir):
     full = oh.forward(p, {k: out[k] for k in ("f8_l", "f8_r", "f4_l", "f4_r", "spx_pred", "pred_label")}, 64, signed=True)
     diff = (full["pred_up"] * 4 - torch.from_numpy(g["model_disp"])).abs()
     assert diff.median().item() <= 1e-3 and (diff > 1e-2).float().mean().item() <= 0.02     # top-k ties may flip isolated pixels
+
+
+def test_attention_block_padded_and_masked_windows(golden_dir):
+    """attention_block on H / W that are not multiples of the window (submodule_other.py:809-812, 822-829, 835-836): pad on one side
+    only (the reference's `-0:` slice makes the mask all ones: nothing is masked) and on both (masked), both window shapes;
+    tests/golden/att_padded.npz holds outputs of the unmodified reference module (oracle/make_golden_attpad.py)."""
+    from oracle.make_golden_attpad import CASES
+    g = dict(np.load(os.path.join(golden_dir, "att_padded.npz")))
+    p = make_params(seed=2)
+    for name, (block, shape) in CASES.items():
+        x = torch.from_numpy(g["in_" + name])
+        assert tuple(x.shape) == shape
+        close(oo.window_attention3d(x, p, "hourglass.attention_block", 16, block), g["out_" + name], 2e-5, name)
