@@ -235,9 +235,10 @@ def test_error_behaviour():
         sub_s.disparity_regression(torch.zeros(1, 8, 4, device=DEV), 4)
     with pytest.raises(RuntimeError):
         sub_s.disparity_regression(torch.zeros(1, 6, 4, 4, device=DEV), 4)   # bins != 2*maxdisp
-    with pytest.raises(NotImplementedError):
-        ops.window_attention3d(torch.zeros(1, 128, 4, 6, 8, device=DEV), torch.zeros(128, 384, device=DEV), torch.zeros(384, device=DEV),
-                               torch.zeros(128, 128, device=DEV), torch.zeros(128, device=DEV), (4, 4, 4))
+    for shape in ((1, 128, 4, 6, 10), (1, 128, 5, 8, 8)):      # H and W both need window padding (masked branch) / D does not divide
+        with pytest.raises(NotImplementedError):
+            ops.window_attention3d(torch.zeros(shape, device=DEV), torch.zeros(128, 384, device=DEV), torch.zeros(384, device=DEV),
+                                   torch.zeros(128, 128, device=DEV), torch.zeros(128, device=DEV), (4, 4, 4))
     with pytest.raises(RuntimeError):
         ops.gwc_volume(torch.zeros(1, 8, 4, 8), torch.zeros(1, 8, 4, 8), 2, 2)   # CPU tensors: no fallback
 
