@@ -23,10 +23,6 @@ __device__ __forceinline__ void lin4(int dst, int n_in, int& i0, int& i1, float&
   l0 = 1.0f - l1;
 }
 
-__device__ __forceinline__ float sel3(float v0, float v1, float v2, int idx, int i0, int i1) {
-  return idx == i0 ? v0 : (idx == i1 ? v1 : v2);
-}
-
 // One thread = 4 consecutive full-res pixels (one low-res column x): the 3x6 upsampled neighbourhood is built from 18
 // low-res loads, spx / label / output move as 128-bit vectors.  The arithmetic per pixel is unchanged.
 // Fast-math sigmoid / softmax pieces of the class gate (ex2.approx + rcp.approx, ~2 ulp each; the gate multiplies a residual
