@@ -321,10 +321,21 @@ SS_API int ss_bn_train_backward(const float* x, const float* grad_out, const flo
 /* attention_block in training mode (submodule_other.py:805-837): the qkv Linear and the final 1x1x1 conv are k = 1 layers of the
  * differentiable conv above; in between, the fp32 softmax core with an fp32 NCDHW output (qkv (B,3C,D,H,W) -> (B,C,D,H,W)) and its
  * backward (grad_out (B,C,D,H,W) -> grad_qkv (B,3C,D,H,W)).  C = 128, 16 heads, windows <= 96 tokens (forward: 64 / 96, bw = 4). */
+/* The masked softmax core of attention_block's padded branch (models/submodule_other.py:809-829) for volumes whose H AND W were both
+ * zero-padded to the window: qkv (B,3C,D,H,W) fp32 is the qkv Linear of the PADDED volume, tokens with h >= H0 or w >= W0 are padding,
+ * a score between a padded and a real token gets -1000 before the softmax.  Output fp32 (B,C,D,H,W), channel = head*hd + j; the caller
+ * crops to (H0, W0) and applies the final 1x1x1 conv.  (With one padded axis the reference masks nothing: the unmasked entry points on
+ * the padded volume are exact.) */
+SS_API int ss_window_attention_core_f32_masked(const float* qkv, float* out_f32, int B, int C, int D, int H, int W, int bd, int bh, int bw,
+                                               int num_heads, int H0, int W0, void* stream);
 SS_API int ss_window_attention_core_f32_out(const float* qkv, float* out_f32, int B, int C, int D, int H, int W, int bd, int bh, int bw,
                                             int num_heads, void* stream);
 SS_API int ss_window_attention_core_backward(const float* qkv, const float* grad_out, float* grad_qkv, int B, int C, int D, int H, int W,
                                              int bd, int bh, int bw, int num_heads, void* stream);
+/* The same backward for the masked core (ss_window_attention_core_f32_masked): qkv / grad_out / grad_qkv of the PADDED volume, tokens with
+ * h >= H0 or w >= W0 are padding.  H0 = H and W0 = W is the unmasked backward. */
+SS_API int ss_window_attention_core_backward_masked(const float* qkv, const float* grad_out, float* grad_qkv, int B, int C, int D, int H, int W,
+                                                    int bd, int bh, int bw, int num_heads, int H0, int W0, void* stream);
 /* F.interpolate(scale_factor 4, bilinear, align_corners=False) of `planes` fp32 (h,w) planes and its VJP (SSR_upsample in training
  * mode, submodule.py:424, composed from differentiable kernels because its BatchNorm layers then need batch statistics). */
 SS_API int ss_bilinear_up4(const float* in, float* out, int planes, int h, int w, void* stream);

@@ -47,7 +47,9 @@ SIGNATURES = {
     "ss_disparity_variance_backward": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "ss_spatial_transformer_grid_backward": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "ss_window_attention_core_f32_out": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "ss_window_attention_core_f32_masked": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "ss_window_attention_core_backward": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "ss_window_attention_core_backward_masked": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "ss_bilinear_up4": [_P, _P, _I, _I, _I, _P],
     "ss_bilinear_up4_backward": [_P, _P, _I, _I, _I, _P],
     "ss_conv3d_wgrad_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],

@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(256, 2) window_attention_core_f32_kernel(const
 //   dQ_i = scale sum_j dS_ij k_j;  dK_j = scale sum_i dS_ij q_i.        qkv, dqkv (B,3C,D,H,W); dO (B,C,D,H,W).
 __global__ void __launch_bounds__(96) window_attention_core_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_out,
                                                                        float* __restrict__ d_qkv, int D, int H, int W, int bd, int bh, int bw,
-                                                                       int nd, int nh, int nw, int T) {
+                                                                       int nd, int nh, int nw, int T, int H0, int W0) {
   extern __shared__ __align__(16) float smem[];
   float* Qs = smem;                    // [T][8]
   float* Ks = Qs + T * kHd;
@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(96) window_attention_core_bwd_kernel(const flo
   float* Gs = Vs + T * kHd;            // dO
   float* Ps = Gs + T * kHd;            // [T][T+1]
   float* Ss = Ps + T * (T + 1);        // dS [T][T+1]
+  float* padf = Ss + T * (T + 1);      // [T] 1 = a zero-padded token (h >= H0 or w >= W0); the masked branch, all 0 otherwise
   const int h = blockIdx.x % kHeads;
   int wid = blockIdx.x / kHeads;
   const int wx = wid % nw;  wid /= nw;
@@ -334,6 +335,7 @@ __global__ void __launch_bounds__(96) window_attention_core_bwd_kernel(const flo
   if (i < T) {
     const int dd = i / bhw, r = i - dd * bhw, hh = r / bw, ww = r - hh * bw;
     vo = wbase + ((size_t)dd * H + hh) * W + ww;
+    padf[i] = (wy * bh + hh >= H0 || wx * bw + ww >= W0) ? 1.0f : 0.0f;
 #pragma unroll
     for (int j = 0; j < kHd; ++j) {
       const size_t c = (size_t)h * kHd + j;
@@ -350,11 +352,13 @@ __global__ void __launch_bounds__(96) window_attention_core_bwd_kernel(const flo
 #pragma unroll
     for (int j = 0; j < kHd; ++j) { q[j] = Qs[i * kHd + j]; g[j] = Gs[i * kHd + j]; }
     float m = -INFINITY;
+    const float pq = padf[i];
     for (int t = 0; t < T; ++t) {
       float x = 0.f;
 #pragma unroll
       for (int j = 0; j < kHd; ++j) x = fmaf(q[j], Ks[t * kHd + j], x);
       x *= scale;
+      if (padf[t] != pq) x += -1000.0f;                  // attn_mask: an additive constant, so only P changes, not the gradient formulas
       Ps[i * (T + 1) + t] = x;
       m = fmaxf(m, x);
     }
@@ -403,6 +407,100 @@ __global__ void __launch_bounds__(96) window_attention_core_bwd_kernel(const flo
 
 }  // namespace
 
+// The MASKED core: the padded / masked branch of attention_block (submodule_other.py:809-829) when BOTH H and W were zero-padded to the
+// window.  qkv is the qkv Linear of the PADDED volume (a padded token carries the bias); tokens with h >= H0 or w >= W0 are padding,
+// and a score between a padded and a real token gets -1000 before the softmax, exactly as the reference's attn_mask.  fp32 output
+// (B,C,D,H,W), channel = head*hd + j; the caller crops it to (H0, W0) and applies the final 1x1x1 conv.  (One padded axis needs no
+// mask -- the reference's `mask[:, -0:, :]` quirk -- and runs on the unmasked kernels, see ops.window_pad.)
+namespace {
+__global__ void __launch_bounds__(256) window_attention_core_f32_masked_kernel(const float* __restrict__ qkv, float* __restrict__ out, int D, int H,
+                                                                                int W, int bd, int bh, int bw, int nd, int nh, int nw, int T,
+                                                                                int H0, int W0) {
+  extern __shared__ __align__(16) float smem[];        // [3][heads][T][hd] then T pad flags
+  int wid = blockIdx.x;
+  const int wx = wid % nw;  wid /= nw;
+  const int wy = wid % nh;  wid /= nh;
+  const int wz = wid % nd;
+  const int b = wid / nd;
+  const size_t cs = (size_t)D * H * W;
+  const size_t wbase = ((size_t)wz * bd * H + (size_t)wy * bh) * W + (size_t)wx * bw;
+  const int bhw = bh * bw;
+  auto tok_off = [&](int t) -> size_t {
+    const int dd = t / bhw, r = t - dd * bhw, hh = r / bw, ww = r - hh * bw;
+    return ((size_t)dd * H + hh) * W + ww;
+  };
+  float* padf = smem + (size_t)3 * kC * T;
+  const float* src = qkv + (size_t)b * 3 * kC * cs + wbase;
+  for (int i = threadIdx.x; i < 3 * kC * T; i += blockDim.x) {
+    const int c = i / T, t = i - c * T;                 // c = which*C + head*hd + j
+    smem[((size_t)(c >> 3) * T + t) * kHd + (c & 7)] = __ldg(src + (size_t)c * cs + tok_off(t));
+  }
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const int r = t % bhw, hh = r / bw, ww = r - hh * bw;
+    padf[t] = (wy * bh + hh >= H0 || wx * bw + ww >= W0) ? 1.0f : 0.0f;
+  }
+  __syncthreads();
+  const float scale = 0.35355339059327379f;             // hd^-0.5 with hd = 8
+  const float* Q = smem;
+  const float* Km = smem + (size_t)kHeads * T * kHd;
+  const float* V = smem + (size_t)2 * kHeads * T * kHd;
+  float* ob = out + (size_t)b * kC * cs + wbase;
+  for (int id = threadIdx.x; id < kHeads * T; id += blockDim.x) {
+    const int tq = id % T, h = id / T;
+    const float pq = padf[tq];
+    float q[kHd];
+    {
+      const float4* qp = reinterpret_cast<const float4*>(Q + ((size_t)h * T + tq) * kHd);
+      const float4 a = qp[0], c = qp[1];
+      q[0] = a.x * scale; q[1] = a.y * scale; q[2] = a.z * scale; q[3] = a.w * scale;
+      q[4] = c.x * scale; q[5] = c.y * scale; q[6] = c.z * scale; q[7] = c.w * scale;
+    }
+    const float4* kp = reinterpret_cast<const float4*>(Km + (size_t)h * T * kHd);
+    const float4* vp = reinterpret_cast<const float4*>(V + (size_t)h * T * kHd);
+    float m = -INFINITY, l = 0.0f, o[kHd];
+#pragma unroll
+    for (int j = 0; j < kHd; ++j) o[j] = 0.0f;
+    for (int tk = 0; tk < T; ++tk) {
+      const float4 a = kp[2 * tk], c = kp[2 * tk + 1];
+      float sc = q[0] * a.x;
+      sc = fmaf(q[1], a.y, sc); sc = fmaf(q[2], a.z, sc); sc = fmaf(q[3], a.w, sc);
+      sc = fmaf(q[4], c.x, sc); sc = fmaf(q[5], c.y, sc); sc = fmaf(q[6], c.z, sc); sc = fmaf(q[7], c.w, sc);
+      if (padf[tk] != pq) sc += -1000.0f;                // attn + attn_mask (submodule_other.py:826-829)
+      const float mn = fmaxf(m, sc);
+      const float corr = expf(m - mn), pe = expf(sc - mn);
+      m = mn;
+      l = fmaf(l, corr, pe);
+      const float4 va = vp[2 * tk], vc = vp[2 * tk + 1];
+      o[0] = fmaf(o[0], corr, pe * va.x); o[1] = fmaf(o[1], corr, pe * va.y); o[2] = fmaf(o[2], corr, pe * va.z); o[3] = fmaf(o[3], corr, pe * va.w);
+      o[4] = fmaf(o[4], corr, pe * vc.x); o[5] = fmaf(o[5], corr, pe * vc.y); o[6] = fmaf(o[6], corr, pe * vc.z); o[7] = fmaf(o[7], corr, pe * vc.w);
+    }
+    const float inv = 1.0f / l;
+    float* op = ob + (size_t)h * kHd * cs + tok_off(tq);
+#pragma unroll
+    for (int j = 0; j < kHd; ++j) op[(size_t)j * cs] = o[j] * inv;
+  }
+}
+}  // namespace
+
+extern "C" int ss_window_attention_core_f32_masked(const float* qkv, float* out_f32, int B, int C, int D, int H, int W, int bd, int bh, int bw,
+                                                   int num_heads, int H0, int W0, void* stream) {
+  SS_REQUIRE(qkv && out_f32, "ss_window_attention_core_f32_masked: null pointer");
+  SS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && bd > 0 && bh > 0 && bw > 0, "ss_window_attention_core_f32_masked: non-positive dimension");
+  SS_REQUIRE(H0 > 0 && H0 <= H && W0 > 0 && W0 <= W, "ss_window_attention_core_f32_masked: the valid extent (H0, W0) must lie inside (H, W)");
+  SS_UNSUPPORTED(C != kC || num_heads != kHeads, "ss_window_attention_core_f32_masked: only C=128 with 16 heads is supported");
+  SS_UNSUPPORTED(D % bd || H % bh || W % bw, "ss_window_attention_core_f32_masked: the PADDED D,H,W must be multiples of the window");
+  const int T = bd * bh * bw;
+  SS_UNSUPPORTED(T > 128, "ss_window_attention_core_f32_masked: window of %d tokens unsupported (<= 128)", T);
+  const size_t smem = ((size_t)3 * kC * T + T) * sizeof(float);
+  const long long nwin = (long long)B * (D / bd) * (H / bh) * (W / bw);
+  SS_UNSUPPORTED(nwin > 0x7fffffffLL, "ss_window_attention_core_f32_masked: too many windows");
+  SS_CUDA(ss_allow_smem(window_attention_core_f32_masked_kernel, smem));
+  window_attention_core_f32_masked_kernel<<<(unsigned)nwin, 256, smem, (cudaStream_t)stream>>>(qkv, out_f32, D, H, W, bd, bh, bw, D / bd, H / bh,
+                                                                                                W / bw, T, H0, W0);
+  SS_CHECK_LAUNCH("ss_window_attention_core_f32_masked");
+  return SS_OK;
+}
+
 // fp32 output variant of the core (training forward) and its backward.
 extern "C" int ss_window_attention_core_f32_out(const float* qkv, float* out_f32, int B, int C, int D, int H, int W, int bd, int bh, int bw,
                                                 int num_heads, void* stream) {
@@ -426,22 +524,29 @@ extern "C" int ss_window_attention_core_f32_out(const float* qkv, float* out_f32
   return SS_OK;
 }
 
-extern "C" int ss_window_attention_core_backward(const float* qkv, const float* grad_out, float* grad_qkv, int B, int C, int D, int H, int W,
-                                                 int bd, int bh, int bw, int num_heads, void* stream) {
+// Backward of the masked core (and, with H0 = H and W0 = W, of the unmasked one).
+extern "C" int ss_window_attention_core_backward_masked(const float* qkv, const float* grad_out, float* grad_qkv, int B, int C, int D, int H,
+                                                        int W, int bd, int bh, int bw, int num_heads, int H0, int W0, void* stream) {
   SS_REQUIRE(qkv && grad_out && grad_qkv, "ss_window_attention_core_backward: null pointer");
   SS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && bd > 0 && bh > 0 && bw > 0, "ss_window_attention_core_backward: non-positive dimension");
+  SS_REQUIRE(H0 > 0 && H0 <= H && W0 > 0 && W0 <= W, "ss_window_attention_core_backward: the valid extent (H0, W0) must lie inside (H, W)");
   SS_UNSUPPORTED(C != kC || num_heads != kHeads, "ss_window_attention_core_backward: only C=128 with 16 heads is supported");
   SS_UNSUPPORTED(D % bd || H % bh || W % bw, "ss_window_attention_core_backward: D,H,W must be multiples of the window");
   const int T = bd * bh * bw;
   SS_UNSUPPORTED(T > 96, "ss_window_attention_core_backward: window of %d tokens unsupported (<= 96)", T);
-  const size_t smem = ((size_t)4 * T * kHd + (size_t)2 * T * (T + 1)) * sizeof(float);
+  const size_t smem = ((size_t)4 * T * kHd + (size_t)2 * T * (T + 1) + T) * sizeof(float);
   const long long nblk = (long long)B * (D / bd) * (H / bh) * (W / bw) * kHeads;
   SS_UNSUPPORTED(nblk > 0x7fffffffLL, "ss_window_attention_core_backward: too many windows");
   SS_CUDA(ss_allow_smem(window_attention_core_bwd_kernel, smem));
   window_attention_core_bwd_kernel<<<(unsigned)nblk, 96, smem, (cudaStream_t)stream>>>(qkv, grad_out, grad_qkv, D, H, W, bd, bh, bw, D / bd, H / bh,
-                                                                                      W / bw, T);
+                                                                                      W / bw, T, H0, W0);
   SS_CHECK_LAUNCH("ss_window_attention_core_backward");
   return SS_OK;
+}
+
+extern "C" int ss_window_attention_core_backward(const float* qkv, const float* grad_out, float* grad_qkv, int B, int C, int D, int H, int W,
+                                                 int bd, int bh, int bw, int num_heads, void* stream) {
+  return ss_window_attention_core_backward_masked(qkv, grad_out, grad_qkv, B, C, D, H, W, bd, bh, bw, num_heads, H, W, stream);
 }
 
 extern "C" int ss_window_attention_core_f32(const float* qkv, void* out_tri, int B, int C, int D, int H, int W, int bd, int bh, int bw,

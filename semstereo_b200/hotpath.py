@@ -341,11 +341,16 @@ class DisparityHotPath(nn.Module):
         c4 = self._tc(c, hg + ".conv4", tc.S1, c3, 128)
         # attention_block (submodule_other.py:805-837): qkv Linear and final 1x1x1 conv as tensor-core 1x1 layers (bias = shift),
         # the per-(window, head) softmax core in between; a head is one channel chunk of the blocked layout
-        c4, H0, W0 = ops.window_pad(c4, block)           # H / W not multiples of the window: zero-pad (one axis), crop after the block
-        qkv = self._tc(c, hg + ".attn_qkv", tc.K1, c4, 384, relu=False)
-        with ops.label(hg + ".attn_core"):
-            att = tc.window_attention_core(qkv, block, 16)
-        c4b = ops.window_crop(self._tc(c, hg + ".attn_out", tc.K1, att, 128, relu=False), H0, W0)
+        if ops.window_needs_mask(c4.shape, block):       # H and W both padded: the reference's masked branch, fp32 (ops.window_attention3d)
+            with ops.label(hg + ".attention_masked"):
+                c4b = tc.to_blocked_bf16(ops.window_attention3d(tc.from_blocked_bf16(c4), c[hg + ".wqkv_t"], c[hg + ".bqkv"], c[hg + ".wo_t"],
+                                                                c[hg + ".bo"], block, 16))
+        else:
+            c4, H0, W0 = ops.window_pad(c4, block)       # H / W not multiples of the window: zero-pad (one axis), crop after the block
+            qkv = self._tc(c, hg + ".attn_qkv", tc.K1, c4, 384, relu=False)
+            with ops.label(hg + ".attn_core"):
+                att = tc.window_attention_core(qkv, block, 16)
+            c4b = ops.window_crop(self._tc(c, hg + ".attn_out", tc.K1, att, 128, relu=False), H0, W0)
         # conv5/conv6 (transposed) with the redir2/redir1 1x1 skip convs fused in as one more GEMM tap on the TMA-staged skip
         # tile (BN scales folded into both weights, shifts summed): relu(bn(deconv(x)) + bn(redir(skip)))  (SemStereo.py:141-142)
         with ops.label(hg + ".conv5"):
@@ -371,12 +376,16 @@ class DisparityHotPath(nn.Module):
         # attention_block (submodule_other.py:805-837): qkv Linear and final 1x1x1 conv as fp32-accurate K-concat GEMMs (a volume is
         # a 2-D image of D*H rows for a 1x1 conv), the fp32 softmax core in between writes the K-concat form directly
         with ops.label(hg + ".attention"):
-            c4, H0, W0 = ops.window_pad(c4, block)       # H / W not multiples of the window: zero-pad (one axis), crop after the block
-            B, C, D, H, W = c4.shape
-            qkv = tc.pointwise_split(tc.to_blocked_tri(c4.view(B, C, D * H, W)), c[hg + ".attn_qkv.tri"], 3 * C, None, c[hg + ".bqkv"])
-            att = tc.window_attention_core_f32(qkv.view(B, 3 * C, D, H, W), block, 16)
-            c4 = tc.pointwise_split(att.view(B, 3 * C // 8, D * H, W, 8), c[hg + ".attn_out.tri"], C, None, c[hg + ".bo"])
-            c4b = tc.to_blocked_bf16(ops.window_crop(c4.view(B, C, D, H, W), H0, W0), split=True)
+            if ops.window_needs_mask(c4.shape, block):   # H and W both padded: the reference's masked branch (ops.window_attention3d)
+                c4b = tc.to_blocked_bf16(ops.window_attention3d(c4, c[hg + ".wqkv_t"], c[hg + ".bqkv"], c[hg + ".wo_t"], c[hg + ".bo"], block, 16),
+                                         split=True)
+            else:
+                c4, H0, W0 = ops.window_pad(c4, block)   # H / W not multiples of the window: zero-pad (one axis), crop after the block
+                B, C, D, H, W = c4.shape
+                qkv = tc.pointwise_split(tc.to_blocked_tri(c4.view(B, C, D * H, W)), c[hg + ".attn_qkv.tri"], 3 * C, None, c[hg + ".bqkv"])
+                att = tc.window_attention_core_f32(qkv.view(B, 3 * C, D, H, W), block, 16)
+                c4 = tc.pointwise_split(att.view(B, 3 * C // 8, D * H, W, 8), c[hg + ".attn_out.tri"], C, None, c[hg + ".bo"])
+                c4b = tc.to_blocked_bf16(ops.window_crop(c4.view(B, C, D, H, W), H0, W0), split=True)
         with ops.label(hg + ".conv5"):
             c5 = tc.conv3d_tc_split(tc.T2, c4b, c[hg + ".conv5.ftcs"], 64, None, c[hg + ".conv5.fshift"], residual_s2d=c2s,
                                     skip_split=c[hg + ".conv5.skipws"], relu=True)

@@ -185,20 +185,26 @@ def conv3d_cout1_f32(x, weight):
 
 
 # ---- K5 ----------------------------------------------------------------------------------------------
-def window_pad(t, block):
+def window_needs_mask(shape, block):
+    """True when BOTH H and W of a (B,C,D,H,W[,8]) volume need padding to the window: the reference's masked branch."""
+    return bool((-shape[3]) % block[1]) and bool((-shape[4]) % block[2])
+
+
+def window_pad(t, block, both=False):
     """Zero-pads axes 3 (H) and 4 (W) of a (B,C,D,H,W) / blocked (B,C/8,D,H,W,8) tensor to multiples of the window, as
     attention_block.forward does before its qkv Linear (submodule_other.py:809-812).  Returns (tensor, H0, W0).
-    Supported: padding on ONE of the two axes -- the reference's mask `mask[:, -pad_b:, :] = 1; mask[:, :, -pad_r:] = 1` is all ones
-    when exactly one pad is 0 (`-0:` selects everything), so nothing is masked and the padded tokens (which carry the qkv bias) simply
-    take part in their window's softmax: the unmodified kernels on the padded volume, cropped afterwards, ARE that computation.
-    Padding on both axes needs the -1000 score mask between padded and real tokens, which the kernels do not have: refused."""
+    Padding on ONE of the two axes: the reference's mask `mask[:, -pad_b:, :] = 1; mask[:, :, -pad_r:] = 1` is all ones when exactly
+    one pad is 0 (`-0:` selects everything), so nothing is masked and the padded tokens (which carry the qkv bias) simply take part in
+    their window's softmax: the unmodified kernels on the padded volume, cropped afterwards, ARE that computation.
+    Padding on BOTH axes needs the -1000 score mask between padded and real tokens: only window_attention3d (the masked fp32 core,
+    ss_window_attention_core_f32_masked) computes that, so callers of the unmasked kernels get a refusal unless they pass both=True."""
     D, H, W = t.shape[2], t.shape[3], t.shape[4]
     if D % block[0]:
         raise NotImplementedError(f"window attention: depth {D} is not a multiple of the window depth {block[0]} (the reference does not pad D)")
     pb, pr = (-H) % block[1], (-W) % block[2]
-    if pb and pr:
+    if pb and pr and not both:
         raise NotImplementedError(f"window attention: H = {H} and W = {W} both need padding to the window {tuple(block)[1:]}: the "
-                                  "reference's masked branch (submodule_other.py:822-829) is not implemented on the B200 path")
+                                  "reference's masked branch (submodule_other.py:822-829) runs through ops.window_attention3d only")
     if not (pb or pr):
         return t, H, W
     shape = list(t.shape)
@@ -213,8 +219,25 @@ def window_crop(t, H0, W0):
     return t if (t.shape[3], t.shape[4]) == (H0, W0) else t[:, :, :, :H0, :W0].contiguous()
 
 
+def window_attention_core_masked(qkv, block, H0, W0, num_heads=16):
+    """The softmax core of the masked branch: qkv (B,3C,D,H,W) fp32 of the PADDED volume -> (B,C,D,H,W) fp32 (submodule_other.py:822-831)."""
+    dev = _require_cuda(qkv)
+    B, C3, D, H, W = qkv.shape
+    out = torch.empty((B, C3 // 3, D, H, W), device=dev, dtype=torch.float32)
+    _call("ss_window_attention_core_f32_masked", dev, _ptr(qkv), _ptr(out), B, C3 // 3, D, H, W, int(block[0]), int(block[1]), int(block[2]),
+          int(num_heads), int(H0), int(W0))
+    return out
+
+
 def window_attention3d(x, wqkv_t, bqkv, wo_t, bo, block, num_heads=16):
     dev = _require_cuda(x, wqkv_t, bqkv, wo_t, bo)
+    if window_needs_mask(x.shape, block):
+        # both axes padded (submodule_other.py:809-836): pad -> qkv Linear (padded tokens = bias) -> masked core -> crop -> final conv
+        xp, H0, W0 = window_pad(x, block, both=True)
+        B, C, D, H, W = xp.shape
+        qkv = pointwise_conv2d(xp.view(B, C, D * H, W), wqkv_t.t().contiguous(), None, bqkv).view(B, 3 * C, D, H, W)
+        att = window_crop(window_attention_core_masked(qkv, block, H0, W0, num_heads), H0, W0)
+        return pointwise_conv2d(att.view(B, C, D * H0, W0), wo_t.t().contiguous(), None, bo).view(B, C, D, H0, W0)
     x, H0, W0 = window_pad(x, block)
     B, C, D, H, W = x.shape
     out = torch.empty_like(x)

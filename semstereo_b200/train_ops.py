@@ -173,15 +173,24 @@ def batch_norm_train(x, bn: torch.nn.modules.batchnorm._BatchNorm):
 # attention_block and SSR_upsample in training mode: compositions of differentiable kernels
 # ---------------------------------------------------------------------------------------------------------------------
 class _AttnCoreFn(torch.autograd.Function):
+    """The softmax core.  valid = (H0, W0): the masked branch -- qkv is that of the volume zero-padded on BOTH axes, tokens beyond
+    (H0, W0) are padding and scores between padded and real tokens get -1000 (submodule_other.py:822-829); None: nothing is masked."""
+
     @staticmethod
-    def forward(ctx, qkv, block, heads):
+    def forward(ctx, qkv, block, heads, valid=None):
         dev = _require_cuda(qkv)
         qkv = qkv.contiguous()
         B, C3, D, H, W = qkv.shape
         out = torch.empty((B, C3 // 3, D, H, W), device=dev, dtype=torch.float32)
-        _call("ss_window_attention_core_f32_out", dev, _ptr(qkv), _ptr(out), B, C3 // 3, D, H, W, int(block[0]), int(block[1]), int(block[2]), int(heads))
+        if valid is None:
+            _call("ss_window_attention_core_f32_out", dev, _ptr(qkv), _ptr(out), B, C3 // 3, D, H, W, int(block[0]), int(block[1]), int(block[2]),
+                  int(heads))
+        else:
+            _call("ss_window_attention_core_f32_masked", dev, _ptr(qkv), _ptr(out), B, C3 // 3, D, H, W, int(block[0]), int(block[1]),
+                  int(block[2]), int(heads), int(valid[0]), int(valid[1]))
         ctx.save_for_backward(qkv)
         ctx.block, ctx.heads = tuple(int(v) for v in block), int(heads)
+        ctx.valid = (H, W) if valid is None else (int(valid[0]), int(valid[1]))
         return out
 
     @staticmethod
@@ -189,9 +198,9 @@ class _AttnCoreFn(torch.autograd.Function):
         (qkv,) = ctx.saved_tensors
         B, C3, D, H, W = qkv.shape
         dq = torch.empty_like(qkv)
-        _call("ss_window_attention_core_backward", qkv.device, _ptr(qkv), _ptr(dout.contiguous().float()), _ptr(dq), B, C3 // 3, D, H, W,
-              ctx.block[0], ctx.block[1], ctx.block[2], ctx.heads)
-        return dq, None, None
+        _call("ss_window_attention_core_backward_masked", qkv.device, _ptr(qkv), _ptr(dout.contiguous().float()), _ptr(dq), B, C3 // 3, D, H, W,
+              ctx.block[0], ctx.block[1], ctx.block[2], ctx.heads, ctx.valid[0], ctx.valid[1])
+        return dq, None, None, None
 
 
 def attention_block_train(mod, x):
@@ -201,12 +210,11 @@ def attention_block_train(mod, x):
     C = mod.qkv_3d.in_features
     H0, W0 = x.shape[3], x.shape[4]
     pb, pr = (-H0) % block[1], (-W0) % block[2]
-    if pb and pr:       # the reference's -1000 mask between padded and real tokens (submodule_other.py:822-829); see ops.window_pad
-        raise NotImplementedError("attention_block (training): H and W both need padding to the window: masked branch not implemented")
-    if pb or pr:        # one axis: zero-pad before the qkv Linear, crop before the final conv -- nothing is masked (ops.window_pad)
+    if pb or pr:        # zero-pad before the qkv Linear (padded tokens carry the bias), crop before the final conv
         x = torch.nn.functional.pad(x, (0, pr, 0, pb))
     qkv = conv3d(x, mod.qkv_3d.weight.view(3 * C, C, 1, 1, 1), 1) + mod.qkv_3d.bias.view(1, -1, 1, 1, 1)
-    o = _AttnCoreFn.apply(qkv, block, mod.num_heads)[:, :, :, :H0, :W0]
+    # one padded axis: the reference masks nothing (ops.window_pad); both: -1000 between padded and real tokens (submodule_other.py:822-829)
+    o = _AttnCoreFn.apply(qkv, block, mod.num_heads, (H0, W0) if (pb and pr) else None)[:, :, :, :H0, :W0]
     return conv3d(o, mod.final1x1.weight, 1) + mod.final1x1.bias.view(1, -1, 1, 1, 1)
 
 

@@ -303,13 +303,15 @@ def test_path_is_bitwise_reproducible(precision):
             assert torch.equal(v, outs[0][k]), k
 
 
+@pytest.mark.parametrize("shape", [(128, 192), (192, 192)])
 @pytest.mark.parametrize("precision", ["fp32", "split", "bf16"])
-def test_width_that_needs_window_padding(precision):
+def test_width_that_needs_window_padding(precision, shape):
     """128 x 192 images: the attention-branch hourglass reaches its attention block at W/32 = 6, not a multiple of the 4-wide window,
     so the block zero-pads W to 8 (one axis: the reference masks nothing there) and crops afterwards (submodule_other.py:809-836).
-    The oracle restates that branch and is pinned to the reference module by tests/golden/att_padded.npz."""
+    192 x 192: H/32 = W/32 = 6, both axes padded -- the reference's masked branch (-1000 between padded and real tokens).
+    The oracle restates both branches and is pinned to the reference module by tests/golden/att_padded.npz."""
     p = make_params(seed=1, peaked=20.0)
-    inp = make_inputs(9, 1, 128, 192)
+    inp = make_inputs(9, 1, *shape)
     ref = oh.forward(p, inp, 64, signed=True, keep=True)
     m = DisparityHotPath(64, False, True, precision=precision)
     m.load_state_dict(p, strict=True)

@@ -235,10 +235,11 @@ def test_error_behaviour():
         sub_s.disparity_regression(torch.zeros(1, 8, 4, device=DEV), 4)
     with pytest.raises(RuntimeError):
         sub_s.disparity_regression(torch.zeros(1, 6, 4, 4, device=DEV), 4)   # bins != 2*maxdisp
-    for shape in ((1, 128, 4, 6, 10), (1, 128, 5, 8, 8)):      # H and W both need window padding (masked branch) / D does not divide
-        with pytest.raises(NotImplementedError):
-            ops.window_attention3d(torch.zeros(shape, device=DEV), torch.zeros(128, 384, device=DEV), torch.zeros(384, device=DEV),
-                                   torch.zeros(128, 128, device=DEV), torch.zeros(128, device=DEV), (4, 4, 4))
+    with pytest.raises(NotImplementedError):                    # D does not divide by the window (the reference does not pad D)
+        ops.window_attention3d(torch.zeros(1, 128, 5, 8, 8, device=DEV), torch.zeros(128, 384, device=DEV), torch.zeros(384, device=DEV),
+                               torch.zeros(128, 128, device=DEV), torch.zeros(128, device=DEV), (4, 4, 4))
+    with pytest.raises(NotImplementedError):                    # the unmasked kernels refuse a volume that needs the score mask
+        ops.window_pad(torch.zeros(1, 128, 4, 6, 10, device=DEV), (4, 4, 4))
     with pytest.raises(RuntimeError):
         ops.gwc_volume(torch.zeros(1, 8, 4, 8), torch.zeros(1, 8, 4, 8), 2, 2)   # CPU tensors: no fallback
 
@@ -271,8 +272,8 @@ def test_torch_library_ops_match_the_wrappers():
 
 def test_window_attention_on_padded_windows(golden_dir):
     """attention_block on H / W that are not multiples of the window, against outputs of the unmodified reference module
-    (tests/golden/att_padded.npz): padding on one axis is supported (nothing is masked there, see ops.window_pad); padding on both
-    axes needs the reference's score mask and is refused loudly."""
+    (tests/golden/att_padded.npz): padding on one axis masks nothing (see ops.window_pad) and runs on the unmasked kernels; padding
+    on both axes takes the masked core (-1000 between padded and real tokens, ss_window_attention_core_f32_masked)."""
     from oracle.make_golden_attpad import CASES
     g = dict(np.load(os.path.join(golden_dir, "att_padded.npz")))
     p = make_params(seed=2)
@@ -281,8 +282,7 @@ def test_window_attention_on_padded_windows(golden_dir):
     args = (cu(wq), cu(p["hourglass.attention_block.qkv_3d.bias"]), cu(wo), cu(p["hourglass.attention_block.final1x1.bias"]))
     for name, (block, shape) in CASES.items():
         x = cu(torch.from_numpy(g["in_" + name]))
-        if name.startswith("both"):
-            with pytest.raises(NotImplementedError):
-                ops.window_attention3d(x, *args, block, 16)
-        else:
-            assert err(ops.window_attention3d(x, *args, block, 16), g["out_" + name]) <= 5e-5, name
+        assert err(ops.window_attention3d(x, *args, block, 16), g["out_" + name]) <= 5e-5, name
+        if name.startswith("both"):     # and against the oracle's restatement of the same branch
+            want = oo.window_attention3d(torch.from_numpy(g["in_" + name]), p, "hourglass.attention_block", 16, block)
+            assert err(ops.window_attention3d(x, *args, block, 16), want) <= 5e-5, name

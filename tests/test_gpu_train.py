@@ -92,7 +92,8 @@ def test_surface_modules_train():
     assert relerr(e, t(x.detach())) <= 1e-4
 
 
-@pytest.mark.parametrize("D,H,W,block", [(4, 8, 8, (4, 4, 4)), (6, 8, 12, (6, 4, 4)), (4, 8, 10, (4, 4, 4))])      # the last one: W padded to the window
+# (4, 8, 10): W padded to the window (nothing masked); (4, 6, 10) and (6, 6, 6): H and W both padded, the masked branch
+@pytest.mark.parametrize("D,H,W,block", [(4, 8, 8, (4, 4, 4)), (6, 8, 12, (6, 4, 4)), (4, 8, 10, (4, 4, 4)), (4, 6, 10, (4, 4, 4)), (6, 6, 6, (6, 4, 4))])
 def test_attention_block_train(D, H, W, block):
     """attention_block in training mode (k = 1 convs + softmax core kernels, forward and backward) vs torch autograd through the oracle."""
     from oracle import ops as oo
