@@ -204,7 +204,7 @@ def make_decoder_params(seed: int = 2) -> "OrderedDict[str, torch.Tensor]":
 def make_backbone_features(seed: int, B: int, H: int, W: int, max_shift: int = 3):
     """Seeded stand-ins for `Feature` outputs [x2, x4, x8, x16, x32] of the left and right image (CPU fp32): right = left shifted
     along x by a row-block-dependent amount plus noise, like make_inputs."""
-    assert H % 128 == 0 and W % 128 == 0, "H and W must be multiples of 128"
+    assert H % 64 == 0 and W % 64 == 0, "H and W must be multiples of 64"
     g = torch.Generator().manual_seed(seed)
     fl, fr = [], []
     for c, s in zip(BACKBONE_CHANS, (2, 4, 8, 16, 32)):

@@ -93,7 +93,8 @@ def test_backbone_matches_the_huggingface_architecture(B, H, W):
         assert rmax <= 4e-2 and rmean <= 3e-2, (i, rmax, rmean)      # bf16 activations through up to ~45 layers: measured 0.5 % (x2) .. 2 % (x32)
 
 
-def test_full_model_images_to_disparity():
+@pytest.mark.parametrize("H,W", [(128, 256), (192, 192)])          # 192: multiples of 64 only -> padded + masked attention windows
+def test_full_model_images_to_disparity(H, W):
     """SemStereoB200 = backbone + decoder + path: images in, what SemStereo.forward returns out; against the oracles chained on the CPU."""
     from oracle import backbone as ob, decoder as od, hotpath as oh
     from semstereo_b200.params import make_decoder_params, make_params
@@ -101,7 +102,7 @@ def test_full_model_images_to_disparity():
     sd.update(make_decoder_params(seed=2))
     pb = make_backbone_params(seed=4)
     sd.update({"feature." + k: v for k, v in pb.items()})
-    left, right = make_images(6, 1, 128, 256)
+    left, right = make_images(6, 1, H, W)
     fl, fr = ob.forward(pb, left), ob.forward(pb, right)
     d = od.forward(sd, fl, fr, right_label=False)
     ref = oh.forward(sd, {k: d[k] for k in ("f8_l", "f8_r", "f4_l", "f4_r", "spx_pred", "pred_label")}, 64, signed=True)
@@ -111,7 +112,7 @@ def test_full_model_images_to_disparity():
     out = model.to(DEV)(left.to(DEV), right.to(DEV))
     torch.cuda.synchronize()
     disp, label = model.as_model_outputs(out)
-    assert tuple(disp[0].shape) == (1, 128, 256) and tuple(label.shape) == (1, 6, 128, 256)
+    assert tuple(disp[0].shape) == (1, H, W) and tuple(label.shape) == (1, 6, H, W)
     rmax, rmean = rel(label.cpu(), d["pred_label"])
     med = (out["pred_up"].cpu() - ref["pred_up"]).abs().median().item()
     print(f"full model: pred_label max rel {rmax:.4f}, median |pred_up - oracle| {med:.4f} px (1/4-res units)")
