@@ -1,6 +1,7 @@
 """Kernel launch shares of one pass of the path from an ncu launch list (--metrics gpu__time_duration.sum --csv):
     python tools/launch_shares.py profiles/r02_launches_split_batch2.csv > profiles/r02_launch_shares.txt
-The CSV holds the warm-up pass and the measured pass of tools/ncu_path_once.py: the second half of this library's launches is used."""
+The CSV holds the warm-up pass and the measured pass of tools/ncu_path_once.py: the second half of this library's launches is used
+(for the whole model: everything from the last stem conv on)."""
 import csv, re, sys, collections
 
 rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10]
@@ -8,7 +9,9 @@ h = rows[0]
 ik, iv, iu = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
 ours = [(r[ik], float(r[iv].replace(",", "")) / (1000.0 if r[iu] in ("ns", "nsecond") else 1.0)) for r in rows[1:]
         if "<unnamed>" in r[ik] or "ss_" in r[ik]]
-ours = ours[len(ours) // 2:]
+stems = [i for i, (k, _) in enumerate(ours) if "stem_conv_kernel" in k]
+# whole model: a pass starts at its (single) stem conv -- the warm-up pass also packs weights, so halving would misplace the boundary
+ours = ours[stems[-1]:] if stems else ours[len(ours) // 2:]
 tot = sum(t for _, t in ours)
 agg = collections.OrderedDict()
 for k, t in ours:
