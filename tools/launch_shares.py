@@ -9,9 +9,18 @@ h = rows[0]
 ik, iv, iu = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
 ours = [(r[ik], float(r[iv].replace(",", "")) / (1000.0 if r[iu] in ("ns", "nsecond") else 1.0)) for r in rows[1:]
         if "<unnamed>" in r[ik] or "ss_" in r[ik]]
+# pass boundary: the whole model starts a pass at its (single) stem conv; a multi-pass list of the path (bench.py under ncu) at the
+# gwc volume kernel -- a pass from the middle of the run is used.  A two-pass list of tools/ncu_path_once.py: the second half.
 stems = [i for i, (k, _) in enumerate(ours) if "stem_conv_kernel" in k]
-# whole model: a pass starts at its (single) stem conv -- the warm-up pass also packs weights, so halving would misplace the boundary
-ours = ours[stems[-1]:] if stems else ours[len(ours) // 2:]
+gwcs = [i for i, (k, _) in enumerate(ours) if "gwc_volume" in k]
+if stems:
+    ours = ours[stems[-1]:]
+elif len(gwcs) > 2:
+    m = len(gwcs) // 2                         # a pass from the middle of the run (bench.py: the timed K steps)
+    per, lead = gwcs[m + 1] - gwcs[m], gwcs[0]  # launches per pass; launches of a pass before its gwc kernel
+    ours = ours[gwcs[m] - lead:gwcs[m] - lead + per]
+else:
+    ours = ours[len(ours) // 2:]
 tot = sum(t for _, t in ours)
 agg = collections.OrderedDict()
 for k, t in ours:
