@@ -586,7 +586,8 @@ extern "C" int ss_window_attention3d(const float* x, const float* wqkv_t, const 
   SS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && bd > 0 && bh > 0 && bw > 0, "ss_window_attention3d: non-positive dimension");
   SS_UNSUPPORTED(C != kC || num_heads != kHeads, "ss_window_attention3d: only C=128 with 16 heads is supported (got C=%d, heads=%d)", C, num_heads);
   // The reference pads H/W to the window and masks (submodule_other.py:809-829).  The host wrapper (ops.window_pad) pads one axis
-  // around this kernel -- the reference masks nothing in that case -- and refuses two; the kernel itself takes divisible volumes.
+  // around this kernel -- the reference masks nothing in that case -- and routes two through ss_window_attention_core_f32_masked;
+  // the kernel itself takes divisible volumes.
   SS_UNSUPPORTED(D % bd || H % bh || W % bw, "ss_window_attention3d: D,H,W (%d,%d,%d) must be multiples of the window (%d,%d,%d)", D, H, W, bd, bh, bw);
   const int T = bd * bh * bw;
   SS_UNSUPPORTED(T % 16 || T > 96, "ss_window_attention3d: window of %d tokens unsupported (multiple of 16, <= 96)", T);
