@@ -106,7 +106,8 @@ class ShardedHotPath:
 # ---------------------------------------------------------------------------------------------------------------------
 # Large single images: row tiles with halos, tiles spread over the ranks ("large single images")
 # ---------------------------------------------------------------------------------------------------------------------
-TILE_UNIT = 128          # the path needs H % 128 == 0 and tile origins on the window-attention grid (128 px at 1/32 resolution)
+TILE_UNIT = 128          # tiles are whole 128-row units with origins on the window-attention grid (128 px at 1/32 resolution), so a
+                         # tile sees the same (unpadded) windows as the whole image
 EXACT_HALO = 384         # >= the vertical receptive field of the whole path (~380 px)
 
 

@@ -114,10 +114,10 @@ def make_params(seed: int = 1, peaked: float = 1.0, gamma: float = 0.05) -> "Ord
 def make_inputs(seed: int, B: int, H: int, W: int, num_classes: int = 6, max_shift: int = 3):
     """Seeded synthetic inputs of the hot path for a (B,3,H,W) stereo pair (CPU fp32).
     Right features are the left ones displaced along x by a row-block-dependent shift plus noise,
-    so the cost volumes have real structure.  H, W must be multiples of 64 (three stride-2 stages below 1/4 resolution, and the
-    4-wide attention window of the main hourglass at H/16); a multiple of 64 that is not one of 128 makes the attention-branch
-    hourglass pad its window at H/32 (attention_block's padded branch, submodule_other.py:809-836)."""
-    assert H % 64 == 0 and W % 64 == 0, "H and W must be multiples of 64"
+    so the cost volumes have real structure.  H, W must be multiples of 32 (the 1/8-resolution attention branch halves twice and its
+    transposed convs double back: H/8 must be a multiple of 4); a size that is not a multiple of 128 makes the hourglasses pad their
+    4-wide attention windows at H/16 / H/32 (attention_block's padded branch, submodule_other.py:809-836)."""
+    assert H % 32 == 0 and W % 32 == 0, "H and W must be multiples of 32"
     g = torch.Generator().manual_seed(seed)
 
     def pair(c, h, w, scale):

@@ -303,7 +303,7 @@ def test_path_is_bitwise_reproducible(precision):
             assert torch.equal(v, outs[0][k]), k
 
 
-@pytest.mark.parametrize("shape", [(128, 192), (192, 192)])
+@pytest.mark.parametrize("shape", [(128, 192), (192, 192), (96, 160)])
 @pytest.mark.parametrize("precision", ["fp32", "split", "bf16"])
 def test_width_that_needs_window_padding(precision, shape):
     """128 x 192 images: the attention-branch hourglass reaches its attention block at W/32 = 6, not a multiple of the 4-wide window,
